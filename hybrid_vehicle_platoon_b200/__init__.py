@@ -1,0 +1,11 @@
+"""hybrid_vehicle_platoon_b200 -- B200-native (sm_100a) batched hybrid-MPC hot path for
+Kevindqz/hybrid-vehicle-platoon: rollout/stage-cost kernel and per-vehicle MIQP
+branch-and-bound kernel behind a C ABI (include/hvp.h), with reference-shaped Python classes.
+"""
+from . import _lib  # noqa: F401
+from ._lib import FRONT, LEADER, TRAILER, Context, default_context  # noqa: F401
+from .api import (  # noqa: F401
+    env_desc, local_desc, local_miqp, local_miqp_device, rollout_step, rollout_step_device,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,134 @@
+"""ctypes binding of libhvp.so (include/hvp.h).  The CUDA library is the ONLY execution path of
+this package: a missing library or a missing GPU raises, nothing falls back to the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libhvp.so")
+
+OPTIMAL, INFEASIBLE, NODE_LIMIT, NUMERIC = 2, 3, 8, 12
+FRONT, LEADER, TRAILER = 1, 2, 4
+ENV_QUADRATIC, ENV_REAL_VEHICLE_REF, ENV_MASS_PER_SCENARIO = 1, 2, 4
+
+
+class EnvDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("leader_index", C.c_int32), ("flags", C.c_int32),
+                ("reserved", C.c_int32), ("d0", C.c_double), ("t0", C.c_double),
+                ("d_safe", C.c_double)]
+
+
+class LocalDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("max_nodes", C.c_int32), ("d0", C.c_double), ("t0", C.c_double),
+                ("tight", C.c_double)]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libhvp.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC, "libhvp.so"], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode:
+        raise RuntimeError("building libhvp.so failed")
+    return LIB_PATH
+
+
+_lib = None
+_vp = C.c_void_p
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(hybrid_vehicle_platoon_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.hvp_version.restype = C.c_int
+    L.hvp_last_error.argtypes = [C.c_char_p, C.c_int]
+    L.hvp_device_count.restype = C.c_int
+    L.hvp_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
+    L.hvp_ctx_destroy.argtypes = [_vp]
+    L.hvp_ctx_stream.argtypes = [_vp]
+    L.hvp_ctx_stream.restype = _vp
+    L.hvp_ctx_synchronize.argtypes = [_vp]
+    L.hvp_ctx_launch_count.argtypes = [_vp]
+    L.hvp_ctx_launch_count.restype = C.c_int64
+    L.hvp_ctx_last_kernel_ms.argtypes = [_vp]
+    L.hvp_ctx_last_kernel_ms.restype = C.c_float
+    roll = [_vp, C.POINTER(EnvDesc), C.c_int64] + [_vp] * 9
+    L.hvp_rollout_step_dev.argtypes = roll + [_vp]
+    L.hvp_rollout_step_host.argtypes = roll
+    loc = [_vp, C.POINTER(LocalDesc), C.c_int64] + [_vp] * 12
+    L.hvp_local_miqp_dev.argtypes = loc + [_vp]
+    L.hvp_local_miqp_host.argtypes = loc
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    lib().hvp_last_error(buf, 512)
+    return buf.value.decode()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"libhvp error {rc}: {last_error()}")
+
+
+class Context:
+    """One device + one stream (hvp_ctx)."""
+
+    def __init__(self, device: int = 0):
+        L = lib()
+        if L.hvp_device_count() <= 0:
+            raise RuntimeError("no CUDA device visible: hybrid_vehicle_platoon_b200 has no CPU path")
+        h = _vp()
+        check(L.hvp_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self) -> int:
+        return lib().hvp_ctx_stream(self._h) or 0
+
+    def synchronize(self):
+        check(lib().hvp_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return lib().hvp_ctx_launch_count(self._h)
+
+    def last_kernel_ms(self) -> float:
+        return lib().hvp_ctx_last_kernel_ms(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hvp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,89 @@
+"""Batched array-level entry points over the C ABI (numpy = host buffers, torch = device buffers)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EnvDesc, LocalDesc, check, default_context, lib
+
+
+def _hp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def env_desc(n, leader_index=0, d0=50.0, t0=0.0, d_safe=25.0, quadratic=True, real_ref=False,
+             mass_per_scenario=False) -> EnvDesc:
+    flags = (_lib.ENV_QUADRATIC if quadratic else 0) | (_lib.ENV_REAL_VEHICLE_REF if real_ref else 0) \
+        | (_lib.ENV_MASS_PER_SCENARIO if mass_per_scenario else 0)
+    return EnvDesc(int(n), int(leader_index), int(flags), 0, float(d0), float(t0), float(d_safe))
+
+
+def rollout_step(x, u, gear=None, mass=None, leader=None, *, d0=50.0, t0=0.0, leader_index=0,
+                 d_safe=25.0, quadratic=True, real_ref=False, ctx=None):
+    """Batched PlatoonEnv.step (env.py:182-212) on host (numpy) buffers.
+    x (B,2n), u (B,n), gear (B,n) int32|None, mass (n,)|(B,n)|None, leader (B,2).
+    Returns x_new (B,2n), cost (B,), viol (B,) uint8, err (B,) int32."""
+    ctx = ctx or default_context()
+    x = _c(x, np.float64); u = _c(u, np.float64)
+    B, n2 = x.shape
+    n = n2 // 2
+    gear = _c(gear, np.int32); mass = _c(mass, np.float64)
+    leader = _c(leader, np.float64).reshape(B, 2)
+    per = mass is not None and mass.ndim == 2
+    d = env_desc(n, leader_index, d0, t0, d_safe, quadratic, real_ref, per)
+    x_out = np.empty_like(x); cost = np.empty(B); viol = np.empty(B, np.uint8); err = np.empty(B, np.int32)
+    check(lib().hvp_rollout_step_host(ctx.handle, C.byref(d), B, _hp(x), _hp(u), _hp(gear), _hp(mass),
+                                      _hp(leader), _hp(x_out), _hp(cost), _hp(viol), _hp(err)))
+    return x_out, cost, viol, err
+
+
+def rollout_step_device(desc: EnvDesc, batch, x, u, gear, mass, leader, x_out, cost, viol, err, *,
+                        ctx=None, stream=None):
+    """Same on DEVICE buffers (torch CUDA tensors); asynchronous on `stream` (int cudaStream_t)."""
+    ctx = ctx or default_context()
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    check(lib().hvp_rollout_step_dev(ctx.handle, C.byref(desc), int(batch), p(x), p(u), p(gear), p(mass),
+                                     p(leader), p(x_out), p(cost), p(viol), p(err),
+                                     C.c_void_p(stream) if stream else None))
+
+
+def local_desc(N, d0=50.0, t0=0.0, tight=0.0, max_nodes=0) -> LocalDesc:
+    return LocalDesc(int(N), int(max_nodes), float(d0), float(t0), float(tight))
+
+
+def local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0, tight=0.0,
+               max_nodes=0, ctx=None):
+    """Batched LocalMpcMld solves (fleet_decent_mld.py:21-223) on host (numpy) buffers.
+    x0 (B,2); xf/xb/xl (B,2,N+1) or None; flags (B,) of FRONT|LEADER|TRAILER; mass (B,)."""
+    ctx = ctx or default_context()
+    x0 = _c(x0, np.float64)
+    B = x0.shape[0]
+    flags = _c(np.broadcast_to(flags, (B,)), np.int32)
+    mass = _c(np.broadcast_to(mass, (B,)), np.float64)
+    xf = _c(xf, np.float64); xb = _c(xb, np.float64); xl = _c(xl, np.float64)
+    for a in (xf, xb, xl):
+        if a is not None and a.size != B * 2 * (N + 1):
+            raise ValueError(f"reference arrays must have shape ({B}, 2, {N + 1})")
+    d = local_desc(N, d0, t0, tight, max_nodes)
+    u = np.empty((B, N)); x = np.empty((B, 2, N + 1)); modes = np.empty((B, N), np.int32)
+    obj = np.empty(B); status = np.empty(B, np.int32); nodes = np.empty(B, np.int32)
+    check(lib().hvp_local_miqp_host(ctx.handle, C.byref(d), B, _hp(flags), _hp(mass), _hp(x0), _hp(xf),
+                                    _hp(xb), _hp(xl), _hp(u), _hp(x), _hp(modes), _hp(obj), _hp(status),
+                                    _hp(nodes)))
+    return dict(u=u, x=x, modes=modes, obj=obj, status=status, nodes=nodes)
+
+
+def local_miqp_device(desc: LocalDesc, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status,
+                      nodes, *, ctx=None, stream=None):
+    """Same on DEVICE buffers (torch CUDA tensors); asynchronous on `stream`."""
+    ctx = ctx or default_context()
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    check(lib().hvp_local_miqp_dev(ctx.handle, C.byref(desc), int(batch), p(flags), p(mass), p(x0), p(xf),
+                                   p(xb), p(xl), p(u), p(x), p(modes), p(obj), p(status), p(nodes),
+                                   C.c_void_p(stream) if stream else None))

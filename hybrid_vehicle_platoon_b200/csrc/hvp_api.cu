@@ -1,0 +1,281 @@
+// hvp_api.cu -- the C ABI of libhvp.so (include/hvp.h): contexts, error reporting, host-buffer
+// wrappers.  No torch types, no CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hvp.h"
+#include "hvp_internal.h"
+#include "vehicle_model.h"
+
+using namespace hvp;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(-100 - (int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+struct hvp_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    bool timed;
+    int64_t launches;
+    // grow-only device staging for the *_host entry points
+    char* dbuf;
+    size_t dcap;
+};
+
+extern "C" int hvp_version(void) { return HVP_VERSION; }
+
+extern "C" int hvp_last_error(char* buf, int len) {
+    if (buf && len > 0) {
+        strncpy(buf, g_err, (size_t)len - 1);
+        buf[len - 1] = 0;
+    }
+    return (int)strlen(g_err);
+}
+
+extern "C" int hvp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
+    if (!out) return fail(-1, "hvp_ctx_create: out is NULL");
+    int n = hvp_device_count();
+    if (n <= 0) return fail(-2, "hvp_ctx_create: no CUDA device visible (this library has no CPU path)");
+    if (device < 0 || device >= n) return fail(-3, "hvp_ctx_create: device %d out of range [0,%d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    hvp_ctx* c = new hvp_ctx();
+    c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->dbuf) cudaFree(c->dbuf);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" void* hvp_ctx_stream(hvp_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int hvp_ctx_synchronize(hvp_ctx* c) {
+    if (!c) return fail(-1, "ctx is NULL");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int64_t hvp_ctx_launch_count(hvp_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" float hvp_ctx_last_kernel_ms(hvp_ctx* c) {
+    if (!c || !c->timed) return -1.f;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+static int ensure_dbuf(hvp_ctx* c, size_t bytes) {
+    if (bytes <= c->dcap) return 0;
+    if (c->dbuf) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->dbuf)); c->dbuf = nullptr; c->dcap = 0; }
+    size_t cap = bytes + bytes / 4 + 4096;
+    CUDA_TRY(cudaMalloc(&c->dbuf, cap));
+    c->dcap = cap;
+    return 0;
+}
+
+static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// ------------------------------------------------------------------------------------------
+// rollout
+// ------------------------------------------------------------------------------------------
+static int fill_rollout_params(RolloutParams& P, const hvp_env_desc* d) {
+    if (!d) return fail(-1, "rollout: desc is NULL");
+    if (d->n < 1 || d->n > ROLLOUT_BLOCK) return fail(-4, "rollout: n=%d out of range [1,%d]", d->n, ROLLOUT_BLOCK);
+    if (d->leader_index < 0 || d->leader_index >= d->n)
+        return fail(-4, "rollout: leader_index=%d out of range for n=%d", d->leader_index, d->n);
+    if ((d->flags & HVP_ENV_REAL_VEHICLE_REF) && d->leader_index != 0)
+        return fail(-4, "rollout: real_vehicle_as_reference needs leader_index 0 (env.py:60-63)");
+    VehicleModel M;
+    P.n = d->n; P.leader_index = d->leader_index; P.flags = d->flags;
+    P.scen_per_block = ROLLOUT_BLOCK / d->n;
+    P.d0 = d->d0; P.t0 = d->t0; P.d_safe = d->d_safe;
+    memcpy(P.tr_t, M.tr_t, sizeof P.tr_t);
+    memcpy(P.tr_v, M.tr_v, sizeof P.tr_v);
+    M.gear_limits(P.lim);
+    P.c_fric = M.c_fric; P.mug = M.mu * M.grav; P.default_mass = 800.0;
+    return 0;
+}
+
+extern "C" int hvp_rollout_step_dev(hvp_ctx* c, const hvp_env_desc* desc, int64_t batch, const double* x,
+                                    const double* u, const int32_t* gear, const double* mass,
+                                    const double* leader, double* x_out, double* cost, uint8_t* viol,
+                                    int32_t* err, void* stream) {
+    if (!c) return fail(-1, "rollout: ctx is NULL");
+    if (batch < 0) return fail(-4, "rollout: negative batch");
+    RolloutParams P;
+    int rc = fill_rollout_params(P, desc);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    if (!x || !u || !leader || !x_out || !cost || !viol || !err) return fail(-1, "rollout: NULL array argument");
+    if (((uintptr_t)x & 15) || ((uintptr_t)x_out & 15)) return fail(-5, "rollout: x / x_out must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(launch_rollout(P, batch, x, u, gear, mass, leader, x_out, cost, viol, err, st));
+    CUDA_TRY(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int hvp_rollout_step_host(hvp_ctx* c, const hvp_env_desc* desc, int64_t batch, const double* x,
+                                     const double* u, const int32_t* gear, const double* mass,
+                                     const double* leader, double* x_out, double* cost, uint8_t* viol,
+                                     int32_t* err) {
+    if (!c) return fail(-1, "rollout: ctx is NULL");
+    if (!desc) return fail(-1, "rollout: desc is NULL");
+    if (batch < 0) return fail(-4, "rollout: negative batch");
+    if (batch == 0) return 0;
+    if (!x || !u || !leader || !x_out || !cost || !viol || !err) return fail(-1, "rollout: NULL array argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)desc->n, B = (size_t)batch;
+    const bool mass_per = desc->flags & HVP_ENV_MASS_PER_SCENARIO;
+    const size_t bx = align256(B * 2 * n * 8), bu = align256(B * n * 8), bg = gear ? align256(B * n * 4) : 0;
+    const size_t bm = mass ? align256((mass_per ? B : 1) * n * 8) : 0, bl = align256(B * 16);
+    const size_t bc = align256(B * 8), bv = align256(B), be = align256(B * 4);
+    int rc = ensure_dbuf(c, bx * 2 + bu + bg + bm + bl + bc + bv + be);
+    if (rc) return rc;
+    char* q = c->dbuf;
+    double* dx = (double*)q; q += bx;
+    double* dxo = (double*)q; q += bx;
+    double* du = (double*)q; q += bu;
+    int32_t* dg = gear ? (int32_t*)q : nullptr; q += bg;
+    double* dm = mass ? (double*)q : nullptr; q += bm;
+    double* dl = (double*)q; q += bl;
+    double* dc = (double*)q; q += bc;
+    uint8_t* dv = (uint8_t*)q; q += bv;
+    int32_t* de = (int32_t*)q;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(dx, x, B * 2 * n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(du, u, B * n * 8, cudaMemcpyHostToDevice, st));
+    if (gear) CUDA_TRY(cudaMemcpyAsync(dg, gear, B * n * 4, cudaMemcpyHostToDevice, st));
+    if (mass) CUDA_TRY(cudaMemcpyAsync(dm, mass, (mass_per ? B : 1) * n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dl, leader, B * 16, cudaMemcpyHostToDevice, st));
+    rc = hvp_rollout_step_dev(c, desc, batch, dx, du, dg, dm, dl, dxo, dc, dv, de, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(x_out, dxo, B * 2 * n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(cost, dc, B * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(viol, dv, B, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(err, de, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// local MIQP
+// ------------------------------------------------------------------------------------------
+static int check_local_desc(const hvp_local_desc* d) {
+    if (!d) return fail(-1, "local_miqp: desc is NULL");
+    if (d->N < 2 || d->N > 12) return fail(-4, "local_miqp: N=%d out of range [2,12]", d->N);
+    if (d->max_nodes < 0) return fail(-4, "local_miqp: negative max_nodes");
+    return 0;
+}
+
+extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
+                                  const double* mass, const double* x0, const double* xf, const double* xb,
+                                  const double* xl, double* u, double* x, int32_t* modes, double* obj,
+                                  int32_t* status, int32_t* nodes, void* stream) {
+    if (!c) return fail(-1, "local_miqp: ctx is NULL");
+    int rc = check_local_desc(desc);
+    if (rc) return rc;
+    if (batch < 0) return fail(-4, "local_miqp: negative batch");
+    if (batch == 0) return 0;
+    if (!flags || !mass || !x0 || !u || !x || !modes || !obj || !status || !nodes)
+        return fail(-1, "local_miqp: NULL array argument");
+    LocalParams P;
+    fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes);
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(launch_local_miqp(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, st));
+    CUDA_TRY(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
+                                   const double* mass, const double* x0, const double* xf, const double* xb,
+                                   const double* xl, double* u, double* x, int32_t* modes, double* obj,
+                                   int32_t* status, int32_t* nodes) {
+    if (!c) return fail(-1, "local_miqp: ctx is NULL");
+    int rc = check_local_desc(desc);
+    if (rc) return rc;
+    if (batch < 0) return fail(-4, "local_miqp: negative batch");
+    if (batch == 0) return 0;
+    if (!flags || !mass || !x0 || !u || !x || !modes || !obj || !status || !nodes)
+        return fail(-1, "local_miqp: NULL array argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t B = (size_t)batch, N = (size_t)desc->N, S = 2 * (N + 1);
+    const size_t bf = align256(B * 4), bm = align256(B * 8), b0 = align256(B * 16), br = align256(B * S * 8);
+    const size_t bu = align256(B * N * 8), bmo = align256(B * N * 4), bo = align256(B * 8), bs = align256(B * 4);
+    const size_t nref = (xf ? 1 : 0) + (xb ? 1 : 0) + (xl ? 1 : 0);
+    rc = ensure_dbuf(c, bf + bm + b0 + br * nref + bu + br + bmo + bo + bs * 2);
+    if (rc) return rc;
+    char* q = c->dbuf;
+    int32_t* dfl = (int32_t*)q; q += bf;
+    double* dma = (double*)q; q += bm;
+    double* dx0 = (double*)q; q += b0;
+    double* dxf = xf ? (double*)q : nullptr; q += xf ? br : 0;
+    double* dxb = xb ? (double*)q : nullptr; q += xb ? br : 0;
+    double* dxl = xl ? (double*)q : nullptr; q += xl ? br : 0;
+    double* du = (double*)q; q += bu;
+    double* dx = (double*)q; q += br;
+    int32_t* dmo = (int32_t*)q; q += bmo;
+    double* dob = (double*)q; q += bo;
+    int32_t* dst = (int32_t*)q; q += bs;
+    int32_t* dno = (int32_t*)q;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(dfl, flags, B * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dma, mass, B * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dx0, x0, B * 16, cudaMemcpyHostToDevice, st));
+    if (xf) CUDA_TRY(cudaMemcpyAsync(dxf, xf, B * S * 8, cudaMemcpyHostToDevice, st));
+    if (xb) CUDA_TRY(cudaMemcpyAsync(dxb, xb, B * S * 8, cudaMemcpyHostToDevice, st));
+    if (xl) CUDA_TRY(cudaMemcpyAsync(dxl, xl, B * S * 8, cudaMemcpyHostToDevice, st));
+    rc = hvp_local_miqp_dev(c, desc, batch, dfl, dma, dx0, dxf, dxb, dxl, du, dx, dmo, dob, dst, dno, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(u, du, B * N * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(x, dx, B * S * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(modes, dmo, B * N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(obj, dob, B * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status, dst, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nodes, dno, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -1,0 +1,33 @@
+// hvp_internal.h -- declarations shared by the translation units of libhvp.so (not public).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "miqp_core.cuh"
+
+namespace hvp {
+
+constexpr int LOCAL_BLOCK = 64;     // threads (= MIQPs) per CTA of the local-MIQP kernel
+constexpr int ROLLOUT_BLOCK = 256;  // threads per CTA of the rollout kernel
+
+// Constants of the rollout kernel (kernel argument; filled by fill_rollout_params).
+struct RolloutParams {
+    int n, leader_index, flags;
+    int scen_per_block;             // whole scenarios handled by one CTA
+    double d0, t0, d_safe;
+    double tr_t[6][3], tr_v[6][4];  // traction curve (models.py:13-28)
+    double lim[5];                  // gear-switch velocities (models.py:401-403)
+    double c_fric, mug;             // friction, mu*g
+    double default_mass;
+};
+
+cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
+                              const double* x0, const double* xf, const double* xb, const double* xl,
+                              double* u, double* x, int32_t* modes, double* obj, int32_t* status,
+                              int32_t* nodes, cudaStream_t stream);
+
+cudaError_t launch_rollout(const RolloutParams& P, int64_t batch, const double* x, const double* u,
+                           const int32_t* gear, const double* mass, const double* leader, double* x_out,
+                           double* cost, uint8_t* viol, int32_t* err, cudaStream_t stream);
+
+}  // namespace hvp

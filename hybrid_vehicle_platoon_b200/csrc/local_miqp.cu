@@ -1,0 +1,55 @@
+// local_miqp.cu -- batched per-vehicle hybrid-MPC MIQPs on sm_100a: one thread per MIQP.
+//
+// Replaces the Gurobi solve behind LocalMpcMld.solve_mpc (fleet_decent_mld.py:21-223 /
+// fleet_seq_mld.py:21-234 via dmpcpwa MpcMld.solve_mpc).  Each thread runs the whole
+// branch-and-bound of miqp_core.cuh for one problem: the node QPs are 4..12-variable dense
+// problems, far too small to spread over a CTA, so the parallel axis is the batch
+// (scenario x vehicle x ADMM round) and a warp holds 32 independent trees.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hvp_internal.h"
+#include "miqp_core.cuh"
+
+namespace hvp {
+
+template <int NMAX>
+__global__ void __launch_bounds__(LOCAL_BLOCK)
+local_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int32_t* __restrict__ flags,
+                  const double* __restrict__ mass, const double* __restrict__ x0,
+                  const double* __restrict__ xf, const double* __restrict__ xb,
+                  const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
+                  int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
+                  int32_t* __restrict__ nodes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const int N = P.N;
+    const size_t S = 2 * (size_t)(N + 1);
+    LocalSolver<NMAX> sol;
+    sol.setup(&P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr, xb ? xb + S * i : nullptr,
+              xl ? xl + S * i : nullptr);
+    LocalResult R = sol.solve(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
+    obj[i] = R.obj;
+    status[i] = R.status;
+    nodes[i] = R.nodes;
+}
+
+cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
+                              const double* x0, const double* xf, const double* xb, const double* xl,
+                              double* u, double* x, int32_t* modes, double* obj, int32_t* status,
+                              int32_t* nodes, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((batch + LOCAL_BLOCK - 1) / LOCAL_BLOCK);
+    if (P.N <= 6)
+        local_miqp_kernel<6><<<grid, LOCAL_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x,
+                                                              modes, obj, status, nodes);
+    else if (P.N <= 8)
+        local_miqp_kernel<8><<<grid, LOCAL_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x,
+                                                              modes, obj, status, nodes);
+    else
+        local_miqp_kernel<12><<<grid, LOCAL_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x,
+                                                               modes, obj, status, nodes);
+    return cudaGetLastError();
+}
+
+}  // namespace hvp

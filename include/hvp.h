@@ -1,0 +1,130 @@
+/*
+ * hvp.h -- C ABI of the B200-native hybrid-MPC hot path (libhvp.so).
+ *
+ * This is the drop-in boundary for ONE path of Kevindqz/hybrid-vehicle-platoon: the
+ * per-timestep MLD/PWA mixed-integer QP solves and the nonlinear hybrid rollout + stage cost.
+ * The reference has no FFI for this path (it is Python calling gurobipy); the entry points
+ * below are what its Python layer binds through ctypes (INTEGRATION.md shows the stubs).
+ * `file:line` citations are into the reference tree.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / CUDA types in signatures
+ *     (`stream` is a cudaStream_t passed as void*; NULL = default stream).
+ *   - `*_dev` entry points take DEVICE pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()); they enqueue work on `stream` and return without synchronising.
+ *   - `*_host` entry points take HOST pointers, copy host->device, run the same kernels, copy the
+ *     results back and synchronise before returning (the reference-facing call: numpy in, numpy out).
+ *   - All arrays are dense row-major, float64 unless stated.  Batches are [batch][...].
+ *   - Every function returns 0 on success, <0 on API misuse / CUDA error (text via
+ *     hvp_last_error).  Per-problem outcomes are reported in status[] with the Gurobi codes the
+ *     reference tests for (mpcs/mpc_gear.py:119,156; fleet_event_based.py:323):
+ *     2 OPTIMAL, 3 INFEASIBLE, 8 NODE_LIMIT, 12 NUMERIC.
+ *   - A context is bound to one device and one stream and is not thread-safe; distinct contexts
+ *     are independent.  There is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef HVP_H
+#define HVP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVP_VERSION 100
+
+/* status[] codes (Gurobi numbering, mpcs/mpc_gear.py:119) */
+#define HVP_OPTIMAL 2
+#define HVP_INFEASIBLE 3
+#define HVP_NODE_LIMIT 8
+#define HVP_NUMERIC 12
+
+/* per-vehicle role flags of a local problem (fleet_decent_mld.py:33-45: is_front/is_leader/is_trailer) */
+#define HVP_FRONT 1
+#define HVP_LEADER 2
+#define HVP_TRAILER 4
+
+/* rollout err[] codes = code | vehicle<<8 | substep<<16 of the FIRST exception the reference
+ * would raise (models.py:32-42,119-122); 0 = none */
+#define HVP_ERR_VELOCITY_BOUNDS 1 /* models.py:119-122 / :34-35 */
+#define HVP_ERR_GEAR_INDEX 2      /* models.py:32-33 */
+#define HVP_ERR_GEAR_RANGE 3      /* models.py:39-42 */
+
+int hvp_version(void);
+/* copies the calling thread's last error text into buf (NUL-terminated); returns its length */
+int hvp_last_error(char* buf, int len);
+/* number of visible CUDA devices (<=0: none -> nothing in this library can run) */
+int hvp_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+typedef struct hvp_ctx hvp_ctx;
+int hvp_ctx_create(int device, hvp_ctx** out);
+int hvp_ctx_destroy(hvp_ctx* ctx);
+/* the context's own stream as a cudaStream_t (for callers that want to order work after it) */
+void* hvp_ctx_stream(hvp_ctx* ctx);
+int hvp_ctx_synchronize(hvp_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t hvp_ctx_launch_count(hvp_ctx* ctx);
+/* duration in ms of the kernels of the most recent *_host/_dev call made through the context's
+ * timed wrappers (CUDA events on the context stream); <0 if none */
+float hvp_ctx_last_kernel_ms(hvp_ctx* ctx);
+
+/* ---- (c) rollout + stage cost: replaces PlatoonEnv.step (env.py:182-212) -------------------
+ * = get_stage_cost on the PRE-step state (env.py:126-180), optional gear derivation
+ * (env.py:198-204 -> models.py:494-515) and Platoon.step_platoon (models.py:236-257: ten explicit
+ * Euler sub-steps of Vehicle.step models.py:114-125 with GearTransimission.get_traction :30-51). */
+typedef struct {
+    int32_t n;            /* vehicles per platoon */
+    int32_t leader_index; /* env.py:31 */
+    int32_t flags;        /* HVP_ENV_* */
+    int32_t reserved;
+    double d0, t0;        /* spacing policy sigma(x) = [-t0*v - d0, 0] (misc/spacing_policy.py:13-37) */
+    double d_safe;        /* env.py:38 */
+} hvp_env_desc;
+#define HVP_ENV_QUADRATIC 1         /* env.py:55-58: x'Qx, else ||Qx||_1 */
+#define HVP_ENV_REAL_VEHICLE_REF 2  /* env.py:141-151 */
+#define HVP_ENV_MASS_PER_SCENARIO 4 /* mass is [batch][n] instead of [n] */
+
+/* x [batch][2n] = [p0 v0 p1 v1 ...] (env.py:79 ordering), u [batch][n], gear [batch][n] int32 or
+ * NULL (derive from velocity), mass [n] / [batch][n] / NULL (800 kg), leader [batch][2] =
+ * leader_x[:, step_counter].  Outputs: x_out [batch][2n], cost [batch], viol [batch] (0/1,
+ * env.py:165-176), err [batch].  x_out of a scenario with err != 0 is NaN. */
+int hvp_rollout_step_dev(hvp_ctx* ctx, const hvp_env_desc* desc, int64_t batch, const double* x,
+                         const double* u, const int32_t* gear, const double* mass,
+                         const double* leader, double* x_out, double* cost, uint8_t* viol,
+                         int32_t* err, void* stream);
+int hvp_rollout_step_host(hvp_ctx* ctx, const hvp_env_desc* desc, int64_t batch, const double* x,
+                          const double* u, const int32_t* gear, const double* mass,
+                          const double* leader, double* x_out, double* cost, uint8_t* viol,
+                          int32_t* err);
+
+/* ---- (a) per-vehicle local MIQP: replaces LocalMpcMld(...).solve_mpc(state) ----------------
+ * Problem definition: fleet_decent_mld.py:61-208 (identical in fleet_seq_mld.py:63-219) on top
+ * of dmpcpwa MpcMld (PWA->MLD), pwa_gear model (models.py:397-492).
+ * Solved to proven optimality (gap 0) by branch-and-bound over the PWA region sequence. */
+typedef struct {
+    int32_t N;          /* horizon (<= 12) */
+    int32_t max_nodes;  /* per problem; 0 = unlimited */
+    double d0, t0;      /* spacing policy */
+    double tight;       /* accel_cnstr_tightening (fleet_decent_mld.py:43) */
+} hvp_local_desc;
+
+/* flags [batch] (HVP_FRONT|HVP_LEADER|HVP_TRAILER), mass [batch], x0 [batch][2],
+ * xf / xb / xl [batch][2][N+1] = x_front / x_back / leader_x parameters (set_x_front, set_x_back,
+ * set_leader_x: fleet_decent_mld.py:210-223); unused ones may be NULL.
+ * Outputs: u [batch][N], x [batch][2][N+1], modes [batch][N] int32 (active PWA region per stage,
+ * = argmax_r delta[r,k]), obj [batch] (objVal incl. constant terms; +inf if infeasible),
+ * status [batch] int32, nodes [batch] int32 (B&B nodes = QPs solved). */
+int hvp_local_miqp_dev(hvp_ctx* ctx, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
+                       const double* mass, const double* x0, const double* xf, const double* xb,
+                       const double* xl, double* u, double* x, int32_t* modes, double* obj,
+                       int32_t* status, int32_t* nodes, void* stream);
+int hvp_local_miqp_host(hvp_ctx* ctx, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
+                        const double* mass, const double* x0, const double* xf, const double* xb,
+                        const double* xl, double* u, double* x, int32_t* modes, double* obj,
+                        int32_t* status, int32_t* nodes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVP_H */

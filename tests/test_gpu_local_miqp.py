@@ -1,0 +1,93 @@
+"""GPU: local-MIQP kernel through the C ABI vs the oracle (exhaustive leaf enumeration + exact QP).
+Tolerances are BASELINE.json's: objective 1e-6 relative, inputs 1e-5, modes identical where the
+optimum is unique (tests assert much tighter: 1e-9 / 1e-7)."""
+import numpy as np
+import pytest
+
+import hybrid_vehicle_platoon_b200 as hvp
+from gen_cases import platoon_local_problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(r, ro):
+    np.testing.assert_array_equal(r["status"], ro["status"])
+    ok = ro["status"] == 2
+    np.testing.assert_allclose(r["obj"][ok], ro["obj"][ok], rtol=1e-9)
+    assert np.abs(r["u"][ok] - ro["u"][ok]).max() < 1e-7
+    assert np.abs(r["x"][ok] - ro["x"][ok]).max() < 1e-6
+    uniq = ok & ((ro["second"] - ro["obj"]) > 1e-6 * np.abs(ro["obj"]))
+    np.testing.assert_array_equal(r["modes"][uniq], ro["modes"][uniq])
+    assert np.isinf(r["obj"][~ok]).all()
+
+
+@pytest.mark.parametrize("N,n,stress,hetero,d0,t0,li,n_scen", [
+    (6, 10, False, False, 50.0, 0.0, 0, 200),     # BASELINE config 2 shape
+    (6, 10, True, True, 10.0, 3.0, 0, 200),
+    (6, 10, True, True, 10.0, 3.0, 9, 100),       # leader at the back
+    (4, 5, True, False, 50.0, 0.0, 2, 100),
+    (5, 3, True, True, 10.0, 3.0, 1, 100),
+    (8, 15, True, True, 10.0, 3.0, 0, 8),         # config-3 shape (n=15, N=8)
+    (7, 10, False, True, 50.0, 0.0, 0, 20),
+])
+def test_matches_oracle(hvp_ctx, oracle, N, n, stress, hetero, d0, t0, li, n_scen):
+    rng = np.random.default_rng(N * 100 + n + li)
+    c = platoon_local_problems(rng, n_scen, n, N, li, stress, hetero)
+    args = (N, c["flags"], c["mass"], c["x0"], c["xf"], c["xb"], c["xl"])
+    r = hvp.local_miqp(*args, d0=d0, t0=t0, ctx=hvp_ctx)
+    ro = oracle.local_miqp(*args, d0=d0, t0=t0)
+    _check(r, ro)
+    assert r["nodes"].mean() < ro["leaves"].mean()
+
+
+def test_horizon_10(hvp_ctx, oracle):
+    rng = np.random.default_rng(1)
+    c = platoon_local_problems(rng, 4, 5, 10)
+    args = (10, c["flags"], c["mass"], c["x0"], c["xf"], c["xb"], c["xl"])
+    _check(hvp.local_miqp(*args, ctx=hvp_ctx), oracle.local_miqp(*args))
+
+
+def test_infeasible_edge_and_tightening(hvp_ctx, oracle):
+    N = 6
+    k = np.arange(N + 1)
+    xl = np.stack([3000 + 20.0 * k, np.full(N + 1, 20.0)])[None]
+    edge = oracle.pwa_gear_system(800.0)[4][2]
+    x0 = np.array([[3000.0, 1.0], [3000.0, edge], [3000.0, 45.84], [3000.0, 3.94], [9990.0, 30.0]])
+    xls = np.repeat(xl, len(x0), 0)
+    z = np.zeros_like(xls)
+    for tight in (0.0, 0.2):
+        r = hvp.local_miqp(N, 7, 800.0, x0, z, z, xls, tight=tight, ctx=hvp_ctx)
+        ro = oracle.local_miqp(N, np.full(len(x0), 7), 800.0, x0, z, z, xls, tight=tight)
+        _check(r, ro)
+    assert r["status"][0] == 3
+
+
+def test_empty_batch_and_bad_args(hvp_ctx):
+    r = hvp.local_miqp(6, np.zeros(0, np.int32), np.zeros(0), np.zeros((0, 2)), ctx=hvp_ctx)
+    assert r["u"].shape == (0, 6)
+    with pytest.raises(RuntimeError, match="out of range"):
+        hvp.local_miqp(40, 7, 800.0, np.zeros((1, 2)), ctx=hvp_ctx)
+
+
+def test_bench_size_properties(hvp_ctx, oracle):
+    """BASELINE size (4096 scenarios x 10 vehicles, N=6): every problem optimal; cost invariant under
+    a common translation of all positions; subset agrees with the oracle."""
+    rng = np.random.default_rng(1234 + 1)
+    N, n, S = 6, 10, 4096
+    c = platoon_local_problems(rng, S, n, N)
+    args = (N, c["flags"], c["mass"], c["x0"])
+    r = hvp.local_miqp(*args, c["xf"], c["xb"], c["xl"], ctx=hvp_ctx)
+    assert (r["status"] == 2).all()
+    sh = 64.0
+    x0 = c["x0"].copy(); x0[:, 0] += sh
+    xf, xb, xl = c["xf"].copy(), c["xb"].copy(), c["xl"].copy()
+    for a in (xf, xb, xl):
+        a[:, 0, :] += sh
+    r2 = hvp.local_miqp(N, c["flags"], c["mass"], x0, xf, xb, xl, ctx=hvp_ctx)
+    np.testing.assert_allclose(r2["obj"], r["obj"], rtol=1e-9)
+    assert np.abs(r2["u"] - r["u"]).max() < 1e-7
+    idx = rng.choice(S * n, 2000, replace=False)
+    ro = oracle.local_miqp(N, c["flags"][idx], c["mass"][idx], c["x0"][idx], c["xf"][idx], c["xb"][idx],
+                           c["xl"][idx])
+    sub = {k: v[idx] for k, v in r.items()}
+    _check(sub, ro)
