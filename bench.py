@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hybrid-MPC hot path (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scenarios S]
+
+Workload (BASELINE.json configs[1]): the per-vehicle local MIQPs of fleet_decent_mld.py /
+fleet_seq_mld.py at n = 10 vehicles, horizon N = 6, pwa_gear model.  One STEP = one pass of the
+hot path over one batch: S synthetic platoon scenarios x 10 vehicles = 10*S MIQPs, each solved to
+proven optimality.  metric = hybrid-MPC solves/s (whole job, all GPUs).
+
+    value : device-timed (CUDA events on the launching stream), inputs resident in HBM
+    e2e   : same batch through the reference-facing C-ABI call with HOST (pinned) buffers,
+            H2D + kernel + D2H inside the timed region
+    roofline / fp64_pipe / rollout : how close the kernels run to the hardware
+    cpu_baseline : the CPU oracle (exhaustive leaf enumeration, OpenMP) on a bounded sample
+
+Under torchrun (N > 1) every rank runs the same per-GPU batch on its own seed (weak scaling, no
+data-path collective: scenarios are independent); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_VEH, HORIZON = 10, 6
+METRIC = "hybrid-MPC solves/sec at n=10,N=6 (per-vehicle local MIQPs, proven optimal)"
+
+
+def make_batch(seed, scenarios):
+    from gen_cases import platoon_local_problems
+    rng = np.random.default_rng(seed)
+    return platoon_local_problems(rng, scenarios, N_VEH, HORIZON)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(len(r) >= 6 and r[2 + k].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_leg(scenarios_hint, budget_s=12.0):
+    """The oracle port (exhaustive leaf enumeration + exact QP, oracle/hvp_oracle.c) on the host
+    cores, bounded sample of the same workload."""
+    from oracle import oracle as O
+    O.build()
+    cal = make_batch(999, 16)
+    t = time.perf_counter()
+    O.local_miqp(HORIZON, cal["flags"], cal["mass"], cal["x0"], cal["xf"], cal["xb"], cal["xl"])
+    per = (time.perf_counter() - t) / (16 * N_VEH)
+    scen = int(max(32, min(scenarios_hint, budget_s / max(per, 1e-7) / N_VEH)))
+    b = make_batch(1234 + 1, scen)
+    t = time.perf_counter()
+    r = O.local_miqp(HORIZON, b["flags"], b["mass"], b["x0"], b["xf"], b["xb"], b["xl"])
+    dt = time.perf_counter() - t
+    assert (r["status"] == 2).all()
+    return {"value": scen * N_VEH / dt, "unit": "solves/s", "cores": O.max_threads(), "kind": "port",
+            "sample": f"{scen} scenarios x {N_VEH} vehicles (N={HORIZON}) of the bench distribution, "
+                      f"{dt:.2f} s, oracle = exhaustive leaf enumeration + exact dual active-set QP, "
+                      f"OpenMP over {O.max_threads()} threads; Gurobi/dmpcpwa unavailable",
+            "leaves_per_solve": float(r["leaves"].mean())}, dt, scen
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    times, solves = [], 0
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, dt, scen = cpu_reference_leg(args.scenarios, budget_s=2.0)
+        if i >= args.warmup:
+            times.append(dt)
+            solves += scen * N_VEH
+    val = solves / sum(times)
+    base["value"] = val
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"fleet_decent_mld local MIQPs n={N_VEH} N={HORIZON} pwa_gear; bounded "
+                                   f"sample per step on host cores (reference solver Gurobi is not "
+                                   f"installable: CPU stand-in is the oracle port)"},
+            "cpu_baseline": base,
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scenarios", type=int, default=32768, help="platoon scenarios per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = hvp.Context(local_rank)
+    S, B = args.scenarios, args.scenarios * N_VEH
+    batch = make_batch(1234 + 1 + 7919 * rank, S)
+
+    # ---- device-resident inputs / outputs ----
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_flags, d_mass, d_x0 = t(batch["flags"]), t(batch["mass"]), t(batch["x0"])
+    d_xf, d_xb, d_xl = t(batch["xf"]), t(batch["xb"]), t(batch["xl"])
+    d_u = torch.empty((B, HORIZON), dtype=torch.float64, device=dev)
+    d_x = torch.empty((B, 2, HORIZON + 1), dtype=torch.float64, device=dev)
+    d_modes = torch.empty((B, HORIZON), dtype=torch.int32, device=dev)
+    d_obj = torch.empty(B, dtype=torch.float64, device=dev)
+    d_status = torch.empty(B, dtype=torch.int32, device=dev)
+    d_nodes = torch.empty(B, dtype=torch.int32, device=dev)
+    d_iters = torch.empty(B, dtype=torch.int32, device=dev)
+    desc = api.local_desc(HORIZON)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        api.local_miqp_device(desc, B, d_flags, d_mass, d_x0, d_xf, d_xb, d_xl, d_u, d_x, d_modes, d_obj,
+                              d_status, d_nodes, d_iters, ctx=ctx, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = ctx.launch_count
+    for _ in range(args.warmup):
+        step_dev()
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches_t0 = ctx.launch_count
+    for a, b_ in ev:
+        a.record()
+        step_dev()
+        b_.record()
+        flush.fill_(1)          # L2 flush between timed steps (outside the event pairs)
+    barrier()
+    launches_timed = ctx.launch_count - launches_t0
+    ms = np.array([a.elapsed_time(b_) for a, b_ in ev])
+    total_ms = float(ms.sum())
+    assert bool((d_status == 2).all()), "a bench problem was not solved to optimality"
+    nodes_mean = float(d_nodes.double().mean())
+    iters_mean = float(d_iters.double().mean())
+
+    # ---- e2e: reference-facing host call with pinned host buffers ----
+    def pinned(a):
+        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return tt, tt.numpy()
+    keep = []
+    h = {}
+    for k in ("flags", "mass", "x0", "xf", "xb", "xl"):
+        tt, h[k] = pinned(batch[k]); keep.append(tt)
+    ho = {}
+    for k, shape, dt in (("u", (B, HORIZON), np.float64), ("x", (B, 2, HORIZON + 1), np.float64),
+                         ("modes", (B, HORIZON), np.int32), ("obj", (B,), np.float64),
+                         ("status", (B,), np.int32), ("nodes", (B,), np.int32)):
+        tt, ho[k] = pinned(np.empty(shape, dt)); keep.append(tt)
+    import ctypes as C
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    L = hvp._lib.lib()
+
+    def step_host():
+        hvp._lib.check(L.hvp_local_miqp_host(ctx.handle, C.byref(desc), B, hp(h["flags"]), hp(h["mass"]),
+                                             hp(h["x0"]), hp(h["xf"]), hp(h["xb"]), hp(h["xl"]), hp(ho["u"]),
+                                             hp(ho["x"]), hp(ho["modes"]), hp(ho["obj"]), hp(ho["status"]),
+                                             hp(ho["nodes"]), None))
+    h2d = sum(h[k].nbytes for k in h)
+    d2h = sum(ho[k].nbytes for k in ho)
+    for _ in range(3):
+        step_host()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(ho["status"], d_status.cpu().numpy())
+    assert np.allclose(ho["obj"], d_obj.cpu().numpy(), rtol=0, atol=0)
+    clocks = sampler.stop()
+
+    # ---- max over ranks ----
+    tm = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(tm[0]), float(tm[1])
+    value = world * B * args.steps / (total_ms * 1e-3)
+    e2e_value = world * B * e2e_steps / e2e_s
+
+    out = None
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        bytes_per_solve = 4 + 8 + 16 + 3 * 16 * (HORIZON + 1) + 8 * HORIZON + 16 * (HORIZON + 1) + 4 * HORIZON + 8 + 4 + 4 + 4
+        kern_ms = total_ms / args.steps
+        achieved = B * bytes_per_solve / (kern_ms * 1e-3) / 1e9
+        # FP64 work model: flops per node (build + factor + objective) and per active-set iteration
+        n = HORIZON
+        f_node = 2 * n * n + n ** 3 / 3 + 2 * n ** 3 + 2 * n * n + 4 * n * n
+        f_iter = 14 * n + 2 * n * n + 2 * n * n + n ** 3 / 3 + 2 * n * n + 2 * n * n + 2 * n * n
+        flops_per_solve = nodes_mean * f_node + iters_mean * f_iter
+        fp64_peak = hvp.microbench_fp64(20000, ctx=ctx)
+        fp64_ach = B * flops_per_solve / (kern_ms * 1e-3) / 1e12
+
+        # ---- rollout kernel (c): HBM-bound, 1M scenario-steps ----
+        rb = 1 << 20
+        rng = np.random.default_rng(4321)
+        v = rng.uniform(6, 33, (rb, N_VEH)); gaps = rng.uniform(30, 150, (rb, N_VEH))
+        p = 3000.0 - np.cumsum(gaps, 1)
+        xs = np.empty((rb, 2 * N_VEH)); xs[:, 0::2] = p; xs[:, 1::2] = v
+        rx = t(xs); ru = t(rng.uniform(-1, 1, (rb, N_VEH)))
+        rg = t(np.clip(np.digitize(v, [9.235, 12.855, 16.93, 23.315, 32.47]) + 1, 1, 6).astype(np.int32))
+        rm = t(rng.uniform(700, 1000, (rb, N_VEH)))
+        rl = t(np.stack([p[:, 0] + 5, np.full(rb, 20.0)], 1))
+        rxo = torch.empty_like(rx); rc = torch.empty(rb, dtype=torch.float64, device=dev)
+        rv = torch.empty(rb, dtype=torch.uint8, device=dev); re_ = torch.empty(rb, dtype=torch.int32, device=dev)
+        rdesc = api.env_desc(N_VEH, mass_per_scenario=True)
+        rms = []
+        for i in range(args.warmup + args.steps):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            api.rollout_step_device(rdesc, rb, rx, ru, rg, rm, rl, rxo, rc, rv, re_, ctx=ctx, stream=stream)
+            b_.record()
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            if i >= args.warmup:
+                rms.append(a.elapsed_time(b_))
+        r_ms = float(np.mean(rms))
+        r_bytes = 52 * N_VEH + 29
+        r_ach = rb * r_bytes / (r_ms * 1e-3) / 1e9
+        rollout = {"metric": "rollout scenario-steps/s (n=10, given gears, per-scenario masses)",
+                   "value": rb / (r_ms * 1e-3), "unit": "scenario-steps/s", "ms_per_launch": r_ms,
+                   "batch": rb, "errors": int((re_ != 0).sum()),
+                   "roofline": {"bound": "hbm", "achieved": r_ach, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": r_ach / hbm_peak, "traffic": None,
+                                "algorithmic_bytes_per_scenario_step": r_bytes, "peak_source": peak_src}}
+
+        # ---- p99 per-timestep latency: one scenario (10 MIQPs) through the host call ----
+        one = make_batch(77, 1)
+        lat = []
+        for i in range(1200):
+            t0 = time.perf_counter()
+            hvp.local_miqp(HORIZON, one["flags"], one["mass"], one["x0"], one["xf"], one["xb"], one["xl"], ctx=ctx)
+            lat.append(time.perf_counter() - t0)
+        lat = np.array(lat[200:]) * 1e3
+
+        cpu = None
+        if not args.no_cpu:
+            cpu, _, _ = cpu_reference_leg(S, budget_s=12.0)
+
+        out = {
+            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"fleet_decent_mld.py per-vehicle local MIQPs (LocalMpcMld, pwa_gear), "
+                                   f"n={N_VEH}, N={HORIZON}; {S} scenarios x {N_VEH} vehicles = {B} MIQPs per "
+                                   f"GPU per step, reference reset distribution, constant-velocity neighbour "
+                                   f"predictions, gap 0 (proven optimal)",
+                       "l2": "flushed (256 MiB write) between timed steps; steps timed individually with CUDA events",
+                       "scenarios_per_gpu": S, "n": N_VEH, "N": HORIZON},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "call": "hvp_local_miqp_host (pinned numpy in, numpy out)"},
+            "gpu_launches": int(launches_timed),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "algorithmic_bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
+                         "kernel": "local_miqp_kernel<6>",
+                         "note": "on-chip FP64 branch-and-bound: HBM traffic is parameters in + solution "
+                                 "out only, so the HBM fraction is small by construction; see fp64_pipe"},
+            "fp64_pipe": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,
+                          "peak_source": "hvp_microbench_fp64 (measured DFMA issue peak)",
+                          "flops_per_solve_model": flops_per_solve, "nodes_per_solve": nodes_mean,
+                          "qp_iters_per_solve": iters_mean},
+            "latency": {"what": "one scenario-timestep = 10 local MIQPs through hvp_local_miqp_host",
+                        "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                        "samples": int(lat.size)},
+            "rollout": rollout,
+            "cpu_baseline": cpu,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -5,7 +5,8 @@ branch-and-bound kernel behind a C ABI (include/hvp.h), with reference-shaped Py
 from . import _lib  # noqa: F401
 from ._lib import FRONT, LEADER, TRAILER, Context, default_context  # noqa: F401
 from .api import (  # noqa: F401
-    env_desc, local_desc, local_miqp, local_miqp_device, rollout_step, rollout_step_device,
+    env_desc, local_desc, local_miqp, local_miqp_device, microbench_fp64, rollout_step,
+    rollout_step_device,
 )
 
 __version__ = "0.1.0"

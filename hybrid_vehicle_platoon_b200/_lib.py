@@ -65,9 +65,10 @@ def lib():
     roll = [_vp, C.POINTER(EnvDesc), C.c_int64] + [_vp] * 9
     L.hvp_rollout_step_dev.argtypes = roll + [_vp]
     L.hvp_rollout_step_host.argtypes = roll
-    loc = [_vp, C.POINTER(LocalDesc), C.c_int64] + [_vp] * 12
+    loc = [_vp, C.POINTER(LocalDesc), C.c_int64] + [_vp] * 13
     L.hvp_local_miqp_dev.argtypes = loc + [_vp]
     L.hvp_local_miqp_host.argtypes = loc
+    L.hvp_microbench_fp64.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 

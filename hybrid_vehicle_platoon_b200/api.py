@@ -73,17 +73,26 @@ def local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0
     d = local_desc(N, d0, t0, tight, max_nodes)
     u = np.empty((B, N)); x = np.empty((B, 2, N + 1)); modes = np.empty((B, N), np.int32)
     obj = np.empty(B); status = np.empty(B, np.int32); nodes = np.empty(B, np.int32)
+    iters = np.empty(B, np.int32)
     check(lib().hvp_local_miqp_host(ctx.handle, C.byref(d), B, _hp(flags), _hp(mass), _hp(x0), _hp(xf),
                                     _hp(xb), _hp(xl), _hp(u), _hp(x), _hp(modes), _hp(obj), _hp(status),
-                                    _hp(nodes)))
-    return dict(u=u, x=x, modes=modes, obj=obj, status=status, nodes=nodes)
+                                    _hp(nodes), _hp(iters)))
+    return dict(u=u, x=x, modes=modes, obj=obj, status=status, nodes=nodes, qp_iters=iters)
 
 
 def local_miqp_device(desc: LocalDesc, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status,
-                      nodes, *, ctx=None, stream=None):
+                      nodes, qp_iters=None, *, ctx=None, stream=None):
     """Same on DEVICE buffers (torch CUDA tensors); asynchronous on `stream`."""
     ctx = ctx or default_context()
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     check(lib().hvp_local_miqp_dev(ctx.handle, C.byref(desc), int(batch), p(flags), p(mass), p(x0), p(xf),
                                    p(xb), p(xl), p(u), p(x), p(modes), p(obj), p(status), p(nodes),
-                                   C.c_void_p(stream) if stream else None))
+                                   p(qp_iters), C.c_void_p(stream) if stream else None))
+
+
+def microbench_fp64(iters: int = 20000, ctx=None) -> float:
+    """Measured FP64 FMA peak of the device in TFLOP/s (roofline denominator of the QP kernel)."""
+    ctx = ctx or default_context()
+    t = C.c_double(0)
+    check(lib().hvp_microbench_fp64(ctx.handle, int(iters), C.byref(t)))
+    return t.value

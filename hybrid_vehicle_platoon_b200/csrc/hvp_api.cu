@@ -210,7 +210,7 @@ static int check_local_desc(const hvp_local_desc* d) {
 extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
                                   const double* mass, const double* x0, const double* xf, const double* xb,
                                   const double* xl, double* u, double* x, int32_t* modes, double* obj,
-                                  int32_t* status, int32_t* nodes, void* stream) {
+                                  int32_t* status, int32_t* nodes, int32_t* qp_iters, void* stream) {
     if (!c) return fail(-1, "local_miqp: ctx is NULL");
     int rc = check_local_desc(desc);
     if (rc) return rc;
@@ -223,7 +223,7 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    CUDA_TRY(launch_local_miqp(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, st));
+    CUDA_TRY(launch_local_miqp(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     c->launches += 1;
@@ -233,7 +233,7 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
 extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
                                    const double* mass, const double* x0, const double* xf, const double* xb,
                                    const double* xl, double* u, double* x, int32_t* modes, double* obj,
-                                   int32_t* status, int32_t* nodes) {
+                                   int32_t* status, int32_t* nodes, int32_t* qp_iters) {
     if (!c) return fail(-1, "local_miqp: ctx is NULL");
     int rc = check_local_desc(desc);
     if (rc) return rc;
@@ -246,7 +246,7 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
     const size_t bf = align256(B * 4), bm = align256(B * 8), b0 = align256(B * 16), br = align256(B * S * 8);
     const size_t bu = align256(B * N * 8), bmo = align256(B * N * 4), bo = align256(B * 8), bs = align256(B * 4);
     const size_t nref = (xf ? 1 : 0) + (xb ? 1 : 0) + (xl ? 1 : 0);
-    rc = ensure_dbuf(c, bf + bm + b0 + br * nref + bu + br + bmo + bo + bs * 2);
+    rc = ensure_dbuf(c, bf + bm + b0 + br * nref + bu + br + bmo + bo + bs * 3);
     if (rc) return rc;
     char* q = c->dbuf;
     int32_t* dfl = (int32_t*)q; q += bf;
@@ -260,7 +260,8 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
     int32_t* dmo = (int32_t*)q; q += bmo;
     double* dob = (double*)q; q += bo;
     int32_t* dst = (int32_t*)q; q += bs;
-    int32_t* dno = (int32_t*)q;
+    int32_t* dno = (int32_t*)q; q += bs;
+    int32_t* dit = qp_iters ? (int32_t*)q : nullptr;
     cudaStream_t st = c->stream;
     CUDA_TRY(cudaMemcpyAsync(dfl, flags, B * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dma, mass, B * 8, cudaMemcpyHostToDevice, st));
@@ -268,7 +269,7 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
     if (xf) CUDA_TRY(cudaMemcpyAsync(dxf, xf, B * S * 8, cudaMemcpyHostToDevice, st));
     if (xb) CUDA_TRY(cudaMemcpyAsync(dxb, xb, B * S * 8, cudaMemcpyHostToDevice, st));
     if (xl) CUDA_TRY(cudaMemcpyAsync(dxl, xl, B * S * 8, cudaMemcpyHostToDevice, st));
-    rc = hvp_local_miqp_dev(c, desc, batch, dfl, dma, dx0, dxf, dxb, dxl, du, dx, dmo, dob, dst, dno, st);
+    rc = hvp_local_miqp_dev(c, desc, batch, dfl, dma, dx0, dxf, dxb, dxl, du, dx, dmo, dob, dst, dno, dit, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(u, du, B * N * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(x, dx, B * S * 8, cudaMemcpyDeviceToHost, st));
@@ -276,6 +277,37 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
     CUDA_TRY(cudaMemcpyAsync(obj, dob, B * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(status, dst, B * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(nodes, dno, B * 4, cudaMemcpyDeviceToHost, st));
+    if (qp_iters) CUDA_TRY(cudaMemcpyAsync(qp_iters, dit, B * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// measurement helper: FP64 FMA peak
+// ------------------------------------------------------------------------------------------
+extern "C" int hvp_microbench_fp64(hvp_ctx* c, int iters, double* tflops) {
+    if (!c || !tflops) return fail(-1, "microbench: NULL argument");
+    if (iters < 1) return fail(-4, "microbench: iters < 1");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 8 * 1024));
+    int blocks = 0, threads = 0;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(launch_fp64_microbench(iters, sink, &blocks, &threads, st));   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(c->ev0, st));
+        CUDA_TRY(launch_fp64_microbench(iters, sink, &blocks, &threads, st));
+        CUDA_TRY(cudaEventRecord(c->ev1, st));
+        CUDA_TRY(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (ms < best) best = ms;
+        c->launches += 1;
+    }
+    c->launches += 1;
+    CUDA_TRY(cudaFree(sink));
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
     return 0;
 }

@@ -24,7 +24,9 @@ struct RolloutParams {
 cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
                               double* u, double* x, int32_t* modes, double* obj, int32_t* status,
-                              int32_t* nodes, cudaStream_t stream);
+                              int32_t* nodes, int32_t* qp_iters, cudaStream_t stream);
+
+cudaError_t launch_fp64_microbench(int iters, double* sink, int* blocks, int* threads, cudaStream_t stream);
 
 cudaError_t launch_rollout(const RolloutParams& P, int64_t batch, const double* x, const double* u,
                            const int32_t* gear, const double* mass, const double* leader, double* x_out,

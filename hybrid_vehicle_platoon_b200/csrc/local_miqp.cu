@@ -20,7 +20,7 @@ local_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const in
                   const double* __restrict__ xf, const double* __restrict__ xb,
                   const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
                   int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
-                  int32_t* __restrict__ nodes) {
+                  int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     const int N = P.N;
@@ -32,23 +32,24 @@ local_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const in
     obj[i] = R.obj;
     status[i] = R.status;
     nodes[i] = R.nodes;
+    if (qp_iters) qp_iters[i] = R.qp_iters;
 }
 
 cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
                               double* u, double* x, int32_t* modes, double* obj, int32_t* status,
-                              int32_t* nodes, cudaStream_t stream) {
+                              int32_t* nodes, int32_t* qp_iters, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((batch + LOCAL_BLOCK - 1) / LOCAL_BLOCK);
     if (P.N <= 6)
         local_miqp_kernel<6><<<grid, LOCAL_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x,
-                                                              modes, obj, status, nodes);
+                                                              modes, obj, status, nodes, qp_iters);
     else if (P.N <= 8)
         local_miqp_kernel<8><<<grid, LOCAL_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x,
-                                                              modes, obj, status, nodes);
+                                                              modes, obj, status, nodes, qp_iters);
     else
         local_miqp_kernel<12><<<grid, LOCAL_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x,
-                                                               modes, obj, status, nodes);
+                                                               modes, obj, status, nodes, qp_iters);
     return cudaGetLastError();
 }
 

@@ -114,15 +114,21 @@ typedef struct {
  * set_leader_x: fleet_decent_mld.py:210-223); unused ones may be NULL.
  * Outputs: u [batch][N], x [batch][2][N+1], modes [batch][N] int32 (active PWA region per stage,
  * = argmax_r delta[r,k]), obj [batch] (objVal incl. constant terms; +inf if infeasible),
- * status [batch] int32, nodes [batch] int32 (B&B nodes = QPs solved). */
+ * status [batch] int32, nodes [batch] int32 (B&B nodes = QPs solved), qp_iters [batch] int32 or
+ * NULL (active-set iterations summed over the nodes). */
 int hvp_local_miqp_dev(hvp_ctx* ctx, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
                        const double* mass, const double* x0, const double* xf, const double* xb,
                        const double* xl, double* u, double* x, int32_t* modes, double* obj,
-                       int32_t* status, int32_t* nodes, void* stream);
+                       int32_t* status, int32_t* nodes, int32_t* qp_iters, void* stream);
 int hvp_local_miqp_host(hvp_ctx* ctx, const hvp_local_desc* desc, int64_t batch, const int32_t* flags,
                         const double* mass, const double* x0, const double* xf, const double* xb,
                         const double* xl, double* u, double* x, int32_t* modes, double* obj,
-                        int32_t* status, int32_t* nodes);
+                        int32_t* status, int32_t* nodes, int32_t* qp_iters);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------
+ * FP64 FMA issue peak of the device: `iters` dependent-chain FMAs x 8 independent chains per
+ * thread over a full grid; returns achieved TFLOP/s (2 flop per FMA) in *tflops. */
+int hvp_microbench_fp64(hvp_ctx* ctx, int iters, double* tflops);
 
 #ifdef __cplusplus
 }
