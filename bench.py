@@ -142,6 +142,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenarios", type=int, default=32768, help="platoon scenarios per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: device-timed MIQP steps + rollout launches only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -212,6 +214,27 @@ def main():
     assert bool((d_status == 2).all()), "a bench problem was not solved to optimality"
     nodes_mean = float(d_nodes.double().mean())
     iters_mean = float(d_iters.double().mean())
+
+    if args.profile:
+        rb = 1 << 20
+        rng = np.random.default_rng(4321)
+        v = rng.uniform(6, 33, (rb, N_VEH)); gaps = rng.uniform(30, 150, (rb, N_VEH))
+        p = 3000.0 - np.cumsum(gaps, 1)
+        xs = np.empty((rb, 2 * N_VEH)); xs[:, 0::2] = p; xs[:, 1::2] = v
+        rx = t(xs); ru = t(rng.uniform(-1, 1, (rb, N_VEH)))
+        rg = t(np.clip(np.digitize(v, [9.235, 12.855, 16.93, 23.315, 32.47]) + 1, 1, 6).astype(np.int32))
+        rm = t(rng.uniform(700, 1000, (rb, N_VEH)))
+        rl = t(np.stack([p[:, 0] + 5, np.full(rb, 20.0)], 1))
+        rxo = torch.empty_like(rx); rc = torch.empty(rb, dtype=torch.float64, device=dev)
+        rv = torch.empty(rb, dtype=torch.uint8, device=dev); re_ = torch.empty(rb, dtype=torch.int32, device=dev)
+        rdesc = api.env_desc(N_VEH, mass_per_scenario=True)
+        for i in range(args.steps):
+            api.rollout_step_device(rdesc, rb, rx, ru, rg, rm, rl, rxo, rc, rv, re_, ctx=ctx, stream=stream)
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_run": True, "ms_per_step": float(ms.mean()), "solves_per_s": B / (ms.mean() * 1e-3),
+                          "nodes_per_solve": nodes_mean, "qp_iters_per_solve": iters_mean}))
+        return
 
     # ---- e2e: reference-facing host call with pinned host buffers ----
     def pinned(a):

@@ -13,6 +13,14 @@ def _hp(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _stream_arg(stream):
+    """None -> the context's own stream; 0 (torch's default stream handle) -> cudaStreamLegacy;
+    anything else is a cudaStream_t."""
+    if stream is None:
+        return None
+    return C.c_void_p(1 if int(stream) == 0 else int(stream))
+
+
 def _c(a, dt):
     return None if a is None else np.ascontiguousarray(a, dtype=dt)
 
@@ -50,7 +58,7 @@ def rollout_step_device(desc: EnvDesc, batch, x, u, gear, mass, leader, x_out, c
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     check(lib().hvp_rollout_step_dev(ctx.handle, C.byref(desc), int(batch), p(x), p(u), p(gear), p(mass),
                                      p(leader), p(x_out), p(cost), p(viol), p(err),
-                                     C.c_void_p(stream) if stream else None))
+                                     _stream_arg(stream)))
 
 
 def local_desc(N, d0=50.0, t0=0.0, tight=0.0, max_nodes=0) -> LocalDesc:
@@ -87,7 +95,7 @@ def local_miqp_device(desc: LocalDesc, batch, flags, mass, x0, xf, xb, xl, u, x,
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     check(lib().hvp_local_miqp_dev(ctx.handle, C.byref(desc), int(batch), p(flags), p(mass), p(x0), p(xf),
                                    p(xb), p(xl), p(u), p(x), p(modes), p(obj), p(status), p(nodes),
-                                   p(qp_iters), C.c_void_p(stream) if stream else None))
+                                   p(qp_iters), _stream_arg(stream)))
 
 
 def microbench_fp64(iters: int = 20000, ctx=None) -> float:

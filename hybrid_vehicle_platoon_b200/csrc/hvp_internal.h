@@ -7,7 +7,7 @@
 
 namespace hvp {
 
-constexpr int LOCAL_BLOCK = 64;     // threads (= MIQPs) per CTA of the local-MIQP kernel
+constexpr int LOCAL_BLOCK = 32;     // threads (= MIQPs) per CTA of the local-MIQP kernel (one warp)
 constexpr int ROLLOUT_BLOCK = 256;  // threads per CTA of the rollout kernel
 
 // Constants of the rollout kernel (kernel argument; filled by fill_rollout_params).

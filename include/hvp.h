@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - extern "C", plain pointers and sizes, no torch / CUDA types in signatures
- *     (`stream` is a cudaStream_t passed as void*; NULL = default stream).
+ *     (`stream` is a cudaStream_t passed as void*; NULL = the context's own stream; pass
+ *     cudaStreamLegacy ((void*)1) for the legacy default stream).
  *   - `*_dev` entry points take DEVICE pointers owned by the caller (e.g. torch tensors'
  *     data_ptr()); they enqueue work on `stream` and return without synchronising.
  *   - `*_host` entry points take HOST pointers, copy host->device, run the same kernels, copy the

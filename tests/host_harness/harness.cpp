@@ -13,8 +13,9 @@ extern "C" void hvh_local_miqp_batch(int batch, int N, const int32_t* flags, dou
     hvp::fill_local_params(P, N, d0, t0, tight, max_nodes);
     size_t S = 2 * (size_t)(N + 1);
     for (int i = 0; i < batch; ++i) {
-        hvp::LocalSolver<12> sol;
-        sol.setup(&P, flags[i], mass[i], x0 + 2 * (size_t)i, xf ? xf + S * i : nullptr,
+        hvp::LocalSolver<12, 1> sol;
+        double W[hvp::LocalLayout<12>::SIZE];
+        sol.setup(W, &P, flags[i], mass[i], x0 + 2 * (size_t)i, xf ? xf + S * i : nullptr,
                   xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr);
         hvp::LocalResult R = sol.solve(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
         obj[i] = R.obj; status[i] = R.status; nodes[i] = R.nodes; qp_iters[i] = R.qp_iters;
