@@ -10,3 +10,14 @@ from .api import (  # noqa: F401
 )
 
 __version__ = "0.1.0"
+from .agents import (  # noqa: F401,E402
+    MldAgent, MonitorEpisodes, TimeLimit, TrackingDecentMldCoordinator, TrackingSequentialMldCoordinator,
+    simulate,
+)
+from .env import BatchedPlatoonEnv, PlatoonEnv  # noqa: F401,E402
+from .misc import (  # noqa: F401,E402
+    ConstantSpacingPolicy, ConstantTimePolicy, ConstantVelocityLeaderTrajectory, Params, Sim, Sim_n_task_1,
+    Sim_n_task_2, StopAndGoLeaderTrajectory,
+)
+from .models import Platoon, PwaGearVehicle, Vehicle  # noqa: F401,E402
+from .mpc import LocalMpcMld, solve_local_batch  # noqa: F401,E402

@@ -85,7 +85,8 @@ def local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0
     check(lib().hvp_local_miqp_host(ctx.handle, C.byref(d), B, _hp(flags), _hp(mass), _hp(x0), _hp(xf),
                                     _hp(xb), _hp(xl), _hp(u), _hp(x), _hp(modes), _hp(obj), _hp(status),
                                     _hp(nodes), _hp(iters)))
-    return dict(u=u, x=x, modes=modes, obj=obj, status=status, nodes=nodes, qp_iters=iters)
+    return dict(u=u, x=x, modes=modes, obj=obj, status=status, nodes=nodes, qp_iters=iters,
+                run_time=max(ctx.last_kernel_ms(), 0.0) * 1e-3)
 
 
 def local_miqp_device(desc: LocalDesc, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status,
