@@ -274,10 +274,8 @@ def main():
     clocks = sampler.stop()
 
     # ---- max over ranks ----
-    tm = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = float(tm[0]), float(tm[1])
+    from hybrid_vehicle_platoon_b200.dist import max_over_ranks
+    total_ms, e2e_s = max_over_ranks([total_ms, e2e_s], device=dev)
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * e2e_steps / e2e_s
 
@@ -359,7 +357,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
                          "algorithmic_bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
-                         "kernel": "local_miqp_kernel<6>",
+                         "kernel": "coop_miqp_kernel<8>",
                          "note": "on-chip FP64 branch-and-bound: HBM traffic is parameters in + solution "
                                  "out only, so the HBM fraction is small by construction; see fp64_pipe"},
             "fp64_pipe": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,

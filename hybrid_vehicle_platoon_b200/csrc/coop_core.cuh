@@ -128,281 +128,25 @@ struct CoopSolver {
         return c < j ? sgn : 0.0;
     }
 
-    // -------------------------------------------------------------------------------------
-    // node QP (modes 0..L-1 fixed): 0 optimal, 1 infeasible, 2 numeric trouble
-    HVP_CD int solve_node(double* obj) {
-        const double tol = 1e-9;
-        const double qu = P->qu, ww = P->w;
-        const I ln = bk.lane();
-        const Bm valid = ln < N;
-        const D lnd = bk.todouble(ln);
-        const D hoff_l = hw1 * ((double)(N - 1) - lnd) + hw2;     // H_t[i][j], i<j, depends on j only
-        const D hdiag_l = hw1 * ((double)(N - 1) - lnd) + hd;
-        // ---- H rows: lane i holds row i.  H[i][c] = Hoff(max(i,c)), diag Hdiag(i) ----
-        D g = gt;
-#pragma unroll
-        for (int c = 0; c < G; ++c) {
-            const double hoff_c = hw1 * (double)(N - 1 - c) + hw2;
-            D h = bk.sel(ln > c, hoff_l, bk.splat(hoff_c));       // off-diagonal
-            h = bk.sel(ln == c, hdiag_l, h);
-            // padding lanes / columns: identity
-            h = bk.sel(valid & (c < N), h, bk.sel(ln == c, bk.splat(1.0), bk.splat(0.0)));
-            hinv[c] = h;
-        }
-        {   // input cost of fixed stages: u_k = (x_k - a x_{k-1} - c)/b   (x_{-1} = v0)
-#pragma unroll
-            for (int k = 0; k < G; ++k) {
-                if (k < L) {
-                    const int rg = mode(k);
-                    const double ib = 1.0 / rb(rg), ea = -ra(rg) * ib;
-                    const double kc = (k == 0) ? -(ra(rg) * v0 + rc(rg)) * ib : -rc(rg) * ib;
-                    hinv[k] += bk.sel(ln == k, bk.splat(2.0 * qu * ib * ib), bk.splat(0.0));
-                    g += bk.sel(ln == k, bk.splat(2.0 * qu * kc * ib), bk.splat(0.0));
-                    if (k >= 1) {
-                        hinv[k] += bk.sel(ln == k - 1, bk.splat(2.0 * qu * ea * ib), bk.splat(0.0));
-                        hinv[k - 1] += bk.sel(ln == k, bk.splat(2.0 * qu * ea * ib),
-                                              bk.sel(ln == k - 1, bk.splat(2.0 * qu * ea * ea), bk.splat(0.0)));
-                        g += bk.sel(ln == k - 1, bk.splat(2.0 * qu * kc * ea), bk.splat(0.0));
-                    }
-                }
-            }
-        }
-        // ---- in-place Gauss-Jordan inversion, rows distributed (H is SPD: no pivoting) ----
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-            if (k < N) {
-                const double piv = bk.bcast(hinv[k], k);
-                if (!(piv > 0.0)) return 2;
-                const double pinv = 1.0 / piv;
-                const D f = hinv[k];
-                const Bm isk = ln == k;
-#pragma unroll
-                for (int c = 0; c < G; ++c) {
-                    if (c == k) continue;
-                    const double rk = bk.bcast(hinv[c], k) * pinv;
-                    hinv[c] = bk.sel(isk, bk.splat(rk), hinv[c] - f * rk);
-                }
-                hinv[k] = bk.sel(isk, bk.splat(pinv), -(f * pinv));
-            }
-        }
-        // ---- unconstrained minimiser x = -H^-1 g ----
-        {
-            D acc = bk.splat(0.0);
-#pragma unroll
-            for (int c = 0; c < G; ++c) acc -= hinv[c] * bk.bcast(g, c);
-            x = bk.sel(valid, acc, bk.splat(0.0));
-        }
-        q = 0; satf = 0; satb = 0; am_lo = am_hi = 0;
-        lam = bk.splat(0.0); s_sgn = bk.splat(0.0); s_coef = bk.splat(0.0);
-        s_kind = bk.splati(0); s_j = bk.splati(0); s_id = bk.splati(0);
-#pragma unroll
-        for (int c = 0; c < G; ++c) { Y[c] = bk.splat(0.0); ginv[c] = bk.splat(0.0); }
-        const int maxit = 40 * N + 60;
-        int it = 0;
-        const D accmax = P->a_acc - lnd * P->tight, decmin = P->a_dec + lnd * P->tight;
-        const D NEG = bk.splat(-1.0);
+    // =====================================================================================
+    // Flat state machine.  One trip of the loop in run() executes, in this order and each at most
+    // once: NEXT (branch-and-bound bookkeeping) -> BUILD (node Hessian, H^-1, unconstrained
+    // minimiser) -> SELECT (violation scan / node finished) -> STEP (one dual active-set step).
+    // The four groups of a warp all run this same loop, so whatever their individual progress they
+    // re-converge at every block boundary instead of serialising whole solves.
+    // =====================================================================================
+    enum : int { S_NEXT = 0, S_BUILD, S_SELECT, S_STEP, S_DONE };
 
-        for (;;) {
-            // ---- violation scan: lane j evaluates every row type with index j ----
-            const D xm = bk.up1(x, 0.0);
-            const D PS = bk.scan_excl(x);
-            D bv = bk.splat(tol), brhs = bk.splat(0.0);
-            I bid = bk.splati(-1);
-            const Bm j1 = (ln >= 1) & valid;
-#define HVP_CAND(T, OK, S, RHS)                                                           \
-    {                                                                                     \
-        const I id__ = ln + (T) * 12;                                                     \
-        const D s__ = (S);                                                                \
-        const Bm take__ = (OK) & (s__ > bv) & !bk.bit128(am_lo, am_hi, id__);             \
-        bv = bk.sel(take__, s__, bv); bid = bk.seli(take__, id__, bid);                   \
-        brhs = bk.sel(take__, (RHS), brhs);                                               \
-    }
-            HVP_CAND(T_UB, valid, x - ub, ub);
-            HVP_CAND(T_LB, valid, lb - x, -lb);
-            const D dv = x - xm;
-            HVP_CAND(T_ACC, j1, dv - accmax, accmax);
-            HVP_CAND(T_DEC, j1, decmin - dv, -decmin);
-            {
-                const Bm fx = j1 & (ln < L);
-                const I rg = bk.bits3(modes_pk, ln);
-                const D al = ra_l(rg), cl = rc_l(rg), bl = rb_l(rg);
-                const D du = x - al * xm - cl;
-                HVP_CAND(T_UHI, fx, du - bl * P->umax, cl + bl * P->umax);
-                HVP_CAND(T_ULO, fx, bl * P->umin - du, -(cl + bl * P->umin));
-            }
-            HVP_CAND(T_PHI, j1, PS - (P->pmax - pc), bk.splat(P->pmax - pc));
-            HVP_CAND(T_PLO, j1, (P->pmin - pc) - PS, bk.splat(-(P->pmin - pc)));
-            if (has_sf) {
-                const D o = bk.sel(bk.bit32(satf, ln), NEG, bk.splat(1.0));
-                HVP_CAND(T_SF, j1, o * (PS - sf), o * sf);
-            }
-            if (has_sb) {
-                const D o = bk.sel(bk.bit32(satb, ln), NEG, bk.splat(1.0));
-                HVP_CAND(T_SB, j1, o * (sb - PS), -(o * sb));
-            }
-#undef HVP_CAND
-            double best_v; int pid;
-            bk.gmax_arg(bv, bid, best_v, pid);
-            if (pid < 0) break;
-            // ---- decode p (group-uniform) ----
-            const int pt = pid / 12, pj = pid - 12 * pt;
-            const double prhs = bk.bcast(brhs, pj);
-            int pkind; double psgn, pcoef = 1.0;
-            switch (pt) {
-                case T_UB: pkind = 0; psgn = 1.0; break;
-                case T_LB: pkind = 0; psgn = -1.0; break;
-                case T_ACC: pkind = 1; psgn = 1.0; break;
-                case T_DEC: pkind = 1; psgn = -1.0; break;
-                case T_UHI: pkind = 1; psgn = 1.0; pcoef = ra(mode(pj)); break;
-                case T_ULO: pkind = 1; psgn = -1.0; pcoef = ra(mode(pj)); break;
-                case T_PHI: pkind = 2; psgn = 1.0; break;
-                case T_PLO: pkind = 2; psgn = -1.0; break;
-                case T_SF: pkind = 2; psgn = ((satf >> pj) & 1u) ? -1.0 : 1.0; break;
-                default: pkind = 2; psgn = ((satb >> pj) & 1u) ? 1.0 : -1.0; break;
-            }
-            const bool p_soft = pt >= T_SF;
-            double npc[G];
-#pragma unroll
-            for (int c = 0; c < G; ++c) npc[c] = coef_at(pkind, pj, psgn, pcoef, c);
-            D np = bk.splat(0.0);
-#pragma unroll
-            for (int c = 0; c < G; ++c) np = bk.sel(ln == c, bk.splat(npc[c]), np);
-            // H^-1 n_p and n_p'H^-1 n_p do not change while p is being added
-            D yp = bk.splat(0.0);
-#pragma unroll
-            for (int c = 0; c < G; ++c) yp += hinv[c] * npc[c];
-            const double nHn = bk.gsum(np * yp);
-            const D yps = bk.scan_excl(yp);
-            double lam_p = 0.0;
-            for (;;) {
-                if (++it > maxit) { iters += it; return 2; }
-                const double cp = bk.gsum(np * x) - prhs;
-                if (cp <= tol) break;
-                // d_a = n_a' yp for slot a (lane a owns its row description)
-                D d;
-                {
-                    const D vj = bk.shfl(yp, s_j), vjm = bk.shfl(yp, s_j - 1), ps = bk.shfl(yps, s_j);
-                    d = s_sgn * bk.sel(s_kind == 0, vj, bk.sel(s_kind == 1, vj - s_coef * vjm, ps));
-                    d = bk.sel(ln < q, d, bk.splat(0.0));
-                }
-                // r = Ginv d
-                D r = bk.splat(0.0);
-#pragma unroll
-                for (int b = 0; b < G; ++b) r += ginv[b] * bk.bcast(d, b);
-                const double nz = nHn - bk.gsum(d * r);
-                const bool dependent = (q == N) || !(nz > 1e-11 * nHn);
-                const double INF = HUGE_VAL;
-                const double t2 = dependent ? INF : cp / nz;
-                double t1, t3; int k1, k3;
-                {
-                    const Bm act_ok = ln < q;
-                    const D c1v = bk.sel(act_ok & (r > 1e-14), lam / bk.sel(r > 1e-14, r, bk.splat(1.0)), bk.splat(INF));
-                    bk.gmin_arg(c1v, ln, t1, k1);
-                    const Bm softneg = act_ok & (r < -1e-14) & (s_id >= T_SF * 12);
-                    const D c3v = bk.sel(softneg, (ww - lam) / bk.sel(softneg, -r, bk.splat(1.0)), bk.splat(INF));
-                    bk.gmin_arg(c3v, ln, t3, k3);
-                }
-                const double t3p = p_soft ? (ww - lam_p) : INF;
-                const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
-                if (!(t < INF)) { iters += it; return 1; }
-                double ru[G];
-#pragma unroll
-                for (int a = 0; a < G; ++a) ru[a] = bk.bcast(r, a);
-                if (!dependent) {
-                    D z = yp;
-#pragma unroll
-                    for (int a = 0; a < G; ++a) z -= Y[a] * ru[a];
-                    x -= t * z;
-                }
-                lam -= t * r;
-                lam_p += t;
-                if (t == t2) {
-                    // p becomes slot q: bordering update of Ginv with Schur complement nz
-                    const double is = 1.0 / nz;
-                    const Bm isq = ln == q;
-#pragma unroll
-                    for (int b = 0; b < G; ++b) {
-                        D nb = ginv[b] + r * (ru[b] * is);
-                        if (b == q) nb = -(r * is);
-                        nb = bk.sel(isq, bk.splat(b == q ? is : -ru[b] * is), nb);
-                        ginv[b] = (b <= q) ? nb : ginv[b];
-                    }
-#pragma unroll
-                    for (int c = 0; c < G; ++c) Y[c] = (c == q) ? yp : Y[c];
-                    lam = bk.sel(isq, bk.splat(lam_p), lam);
-                    s_sgn = bk.sel(isq, bk.splat(psgn), s_sgn);
-                    s_coef = bk.sel(isq, bk.splat(pcoef), s_coef);
-                    s_kind = bk.seli(isq, bk.splati(pkind), s_kind);
-                    s_j = bk.seli(isq, bk.splati(pj), s_j);
-                    s_id = bk.seli(isq, bk.splati(pid), s_id);
-                    mark(pid, true);
-                    ++q;
-                    break;
-                }
-                if (t == t3p) {
-                    if (pt == T_SF) satf ^= (1u << pj); else satb ^= (1u << pj);
-                    break;
-                }
-                int drop;
-                if (t == t1) drop = k1;
-                else {
-                    drop = k3;
-                    const int id = bk.bcasti(s_id, drop), j = id % 12;
-                    if (id / 12 == T_SF) satf ^= (1u << j); else satb ^= (1u << j);
-                }
-                mark(bk.bcasti(s_id, drop), false);
-                {   // Ginv <- Ginv - g_k g_k'/g_kk, delete row/column `drop`, compact slots
-                    D ck = bk.splat(0.0);
-#pragma unroll
-                    for (int c = 0; c < G; ++c) ck = (c == drop) ? ginv[c] : ck;
-                    double rowk[G];
-#pragma unroll
-                    for (int b = 0; b < G; ++b) rowk[b] = bk.bcast(ginv[b], drop);
-                    double gkk = 1.0;
-#pragma unroll
-                    for (int b = 0; b < G; ++b) gkk = (b == drop) ? rowk[b] : gkk;
-                    const double ikk = 1.0 / gkk;
-                    const Bm mv = ln >= drop;
-#pragma unroll
-                    for (int b = 0; b < G; ++b) ginv[b] -= ck * (rowk[b] * ikk);
-#pragma unroll
-                    for (int b = 0; b < G; ++b) ginv[b] = bk.sel(mv, bk.dn1(ginv[b]), ginv[b]);   // rows up
-#pragma unroll
-                    for (int b = 0; b + 1 < G; ++b) {                                             // columns left
-                        ginv[b] = (b >= drop) ? ginv[b + 1] : ginv[b];
-                        Y[b] = (b >= drop) ? Y[b + 1] : Y[b];
-                    }
-                    ginv[G - 1] = bk.splat(0.0); Y[G - 1] = bk.splat(0.0);
-                    lam = bk.sel(mv, bk.dn1(lam), lam);
-                    s_sgn = bk.sel(mv, bk.dn1(s_sgn), s_sgn);
-                    s_coef = bk.sel(mv, bk.dn1(s_coef), s_coef);
-                    s_kind = bk.seli(mv, bk.dn1i(s_kind), s_kind);
-                    s_j = bk.seli(mv, bk.dn1i(s_j), s_j);
-                    s_id = bk.seli(mv, bk.dn1i(s_id), s_id);
-                    --q;
-                    // rows / columns beyond q stay exactly zero
-                    const Bm dead = ln >= q;
-#pragma unroll
-                    for (int b = 0; b < G; ++b) ginv[b] = bk.sel(dead | (b >= q), bk.splat(0.0), ginv[b]);
-                }
-            }
-        }
-        iters += it;
-        // ---- objective at x ----
-        {
-            const D PS = bk.scan_excl(x);
-            const D xprev = bk.up1(x, v0);
-            D term = x * (0.5 * hdiag_l * x + hoff_l * PS + gt);
-            const I rg = bk.bits3(modes_pk, ln);
-            const D uu = (x - ra_l(rg) * xprev - rc_l(rg)) / rb_l(rg);
-            term += bk.sel(ln < L, qu * uu * uu, bk.splat(0.0));
-            const Bm j1 = ln >= 1;
-            if (has_sf) { const D s = PS - sf; term += bk.sel(j1 & (s > 0.0), ww * s, bk.splat(0.0)); }
-            if (has_sb) { const D s = sb - PS; term += bk.sel(j1 & (s > 0.0), ww * s, bk.splat(0.0)); }
-            *obj = ct + bk.gsum(bk.sel(valid, term, bk.splat(0.0)));
-        }
-        return 0;
-    }
+    // persistent across trips -------------------------------------------------------------
+    int state, lev, it, nodes;
+    double inc, nlo_cur, nhi_cur;
+    uint64_t best_modes, cand_lo, cand_hi;
+    bool trouble, limit;
+    // constraint being added
+    int pid, pkind, pj;
+    double psgn, pcoef, prhs, nHn, lam_p;
+    bool p_soft;
+    D np, yp, yps;
 
     HVP_CD static int cand_get(uint64_t lo, uint64_t hi, int lv) {
         const unsigned sh = (unsigned)(7 * (lv < 9 ? lv : lv - 9));
@@ -414,29 +158,26 @@ struct CoopSolver {
         t = (t & ~(0x7full << sh)) | ((uint64_t)val << sh);
     }
 
-    // -------------------------------------------------------------------------------------
-    HVP_CD LocalResult solve(double* u_out, double* x_out, int32_t* mode_out) {
-        LocalResult R;
-        R.obj = HUGE_VAL; R.status = HVP_ST_INFEASIBLE; R.nodes = 0; R.qp_iters = 0;
-        iters = 0; modes_pk = 0;
-        double inc = HUGE_VAL;
-        uint64_t best_modes = 0, cand_lo = 0, cand_hi = 0;
-        const double eps = 1e-9;
-        bool trouble = false, limit = false;
-        const I ln = bk.lane();
-        const Bm valid = ln < N;
+    HVP_CD void begin() {
+        iters = 0; modes_pk = 0; nodes = 0; it = 0;
+        inc = HUGE_VAL; best_modes = 0; cand_lo = cand_hi = 0; trouble = limit = false;
         best = bk.splat(0.0); xstar = bk.splat(v0); rlo = bk.splat(0.0); rhi = bk.splat(0.0);
-        int lev = 0;
-        {
-            int c0 = 0;
-            for (int rg = 0; rg < NREG; ++rg)
-                if (v0 >= P->edge[rg] && v0 <= P->edge[rg + 1]) c0 |= (1 << rg);
-            cand_set(cand_lo, cand_hi, 0, c0);
-        }
+        lev = 0;
+        int c0 = 0;
+        for (int rg = 0; rg < NREG; ++rg)
+            if (v0 >= P->edge[rg] && v0 <= P->edge[rg + 1]) c0 |= (1 << rg);
+        cand_set(cand_lo, cand_hi, 0, c0);
+        state = S_NEXT;
+    }
+
+    // ---- NEXT: pick the next node of the depth-first search (or finish) -------------------
+    HVP_CD void do_next() {
+        const double eps = 1e-9;
+        const I ln = bk.lane();
         for (;;) {
             int cset = cand_get(cand_lo, cand_hi, lev);
             if (cset == 0) {
-                if (lev == 0) break;
+                if (lev == 0) { state = S_DONE; return; }
                 --lev;
                 continue;
             }
@@ -459,41 +200,328 @@ struct CoopSolver {
             double nhi = fmin(ra(rg) * jhi + rc(rg) + rb(rg) * P->umax, jhi + P->a_acc - lev * P->tight);
             nlo = fmax(nlo, P->vmin); nhi = fmin(nhi, P->vmax);
             if (nlo > nhi + eps) continue;
+            if (pc > P->pmax + eps || pc < P->pmin - eps) continue;
+            nlo_cur = nlo; nhi_cur = nhi;
             rlo = bk.sel(ln == lev, bk.splat(nlo - eps), rlo);
             rhi = bk.sel(ln == lev, bk.splat(nhi + eps), rhi);
             L = lev + 1;
-            {   // merged simple bounds
-                const I rgn = bk.bits3(modes_pk, ln + 1);       // region of stage j+1 bounds x_j = v_{j+1}
-                const Bm fixed = (ln + 1) < L;
-                const D elo = bk.lookup(P->edge, rgn), ehi = bk.lookup(P->edge, rgn + 1);
-                lb = bk.sel(fixed, bk.dmax(bk.splat(P->vmin), elo), bk.splat(P->vmin));
-                ub = bk.sel(fixed, bk.dmin(bk.splat(P->vmax), ehi), bk.splat(P->vmax));
-                const int r0 = mode(0);
-                const double l0 = fmax(v0 + P->a_dec, ra(r0) * v0 + rc(r0) + rb(r0) * P->umin);
-                const double u0 = fmin(v0 + P->a_acc, ra(r0) * v0 + rc(r0) + rb(r0) * P->umax);
-                lb = bk.sel(ln == 0, bk.dmax(lb, bk.splat(l0)), lb);
-                ub = bk.sel(ln == 0, bk.dmin(ub, bk.splat(u0)), ub);
-            }
-            if (pc > P->pmax + eps || pc < P->pmin - eps) continue;
-            double obj;
-            const int st = solve_node(&obj);
-            ++R.nodes;
-            if (st == 2) { trouble = true; continue; }
-            if (st == 1) continue;
-            if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) continue;
-            if (L == N) {
-                inc = obj; best = x; best_modes = modes_pk;
-                continue;
-            }
-            if (P->max_nodes > 0 && R.nodes >= P->max_nodes) { limit = true; break; }
-            ++lev;
-            xstar = bk.sel(ln == lev, bk.splat(bk.bcast(x, lev - 1)), xstar);
-            int cn = 0;
-            for (int c = 0; c < NREG; ++c)
-                if (P->edge[c] <= nhi + eps && P->edge[c + 1] >= nlo - eps) cn |= (1 << c);
-            cand_set(cand_lo, cand_hi, lev, cn);
+            // merged simple bounds: state box, regions of fixed stages, stage-0 accel/input rows
+            const I rgn = bk.bits3(modes_pk, ln + 1);
+            const Bm fixed = (ln + 1) < L;
+            const D elo = bk.lookup(P->edge, rgn), ehi = bk.lookup(P->edge, rgn + 1);
+            lb = bk.sel(fixed, bk.dmax(bk.splat(P->vmin), elo), bk.splat(P->vmin));
+            ub = bk.sel(fixed, bk.dmin(bk.splat(P->vmax), ehi), bk.splat(P->vmax));
+            const int r0 = mode(0);
+            const double l0 = fmax(v0 + P->a_dec, ra(r0) * v0 + rc(r0) + rb(r0) * P->umin);
+            const double u0 = fmin(v0 + P->a_acc, ra(r0) * v0 + rc(r0) + rb(r0) * P->umax);
+            lb = bk.sel(ln == 0, bk.dmax(lb, bk.splat(l0)), lb);
+            ub = bk.sel(ln == 0, bk.dmin(ub, bk.splat(u0)), ub);
+            state = S_BUILD;
+            return;
         }
-        R.qp_iters = iters;
+    }
+
+    // outcome of a node: st 0 solved (obj valid), 1 infeasible, 2 numeric trouble
+    HVP_CD void node_done(int st, double obj) {
+        iters += it;
+        ++nodes;
+        state = S_NEXT;
+        if (st == 2) { trouble = true; return; }
+        if (st == 1) return;
+        if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
+        if (L == N) { inc = obj; best = x; best_modes = modes_pk; return; }          // leaf
+        if (P->max_nodes > 0 && nodes >= P->max_nodes) { limit = true; state = S_DONE; return; }
+        const double eps = 1e-9;
+        const I ln = bk.lane();
+        ++lev;
+        xstar = bk.sel(ln == lev, bk.splat(bk.bcast(x, lev - 1)), xstar);
+        int cn = 0;
+        for (int c = 0; c < NREG; ++c)
+            if (P->edge[c] <= nhi_cur + eps && P->edge[c + 1] >= nlo_cur - eps) cn |= (1 << c);
+        cand_set(cand_lo, cand_hi, lev, cn);
+    }
+
+    // ---- BUILD: Hessian rows, in-place Gauss-Jordan inverse, unconstrained minimiser -------
+    HVP_CD void do_build() {
+        const double qu = P->qu;
+        const I ln = bk.lane();
+        const Bm valid = ln < N;
+        const D lnd = bk.todouble(ln);
+        const D hoff_l = hw1 * ((double)(N - 1) - lnd) + hw2;     // H_t[i][j], i<j, depends on j only
+        const D hdiag_l = hw1 * ((double)(N - 1) - lnd) + hd;
+        D g = gt;
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+            const double hoff_c = hw1 * (double)(N - 1 - c) + hw2;
+            D h = bk.sel(ln > c, hoff_l, bk.splat(hoff_c));
+            h = bk.sel(ln == c, hdiag_l, h);
+            h = bk.sel(valid & (c < N), h, bk.sel(ln == c, bk.splat(1.0), bk.splat(0.0)));   // padding: identity
+            hinv[c] = h;
+        }
+        // input cost of fixed stages: u_k = (x_k - a x_{k-1} - c)/b   (x_{-1} = v0)
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            if (k < L) {
+                const int rg = mode(k);
+                const double ib = 1.0 / rb(rg), ea = -ra(rg) * ib;
+                const double kc = (k == 0) ? -(ra(rg) * v0 + rc(rg)) * ib : -rc(rg) * ib;
+                hinv[k] += bk.sel(ln == k, bk.splat(2.0 * qu * ib * ib), bk.splat(0.0));
+                g += bk.sel(ln == k, bk.splat(2.0 * qu * kc * ib), bk.splat(0.0));
+                if (k >= 1) {
+                    hinv[k] += bk.sel(ln == k - 1, bk.splat(2.0 * qu * ea * ib), bk.splat(0.0));
+                    hinv[k - 1] += bk.sel(ln == k, bk.splat(2.0 * qu * ea * ib),
+                                          bk.sel(ln == k - 1, bk.splat(2.0 * qu * ea * ea), bk.splat(0.0)));
+                    g += bk.sel(ln == k - 1, bk.splat(2.0 * qu * kc * ea), bk.splat(0.0));
+                }
+            }
+        }
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            if (k < N) {
+                const double piv = bk.bcast(hinv[k], k);
+                bad = bad || !(piv > 0.0);
+                const double pinv = 1.0 / piv;
+                const D f = hinv[k];
+                const Bm isk = ln == k;
+#pragma unroll
+                for (int c = 0; c < G; ++c) {
+                    if (c == k) continue;
+                    const double rk = bk.bcast(hinv[c], k) * pinv;
+                    hinv[c] = bk.sel(isk, bk.splat(rk), hinv[c] - f * rk);
+                }
+                hinv[k] = bk.sel(isk, bk.splat(pinv), -(f * pinv));
+            }
+        }
+        it = 0;
+        if (bad) { node_done(2, 0.0); return; }
+        D acc = bk.splat(0.0);
+#pragma unroll
+        for (int c = 0; c < G; ++c) acc -= hinv[c] * bk.bcast(g, c);
+        x = bk.sel(valid, acc, bk.splat(0.0));
+        q = 0; satf = 0; satb = 0; am_lo = am_hi = 0;
+        lam = bk.splat(0.0); s_sgn = bk.splat(0.0); s_coef = bk.splat(0.0);
+        s_kind = bk.splati(0); s_j = bk.splati(0); s_id = bk.splati(0);
+#pragma unroll
+        for (int c = 0; c < G; ++c) { Y[c] = bk.splat(0.0); ginv[c] = bk.splat(0.0); }
+        state = S_SELECT;
+    }
+
+    // ---- SELECT: most violated row, or the node is solved ---------------------------------
+    HVP_CD void do_select() {
+        const double tol = 1e-9;
+        const double qu = P->qu, ww = P->w;
+        const I ln = bk.lane();
+        const Bm valid = ln < N;
+        const D lnd = bk.todouble(ln);
+        const D accmax = P->a_acc - lnd * P->tight, decmin = P->a_dec + lnd * P->tight;
+        const D NEG = bk.splat(-1.0);
+        const D xm = bk.up1(x, v0);
+        const D PS = bk.scan_excl(x);
+        const I rg = bk.bits3(modes_pk, ln);
+        const D al = ra_l(rg), cl = rc_l(rg), bl = rb_l(rg);
+        const D du = x - al * xm - cl;
+        D bv = bk.splat(tol), brhs = bk.splat(0.0);
+        I bid = bk.splati(-1);
+        const Bm j1 = (ln >= 1) & valid;
+#define HVP_CAND(T, OK, S, RHS)                                                           \
+    {                                                                                     \
+        const I id__ = ln + (T) * 12;                                                     \
+        const D s__ = (S);                                                                \
+        const Bm take__ = (OK) & (s__ > bv) & !bk.bit128(am_lo, am_hi, id__);             \
+        bv = bk.sel(take__, s__, bv); bid = bk.seli(take__, id__, bid);                   \
+        brhs = bk.sel(take__, (RHS), brhs);                                               \
+    }
+        HVP_CAND(T_UB, valid, x - ub, ub);
+        HVP_CAND(T_LB, valid, lb - x, -lb);
+        const D dv = x - xm;
+        HVP_CAND(T_ACC, j1, dv - accmax, accmax);
+        HVP_CAND(T_DEC, j1, decmin - dv, -decmin);
+        {
+            const Bm fx = j1 & (ln < L);
+            HVP_CAND(T_UHI, fx, du - bl * P->umax, cl + bl * P->umax);
+            HVP_CAND(T_ULO, fx, bl * P->umin - du, -(cl + bl * P->umin));
+        }
+        HVP_CAND(T_PHI, j1, PS - (P->pmax - pc), bk.splat(P->pmax - pc));
+        HVP_CAND(T_PLO, j1, (P->pmin - pc) - PS, bk.splat(-(P->pmin - pc)));
+        if (has_sf) {
+            const D o = bk.sel(bk.bit32(satf, ln), NEG, bk.splat(1.0));
+            HVP_CAND(T_SF, j1, o * (PS - sf), o * sf);
+        }
+        if (has_sb) {
+            const D o = bk.sel(bk.bit32(satb, ln), NEG, bk.splat(1.0));
+            HVP_CAND(T_SB, j1, o * (sb - PS), -(o * sb));
+        }
+#undef HVP_CAND
+        double best_v;
+        bk.gmax_arg(bv, bid, best_v, pid);
+        if (pid < 0) {
+            // ---- node solved: objective = tracking closed form + input cost + L1 penalties ----
+            const D hoff_l = hw1 * ((double)(N - 1) - lnd) + hw2;
+            const D hdiag_l = hw1 * ((double)(N - 1) - lnd) + hd;
+            D term = x * (0.5 * hdiag_l * x + hoff_l * PS + gt);
+            const D uu = du / bl;
+            term += bk.sel(ln < L, qu * uu * uu, bk.splat(0.0));
+            if (has_sf) { const D s = PS - sf; term += bk.sel((ln >= 1) & (s > 0.0), ww * s, bk.splat(0.0)); }
+            if (has_sb) { const D s = sb - PS; term += bk.sel((ln >= 1) & (s > 0.0), ww * s, bk.splat(0.0)); }
+            node_done(0, ct + bk.gsum(bk.sel(valid, term, bk.splat(0.0))));
+            return;
+        }
+        const int pt = pid / 12;
+        pj = pid - 12 * pt;
+        prhs = bk.bcast(brhs, pj);
+        pcoef = 1.0;
+        switch (pt) {
+            case T_UB: pkind = 0; psgn = 1.0; break;
+            case T_LB: pkind = 0; psgn = -1.0; break;
+            case T_ACC: pkind = 1; psgn = 1.0; break;
+            case T_DEC: pkind = 1; psgn = -1.0; break;
+            case T_UHI: pkind = 1; psgn = 1.0; pcoef = ra(mode(pj)); break;
+            case T_ULO: pkind = 1; psgn = -1.0; pcoef = ra(mode(pj)); break;
+            case T_PHI: pkind = 2; psgn = 1.0; break;
+            case T_PLO: pkind = 2; psgn = -1.0; break;
+            case T_SF: pkind = 2; psgn = ((satf >> pj) & 1u) ? -1.0 : 1.0; break;
+            default: pkind = 2; psgn = ((satb >> pj) & 1u) ? 1.0 : -1.0; break;
+        }
+        p_soft = pt >= T_SF;
+        // n_p, H^-1 n_p and n_p'H^-1 n_p stay fixed while p is being added
+        np = bk.splat(0.0); yp = bk.splat(0.0);
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+            const double cc = coef_at(pkind, pj, psgn, pcoef, c);
+            np = bk.sel(ln == c, bk.splat(cc), np);
+            yp += hinv[c] * cc;
+        }
+        nHn = bk.gsum(np * yp);
+        yps = bk.scan_excl(yp);
+        lam_p = 0.0;
+        state = S_STEP;
+    }
+
+    // ---- STEP: one primal-dual step towards adding p ----------------------------------------
+    HVP_CD void do_step() {
+        const double tol = 1e-9, ww = P->w;
+        const I ln = bk.lane();
+        if (++it > 40 * N + 60) { node_done(2, 0.0); return; }
+        const double cp = bk.gsum(np * x) - prhs;
+        if (cp <= tol) { state = S_SELECT; return; }
+        // d_a = n_a' yp for slot a (lane a owns its row description);  r = Ginv d
+        D d;
+        {
+            const D vj = bk.shfl(yp, s_j), vjm = bk.shfl(yp, s_j - 1), ps = bk.shfl(yps, s_j);
+            d = s_sgn * bk.sel(s_kind == 0, vj, bk.sel(s_kind == 1, vj - s_coef * vjm, ps));
+            d = bk.sel(ln < q, d, bk.splat(0.0));
+        }
+        D r = bk.splat(0.0);
+#pragma unroll
+        for (int b = 0; b < G; ++b) r += ginv[b] * bk.bcast(d, b);
+        const double nz = nHn - bk.gsum(d * r);
+        const bool dependent = (q == N) || !(nz > 1e-11 * nHn);
+        const double INF = HUGE_VAL;
+        const double t2 = dependent ? INF : cp / nz;
+        double t1, t3; int k1, k3;
+        {
+            const Bm act_ok = ln < q;
+            const Bm pos = act_ok & (r > 1e-14);
+            const D c1v = bk.sel(pos, lam / bk.sel(pos, r, bk.splat(1.0)), bk.splat(INF));
+            bk.gmin_arg(c1v, ln, t1, k1);
+            const Bm softneg = act_ok & (r < -1e-14) & (s_id >= T_SF * 12);
+            const D c3v = bk.sel(softneg, (ww - lam) / bk.sel(softneg, -r, bk.splat(1.0)), bk.splat(INF));
+            bk.gmin_arg(c3v, ln, t3, k3);
+        }
+        const double t3p = p_soft ? (ww - lam_p) : INF;
+        const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
+        if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
+        double ru[G];
+#pragma unroll
+        for (int a = 0; a < G; ++a) ru[a] = bk.bcast(r, a);
+        if (!dependent) {
+            D z = yp;
+#pragma unroll
+            for (int a = 0; a < G; ++a) z -= Y[a] * ru[a];
+            x -= t * z;
+        }
+        lam -= t * r;
+        lam_p += t;
+        if (t == t2) {
+            // p becomes slot q: bordering update of Ginv with Schur complement nz
+            const double is = 1.0 / nz;
+            const Bm isq = ln == q;
+#pragma unroll
+            for (int b = 0; b < G; ++b) {
+                D nb = ginv[b] + r * (ru[b] * is);
+                nb = (b == q) ? -(r * is) : nb;
+                nb = bk.sel(isq, bk.splat(b == q ? is : -ru[b] * is), nb);
+                ginv[b] = (b <= q) ? nb : ginv[b];
+            }
+#pragma unroll
+            for (int c = 0; c < G; ++c) Y[c] = (c == q) ? yp : Y[c];
+            lam = bk.sel(isq, bk.splat(lam_p), lam);
+            s_sgn = bk.sel(isq, bk.splat(psgn), s_sgn);
+            s_coef = bk.sel(isq, bk.splat(pcoef), s_coef);
+            s_kind = bk.seli(isq, bk.splati(pkind), s_kind);
+            s_j = bk.seli(isq, bk.splati(pj), s_j);
+            s_id = bk.seli(isq, bk.splati(pid), s_id);
+            mark(pid, true);
+            ++q;
+            state = S_SELECT;
+            return;
+        }
+        if (t == t3p) {                                          // soft p saturates: flip, not added
+            if (pid / 12 == T_SF) satf ^= (1u << pj); else satb ^= (1u << pj);
+            state = S_SELECT;
+            return;
+        }
+        int drop;
+        if (t == t1) drop = k1;
+        else {                                                   // active soft row saturates: flip + drop
+            drop = k3;
+            const int id = bk.bcasti(s_id, drop), j = id % 12;
+            if (id / 12 == T_SF) satf ^= (1u << j); else satb ^= (1u << j);
+        }
+        mark(bk.bcasti(s_id, drop), false);
+        {   // Ginv <- Ginv - g_k g_k'/g_kk, delete row/column `drop`, compact slots
+            D ck = bk.splat(0.0);
+#pragma unroll
+            for (int c = 0; c < G; ++c) ck = (c == drop) ? ginv[c] : ck;
+            double rowk[G];
+#pragma unroll
+            for (int b = 0; b < G; ++b) rowk[b] = bk.bcast(ginv[b], drop);
+            double gkk = 1.0;
+#pragma unroll
+            for (int b = 0; b < G; ++b) gkk = (b == drop) ? rowk[b] : gkk;
+            const double ikk = 1.0 / gkk;
+            const Bm mv = ln >= drop;
+#pragma unroll
+            for (int b = 0; b < G; ++b) ginv[b] -= ck * (rowk[b] * ikk);
+#pragma unroll
+            for (int b = 0; b < G; ++b) ginv[b] = bk.sel(mv, bk.dn1(ginv[b]), ginv[b]);   // rows up
+#pragma unroll
+            for (int b = 0; b + 1 < G; ++b) {                                             // columns left
+                ginv[b] = (b >= drop) ? ginv[b + 1] : ginv[b];
+                Y[b] = (b >= drop) ? Y[b + 1] : Y[b];
+            }
+            ginv[G - 1] = bk.splat(0.0); Y[G - 1] = bk.splat(0.0);
+            lam = bk.sel(mv, bk.dn1(lam), lam);
+            s_sgn = bk.sel(mv, bk.dn1(s_sgn), s_sgn);
+            s_coef = bk.sel(mv, bk.dn1(s_coef), s_coef);
+            s_kind = bk.seli(mv, bk.dn1i(s_kind), s_kind);
+            s_j = bk.seli(mv, bk.dn1i(s_j), s_j);
+            s_id = bk.seli(mv, bk.dn1i(s_id), s_id);
+            --q;
+            const Bm dead = ln >= q;                              // rows / columns beyond q stay zero
+#pragma unroll
+            for (int b = 0; b < G; ++b) ginv[b] = bk.sel(dead | (b >= q), bk.splat(0.0), ginv[b]);
+        }
+        // state stays S_STEP: continue with the same p
+    }
+
+    // ---- results -----------------------------------------------------------------------------
+    HVP_CD LocalResult finish(double* u_out, double* x_out, int32_t* mode_out) {
+        LocalResult R;
+        R.nodes = nodes; R.qp_iters = iters;
+        const I ln = bk.lane();
+        const Bm valid = ln < N;
         const int np1 = N + 1;
         if (inc < HUGE_VAL) {
             R.obj = inc;
@@ -509,6 +537,7 @@ struct CoopSolver {
             bk.st(x_out, ln, bk.splat(p0), ln == 0);
             bk.st(x_out, ln + np1, bk.splat(v0), ln == 0);
         } else {
+            R.obj = HUGE_VAL;
             R.status = limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_INFEASIBLE);
             bk.st(u_out, ln, bk.splat(0.0), valid);
             bk.sti(mode_out, ln, bk.splati(-1), valid);
@@ -518,6 +547,20 @@ struct CoopSolver {
             bk.st(x_out, ln + np1, bk.splat(0.0), ln == 0);
         }
         return R;
+    }
+
+    // one trip of the state machine (each block at most once, in pipeline order)
+    HVP_CD void trip() {
+        if (state == S_NEXT) do_next();
+        if (state == S_BUILD) do_build();
+        if (state == S_SELECT) do_select();
+        if (state == S_STEP) do_step();
+    }
+
+    HVP_CD LocalResult solve(double* u_out, double* x_out, int32_t* mode_out) {
+        begin();
+        while (state != S_DONE) trip();
+        return finish(u_out, x_out, mode_out);
     }
 };
 

@@ -1,0 +1,48 @@
+"""CPU: the N > 1 host logic (scenario sharding, max-over-ranks timing) on gloo, world size 2."""
+import os
+import socket
+
+import pytest
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from hybrid_vehicle_platoon_b200.dist import max_over_ranks, shard_range, sum_over_ranks
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(4097, rank, world)
+    t = max_over_ranks([1.0 + rank, 5.0 - rank])
+    n = sum_over_ranks([hi - lo])
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, lo, hi, t, n))
+
+
+def test_sharding_and_reductions_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    out = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    (r0, lo0, hi0, t0, n0), (r1, lo1, hi1, t1, n1) = out
+    assert (lo0, hi0, lo1, hi1) == (0, 2049, 2049, 4097)
+    assert t0 == t1 == [2.0, 5.0]
+    assert n0 == n1 == [4097.0]
+
+
+def test_shard_range_properties():
+    from hybrid_vehicle_platoon_b200.dist import shard_range
+    for total in (0, 1, 7, 4096, 4097):
+        for world in (1, 2, 4, 8):
+            blocks = [shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
