@@ -1,0 +1,610 @@
+// flat_core.cuh -- per-vehicle local hybrid-MPC MIQP, one GPU THREAD per problem, written as a
+// COMPACT flat state machine.
+//
+// Same mathematics as coop_core.cuh / miqp_core.cuh (problem: LocalMpcMld,
+// fleet_decent_mld.py:61-208 on the pwa_gear model models.py:397-492; velocity-space node QPs,
+// bounded-dual Goldfarb-Idnani with exact L1 slack elimination, depth-first branch and bound with
+// relaxed-tail lower bounds).  The execution shape is what three rounds of ncu asked for:
+//   * (r01a) one thread per problem with nested data-dependent loops: 5.8 of 32 lanes active;
+//   * (r01b/c) fully unrolled / all-register variants: 6-9 k instructions of straight-line code,
+//     55 % of the stall samples "no instruction" -- the kernel was bound by INSTRUCTION FETCH;
+//   => this version keeps every loop rolled (#pragma unroll 1): the hot path (SELECT + STEP) is a
+//      few hundred instructions and stays in the instruction cache; the per-thread vectors live in
+//      a strided shared-memory slab (element e of lane l at slab[e*32 + l], conflict free);
+//   * H^-1 is not rebuilt per node: moving between nodes of the depth-first search adds or removes
+//     the input-cost term of one stage, a rank-1 change, so H^-1 follows by Sherman-Morrison
+//     up/down-dates (O(N^2)) from the node it was last valid for;
+//   * the solver is a state machine NEXT -> BUILD -> SELECT -> STEP; one trip() runs each block at
+//     most once, in that order, so the 32 lanes of a warp (32 different problems) re-converge at
+//     every block boundary; the kernel is persistent and a lane that finishes refills at once.
+//
+// Host + device (tests compile it with g++, ST = 1); the product only runs it inside local_miqp.cu.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "miqp_core.cuh"   // LocalParams, LocalResult, status codes, constraint type ids, HVP_HD
+
+#if defined(__CUDACC__)
+#define HVP_ROLL _Pragma("unroll 1")
+#else
+#define HVP_ROLL
+#endif
+
+namespace hvp {
+
+// reciprocal to ~1 ulp without the slow paths of the IEEE division sequence
+HVP_HD double hvp_rcp(double v) {
+#if defined(__CUDA_ARCH__)
+    double r = (double)__frcp_rn((float)v);
+    r = r * (2.0 - v * r);
+    r = r * (2.0 - v * r);
+    r = r * (2.0 - v * r);
+    return r;
+#else
+    return 1.0 / v;
+#endif
+}
+
+template <int N>
+struct FlatLayout {
+    static constexpr int TRI = N * (N + 1) / 2;
+    static constexpr int O_HINV = 0;              // H^-1, full square (symmetric), row-major
+    static constexpr int O_GINV = N * N;          // packed lower (N'H^-1N)^-1, slots a >= b
+    static constexpr int O_X = O_GINV + TRI;
+    static constexpr int O_LAM = O_X + N;
+    static constexpr int O_SSGN = O_LAM + N;      // sign (incl. soft orientation) of slot a's row
+    static constexpr int O_SCOEF = O_SSGN + N;    // difference coefficient of slot a's row
+    static constexpr int O_YP = O_SCOEF + N;      // H^-1 n_p
+    static constexpr int O_WV = O_YP + N;         // n_p - N r ; scratch
+    static constexpr int O_D = O_WV + N;
+    static constexpr int O_R = O_D + N;
+    static constexpr int SIZE = O_R + N;          // doubles per thread (105 at N = 6)
+};
+
+template <int N, int ST>
+struct FlatSolver {
+    using LY = FlatLayout<N>;
+    enum : int { S_NEXT = 0, S_BUILD, S_SELECT, S_STEP, S_DONE };
+
+    double* W;
+    const LocalParams* P;
+    const double* xf_;                  // soft-row data is read from the caller's arrays
+    const double* xb_;
+    double* best_;                      // incumbent velocities go straight to the output trajectory
+    // cold per-problem arrays (touched once per node): thread-local memory
+    double gt[N], xstar[N], rlo[N + 1], rhi[N + 1];
+    double p0, v0, pc, inv_m, a_lo, a_hi, c_lo, c_hi, hw1, hw2, hd, ct;
+    bool has_sf, has_sb;
+    // branch and bound
+    int state, lev, L, nodes, iters, it;
+    double inc;
+    uint64_t modes_pk, best_modes, cand_pk, built_pk;   // 3 bits / stage; 7 candidate bits / level
+    int built_L;                                        // H^-1 currently holds stages 0..built_L-1 of built_pk
+    bool trouble, limit;
+    // active set
+    int q;
+    uint64_t act_lo, act_hi;                            // slot ids, 8 bits each
+    uint32_t satf, satb;
+    // constraint being added
+    int pid, pkind, pj;
+    double psgn, pcoef, nHn, lam_p, cp;
+    bool p_soft;
+
+    HVP_HD double& w(int off, int i) const { return W[(size_t)(off + i) * ST]; }
+    HVP_HD static int tri(int a, int b) { return a * (a + 1) / 2 + b; }          // a >= b
+    HVP_HD double ra(int rg) const { return rg < 4 ? a_lo : a_hi; }
+    HVP_HD double rc(int rg) const { return rg < 4 ? c_lo : c_hi; }
+    HVP_HD double rb(int rg) const { return P->bgear[rg] * inv_m; }
+    HVP_HD static int mode_of(uint64_t pk, int k) { return (int)((pk >> (3 * k)) & 7u); }
+    HVP_HD int mode(int k) const { return mode_of(modes_pk, k); }
+    HVP_HD void set_mode(int k, int rg) { modes_pk = (modes_pk & ~(7ull << (3 * k))) | ((uint64_t)rg << (3 * k)); }
+    HVP_HD int cand(int lv) const { return (int)((cand_pk >> (7 * lv)) & 0x7fu); }
+    HVP_HD void set_cand(int lv, int v) { cand_pk = (cand_pk & ~(0x7full << (7 * lv))) | ((uint64_t)v << (7 * lv)); }
+    HVP_HD int act(int a) const { return (int)(((a < 8 ? act_lo >> (8 * a) : act_hi >> (8 * (a - 8)))) & 0xffu); }
+    HVP_HD void set_act(int a, int id) {
+        if (a < 8) act_lo = (act_lo & ~(0xffull << (8 * a))) | ((uint64_t)id << (8 * a));
+        else act_hi = (act_hi & ~(0xffull << (8 * (a - 8)))) | ((uint64_t)id << (8 * (a - 8)));
+    }
+    HVP_HD double Hoff(int j) const { return hw1 * (double)(N - 1 - j) + hw2; }
+    HVP_HD double Hdiag(int j) const { return hw1 * (double)(N - 1 - j) + hd; }
+    HVP_HD double sf(int j) const { return xf_[j + 1] - P->d_safe - pc; }       // rows PS_j <= sf(j)
+    HVP_HD double sb(int j) const { return xb_[j + 1] + P->d_safe - pc; }       // rows PS_j >= sb(j)
+
+    // -------------------------------------------------------------------------------------
+    HVP_HD void setup(double* W_, const LocalParams* P_, int flags, double mass, const double* x0,
+                      const double* xf, const double* xb, const double* xl, double* best_out) {
+        W = W_; P = P_; xf_ = xf; xb_ = xb; best_ = best_out;
+        p0 = x0[0]; v0 = x0[1]; pc = p0 + v0;
+        inv_m = hvp_rcp(mass);
+        a_lo = 1.0 - P->c1 * inv_m; a_hi = 1.0 - P->c2 * inv_m;
+        c_lo = -P->mug; c_hi = -P->mug - P->dfr * inv_m;
+        const bool is_front = flags & 1, is_leader = flags & 2, is_trailer = flags & 4;
+        const bool tf = !is_front && !is_leader, tb = !is_trailer && !is_leader, tl = is_leader;
+        const double wp = P->qxp, wvv = P->qxv, t0 = P->t0, d0 = P->d0;
+        const int np1 = N + 1;
+        const double nterm = (tf ? 1.0 : 0.0) + (tb ? 1.0 : 0.0) + (tl ? 1.0 : 0.0);
+        hw1 = 2.0 * wp * nterm;
+        hw2 = 2.0 * wp * (tf ? t0 : 0.0);
+        hd = 2.0 * wp * (tf ? t0 * t0 : 0.0) + 2.0 * wvv * nterm;
+        HVP_ROLL
+        for (int j = 0; j < N; ++j) gt[j] = 0.0;
+        ct = 0.0;
+        HVP_ROLL
+        for (int kind = 0; kind < 3; ++kind) {
+            const double* ref = kind == 0 ? xf : (kind == 1 ? xb : xl);
+            const bool on = kind == 0 ? tf : (kind == 1 ? tb : tl);
+            if (!on) continue;
+            const double tau = kind == 0 ? t0 : 0.0;
+            double suffix = 0.0;
+            HVP_ROLL
+            for (int k = N; k >= 0; --k) {
+                const double pk = ref[k], vk = ref[np1 + k];
+                const double Pk = (kind == 0) ? (pk - d0) : (kind == 1) ? (pk + t0 * vk + d0) : pk;
+                if (k >= 1) {
+                    const double rho = pc - Pk;
+                    gt[k - 1] += 2.0 * wp * (suffix + tau * rho) - 2.0 * wvv * vk;
+                    ct += wp * rho * rho + wvv * vk * vk;
+                    suffix += rho;
+                } else {
+                    const double e0 = p0 + tau * v0 - Pk, e1 = v0 - vk;
+                    ct += wp * e0 * e0 + wvv * e1 * e1;
+                }
+            }
+        }
+        has_sf = !is_front; has_sb = !is_trailer;
+        const double ww = P->w, ds = P->d_safe;
+        if (has_sf) {
+            const double s0 = p0 - (xf[0] - ds), s1 = pc - (xf[1] - ds);
+            ct += ww * (s0 > 0 ? s0 : 0.0) + ww * (s1 > 0 ? s1 : 0.0);
+        }
+        if (has_sb) {
+            const double s0 = (xb[0] + ds) - p0, s1 = (xb[1] + ds) - pc;
+            ct += ww * (s0 > 0 ? s0 : 0.0) + ww * (s1 > 0 ? s1 : 0.0);
+        }
+        // ---- H^-1 of the pure tracking Hessian (no stage fixed) by in-place Gauss-Jordan ----
+        HVP_ROLL
+        for (int i = 0; i < N; ++i) {
+            HVP_ROLL
+            for (int j = 0; j < N; ++j) w(LY::O_HINV, i * N + j) = (i == j) ? Hdiag(i) : Hoff(i > j ? i : j);
+        }
+        HVP_ROLL
+        for (int k = 0; k < N; ++k) {
+            const double pinv = hvp_rcp(w(LY::O_HINV, k * N + k));
+            HVP_ROLL
+            for (int j = 0; j < N; ++j) w(LY::O_HINV, k * N + j) *= pinv;
+            w(LY::O_HINV, k * N + k) = pinv;
+            HVP_ROLL
+            for (int i = 0; i < N; ++i) {
+                if (i == k) continue;
+                const double f = w(LY::O_HINV, i * N + k);
+                HVP_ROLL
+                for (int j = 0; j < N; ++j)
+                    w(LY::O_HINV, i * N + j) = (j == k) ? -f * pinv : w(LY::O_HINV, i * N + j) - f * w(LY::O_HINV, k * N + j);
+            }
+        }
+        built_L = 0; built_pk = 0;
+        // ---- start of the search ----
+        iters = 0; nodes = 0; it = 0; modes_pk = 0; best_modes = 0; cand_pk = 0;
+        inc = HUGE_VAL; trouble = limit = false; lev = 0;
+        int c0 = 0;
+        HVP_ROLL
+        for (int rg = 0; rg < NREG; ++rg)
+            if (v0 >= P->edge[rg] && v0 <= P->edge[rg + 1]) c0 |= (1 << rg);
+        set_cand(0, c0);
+        xstar[0] = v0; rlo[0] = v0; rhi[0] = v0;
+        state = S_NEXT;
+    }
+
+    // ---- NEXT: next node of the depth-first search (or finished) --------------------------
+    HVP_HD void do_next() {
+        const double eps = 1e-9;
+        for (;;) {
+            int cset = cand(lev);
+            if (cset == 0) {
+                if (lev == 0) { state = S_DONE; return; }
+                --lev;
+                continue;
+            }
+            int rg = -1; double bd = HUGE_VAL;
+            const double xs = xstar[lev];
+            HVP_ROLL
+            for (int c = 0; c < NREG; ++c) {
+                if (!((cset >> c) & 1)) continue;
+                const double lo = P->edge[c], hi = P->edge[c + 1];
+                const double dist = xs < lo ? lo - xs : (xs > hi ? xs - hi : 0.0);
+                if (dist < bd) { bd = dist; rg = c; }
+            }
+            set_cand(lev, cset & ~(1 << rg));
+            set_mode(lev, rg);
+            const double jlo = fmax(rlo[lev], P->edge[rg]), jhi = fmin(rhi[lev], P->edge[rg + 1]);
+            if (jlo > jhi + eps) continue;
+            double nlo = fmax(ra(rg) * jlo + rc(rg) + rb(rg) * P->umin, jlo + P->a_dec + lev * P->tight);
+            double nhi = fmin(ra(rg) * jhi + rc(rg) + rb(rg) * P->umax, jhi + P->a_acc - lev * P->tight);
+            nlo = fmax(nlo, P->vmin); nhi = fmin(nhi, P->vmax);
+            if (nlo > nhi + eps) continue;
+            if (pc > P->pmax + eps || pc < P->pmin - eps) continue;
+            rlo[lev + 1] = nlo - eps; rhi[lev + 1] = nhi + eps;
+            L = lev + 1;
+            state = S_BUILD;
+            return;
+        }
+    }
+
+    HVP_HD void node_done(int st, double obj) {
+        iters += it;
+        ++nodes;
+        state = S_NEXT;
+        if (st == 2) { trouble = true; return; }
+        if (st == 1) return;
+        if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
+        if (L == N) {                                                                // leaf
+            inc = obj; best_modes = modes_pk;
+            HVP_ROLL
+            for (int j = 0; j < N; ++j) best_[j] = w(LY::O_X, j);
+            return;
+        }
+        if (P->max_nodes > 0 && nodes >= P->max_nodes) { limit = true; state = S_DONE; return; }
+        ++lev;
+        xstar[lev] = w(LY::O_X, lev - 1);                                             // relaxed v_lev
+        int cn = 0;
+        HVP_ROLL
+        for (int c = 0; c < NREG; ++c)
+            if (P->edge[c] <= rhi[lev] && P->edge[c + 1] >= rlo[lev]) cn |= (1 << c);
+        set_cand(lev, cn);
+    }
+
+    // H <- H + s * 2*qu * e e'  with  e = (e_k - a e_{k-1})/b  (stage k, region rg):
+    // Sherman-Morrison on the stored H^-1;  s = +1 adds the stage's input cost, -1 removes it.
+    HVP_HD void rank1(int k, int rg, double s) {
+        const double ib = hvp_rcp(rb(rg)), ea = (k >= 1) ? -ra(rg) * ib : 0.0;
+        double ev = 0.0;                                   // e' H^-1 e
+        HVP_ROLL
+        for (int i = 0; i < N; ++i) {
+            double v = ib * w(LY::O_HINV, i * N + k);
+            if (k >= 1) v += ea * w(LY::O_HINV, i * N + k - 1);
+            w(LY::O_WV, i) = v;                            // v = H^-1 e
+        }
+        ev = ib * w(LY::O_WV, k) + ((k >= 1) ? ea * w(LY::O_WV, k - 1) : 0.0);
+        const double den = hvp_rcp(1.0 / (2.0 * P->qu) * s + ev);     // (1/(s*2qu) + e'H^-1e)^-1, s = +-1
+        HVP_ROLL
+        for (int i = 0; i < N; ++i) {
+            const double vi = w(LY::O_WV, i) * den;
+            HVP_ROLL
+            for (int j = 0; j < N; ++j) w(LY::O_HINV, i * N + j) -= vi * w(LY::O_WV, j);
+        }
+    }
+
+    // ---- BUILD: bring H^-1 to this node, gradient, unconstrained minimiser -----------------
+    HVP_HD void do_build() {
+        const double qu = P->qu;
+        // common prefix of the stages H^-1 currently contains and the stages this node fixes
+        int c = 0;
+        while (c < built_L && c < L && mode_of(built_pk, c) == mode(c)) ++c;
+        HVP_ROLL
+        for (int k = built_L - 1; k >= c; --k) rank1(k, mode_of(built_pk, k), -1.0);
+        HVP_ROLL
+        for (int k = c; k < L; ++k) rank1(k, mode(k), 1.0);
+        built_L = L; built_pk = modes_pk;
+        // gradient g = gt + input-cost terms (into O_D), then x = -H^-1 g
+        HVP_ROLL
+        for (int i = 0; i < N; ++i) w(LY::O_D, i) = gt[i];
+        HVP_ROLL
+        for (int k = 0; k < L; ++k) {
+            const int rg = mode(k);
+            const double ib = hvp_rcp(rb(rg)), ea = -ra(rg) * ib;
+            const double kc = (k == 0) ? -(ra(rg) * v0 + rc(rg)) * ib : -rc(rg) * ib;
+            w(LY::O_D, k) += 2.0 * qu * kc * ib;
+            if (k >= 1) w(LY::O_D, k - 1) += 2.0 * qu * kc * ea;
+        }
+        HVP_ROLL
+        for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+            HVP_ROLL
+            for (int j = 0; j < N; ++j) s -= w(LY::O_HINV, i * N + j) * w(LY::O_D, j);
+            w(LY::O_X, i) = s;
+        }
+        it = 0; q = 0; satf = 0; satb = 0; act_lo = act_hi = 0;
+        state = S_SELECT;
+    }
+
+    // merged simple bounds of x_j = v_{j+1}: state box, region of stage j+1 if fixed, stage-0 rows
+    HVP_HD void bounds(int j, double& lo, double& hi) const {
+        lo = P->vmin; hi = P->vmax;
+        if (j + 1 < L) {
+            const int rg = mode(j + 1);
+            lo = fmax(lo, P->edge[rg]); hi = fmin(hi, P->edge[rg + 1]);
+        }
+        if (j == 0) {
+            const int r0 = mode(0);
+            const double m = ra(r0) * v0 + rc(r0), bb = rb(r0);
+            lo = fmax(lo, fmax(v0 + P->a_dec, m + bb * P->umin));
+            hi = fmin(hi, fmin(v0 + P->a_acc, m + bb * P->umax));
+        }
+    }
+
+    // ---- SELECT: most violated row, or the node is solved ---------------------------------
+    HVP_HD void do_select() {
+        const double tol = 1e-9;
+        const double qu = P->qu, ww = P->w;
+        double best = tol; int bid = -1;
+        double PS = 0.0, xm = v0;
+#define HVP_CAND(T, J, S)                                              \
+    {                                                                  \
+        const double s__ = (S);                                        \
+        if (s__ > best) { best = s__; bid = (T) * 12 + (J); }          \
+    }
+        HVP_ROLL
+        for (int j = 0; j < N; ++j) {
+            const double xv = w(LY::O_X, j);
+            double lo, hi;
+            bounds(j, lo, hi);
+            HVP_CAND(T_UB, j, xv - hi);
+            HVP_CAND(T_LB, j, lo - xv);
+            if (j >= 1) {
+                if (j < L) {
+                    const int rg = mode(j);
+                    const double du = xv - ra(rg) * xm - rc(rg), bb = rb(rg);
+                    HVP_CAND(T_UHI, j, du - bb * P->umax);
+                    HVP_CAND(T_ULO, j, bb * P->umin - du);
+                }
+                const double dv = xv - xm;
+                HVP_CAND(T_ACC, j, dv - (P->a_acc - j * P->tight));
+                HVP_CAND(T_DEC, j, (P->a_dec + j * P->tight) - dv);
+                if (has_sf) {
+                    const double s = PS - sf(j);
+                    HVP_CAND(T_SF, j, ((satf >> j) & 1u) ? -s : s);
+                }
+                if (has_sb) {
+                    const double s = sb(j) - PS;
+                    HVP_CAND(T_SB, j, ((satb >> j) & 1u) ? -s : s);
+                }
+                // position box: prefix sums increase with j once the velocity bounds hold, so the
+                // smallest (j = 1) and largest (j = N-1) are the rows that can stay violated
+                if (j == 1) HVP_CAND(T_PLO, j, (P->pmin - pc) - PS);
+                if (j == N - 1) HVP_CAND(T_PHI, j, PS - (P->pmax - pc));
+            }
+            PS += xv; xm = xv;
+        }
+#undef HVP_CAND
+        if (bid < 0) {
+            // ---- node solved: objective = tracking closed form + input cost + L1 penalties ----
+            double f = ct;
+            PS = 0.0; xm = v0;
+            HVP_ROLL
+            for (int j = 0; j < N; ++j) {
+                const double xv = w(LY::O_X, j);
+                f += xv * (0.5 * Hdiag(j) * xv + Hoff(j) * PS + gt[j]);
+                if (j < L) {
+                    const int rg = mode(j);
+                    const double uu = (xv - ra(rg) * xm - rc(rg)) * hvp_rcp(rb(rg));
+                    f += qu * uu * uu;
+                }
+                if (j >= 1) {
+                    if (has_sf) { const double s = PS - sf(j); if (s > 0) f += ww * s; }
+                    if (has_sb) { const double s = sb(j) - PS; if (s > 0) f += ww * s; }
+                }
+                PS += xv; xm = xv;
+            }
+            node_done(0, f);
+            return;
+        }
+        // a selected row can never already be active (active rows have residual ~1e-13 << tol)
+        HVP_ROLL
+        for (int a = 0; a < q; ++a)
+            if (act(a) == bid) { node_done(2, 0.0); return; }
+        pid = bid;
+        const int pt = pid / 12;
+        pj = pid - 12 * pt;
+        pkind = (pt < T_ACC) ? 0 : (pt < T_PHI ? 1 : 2);
+        psgn = (pt & 1) ? -1.0 : 1.0;
+        pcoef = (pt == T_UHI || pt == T_ULO) ? ra(mode(pj)) : 1.0;
+        if (pt == T_SF) psgn = ((satf >> pj) & 1u) ? -1.0 : 1.0;
+        if (pt == T_SB) psgn = ((satb >> pj) & 1u) ? 1.0 : -1.0;
+        p_soft = pt >= T_SF;
+        // yp = H^-1 n_p and nHn = n_p' yp
+        double acc = 0.0;
+        HVP_ROLL
+        for (int i = 0; i < N; ++i) {
+            double s;
+            if (pkind == 0) s = w(LY::O_HINV, pj * N + i);
+            else if (pkind == 1) s = w(LY::O_HINV, pj * N + i) - pcoef * w(LY::O_HINV, (pj - 1) * N + i);
+            else {
+                s = 0.0;
+                HVP_ROLL
+                for (int k = 0; k < pj; ++k) s += w(LY::O_HINV, k * N + i);
+            }
+            s *= psgn;
+            w(LY::O_YP, i) = s;
+            // n_p' yp accumulates with the same structure
+            if (pkind == 0) acc += (i == pj) ? s : 0.0;
+            else if (pkind == 1) acc += (i == pj) ? s : ((i == pj - 1) ? -pcoef * s : 0.0);
+            else acc += (i < pj) ? s : 0.0;
+        }
+        nHn = psgn * acc;
+        cp = best;
+        lam_p = 0.0;
+        state = S_STEP;
+    }
+
+    // n_a' v for slot a's row, v in the work array at `off`
+    HVP_HD double slot_dot(int a, int off) const {
+        const int id = act(a), t = id / 12, j = id - 12 * t;
+        double s;
+        if (t < T_ACC) s = w(off, j);
+        else if (t < T_PHI) s = w(off, j) - w(LY::O_SCOEF, a) * w(off, j - 1);
+        else {
+            s = 0.0;
+            HVP_ROLL
+            for (int i = 0; i < j; ++i) s += w(off, i);
+        }
+        return w(LY::O_SSGN, a) * s;
+    }
+    HVP_HD void slot_axpy(int a, double c0, int off) const {
+        const int id = act(a), t = id / 12, j = id - 12 * t;
+        const double c = c0 * w(LY::O_SSGN, a);
+        if (t < T_ACC) w(off, j) += c;
+        else if (t < T_PHI) { w(off, j) += c; w(off, j - 1) -= c * w(LY::O_SCOEF, a); }
+        else {
+            HVP_ROLL
+            for (int i = 0; i < j; ++i) w(off, i) += c;
+        }
+    }
+
+    // ---- STEP: one primal-dual step towards adding p ----------------------------------------
+    HVP_HD void do_step() {
+        const double tol = 1e-9, ww = P->w;
+        if (++it > 40 * N + 60) { node_done(2, 0.0); return; }
+        if (cp <= tol) { state = S_SELECT; return; }
+        // d = N' yp ; r = Ginv d ; nz = nHn - d'r
+        HVP_ROLL
+        for (int a = 0; a < q; ++a) w(LY::O_D, a) = slot_dot(a, LY::O_YP);
+        double nz = nHn;
+        // ratio tests without a division per slot: keep the best (numerator, denominator) pair
+        double n1 = 1.0, d1 = 0.0, n3 = 1.0, d3 = 0.0;
+        int k1 = -1, k3 = -1;
+        HVP_ROLL
+        for (int a = 0; a < q; ++a) {
+            double s = 0.0;
+            HVP_ROLL
+            for (int b = 0; b < q; ++b) s += w(LY::O_GINV, a >= b ? tri(a, b) : tri(b, a)) * w(LY::O_D, b);
+            w(LY::O_R, a) = s;
+            nz -= s * w(LY::O_D, a);
+            const double la = w(LY::O_LAM, a);
+            if (s > 1e-14) {
+                if (k1 < 0 || la * d1 < n1 * s) { n1 = la; d1 = s; k1 = a; }
+            } else if (s < -1e-14 && act(a) >= T_SF * 12) {
+                const double num = ww - la, den = -s;
+                if (k3 < 0 || num * d3 < n3 * den) { n3 = num; d3 = den; k3 = a; }
+            }
+        }
+        const bool dependent = (q == N) || !(nz > 1e-11 * nHn);
+        const double INF = HUGE_VAL;
+        const double t2 = dependent ? INF : cp * hvp_rcp(nz);
+        const double t1 = k1 >= 0 ? n1 * hvp_rcp(d1) : INF;
+        const double t3 = k3 >= 0 ? n3 * hvp_rcp(d3) : INF;
+        const double t3p = p_soft ? (ww - lam_p) : INF;
+        const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
+        if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
+        if (!dependent) {
+            // w = n_p - N r ;  x -= t H^-1 w ;  the violation of p shrinks by t * nz
+            HVP_ROLL
+            for (int i = 0; i < N; ++i) {
+                double v;
+                if (pkind == 0) v = (i == pj) ? psgn : 0.0;
+                else if (pkind == 1) v = (i == pj) ? psgn : ((i == pj - 1) ? -psgn * pcoef : 0.0);
+                else v = (i < pj) ? psgn : 0.0;
+                w(LY::O_WV, i) = v;
+            }
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) slot_axpy(a, -w(LY::O_R, a), LY::O_WV);
+            HVP_ROLL
+            for (int i = 0; i < N; ++i) {
+                double s = 0.0;
+                HVP_ROLL
+                for (int j = 0; j < N; ++j) s += w(LY::O_HINV, i * N + j) * w(LY::O_WV, j);
+                w(LY::O_X, i) -= t * s;
+            }
+            cp -= t * nz;
+        }
+        HVP_ROLL
+        for (int a = 0; a < q; ++a) w(LY::O_LAM, a) -= t * w(LY::O_R, a);
+        lam_p += t;
+        if (t == t2) {
+            // p becomes slot q: bordering update of Ginv with Schur complement nz
+            const double is = hvp_rcp(nz);
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) {
+                const double ra_ = w(LY::O_R, a) * is;
+                HVP_ROLL
+                for (int b = 0; b <= a; ++b) w(LY::O_GINV, tri(a, b)) += ra_ * w(LY::O_R, b);
+                w(LY::O_GINV, tri(q, a)) = -ra_;
+            }
+            w(LY::O_GINV, tri(q, q)) = is;
+            set_act(q, pid);
+            w(LY::O_LAM, q) = lam_p;
+            w(LY::O_SSGN, q) = psgn;
+            w(LY::O_SCOEF, q) = pcoef;
+            ++q;
+            state = S_SELECT;
+            return;
+        }
+        if (t == t3p) {                                          // soft p saturates: flip, not added
+            if (pid / 12 == T_SF) satf ^= (1u << pj); else satb ^= (1u << pj);
+            state = S_SELECT;
+            return;
+        }
+        int drop;
+        if (t == t1) drop = k1;
+        else {                                                   // active soft row saturates: flip + drop
+            drop = k3;
+            const int id = act(drop), j = id % 12;
+            if (id / 12 == T_SF) satf ^= (1u << j); else satb ^= (1u << j);
+        }
+        {   // Ginv <- Ginv - g_k g_k'/g_kk, then delete row/column `drop` (packed, in place)
+            const double ikk = hvp_rcp(w(LY::O_GINV, tri(drop, drop)));
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) w(LY::O_D, a) = w(LY::O_GINV, a >= drop ? tri(a, drop) : tri(drop, a));
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) {
+                if (a == drop) continue;
+                const int an = a > drop ? a - 1 : a;
+                const double da = w(LY::O_D, a) * ikk;
+                HVP_ROLL
+                for (int b = 0; b <= a; ++b) {
+                    if (b == drop) continue;
+                    const int bn = b > drop ? b - 1 : b;
+                    w(LY::O_GINV, tri(an, bn)) = w(LY::O_GINV, tri(a, b)) - da * w(LY::O_D, b);
+                }
+            }
+        }
+        HVP_ROLL
+        for (int a = drop; a + 1 < q; ++a) {
+            set_act(a, act(a + 1));
+            w(LY::O_LAM, a) = w(LY::O_LAM, a + 1);
+            w(LY::O_SSGN, a) = w(LY::O_SSGN, a + 1);
+            w(LY::O_SCOEF, a) = w(LY::O_SCOEF, a + 1);
+        }
+        --q;
+        // state stays S_STEP: continue with the same p
+    }
+
+    HVP_HD void trip() {
+        if (state == S_NEXT) do_next();
+        if (state == S_BUILD) do_build();
+        if (state == S_SELECT) do_select();
+        if (state == S_STEP) do_step();
+    }
+
+    // ---- results: best_ (= x_out + N + 2) already holds the incumbent velocities v_1..v_N -------
+    HVP_HD LocalResult finish(double* u_out, double* x_out, int32_t* mode_out) const {
+        LocalResult R;
+        R.nodes = nodes; R.qp_iters = iters;
+        const int np1 = N + 1;
+        if (inc < HUGE_VAL) {
+            R.obj = inc;
+            R.status = limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_OPTIMAL);
+            double p = p0, v = v0;
+            x_out[0] = p; x_out[np1] = v;
+            HVP_ROLL
+            for (int k = 0; k < N; ++k) {
+                const int rg = mode_of(best_modes, k);
+                const double vn = x_out[np1 + k + 1];
+                u_out[k] = (vn - ra(rg) * v - rc(rg)) / rb(rg);
+                mode_out[k] = rg;
+                p = p + v; v = vn;
+                x_out[k + 1] = p;
+            }
+        } else {
+            R.obj = HUGE_VAL;
+            R.status = limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_INFEASIBLE);
+            HVP_ROLL
+            for (int k = 0; k < N; ++k) { u_out[k] = 0.0; mode_out[k] = -1; }
+            HVP_ROLL
+            for (int k = 0; k <= N; ++k) { x_out[k] = 0.0; x_out[np1 + k] = 0.0; }
+        }
+        return R;
+    }
+};
+
+}  // namespace hvp

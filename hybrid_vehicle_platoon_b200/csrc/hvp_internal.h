@@ -9,6 +9,7 @@ namespace hvp {
 
 constexpr int LOCAL_BLOCK = 32;     // threads (= MIQPs) per CTA of the local-MIQP kernel (one warp)
 constexpr int COOP_BLOCK = 128;     // threads per CTA of the cooperative MIQP kernel (16 groups of 8)
+constexpr int FLAT_MIN_BATCH = 16384; // batches at least this large use the persistent flat kernel
 constexpr int ROLLOUT_BLOCK = 256;  // threads per CTA of the rollout kernel
 
 // Constants of the rollout kernel (kernel argument; filled by fill_rollout_params).

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "coop_core.cuh"
+#include "flat_core.cuh"
 #include "hvp_internal.h"
 #include "miqp_core.cuh"
 
@@ -71,20 +72,111 @@ coop_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
     }
 }
 
-static bool use_scalar_kernel() {
+// Persistent flat-state-machine kernel: one warp per CTA, one problem per lane, each warp owns a
+// contiguous share of the batch and a lane that finishes refills from that share at once.
+template <int N>
+__global__ void __launch_bounds__(32)
+flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int32_t* __restrict__ flags,
+                 const double* __restrict__ mass, const double* __restrict__ x0,
+                 const double* __restrict__ xf, const double* __restrict__ xb,
+                 const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
+                 int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
+                 int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
+    extern __shared__ double smem[];
+    using Solver = FlatSolver<N, 32>;
+    const int lane = threadIdx.x;
+    const size_t S = 2 * (size_t)(N + 1);
+    const int64_t chunk = (batch + gridDim.x - 1) / gridDim.x;
+    int64_t next = (int64_t)blockIdx.x * chunk;                   // warp-uniform
+    const int64_t end = next + chunk < batch ? next + chunk : batch;
+    Solver sol;
+    bool have = false;
+    int64_t i = 0;
+    for (;;) {
+        __syncwarp();
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (need) {
+            if (!have) {
+                i = next + __popc(need & ((1u << lane) - 1u));
+                if (i < end) {
+                    sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
+                              xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 2));
+                    have = true;
+                }
+            }
+            next += __popc(need);
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            sol.trip();
+            if (sol.state == Solver::S_DONE) {
+                const LocalResult R = sol.finish(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
+                obj[i] = R.obj;
+                status[i] = R.status;
+                nodes[i] = R.nodes;
+                if (qp_iters) qp_iters[i] = R.qp_iters;
+                have = false;
+            }
+        }
+    }
+}
+
+template <int N>
+static cudaError_t launch_flat(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
+                               const double* x0, const double* xf, const double* xb, const double* xl, double* u,
+                               double* x, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
+                               int32_t* qp_iters, cudaStream_t stream) {
+    const size_t smem = (size_t)FlatLayout<N>::SIZE * 32 * sizeof(double);
+    static int grid_full = 0;
+    if (!grid_full) {
+        cudaError_t e = cudaFuncSetAttribute(flat_miqp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(flat_miqp_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_miqp_kernel<N>, 32, smem);
+        if (e != cudaSuccess) return e;
+        grid_full = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    // persistent grid: every resident warp slot, but never more warps than 32-problem shares
+    int64_t g = (batch + 31) / 32;
+    if (g > grid_full) g = grid_full;
+    flat_miqp_kernel<N><<<(unsigned)g, 32, smem, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
+                                                          status, nodes, qp_iters);
+    return cudaGetLastError();
+}
+
+// 0 auto, 1 scalar (first design), 2 coop, 3 flat
+static int kernel_choice() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("HVP_LOCAL_KERNEL");
-        v = (e && strcmp(e, "scalar") == 0) ? 1 : 0;
+        v = 0;
+        if (e && strcmp(e, "scalar") == 0) v = 1;
+        if (e && strcmp(e, "coop") == 0) v = 2;
+        if (e && strcmp(e, "flat") == 0) v = 3;
     }
-    return v == 1;
+    return v;
 }
+static bool use_scalar_kernel() { return kernel_choice() == 1; }
 
 cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
                               double* u, double* x, int32_t* modes, double* obj, int32_t* status,
                               int32_t* nodes, int32_t* qp_iters, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
+    // throughput path: persistent flat kernel (one problem per lane) once the batch fills the
+    // machine; latency path: cooperative kernel (8 lanes per problem) for small batches
+    const int choice = kernel_choice();
+    const bool flat_ok = P.N >= 4 && P.N <= 9;
+    if (flat_ok && (choice == 3 || (choice == 0 && batch >= FLAT_MIN_BATCH))) {
+#define HVP_FLAT(NN) case NN: return launch_flat<NN>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, stream);
+        switch (P.N) { HVP_FLAT(4) HVP_FLAT(5) HVP_FLAT(6) HVP_FLAT(7) HVP_FLAT(8) HVP_FLAT(9) default: break; }
+#undef HVP_FLAT
+    }
     if (!use_scalar_kernel()) {
         if (P.N <= 8) {
             const int per_block = COOP_BLOCK / 8;

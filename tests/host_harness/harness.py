@@ -16,16 +16,17 @@ def build(force=False):
             os.path.join(_HERE, "../../hybrid_vehicle_platoon_b200/csrc/miqp_core.cuh"),
             os.path.join(_HERE, "../../hybrid_vehicle_platoon_b200/csrc/vehicle_model.h"),
             os.path.join(_HERE, "../../hybrid_vehicle_platoon_b200/csrc/coop_core.cuh"),
-            os.path.join(_HERE, "../../hybrid_vehicle_platoon_b200/csrc/coop_backend.cuh")]
+            os.path.join(_HERE, "../../hybrid_vehicle_platoon_b200/csrc/coop_backend.cuh"),
+            os.path.join(_HERE, "../../hybrid_vehicle_platoon_b200/csrc/flat_core.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-o", _SO, srcs[0]])
     return _SO
 
 
-def local_miqp(N, flags, mass, x0, xf, xb, xl, d0=50.0, t0=0.0, tight=0.0, max_nodes=0, coop=False):
+def local_miqp(N, flags, mass, x0, xf, xb, xl, d0=50.0, t0=0.0, tight=0.0, max_nodes=0, coop=False, flat=False):
     L = C.CDLL(build())
-    fn = L.hvh_coop_miqp_batch if coop else L.hvh_local_miqp_batch
+    fn = L.hvh_flat_miqp_batch if flat else (L.hvh_coop_miqp_batch if coop else L.hvh_local_miqp_batch)
     fn.argtypes = [C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_double,
                                        C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip,
                                        _ip, _ip]
