@@ -1,6 +1,7 @@
 // hvp_api.cu -- the C ABI of libhvp.so (include/hvp.h): contexts, error reporting, host-buffer
 // wrappers.  No torch types, no CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -127,8 +128,13 @@ static int fill_rollout_params(RolloutParams& P, const hvp_env_desc* d) {
     P.d0 = d->d0; P.t0 = d->t0; P.d_safe = d->d_safe;
     memcpy(P.tr_t, M.tr_t, sizeof P.tr_t);
     memcpy(P.tr_v, M.tr_v, sizeof P.tr_v);
+    for (int j = 0; j < 6; ++j) {
+        P.inv_rise[j] = 1.0 / (M.tr_v[j][1] - M.tr_v[j][0]);
+        P.inv_fall[j] = 1.0 / (M.tr_v[j][3] - M.tr_v[j][2]);
+    }
     M.gear_limits(P.lim);
     P.c_fric = M.c_fric; P.mug = M.mu * M.grav; P.default_mass = 800.0;
+    { int ex; P.fric_pow2 = (frexp(M.c_fric, &ex) == 0.5) ? 1 : 0; }
     return 0;
 }
 

