@@ -26,6 +26,18 @@ class LocalDesc(C.Structure):
                 ("tight", C.c_double)]
 
 
+class MpcDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("model", C.c_int32), ("n_local", C.c_int32), ("N", C.c_int32),
+                ("flags", C.c_int32), ("leader_index", C.c_int32), ("n_front", C.c_int32),
+                ("n_behind", C.c_int32), ("max_nodes", C.c_int32), ("reserved", C.c_int32),
+                ("d0", C.c_double), ("t0", C.c_double), ("tight", C.c_double), ("rho", C.c_double)]
+
+
+MPC_CENT, MPC_LOCAL, MPC_EVENT, MPC_ADMM, MPC_GADMM = 1, 2, 3, 4, 5
+MODEL_PWA_GEAR, MODEL_FRICTION_GEAR = 0, 1
+REAL_VEHICLE_REF, NO_LEADER = 8, -100
+
+
 def build(verbose: bool = False) -> str:
     """Compile libhvp.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     out = subprocess.run(["make", "-C", CSRC, "libhvp.so"], capture_output=True, text=True)
@@ -68,6 +80,13 @@ def lib():
     loc = [_vp, C.POINTER(LocalDesc), C.c_int64] + [_vp] * 13
     L.hvp_local_miqp_dev.argtypes = loc + [_vp]
     L.hvp_local_miqp_host.argtypes = loc
+    L.hvp_mpc_create.argtypes = [_vp, C.POINTER(MpcDesc), C.POINTER(_vp)]
+    L.hvp_mpc_destroy.argtypes = [_vp]
+    L.hvp_mpc_info.argtypes = [_vp, C.POINTER(C.c_int32)]
+    L.hvp_mpc_mode_table.argtypes = [_vp, _vp, _vp, _vp]
+    mpc = [_vp, C.c_int64] + [_vp] * 12
+    L.hvp_mpc_solve_dev.argtypes = mpc + [_vp]
+    L.hvp_mpc_solve_host.argtypes = mpc
     L.hvp_microbench_fp64.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import EnvDesc, LocalDesc, check, default_context, lib
+from ._lib import EnvDesc, LocalDesc, MpcDesc, check, default_context, lib
 
 
 def _hp(a):
@@ -97,6 +97,67 @@ def local_miqp_device(desc: LocalDesc, batch, flags, mass, x0, xf, xb, xl, u, x,
     check(lib().hvp_local_miqp_dev(ctx.handle, C.byref(desc), int(batch), p(flags), p(mass), p(x0), p(xf),
                                    p(xb), p(xl), p(u), p(x), p(modes), p(obj), p(status), p(nodes),
                                    p(qp_iters), _stream_arg(stream)))
+
+
+class CompiledMpc:
+    """One compiled MPC formulation on the device (hvp_mpc; include/hvp.h).  Built once -- like the
+    reference builds one Gurobi model per controller -- and solved for batches of (x0, mass, params)."""
+
+    def __init__(self, kind, N, *, n_local=1, model=_lib.MODEL_PWA_GEAR, flags=0, leader_index=0, n_front=0,
+                 n_behind=0, d0=50.0, t0=0.0, tight=0.0, rho=0.5, max_nodes=0, ctx=None):
+        self.ctx = ctx or default_context()
+        self.desc = MpcDesc(int(kind), int(model), int(n_local), int(N), int(flags), int(leader_index),
+                            int(n_front), int(n_behind), int(max_nodes), 0, float(d0), float(t0), float(tight),
+                            float(rho))
+        h = C.c_void_p()
+        check(lib().hvp_mpc_create(self.ctx.handle, C.byref(self.desc), C.byref(h)))
+        self._h = h
+        info = (C.c_int32 * 8)()
+        check(lib().hvp_mpc_info(h, info))
+        (self.n_var, self.n_extra, self.n_param, self.n_modes, self.n_local, self.N, self.n_rows,
+         self.smem_bytes) = list(info)
+        self.mode_lo = np.zeros(self.n_modes); self.mode_hi = np.zeros(self.n_modes)
+        self.mode_gear = np.zeros(self.n_modes, np.int32)
+        check(lib().hvp_mpc_mode_table(h, _hp(self.mode_lo), _hp(self.mode_hi), _hp(self.mode_gear)))
+
+    def solve(self, x0, mass, params, fixed_modes=None):
+        """Host (numpy) buffers: x0 (B,nl,2), mass (B,nl), params (B,n_param), fixed_modes (B,nl,N)|None."""
+        nl, N = self.n_local, self.N
+        x0 = _c(x0, np.float64).reshape(-1, nl, 2)
+        B = x0.shape[0]
+        mass = _c(np.broadcast_to(np.asarray(mass, dtype=np.float64), (B, nl)), np.float64)
+        params = _c(params, np.float64).reshape(B, self.n_param)
+        fm = None if fixed_modes is None else _c(fixed_modes, np.int32).reshape(B, nl, N)
+        u = np.empty((B, nl, N)); x = np.empty((B, nl, 2, N + 1)); extra = np.empty((B, max(self.n_extra, 1)))
+        modes = np.empty((B, nl, N), np.int32); obj = np.empty(B); status = np.empty(B, np.int32)
+        nodes = np.empty(B, np.int32); iters = np.empty(B, np.int32)
+        check(lib().hvp_mpc_solve_host(self._h, B, _hp(x0), _hp(mass), _hp(params), _hp(fm), _hp(u), _hp(x),
+                                       _hp(extra), _hp(modes), _hp(obj), _hp(status), _hp(nodes), _hp(iters)))
+        return dict(u=u, x=x, extra=extra[:, :self.n_extra], modes=modes, obj=obj, status=status, nodes=nodes,
+                    qp_iters=iters, run_time=max(self.ctx.last_kernel_ms(), 0.0) * 1e-3)
+
+    def solve_device(self, batch, x0, mass, params, fixed_modes, u, x, extra, modes, obj, status, nodes,
+                     qp_iters=None, *, stream=None):
+        """DEVICE buffers (torch CUDA tensors); asynchronous on `stream`."""
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        check(lib().hvp_mpc_solve_dev(self._h, int(batch), p(x0), p(mass), p(params), p(fixed_modes), p(u), p(x),
+                                      p(extra), p(modes), p(obj), p(status), p(nodes), p(qp_iters),
+                                      _stream_arg(stream)))
+
+    def gears(self, modes):
+        """Gear (1..6) of each mode index (MpcGear.solve_mpc: argmax sigma + 1, mpc_gear.py:120-125)."""
+        return self.mode_gear[np.clip(modes, 0, self.n_modes - 1)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hvp_mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def microbench_fp64(iters: int = 20000, ctx=None) -> float:

@@ -14,13 +14,14 @@ using namespace hvp;
 
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int hvp_fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
     return code;
 }
+#define fail hvp_fail
 #define CUDA_TRY(call)                                                                         \
     do {                                                                                       \
         cudaError_t e__ = (call);                                                              \
@@ -29,16 +30,6 @@ static int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                   \
     } while (0)
 
-struct hvp_ctx {
-    int device;
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    bool timed;
-    int64_t launches;
-    // grow-only device staging for the *_host entry points
-    char* dbuf;
-    size_t dcap;
-};
 
 extern "C" int hvp_version(void) { return HVP_VERSION; }
 
@@ -101,7 +92,7 @@ extern "C" float hvp_ctx_last_kernel_ms(hvp_ctx* c) {
     return ms;
 }
 
-static int ensure_dbuf(hvp_ctx* c, size_t bytes) {
+int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes) {
     if (bytes <= c->dcap) return 0;
     if (c->dbuf) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->dbuf)); c->dbuf = nullptr; c->dcap = 0; }
     size_t cap = bytes + bytes / 4 + 4096;
@@ -110,6 +101,7 @@ static int ensure_dbuf(hvp_ctx* c, size_t bytes) {
     return 0;
 }
 
+#define ensure_dbuf hvp_ensure_dbuf
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 // ------------------------------------------------------------------------------------------

@@ -4,6 +4,21 @@
 #include <stdint.h>
 
 #include "miqp_core.cuh"
+#include "pm_types.h"
+
+// one device + one stream (include/hvp.h: hvp_ctx)
+struct hvp_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    bool timed;
+    int64_t launches;
+    // grow-only device staging for the *_host entry points
+    char* dbuf;
+    size_t dcap;
+};
+int hvp_fail(int code, const char* fmt, ...);          // records the thread's error text, returns code
+int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes);
 
 namespace hvp {
 
@@ -35,5 +50,11 @@ cudaError_t launch_fp64_microbench(int iters, double* sink, int* blocks, int* th
 cudaError_t launch_rollout(const RolloutParams& P, int64_t batch, const double* x, const double* u,
                            const int32_t* gear, const double* mass, const double* leader, double* x_out,
                            double* cost, uint8_t* viol, int32_t* err, cudaStream_t stream);
+
+void pm_layout(PmDev& S);
+cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
+                           const double* params, const int32_t* fixed_modes, double* u, double* x,
+                           double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
+                           int32_t* qp_iters, cudaStream_t stream);
 
 }  // namespace hvp

@@ -1,0 +1,514 @@
+// pm_build.cu -- host side of the compiled-MPC entry points (include/hvp.h: hvp_mpc_*).
+//
+// hvp_mpc_create() plays the role of the reference's model construction (MpcMldCent.__init__,
+// LocalMpc.__init__, ...: one Gurobi model per controller, built once): it states the cost and the
+// coupling rows of a formulation as affine expressions of the decision vector z and the per-solve
+// parameter vector pvec (pm_types.h), assembles the dense matrices the kernel needs (H0, H0^-1,
+// residual maps, coupling rows) and keeps them on the device.  hvp_mpc_solve_* then only moves
+// (x0, masses, parameters) in and the solution out.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/hvp.h"
+#include "hvp_internal.h"
+#include "vehicle_model.h"
+
+using namespace hvp;
+
+#define fail hvp_fail
+#define CUDA_TRY(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(-100 - (int)e__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+struct hvp_mpc {
+    hvp_ctx* ctx;
+    hvp_mpc_desc desc;
+    PmDev S;
+    std::vector<void*> dev;     // device allocations owned by the handle
+};
+
+namespace {
+
+// affine expression  z . vars + p . pvec
+struct Aff {
+    std::vector<double> z, p;
+    Aff(int nv, int npv) : z(nv, 0.0), p(npv, 0.0) {}
+    Aff& operator+=(const Aff& o) {
+        for (size_t i = 0; i < z.size(); ++i) z[i] += o.z[i];
+        for (size_t i = 0; i < p.size(); ++i) p[i] += o.p[i];
+        return *this;
+    }
+    bool has_z() const {
+        for (double v : z) if (v != 0.0) return true;
+        return false;
+    }
+};
+Aff operator+(Aff a, const Aff& b) { a += b; return a; }
+Aff operator*(double c, Aff a) {
+    for (double& v : a.z) v *= c;
+    for (double& v : a.p) v *= c;
+    return a;
+}
+Aff operator-(Aff a, const Aff& b) { a += (-1.0) * b; return a; }
+
+struct Builder {
+    int nl, N, ne, nv, npar, npv;
+    std::vector<Aff> res; std::vector<double> wres;
+    std::vector<Aff> la, lb;                       // cost += la(pvec) * lb(z, pvec)
+    std::vector<Aff> rows; std::vector<double> wmax;   // e <= 0
+    Builder(int nl_, int N_, int ne_, int npar_)
+        : nl(nl_), N(N_), ne(ne_), nv(nl_ * N_ + ne_), npar(npar_), npv(2 * nl_ + npar_ + 1) {}
+    Aff zero() const { return Aff(nv, npv); }
+    Aff P(int i, int k) const {                    // position of local vehicle i at stage k (ts = 1)
+        Aff a = zero();
+        a.p[2 * i] = 1.0;
+        if (k >= 1) {
+            a.p[2 * i + 1] = 1.0;
+            for (int j = 1; j < k; ++j) a.z[i * N + j - 1] = 1.0;
+        }
+        return a;
+    }
+    Aff V(int i, int k) const {
+        Aff a = zero();
+        if (k == 0) a.p[2 * i + 1] = 1.0; else a.z[i * N + k - 1] = 1.0;
+        return a;
+    }
+    Aff E(int e) const { Aff a = zero(); a.z[nl * N + e] = 1.0; return a; }
+    Aff PAR(int t) const { Aff a = zero(); a.p[2 * nl + t] = 1.0; return a; }
+    // entry (row, k) of the b-th (2, N+1) parameter block
+    Aff PB(int b, int row, int k) const { return PAR(b * 2 * (N + 1) + row * (N + 1) + k); }
+    Aff K(double c) const { Aff a = zero(); a.p[npv - 1] = c; return a; }
+    void residual(const Aff& e, double w) { res.push_back(e); wres.push_back(w); }
+    void product(const Aff& a, const Aff& b) { la.push_back(a); lb.push_back(b); }
+    void row(const Aff& e, double w) { rows.push_back(e); wmax.push_back(w); }
+};
+
+const double QXP = 1.0, QXV = 0.1, QU = 1.0, WSL = 1e4, DSAFE = 25.0;   // Params (common_controller_params.py:14-23)
+
+// ||x - y - sigma(x)||^2_Qx with sigma(x) = [-t0 v - d0, 0]  (spacing_policy.py:13-37)
+void track(Builder& B, const Aff& xp, const Aff& xv, const Aff& yp, const Aff& yv, double d0, double t0) {
+    B.residual(xp - yp + t0 * xv + B.K(d0), QXP);
+    B.residual(xv - yv, QXV);
+}
+
+int build_formulation(const hvp_mpc_desc& d, Builder*& out) {
+    const int N = d.N, np1 = N + 1;
+    const bool front = d.flags & HVP_FRONT, leader = d.flags & HVP_LEADER, trailer = d.flags & HVP_TRAILER;
+    const bool real_ref = d.flags & HVP_REAL_VEHICLE_REF;
+    const double d0 = d.d0, t0 = d.t0;
+    Builder* Bp = nullptr;
+    switch (d.kind) {
+        case HVP_MPC_CENT: {          // mpcs/cent_mld.py:48-177
+            const int n = d.n_local, L = d.leader_index;
+            if (L < 0 || L >= n) return fail(-4, "mpc_create: leader_index %d out of range", L);
+            if (real_ref && L != 0) return fail(-4, "mpc_create: real_vehicle_as_reference needs leader_index 0 (cent_mld.py:63-66)");
+            Bp = new Builder(n, N, 0, 2 * np1);
+            Builder& B = *Bp;
+            for (int k = 0; k <= N; ++k) {
+                if (!real_ref) {      // :83-92
+                    B.residual(B.P(L, k) - B.PB(0, 0, k), QXP);
+                    B.residual(B.V(L, k) - B.PB(0, 1, k), QXV);
+                } else {              // :93-105
+                    track(B, B.P(0, k), B.V(0, k), B.PB(0, 0, k), B.PB(0, 1, k), d0, t0);
+                }
+            }
+            for (int i = 1; i < n; ++i)   // :106-117
+                for (int k = 0; k <= N; ++k) track(B, B.P(i, k), B.V(i, k), B.P(i - 1, k), B.V(i - 1, k), d0, t0);
+            if (real_ref)             // :162-169
+                for (int k = 0; k <= N; ++k) B.row(B.P(0, k) - B.PB(0, 0, k) + B.K(DSAFE), WSL);
+            for (int i = 1; i < n; ++i)   // :170-177
+                for (int k = 0; k <= N; ++k) B.row(B.P(i, k) - B.P(i - 1, k) + B.K(DSAFE), WSL);
+        } break;
+        case HVP_MPC_LOCAL: {         // fleet_decent_mld.py:61-208, fleet_seq_mld.py:63-219
+            Bp = new Builder(1, N, 0, 3 * 2 * np1);
+            Builder& B = *Bp;
+            for (int k = 0; k <= N; ++k) {
+                if (!front && !leader) track(B, B.P(0, k), B.V(0, k), B.PB(0, 0, k), B.PB(0, 1, k), d0, t0);
+                if (!trailer && !leader) track(B, B.PB(1, 0, k), B.PB(1, 1, k), B.P(0, k), B.V(0, k), d0, t0);
+                if (leader) {
+                    if (!real_ref) {
+                        B.residual(B.P(0, k) - B.PB(2, 0, k), QXP);
+                        B.residual(B.V(0, k) - B.PB(2, 1, k), QXV);
+                    } else {
+                        track(B, B.P(0, k), B.V(0, k), B.PB(2, 0, k), B.PB(2, 1, k), d0, t0);
+                    }
+                }
+            }
+            for (int k = 0; k <= N; ++k) {
+                if (!front) B.row(B.P(0, k) - B.PB(0, 0, k) + B.K(DSAFE), WSL);
+                if (!trailer) B.row(B.PB(1, 0, k) + B.K(DSAFE) - B.P(0, k), WSL);
+                // fleet_seq_mld.py:211-219 (shares s_front with safe_front; a leader that is not the
+                // front vehicle would couple the two rows through one slack -- not representable here)
+                if (leader && real_ref && front) B.row(B.P(0, k) - B.PB(2, 0, k) + B.K(DSAFE), WSL);
+            }
+            if (leader && real_ref && !front)
+                return fail(-4, "mpc_create: real_vehicle_as_reference needs the leader at the front");
+        } break;
+        case HVP_MPC_EVENT: {         // fleet_event_based.py:72-291
+            const int nf = d.n_front, nb = d.n_behind;
+            if (nf < 0 || nf > 2 || nb < 0 || nb > 2) return fail(-4, "mpc_create: n_front/n_behind must be 0..2");
+            const int nl = (nf > 0) + 1 + (nb > 0);
+            if (d.n_local != nl) return fail(-4, "mpc_create: event problem with n_front=%d n_behind=%d has %d local vehicles, got %d", nf, nb, nl, d.n_local);
+            const int me = nf > 0 ? 1 : 0, f1 = me - 1, b1 = me + 1;
+            Bp = new Builder(nl, N, 0, 3 * 2 * np1);
+            Builder& B = *Bp;
+            const int rl = d.leader_index;
+            if (rl != HVP_NO_LEADER) {    // :146-165
+                int who;
+                if (rl == -1) who = b1; else if (rl == 0) who = me; else if (rl == 1) who = f1;
+                else return fail(-4, "mpc_create: rel leader index must be -1, 0, or 1 (fleet_event_based.py:163-165)");
+                if (who < 0 || who >= nl) return fail(-4, "mpc_create: rel_leader_index %d refers to a vehicle outside the local problem", rl);
+                for (int k = 0; k <= N; ++k) {
+                    B.residual(B.P(who, k) - B.PB(0, 0, k), QXP);
+                    B.residual(B.V(who, k) - B.PB(0, 1, k), QXV);
+                }
+            }
+            for (int k = 0; k <= N; ++k) {
+                if (nf > 0) track(B, B.P(me, k), B.V(me, k), B.P(f1, k), B.V(f1, k), d0, t0);                    // :168-176
+                if (nf > 1) track(B, B.P(f1, k), B.V(f1, k), B.PB(1, 0, k), B.PB(1, 1, k), d0, t0);              // :177-186
+                if (nb > 0) track(B, B.P(b1, k), B.V(b1, k), B.P(me, k), B.V(me, k), d0, t0);                    // :188-199
+                if (nb > 1) track(B, B.PB(2, 0, k), B.PB(2, 1, k), B.P(b1, k), B.V(b1, k), d0, t0);              // :200-212
+            }
+            for (int k = 0; k <= N; ++k) {   // :256-291
+                if (nf > 0) B.row(B.P(me, k) - B.P(f1, k) + B.K(DSAFE), WSL);
+                if (nf > 1) B.row(B.P(f1, k) - B.PB(1, 0, k) + B.K(DSAFE), WSL);
+                if (nb > 0) B.row(B.P(b1, k) - B.P(me, k) + B.K(DSAFE), WSL);
+                if (nb > 1) B.row(B.PB(2, 0, k) - B.P(b1, k) + B.K(DSAFE), WSL);
+            }
+        } break;
+        case HVP_MPC_ADMM: {          // fleet_naive_admm.py:63-237
+            const int ne = (front ? 0 : 2 * np1) + (trailer ? 0 : 2 * np1);
+            Bp = new Builder(1, N, ne, 5 * 2 * np1);
+            Builder& B = *Bp;
+            const int ef = 0, eb = front ? 0 : 2 * np1;     // extras: x_front (2,N+1) then x_back (2,N+1)
+            const double rho = d.rho;
+            if (!(rho > 0)) return fail(-4, "mpc_create: ADMM needs rho > 0");
+            for (int k = 0; k <= N; ++k) {
+                if (!front && !leader) track(B, B.P(0, k), B.V(0, k), B.E(ef + k), B.E(ef + np1 + k), d0, t0);        // :127-138
+                if (!trailer && !leader) track(B, B.E(eb + k), B.E(eb + np1 + k), B.P(0, k), B.V(0, k), d0, t0);      // :139-150
+                if (leader) {                                                                                      // :151-157
+                    B.residual(B.P(0, k) - B.PB(0, 0, k), QXP);
+                    B.residual(B.V(0, k) - B.PB(0, 1, k), QXV);
+                }
+                for (int row = 0; row < 2; ++row) {
+                    if (!front) {     // :174-186: y'(x_front - z) + rho/2 ||x_front - z||^2
+                        const Aff dlt = B.E(ef + row * np1 + k) - B.PB(2, row, k);
+                        B.product(B.PB(1, row, k), dlt);
+                        B.residual(dlt, 0.5 * rho);
+                    }
+                    if (!trailer) {   // :187-199
+                        const Aff dlt = B.E(eb + row * np1 + k) - B.PB(4, row, k);
+                        B.product(B.PB(3, row, k), dlt);
+                        B.residual(dlt, 0.5 * rho);
+                    }
+                }
+            }
+            for (int k = 0; k <= N; ++k) {   // :219-237
+                if (!front) B.row(B.P(0, k) - B.E(ef + k) + B.K(DSAFE), WSL);
+                if (!trailer) B.row(B.E(eb + k) + B.K(DSAFE) - B.P(0, k), WSL);
+            }
+        } break;
+        case HVP_MPC_GADMM: {         // fleet_g_admm.py:55-158 (+ dmpcrl MpcAdmm augmented state / consensus terms)
+            const int nf = d.n_front, nb = d.n_behind, nc = nf + nb, na = nc + 1;
+            if (nf < 0 || nb < 0 || nc > 4) return fail(-4, "mpc_create: GADMM copies out of range");
+            if (!leader && nf < 1) return fail(-4, "mpc_create: a GADMM follower tracks its first copy (fleet_g_admm.py:136-158): n_front >= 1");
+            Bp = new Builder(1, N, nc * 2 * np1, (1 + 2 * na) * 2 * np1);
+            Builder& B = *Bp;
+            const double rho = d.rho;
+            if (!(rho > 0)) return fail(-4, "mpc_create: GADMM needs rho > 0");
+            // copy c (0..nc-1) entry (row,k); augmented index of copy c: c < nf ? c : c + 1; own state: nf
+            auto CP = [&](int c, int row, int k) { return B.E(c * 2 * np1 + row * np1 + k); };
+            auto YZ = [&](int which, int a, int row, int k) {       // which: 0 = y, 1 = z; a: augmented index
+                return B.PAR(2 * np1 + which * na * 2 * np1 + (2 * a + row) * np1 + k);
+            };
+            for (int k = 0; k <= N; ++k) {
+                if (leader) {         // :112-135
+                    B.residual(B.P(0, k) - B.PB(0, 0, k), QXP);
+                    B.residual(B.V(0, k) - B.PB(0, 1, k), QXV);
+                } else {              // :136-158: follows the FIRST copy
+                    track(B, B.P(0, k), B.V(0, k), CP(0, 0, k), CP(0, 1, k), d0, t0);
+                    B.row(B.P(0, k) - CP(0, 0, k) + B.K(DSAFE), WSL);        // :98-109
+                }
+                for (int a = 0; a < na; ++a)
+                    for (int row = 0; row < 2; ++row) {
+                        Aff xa = (a == nf) ? (row == 0 ? B.P(0, k) : B.V(0, k)) : CP(a < nf ? a : a - 1, row, k);
+                        const Aff dlt = xa - YZ(1, a, row, k);
+                        B.product(YZ(0, a, row, k), dlt);
+                        B.residual(dlt, 0.5 * rho);
+                    }
+            }
+        } break;
+        default:
+            return fail(-4, "mpc_create: unknown kind %d", d.kind);
+    }
+    out = Bp;
+    return 0;
+}
+
+void fill_model(PmModel& M, int model) {
+    VehicleModel V;
+    const double beta = (3 * V.c_fric * V.v_max * V.v_max) / 16;   // models.py:276-282
+    const double alpha = V.v_max / 2;
+    const double c1 = beta / alpha;
+    const double c2 = (V.c_fric * V.v_max * V.v_max - beta) / (V.v_max - alpha);
+    const double dfr = beta - alpha * ((V.c_fric * V.v_max * V.v_max - beta) / (V.v_max - alpha));
+    M.mug = V.mu * V.grav;
+    if (model == HVP_MODEL_PWA_GEAR) {          // models.py:397-492
+        double lim[5];
+        V.gear_limits(lim);
+        const double e[8] = {-HUGE_VAL, lim[0], lim[1], lim[2], alpha, lim[3], lim[4], HUGE_VAL};
+        const int g[7] = {0, 1, 2, 3, 3, 4, 5};
+        M.R = 7;
+        for (int r = 0; r < 7; ++r) {
+            M.cf[r] = r < 4 ? c1 : c2; M.dd[r] = r < 4 ? 0.0 : dfr; M.bg[r] = V.bgear[g[r]];
+            M.lo[r] = e[r]; M.hi[r] = e[r + 1]; M.gear[r] = g[r] + 1;
+        }
+    } else {                                    // pwa_friction (models.py:288-332) x gears (mpc_gear.py:30-114)
+        M.R = 12;
+        for (int f = 0; f < 2; ++f)
+            for (int j = 0; j < 6; ++j) {
+                const int r = f * 6 + j;
+                M.cf[r] = f == 0 ? c1 : c2; M.dd[r] = f == 0 ? 0.0 : dfr; M.bg[r] = V.bgear[j];
+                M.lo[r] = fmax(f == 0 ? -HUGE_VAL : alpha, V.vl[j]);
+                M.hi[r] = fmin(f == 0 ? alpha : HUGE_VAL, V.vh[j]);
+                M.gear[r] = j + 1;
+            }
+    }
+    for (int r = M.R; r < PM_MAXMODES; ++r) { M.cf[r] = M.bg[r] = M.dd[r] = 0; M.lo[r] = 1; M.hi[r] = 0; M.gear[r] = 0; }
+}
+
+// inverse of a symmetric positive definite matrix (Cholesky), row-major n x n; returns false if not PD
+bool spd_inverse(int n, const std::vector<double>& A, std::vector<double>& inv) {
+    std::vector<double> L(A);
+    for (int j = 0; j < n; ++j) {
+        double dg = L[j * n + j];
+        for (int k = 0; k < j; ++k) dg -= L[j * n + k] * L[j * n + k];
+        if (!(dg > 0)) return false;
+        dg = sqrt(dg);
+        L[j * n + j] = dg;
+        for (int i = j + 1; i < n; ++i) {
+            double s = L[i * n + j];
+            for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k];
+            L[i * n + j] = s / dg;
+        }
+    }
+    inv.assign((size_t)n * n, 0.0);
+    std::vector<double> y(n);
+    for (int c = 0; c < n; ++c) {
+        for (int i = 0; i < n; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < i; ++k) s -= L[i * n + k] * y[k];
+            y[i] = s / L[i * n + i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = y[i];
+            for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * y[k];
+            y[i] = s / L[i * n + i];
+        }
+        for (int i = 0; i < n; ++i) inv[(size_t)i * n + c] = y[i];
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) {
+            const double s = 0.5 * (inv[(size_t)i * n + j] + inv[(size_t)j * n + i]);
+            inv[(size_t)i * n + j] = inv[(size_t)j * n + i] = s;
+        }
+    return true;
+}
+
+}  // namespace
+
+static int upload(hvp_mpc* m, const std::vector<double>& h, const double** out) {
+    void* p = nullptr;
+    const size_t bytes = (h.empty() ? 1 : h.size()) * sizeof(double);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    m->dev.push_back(p);
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    *out = (const double*)p;
+    return 0;
+}
+
+extern "C" int hvp_mpc_destroy(hvp_mpc* m) {
+    if (!m) return 0;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    for (void* p : m->dev) cudaFree(p);
+    delete m;
+    return 0;
+}
+
+extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) {
+    if (!c || !d || !out) return fail(-1, "mpc_create: NULL argument");
+    if (d->N < 2 || d->N > 16) return fail(-4, "mpc_create: N=%d out of range [2,16]", d->N);
+    if (d->n_local < 1 || d->n_local > 16) return fail(-4, "mpc_create: n_local=%d out of range [1,16]", d->n_local);
+    if (d->model != HVP_MODEL_PWA_GEAR && d->model != HVP_MODEL_FRICTION_GEAR)
+        return fail(-4, "mpc_create: unknown model %d", d->model);
+    if (d->kind != HVP_MPC_CENT && d->kind != HVP_MPC_EVENT && d->n_local != 1)
+        return fail(-4, "mpc_create: kind %d has exactly one local vehicle", d->kind);
+    if (d->max_nodes < 0) return fail(-4, "mpc_create: negative max_nodes");
+    Builder* Bp = nullptr;
+    int rc = build_formulation(*d, Bp);
+    if (rc) { delete Bp; return rc; }
+    Builder& B = *Bp;
+    hvp_mpc* m = new hvp_mpc();
+    m->ctx = c; m->desc = *d;
+    PmDev& S = m->S;
+    memset(&S, 0, sizeof S);
+    S.nl = B.nl; S.N = B.N; S.ne = B.ne; S.nv = B.nv; S.npar = B.npar; S.npv = B.npv;
+    S.depth = B.nl * B.N; S.max_nodes = d->max_nodes;
+    fill_model(S.M, d->model);
+    VehicleModel V;
+    S.qu = QU; S.w = WSL; S.vmin = V.v_min; S.vmax = V.v_max; S.pmin = V.p_min; S.pmax = V.p_max;
+    S.umin = V.u_min; S.umax = V.u_max; S.a_acc = 2.5; S.a_dec = -2.0; S.tight = d->tight;
+    const int nv = B.nv, npv = B.npv;
+    // split rows into generic (non-zero normal) and constant ones
+    std::vector<int> gen, cst;
+    for (size_t r = 0; r < B.rows.size(); ++r) (B.rows[r].has_z() ? gen : cst).push_back((int)r);
+    S.nres = (int)B.res.size(); S.nlin = (int)B.la.size(); S.ng = (int)gen.size(); S.n0 = (int)cst.size();
+    if (nv > 64 || S.ng > 4000) { delete Bp; delete m; return fail(-4, "mpc_create: problem too large (nv=%d, rows=%d; max 64 variables)", nv, S.ng); }
+    std::vector<double> H0((size_t)nv * nv, 0.0), H0inv, Cres((size_t)S.nres * npv), wres(S.nres), RW2((size_t)nv * S.nres);
+    for (int r = 0; r < S.nres; ++r) {
+        const Aff& e = B.res[r];
+        const double w = B.wres[r];
+        wres[r] = w;
+        for (int t = 0; t < npv; ++t) Cres[(size_t)r * npv + t] = e.p[t];
+        for (int i = 0; i < nv; ++i) {
+            RW2[(size_t)i * S.nres + r] = 2.0 * w * e.z[i];
+            if (e.z[i] == 0.0) continue;
+            for (int j = 0; j < nv; ++j) H0[(size_t)i * nv + j] += 2.0 * w * e.z[i] * e.z[j];
+        }
+    }
+    if (!spd_inverse(nv, H0, H0inv)) {
+        delete Bp; delete m;
+        return fail(-5, "mpc_create: the tracking Hessian of this formulation is not positive definite");
+    }
+    std::vector<double> La((size_t)S.nlin * npv), Lz((size_t)S.nlin * nv), Lp((size_t)S.nlin * npv);
+    for (int l = 0; l < S.nlin; ++l) {
+        if (B.la[l].has_z()) { delete Bp; delete m; return fail(-5, "mpc_create: internal: bilinear cost term"); }
+        for (int t = 0; t < npv; ++t) { La[(size_t)l * npv + t] = B.la[l].p[t]; Lp[(size_t)l * npv + t] = B.lb[l].p[t]; }
+        for (int j = 0; j < nv; ++j) Lz[(size_t)l * nv + j] = B.lb[l].z[j];
+    }
+    std::vector<double> AT((size_t)nv * S.ng), BR((size_t)S.ng * npv), wmax(S.ng), B0((size_t)S.n0 * npv), w0(S.n0);
+    for (int g = 0; g < S.ng; ++g) {
+        const Aff& e = B.rows[gen[g]];
+        for (int j = 0; j < nv; ++j) AT[(size_t)j * S.ng + g] = e.z[j];
+        for (int t = 0; t < npv; ++t) BR[(size_t)g * npv + t] = -e.p[t];
+        wmax[g] = B.wmax[gen[g]];
+    }
+    for (int g = 0; g < S.n0; ++g) {
+        const Aff& e = B.rows[cst[g]];
+        for (int t = 0; t < npv; ++t) B0[(size_t)g * npv + t] = e.p[t];
+        w0[g] = B.wmax[cst[g]];
+    }
+    delete Bp;
+    pm_layout(S);
+    if (S.smem_bytes > 220 * 1024) { delete m; return fail(-4, "mpc_create: problem needs %d bytes of shared memory per warp", S.smem_bytes); }
+    cudaSetDevice(c->device);
+    rc = upload(m, H0, &S.H0); if (!rc) rc = upload(m, H0inv, &S.H0inv);
+    if (!rc) rc = upload(m, Cres, &S.Cres); if (!rc) rc = upload(m, wres, &S.wres); if (!rc) rc = upload(m, RW2, &S.RW2);
+    if (!rc) rc = upload(m, La, &S.La); if (!rc) rc = upload(m, Lz, &S.Lz); if (!rc) rc = upload(m, Lp, &S.Lp);
+    if (!rc) rc = upload(m, AT, &S.AT); if (!rc) rc = upload(m, BR, &S.BR); if (!rc) rc = upload(m, wmax, &S.wmax);
+    if (!rc) rc = upload(m, B0, &S.B0); if (!rc) rc = upload(m, w0, &S.w0);
+    if (rc) { hvp_mpc_destroy(m); return rc; }
+    *out = m;
+    return 0;
+}
+
+extern "C" int hvp_mpc_info(const hvp_mpc* m, int32_t* info) {
+    if (!m || !info) return fail(-1, "mpc_info: NULL argument");
+    const PmDev& S = m->S;
+    info[0] = S.nv; info[1] = S.ne; info[2] = S.npar; info[3] = S.M.R; info[4] = S.nl; info[5] = S.N;
+    info[6] = S.ng; info[7] = S.smem_bytes;
+    return 0;
+}
+
+extern "C" int hvp_mpc_mode_table(const hvp_mpc* m, double* lo, double* hi, int32_t* gear) {
+    if (!m) return fail(-1, "mpc_mode_table: NULL argument");
+    for (int r = 0; r < m->S.M.R; ++r) {
+        if (lo) lo[r] = m->S.M.lo[r];
+        if (hi) hi[r] = m->S.M.hi[r];
+        if (gear) gear[r] = m->S.M.gear[r];
+    }
+    return 0;
+}
+
+extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, const double* mass,
+                                 const double* params, const int32_t* fixed_modes, double* u, double* x,
+                                 double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
+                                 int32_t* qp_iters, void* stream) {
+    if (!m) return fail(-1, "mpc_solve: handle is NULL");
+    if (batch < 0) return fail(-4, "mpc_solve: negative batch");
+    if (batch == 0) return 0;
+    if (!x0 || !mass || !params || !u || !x || !modes || !obj || !status || !nodes)
+        return fail(-1, "mpc_solve: NULL array argument");
+    hvp_ctx* c = m->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(launch_pm_miqp(m->S, batch, x0, mass, params, fixed_modes, u, x, extra, modes, obj, status, nodes,
+                            qp_iters, st));
+    CUDA_TRY(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    c->launches += 1;
+    return 0;
+}
+
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+extern "C" int hvp_mpc_solve_host(hvp_mpc* m, int64_t batch, const double* x0, const double* mass,
+                                  const double* params, const int32_t* fixed_modes, double* u, double* x,
+                                  double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
+                                  int32_t* qp_iters) {
+    if (!m) return fail(-1, "mpc_solve: handle is NULL");
+    if (batch < 0) return fail(-4, "mpc_solve: negative batch");
+    if (batch == 0) return 0;
+    if (!x0 || !mass || !params || !u || !x || !modes || !obj || !status || !nodes)
+        return fail(-1, "mpc_solve: NULL array argument");
+    hvp_ctx* c = m->ctx;
+    const PmDev& S = m->S;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t B = (size_t)batch, nl = S.nl, N = S.N;
+    const size_t b_x0 = al256(B * nl * 16), b_m = al256(B * nl * 8), b_p = al256(B * S.npar * 8);
+    const size_t b_fm = fixed_modes ? al256(B * nl * N * 4) : 0;
+    const size_t b_u = al256(B * nl * N * 8), b_x = al256(B * nl * 2 * (N + 1) * 8);
+    const size_t b_e = extra ? al256(B * (size_t)S.ne * 8 + 8) : 0, b_mo = al256(B * nl * N * 4);
+    const size_t b_o = al256(B * 8), b_s = al256(B * 4);
+    int rc = hvp_ensure_dbuf(c, b_x0 + b_m + b_p + b_fm + b_u + b_x + b_e + b_mo + b_o + 3 * b_s);
+    if (rc) return rc;
+    char* q = c->dbuf;
+    double* dx0 = (double*)q; q += b_x0;
+    double* dm = (double*)q; q += b_m;
+    double* dp = (double*)q; q += b_p;
+    int32_t* dfm = fixed_modes ? (int32_t*)q : nullptr; q += b_fm;
+    double* du = (double*)q; q += b_u;
+    double* dx = (double*)q; q += b_x;
+    double* de = extra ? (double*)q : nullptr; q += b_e;
+    int32_t* dmo = (int32_t*)q; q += b_mo;
+    double* dob = (double*)q; q += b_o;
+    int32_t* dst = (int32_t*)q; q += b_s;
+    int32_t* dno = (int32_t*)q; q += b_s;
+    int32_t* dit = qp_iters ? (int32_t*)q : nullptr;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(dx0, x0, B * nl * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dm, mass, B * nl * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dp, params, B * S.npar * 8, cudaMemcpyHostToDevice, st));
+    if (fixed_modes) CUDA_TRY(cudaMemcpyAsync(dfm, fixed_modes, B * nl * N * 4, cudaMemcpyHostToDevice, st));
+    rc = hvp_mpc_solve_dev(m, batch, dx0, dm, dp, dfm, du, dx, de, dmo, dob, dst, dno, dit, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(u, du, B * nl * N * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(x, dx, B * nl * 2 * (N + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (extra && S.ne) CUDA_TRY(cudaMemcpyAsync(extra, de, B * (size_t)S.ne * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(modes, dmo, B * nl * N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(obj, dob, B * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status, dst, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nodes, dno, B * 4, cudaMemcpyDeviceToHost, st));
+    if (qp_iters) CUDA_TRY(cudaMemcpyAsync(qp_iters, dit, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -1,0 +1,692 @@
+// pm_kernel.cu -- platoon MIQP kernel: ONE WARP per mixed-integer QP, dense node QPs in shared memory.
+//
+// Replaces the Gurobi solves behind MpcMldCent.solve_mpc (mpcs/cent_mld.py:9-182 on dmpcpwa
+// MpcMldCentDecup), the event-based LocalMpc (fleet_event_based.py:26-340), the naive-ADMM
+// LocalMpcADMM (fleet_naive_admm.py:24-258), the g-ADMM fixed-mode LocalMpc (fleet_g_admm.py:22-205)
+// and the MpcGear variants (mpcs/mpc_gear.py:8-170) -- every formulation whose decision vector is
+// larger than the per-vehicle problem of local_miqp.cu.  The formulation itself (cost residuals,
+// coupling rows) arrives compiled into dense matrices (pm_types.h / pm_build.cu); this file is the
+// solver:
+//
+//   * decision vector z = [future velocities v_{i,k} of the nl local vehicles ; free copies];
+//     positions are prefix sums, inputs are the affine map u = (v+ - a v - c)/b of the active mode;
+//   * branch and bound, depth first, over the (stage, vehicle) mode decisions in stage-major order;
+//     a node fixes decisions 0..L-1 and relaxes the rest (no input cost, no input limits, no region
+//     rows: a valid lower bound); children ordered by distance to the relaxed velocity, pruned by
+//     interval reachability and by the incumbent (gap 0);
+//   * node QP: dual active-set (Goldfarb-Idnani) with bounded multipliers for the L1-penalised
+//     (slack-eliminated) rows.  The warp holds H^-1 (nv x nv), the dense normals of the active rows
+//     and the inverse of N'H^-1N in shared memory; lane j owns variable j / slot j, mat-vecs are one
+//     row per lane, reductions and arg-min/max are warp shuffles.  H^-1 follows the search by
+//     Sherman-Morrison rank-1 up/down-dates (one per fixed decision), re-seeded from the shared
+//     H0^-1 whenever the search returns to the root.
+//
+// HBM traffic per problem is parameters in + solution out; the shared structure matrices are read
+// through L1/L2.  All arithmetic is FP64.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "hvp_internal.h"
+#include "pm_types.h"
+
+namespace hvp {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+enum : int { PT_UB = 0, PT_LB, PT_UHI, PT_ULO, PT_ACC, PT_DEC, PT_PHI, PT_PLO, PT_GEN };
+enum : int { PS_NEXT = 0, PS_BUILD, PS_SELECT, PS_STEP, PS_DONE };
+#define PM_ID(t, idx) ((t) * 4096 + (idx))
+#define LANES(j, n) for (int j = lane; j < (n); j += 32)
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+// arg-max over the warp with the smaller id winning ties (every lane gets the same answer)
+__device__ __forceinline__ void wargmax(double& v, int& id) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, v, o);
+        const int oid = __shfl_xor_sync(FULL, id, o);
+        if (ov > v || (ov == v && oid < id)) { v = ov; id = oid; }
+    }
+}
+__device__ __forceinline__ void wargmin(double& v, int& id) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, v, o);
+        const int oid = __shfl_xor_sync(FULL, id, o);
+        if (ov < v || (ov == v && oid < id)) { v = ov; id = oid; }
+    }
+}
+
+struct Warp {
+    const PmDev& S;
+    int lane;
+    // shared-memory views
+    double *Hinv, *Ginv, *Nact;
+    double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best;
+    double *cres, *bgen, *pvec;
+    double *inv_m, *pc, *v0, *xstar, *rlo, *rhi, *am, *bm, *cm;
+    int *act, *cand, *modes, *bmodes, *built, *orient;
+    // warp-uniform scalars (replicated in registers)
+    int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
+    double inc, c0, cp, nHn, lam_p;
+    bool p_soft, trouble, limit;
+
+    __device__ Warp(const PmDev& S_, double* base, int lane_) : S(S_), lane(lane_) {
+        const int nv = S.nv, ld = S.ld;
+        Hinv = base + S.o_hinv; Ginv = base + S.o_ginv; Nact = base + S.o_nact;
+        double* v = base + S.o_vec;
+        x = v; g0 = v + nv; gn = v + 2 * nv; yp = v + 3 * nv; wv = v + 4 * nv; zd = v + 5 * nv;
+        dv = v + 6 * nv; rv = v + 7 * nv; lam = v + 8 * nv; np_ = v + 9 * nv; best = v + 10 * nv;
+        cres = base + S.o_cres; bgen = base + S.o_bgen; pvec = base + S.o_pvec;
+        double* m = base + S.o_misc;
+        const int nl = S.nl, N = S.N, D = S.depth;
+        inv_m = m; pc = m + nl; v0 = m + 2 * nl; xstar = m + 3 * nl; rlo = xstar + D + 1;
+        rhi = rlo + nl * (N + 1); am = rhi + nl * (N + 1); bm = am + D; cm = bm + D;
+        int* ib = reinterpret_cast<int*>(base + S.smem_doubles);
+        act = ib; cand = ib + nv; modes = cand + D + 1; bmodes = modes + D; built = bmodes + D;
+        orient = built + D;
+        (void)ld;
+    }
+
+    __device__ __forceinline__ double ma(int i, int r) const { return 1.0 - S.M.cf[r] * inv_m[i]; }
+    __device__ __forceinline__ double mb(int i, int r) const { return S.M.bg[r] * inv_m[i]; }
+    __device__ __forceinline__ double mc(int i, int r) const { return -S.M.mug - S.M.dd[r] * inv_m[i]; }
+
+    // ---- per-problem setup --------------------------------------------------------------------
+    __device__ void setup(const double* x0, const double* mass, const double* params, const int32_t* fm) {
+        const int nl = S.nl, N = S.N, nv = S.nv, npv = S.npv;
+        LANES(t, 2 * nl) pvec[t] = x0[t];
+        LANES(t, S.npar) pvec[2 * nl + t] = params[t];
+        if (lane == 0) pvec[npv - 1] = 1.0;
+        LANES(i, nl) {
+            inv_m[i] = 1.0 / mass[i];
+            v0[i] = x0[2 * i + 1];
+            pc[i] = x0[2 * i] + x0[2 * i + 1];
+            rlo[i * (N + 1)] = x0[2 * i + 1];
+            rhi[i * (N + 1)] = x0[2 * i + 1];
+        }
+        __syncwarp();
+        // residual constants, param-linear factors, generic right-hand sides, constant rows
+        double c = 0.0;
+        bool infeas = false;
+        LANES(r, S.nres) {
+            double s = 0.0;
+            for (int t = 0; t < npv; ++t) s += S.Cres[(size_t)r * npv + t] * pvec[t];
+            cres[r] = s;
+            c += S.wres[r] * s * s;
+        }
+        LANES(l, S.nlin) {
+            double a = 0.0, p = 0.0;
+            for (int t = 0; t < npv; ++t) {
+                a += S.La[(size_t)l * npv + t] * pvec[t];
+                p += S.Lp[(size_t)l * npv + t] * pvec[t];
+            }
+            cres[S.nres + l] = a;
+            c += a * p;
+        }
+        LANES(r, S.ng) {
+            double s = 0.0;
+            for (int t = 0; t < npv; ++t) s += S.BR[(size_t)r * npv + t] * pvec[t];
+            bgen[r] = s;
+        }
+        LANES(r, S.n0) {
+            double s = 0.0;
+            for (int t = 0; t < npv; ++t) s += S.B0[(size_t)r * npv + t] * pvec[t];
+            if (s > 0.0) {
+                if (isfinite(S.w0[r])) c += S.w0[r] * s;
+                else if (s > 1e-9) infeas = true;
+            }
+        }
+        LANES(i, nl) {   // state row k = 1 on the (constant) position p_1 = p_0 + v_0
+            if (pc[i] > S.pmax + 1e-9 || pc[i] < S.pmin - 1e-9) infeas = true;
+        }
+        __syncwarp();
+        c0 = wsum(c);
+        infeas = __any_sync(FULL, infeas);
+        LANES(j, nv) {
+            double s = 0.0;
+            for (int r = 0; r < S.nres; ++r) s += S.RW2[(size_t)j * S.nres + r] * cres[r];
+            for (int l = 0; l < S.nlin; ++l) s += S.Lz[(size_t)l * nv + j] * cres[S.nres + l];
+            g0[j] = s;
+        }
+        built_L = -1;                      // H^-1 not loaded yet
+        iters = nodes = it = q = 0;
+        inc = HUGE_VAL; trouble = limit = false;
+        lev = 0; L = 0; fixed = (fm != nullptr);
+        if (infeas) { state = PS_DONE; __syncwarp(); return; }
+        if (fixed) {
+            bool bad = false;
+            LANES(d, S.depth) {
+                const int i = d % nl, k = d / nl, r = fm[i * N + k];
+                modes[d] = r;
+                if (r < 0 || r >= S.M.R) bad = true;
+                else if (k == 0 && (v0[i] > S.M.hi[r] + 1e-9 || v0[i] < S.M.lo[r] - 1e-9)) bad = true;
+            }
+            bad = __any_sync(FULL, bad);
+            L = S.depth;
+            state = bad ? PS_DONE : PS_BUILD;
+        } else {
+            if (lane == 0) { open_level(0); }
+            state = PS_NEXT;
+        }
+        __syncwarp();
+    }
+
+    // candidates of decision `lv` (lane 0 only)
+    __device__ void open_level(int lv) {
+        const int nl = S.nl, N = S.N;
+        const int i = lv % nl, k = lv / nl;
+        const double lo = rlo[i * (N + 1) + k], hi = rhi[i * (N + 1) + k];
+        int cn = 0;
+        for (int r = 0; r < S.M.R; ++r)
+            if (S.M.lo[r] <= hi && S.M.hi[r] >= lo && S.M.lo[r] <= S.M.hi[r]) cn |= (1 << r);
+        cand[lv] = cn;
+        xstar[lv] = (k == 0) ? v0[i] : x[i * N + k - 1];
+    }
+
+    // ---- NEXT: next node of the depth-first search (scalar; lane 0, result broadcast) ----------
+    __device__ void do_next() {
+        int st = PS_DONE, nlev = lev, nL = L;
+        if (lane == 0) {
+            const double eps = 1e-9;
+            const int nl = S.nl, N = S.N;
+            for (;;) {
+                const int cset = cand[nlev];
+                if (cset == 0) {
+                    if (nlev == 0) { st = PS_DONE; break; }
+                    --nlev;
+                    continue;
+                }
+                const int i = nlev % nl, k = nlev / nl;
+                int rg = -1; double bd = HUGE_VAL;
+                const double xs = xstar[nlev];
+                for (int c = 0; c < S.M.R; ++c) {
+                    if (!((cset >> c) & 1)) continue;
+                    const double lo = S.M.lo[c], hi = S.M.hi[c];
+                    const double dist = xs < lo ? lo - xs : (xs > hi ? xs - hi : 0.0);
+                    if (dist < bd) { bd = dist; rg = c; }
+                }
+                cand[nlev] = cset & ~(1 << rg);
+                modes[nlev] = rg;
+                const double jlo = fmax(rlo[i * (N + 1) + k], S.M.lo[rg]), jhi = fmin(rhi[i * (N + 1) + k], S.M.hi[rg]);
+                if (jlo > jhi + eps) continue;
+                const double a = ma(i, rg), b = mb(i, rg), c = mc(i, rg);
+                double nlo = fmax(a * jlo + c + b * S.umin, jlo + S.a_dec + k * S.tight);
+                double nhi = fmin(a * jhi + c + b * S.umax, jhi + S.a_acc - k * S.tight);
+                nlo = fmax(nlo, S.vmin); nhi = fmin(nhi, S.vmax);
+                if (nlo > nhi + eps) continue;
+                rlo[i * (N + 1) + k + 1] = nlo - eps; rhi[i * (N + 1) + k + 1] = nhi + eps;
+                nL = nlev + 1;
+                st = PS_BUILD;
+                break;
+            }
+        }
+        __syncwarp();
+        state = __shfl_sync(FULL, st, 0);
+        lev = __shfl_sync(FULL, nlev, 0);
+        L = __shfl_sync(FULL, nL, 0);
+    }
+
+    // st: 0 solved, 1 infeasible, 2 numerical trouble
+    __device__ void node_done(int st, double obj) {
+        iters += it;
+        ++nodes;
+        state = fixed ? PS_DONE : PS_NEXT;
+        if (st == 2) { trouble = true; return; }
+        if (st == 1) return;
+        if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
+        if (L == S.depth) {                                                           // leaf
+            inc = obj;
+            LANES(j, S.nv) best[j] = x[j];
+            LANES(d, S.depth) bmodes[d] = modes[d];
+            __syncwarp();
+            return;
+        }
+        if (S.max_nodes > 0 && nodes >= S.max_nodes) { limit = true; state = PS_DONE; return; }
+        ++lev;
+        if (lane == 0) open_level(lev);
+        __syncwarp();
+    }
+
+    // H <- H + s * 2 qu e e',  e = (e_jk - a e_jm)/b  (decision d in mode rg): Sherman-Morrison on H^-1
+    __device__ void rank1(int d, int rg, double s) {
+        const int nl = S.nl, N = S.N, nv = S.nv, ld = S.ld;
+        const int i = d % nl, k = d / nl, jk = i * N + k, jm = jk - 1;
+        const double ib = 1.0 / mb(i, rg), ea = (k >= 1) ? -ma(i, rg) * ib : 0.0;
+        LANES(j, nv) {
+            double v = ib * Hinv[j * ld + jk];
+            if (k >= 1) v += ea * Hinv[j * ld + jm];
+            wv[j] = v;
+        }
+        __syncwarp();
+        const double ev = ib * wv[jk] + ((k >= 1) ? ea * wv[jm] : 0.0);
+        const double den = 1.0 / (s / (2.0 * S.qu) + ev);
+        LANES(j, nv) {
+            const double vj = wv[j] * den;
+            for (int c = 0; c < nv; ++c) Hinv[j * ld + c] -= vj * wv[c];
+        }
+        __syncwarp();
+    }
+
+    // ---- BUILD: bring H^-1 to this node, gradient, unconstrained minimiser ----------------------
+    __device__ void do_build() {
+        const int nl = S.nl, N = S.N, nv = S.nv, ld = S.ld;
+        int c = 0;
+        if (built_L > 0)
+            while (c < built_L && c < L && built[c] == modes[c]) ++c;
+        const bool reload = built_L < 0 || c == 0 || (built_L - c > c);
+        __syncwarp();
+        if (reload) {
+            for (int e = lane; e < nv * nv; e += 32) Hinv[(e / nv) * ld + (e % nv)] = S.H0inv[e];
+            c = 0; built_L = 0;
+            __syncwarp();
+        }
+        for (int d = built_L - 1; d >= c; --d) rank1(d, built[d], -1.0);
+        for (int d = c; d < L; ++d) rank1(d, modes[d], 1.0);
+        LANES(d, L) {
+            built[d] = modes[d];
+            const int i = d % nl, r = modes[d];
+            am[d] = ma(i, r); bm[d] = mb(i, r); cm[d] = mc(i, r);
+        }
+        built_L = L;
+        __syncwarp();
+        const double qu = S.qu;
+        LANES(j, nv) {
+            double g = g0[j];
+            if (j < nl * N) {
+                const int i = j / N, kk = j % N;
+                const int d0 = kk * nl + i, d1 = d0 + nl;
+                if (d0 < L) {
+                    const double ib = 1.0 / bm[d0];
+                    const double kc = (kk == 0) ? -(am[d0] * v0[i] + cm[d0]) * ib : -cm[d0] * ib;
+                    g += 2.0 * qu * kc * ib;
+                }
+                if (kk + 1 < N && d1 < L) {
+                    const double ib = 1.0 / bm[d1];
+                    g += 2.0 * qu * (-cm[d1] * ib) * (-am[d1] * ib);
+                }
+            }
+            gn[j] = g;
+        }
+        __syncwarp();
+        LANES(j, nv) {
+            double s = 0.0;
+            for (int c2 = 0; c2 < nv; ++c2) s += Hinv[j * ld + c2] * gn[c2];
+            x[j] = -s;
+        }
+        LANES(r, S.ng) orient[r] = 1;
+        it = 0; q = 0;
+        state = PS_SELECT;
+        __syncwarp();
+    }
+
+    // ---- SELECT: most violated row, or the node is solved --------------------------------------
+    __device__ void do_select() {
+        const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
+        const double tol = 1e-9;
+        double best_v = tol; int bid = 0x7fffffff;
+#define PM_CAND(T, IDX, SV)                                                        \
+    {                                                                              \
+        const double s__ = (SV);                                                   \
+        if (s__ > best_v) { best_v = s__; bid = PM_ID(T, IDX); }                   \
+    }
+        LANES(j, nl * N) {
+            const int i = j / N, kk = j % N;
+            const int d0 = kk * nl + i, d1 = d0 + nl;
+            const double xv = x[j];
+            double lo = S.vmin, hi = S.vmax;
+            if (kk + 1 < N && d1 < L) {
+                const int r = modes[d1];
+                lo = fmax(lo, S.M.lo[r]); hi = fmin(hi, S.M.hi[r]);
+            }
+            if (kk == 0) {
+                lo = fmax(lo, v0[i] + S.a_dec); hi = fmin(hi, v0[i] + S.a_acc);
+                if (d0 < L) {
+                    const double m = am[d0] * v0[i] + cm[d0];
+                    lo = fmax(lo, m + bm[d0] * S.umin); hi = fmin(hi, m + bm[d0] * S.umax);
+                }
+            } else {
+                const double xm = x[j - 1];
+                if (d0 < L) {
+                    const double du = xv - am[d0] * xm - cm[d0];
+                    PM_CAND(PT_UHI, j, du - bm[d0] * S.umax);
+                    PM_CAND(PT_ULO, j, bm[d0] * S.umin - du);
+                }
+                const double dvv = xv - xm;
+                PM_CAND(PT_ACC, j, dvv - (S.a_acc - kk * S.tight));
+                PM_CAND(PT_DEC, j, (S.a_dec + kk * S.tight) - dvv);
+            }
+            PM_CAND(PT_UB, j, xv - hi);
+            PM_CAND(PT_LB, j, lo - xv);
+        }
+        if (N >= 2) {
+            LANES(i, nl) {
+                double ps = pc[i];
+                PM_CAND(PT_PLO, i, S.pmin - (ps + x[i * N]));
+                for (int kk = 0; kk + 1 < N; ++kk) ps += x[i * N + kk];
+                PM_CAND(PT_PHI, i, ps - S.pmax);
+            }
+        }
+        LANES(r, ng) {
+            double s = -bgen[r];
+            for (int j = 0; j < nv; ++j) s += S.AT[(size_t)j * ng + r] * x[j];
+            PM_CAND(PT_GEN, r, orient[r] > 0 ? s : -s);
+        }
+#undef PM_CAND
+        wargmax(best_v, bid);
+        if (bid == 0x7fffffff) {
+            // ---- node solved: objective ----
+            double f = 0.0;
+            LANES(j, nv) {
+                double s = 0.0;
+                for (int c = 0; c < nv; ++c) s += S.H0[(size_t)j * nv + c] * x[c];
+                f += x[j] * (g0[j] + 0.5 * s);
+            }
+            LANES(d, L) {
+                const int i = d % nl, k = d / nl, jk = i * N + k;
+                const double xp = (k >= 1) ? x[jk - 1] : v0[i];
+                const double uu = (x[jk] - am[d] * xp - cm[d]) / bm[d];
+                f += S.qu * uu * uu;
+            }
+            LANES(r, ng) {
+                const double wm = S.wmax[r];
+                if (isfinite(wm)) {
+                    double s = -bgen[r];
+                    for (int j = 0; j < nv; ++j) s += S.AT[(size_t)j * ng + r] * x[j];
+                    if (s > 0.0) f += wm * s;
+                }
+            }
+            f = c0 + wsum(f);
+            node_done(0, f);
+            return;
+        }
+        // a selected row can never already be active (active rows have residual ~1e-13 << tol)
+        bool dup = false;
+        LANES(a, q) if (act[a] == bid) dup = true;
+        if (__any_sync(FULL, dup)) { node_done(2, 0.0); return; }
+        pid = bid;
+        const int pt = pid / 4096, idx = pid % 4096;
+        p_soft = false;
+        if (pt == PT_GEN) p_soft = isfinite(S.wmax[idx]);
+        // dense normal of p
+        LANES(j, nv) {
+            double v = 0.0;
+            switch (pt) {
+                case PT_UB: v = (j == idx) ? 1.0 : 0.0; break;
+                case PT_LB: v = (j == idx) ? -1.0 : 0.0; break;
+                case PT_UHI: case PT_ULO: {
+                    const int i = idx / N, kk = idx % N, d0 = kk * nl + i;
+                    v = (j == idx) ? 1.0 : ((j == idx - 1) ? -am[d0] : 0.0);
+                    if (pt == PT_ULO) v = -v;
+                } break;
+                case PT_ACC: v = (j == idx) ? 1.0 : ((j == idx - 1) ? -1.0 : 0.0); break;
+                case PT_DEC: v = (j == idx) ? -1.0 : ((j == idx - 1) ? 1.0 : 0.0); break;
+                case PT_PHI: v = (j >= idx * N && j < idx * N + N - 1) ? 1.0 : 0.0; break;
+                case PT_PLO: v = (j == idx * N) ? -1.0 : 0.0; break;
+                default: v = S.AT[(size_t)j * ng + idx] * (double)orient[idx]; break;
+            }
+            np_[j] = v;
+        }
+        __syncwarp();
+        // yp = H^-1 n_p, nHn = n_p' yp
+        double acc = 0.0;
+        LANES(j, nv) {
+            double s = 0.0;
+            for (int c = 0; c < nv; ++c) s += Hinv[j * S.ld + c] * np_[c];
+            yp[j] = s;
+            acc += s * np_[j];
+        }
+        nHn = wsum(acc);
+        cp = best_v;
+        lam_p = 0.0;
+        state = PS_STEP;
+        __syncwarp();
+    }
+
+    // ---- STEP: one primal-dual step towards adding p -------------------------------------------
+    __device__ void do_step() {
+        const int nv = S.nv, ld = S.ld;
+        const double tol = 1e-9, INF = HUGE_VAL;
+        if (++it > 40 * nv + 200) { node_done(2, 0.0); return; }
+        if (cp <= tol) { state = PS_SELECT; return; }
+        // d = N' yp
+        LANES(a, q) {
+            double s = 0.0;
+            for (int c = 0; c < nv; ++c) s += Nact[a * ld + c] * yp[c];
+            dv[a] = s;
+        }
+        __syncwarp();
+        // r = Ginv d ; nz = nHn - d'r ; ratio tests
+        double part = 0.0, t1 = INF, t3 = INF;
+        int k1 = 0x7fffffff, k3 = 0x7fffffff;
+        LANES(a, q) {
+            double s = 0.0;
+            for (int b = 0; b < q; ++b) s += Ginv[a * ld + b] * dv[b];
+            rv[a] = s;
+            part += s * dv[a];
+            const double la = lam[a];
+            if (s > 1e-14) {
+                const double t = la / s;
+                if (t < t1) { t1 = t; k1 = a; }
+            } else if (s < -1e-14) {
+                const int id = act[a];
+                if (id >= PM_ID(PT_GEN, 0)) {
+                    const double wm = S.wmax[id - PM_ID(PT_GEN, 0)];
+                    if (isfinite(wm)) {
+                        const double t = (wm - la) / (-s);
+                        if (t < t3) { t3 = t; k3 = a; }
+                    }
+                }
+            }
+        }
+        const double nz = nHn - wsum(part);
+        wargmin(t1, k1);
+        wargmin(t3, k3);
+        const bool dependent = (q == nv) || !(nz > 1e-11 * nHn);
+        const double t2 = dependent ? INF : cp / nz;
+        const double t3p = p_soft ? (S.wmax[pid - PM_ID(PT_GEN, 0)] - lam_p) : INF;
+        const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
+        if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
+        __syncwarp();
+        if (!dependent) {
+            // w = n_p - N r ;  x -= t H^-1 w ;  the violation of p shrinks by t nz
+            LANES(j, nv) {
+                double s = np_[j];
+                for (int a = 0; a < q; ++a) s -= rv[a] * Nact[a * ld + j];
+                wv[j] = s;
+            }
+            __syncwarp();
+            LANES(j, nv) {
+                double s = 0.0;
+                for (int c = 0; c < nv; ++c) s += Hinv[j * ld + c] * wv[c];
+                x[j] -= t * s;
+            }
+            cp -= t * nz;
+        }
+        LANES(a, q) lam[a] -= t * rv[a];
+        lam_p += t;
+        if (t == t2) {
+            // p becomes slot q: bordering update of Ginv with Schur complement nz
+            const double is = 1.0 / nz;
+            LANES(a, q) {
+                const double ra = rv[a] * is;
+                for (int b = 0; b < q; ++b) Ginv[a * ld + b] += ra * rv[b];
+                Ginv[a * ld + q] = -ra;
+                Ginv[q * ld + a] = -ra;
+            }
+            LANES(j, nv) Nact[q * ld + j] = np_[j];
+            if (lane == 0) {
+                Ginv[q * ld + q] = is;
+                act[q] = pid;
+                lam[q] = lam_p;
+            }
+            ++q;
+            state = PS_SELECT;
+            __syncwarp();
+            return;
+        }
+        if (t == t3p) {                                          // soft p saturates: flip, not added
+            if (lane == 0) orient[pid - PM_ID(PT_GEN, 0)] = -orient[pid - PM_ID(PT_GEN, 0)];
+            state = PS_SELECT;
+            __syncwarp();
+            return;
+        }
+        int drop;
+        if (t == t1) drop = k1;
+        else {                                                   // active soft row saturates: flip + drop
+            drop = k3;
+            if (lane == 0) { const int r = act[drop] - PM_ID(PT_GEN, 0); orient[r] = -orient[r]; }
+        }
+        __syncwarp();
+        {   // Ginv <- Ginv - g g'/g_dd on the remaining slots, then move the last slot into `drop`
+            const double idd = 1.0 / Ginv[drop * ld + drop];
+            LANES(a, q) dv[a] = Ginv[a * ld + drop];
+            __syncwarp();
+            LANES(a, q) {
+                const double da = dv[a] * idd;
+                for (int b = 0; b < q; ++b) Ginv[a * ld + b] -= da * dv[b];
+            }
+            __syncwarp();
+            const int last = q - 1;
+            if (drop != last) {
+                LANES(b, q) Ginv[drop * ld + b] = Ginv[last * ld + b];
+                __syncwarp();
+                LANES(a, q) Ginv[a * ld + drop] = Ginv[a * ld + last];
+                __syncwarp();
+                if (lane == 0) {
+                    Ginv[drop * ld + drop] = Ginv[last * ld + last];
+                    act[drop] = act[last];
+                    lam[drop] = lam[last];
+                }
+                LANES(j, nv) Nact[drop * ld + j] = Nact[last * ld + j];
+            }
+            --q;
+            __syncwarp();
+        }
+        // state stays PS_STEP: continue with the same p
+    }
+
+    __device__ void solve() {
+        while (state != PS_DONE) {
+            if (state == PS_NEXT) do_next();
+            if (state == PS_BUILD) do_build();
+            if (state == PS_SELECT) do_select();
+            if (state == PS_STEP) do_step();
+        }
+    }
+
+    __device__ void finish(double* u_out, double* x_out, double* e_out, int32_t* m_out, double* obj,
+                           int32_t* status, int32_t* nodes_out, int32_t* iters_out) {
+        const int nl = S.nl, N = S.N, np1 = N + 1;
+        const bool ok = inc < HUGE_VAL;
+        __syncwarp();
+        LANES(i, nl) {
+            double* xo = x_out + (size_t)i * 2 * np1;
+            double* uo = u_out + (size_t)i * N;
+            int32_t* mo = m_out + (size_t)i * N;
+            if (ok) {
+                double p = pvec[2 * i], v = v0[i];
+                xo[0] = p; xo[np1] = v;
+                for (int k = 0; k < N; ++k) {
+                    const int r = bmodes[k * nl + i];
+                    const double vn = best[i * N + k];
+                    uo[k] = (vn - ma(i, r) * v - mc(i, r)) / mb(i, r);
+                    mo[k] = r;
+                    p = p + v; v = vn;
+                    xo[k + 1] = p; xo[np1 + k + 1] = v;
+                }
+            } else {
+                for (int k = 0; k < N; ++k) { uo[k] = 0.0; mo[k] = -1; }
+                for (int k = 0; k <= N; ++k) { xo[k] = 0.0; xo[np1 + k] = 0.0; }
+            }
+        }
+        if (e_out) LANES(e, S.ne) e_out[e] = ok ? best[nl * N + e] : 0.0;
+        if (lane == 0) {
+            *obj = ok ? inc : HUGE_VAL;
+            *status = limit ? HVP_ST_NODE_LIMIT
+                            : (trouble ? HVP_ST_NUMERIC : (ok ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE));
+            *nodes_out = nodes;
+            if (iters_out) *iters_out = iters;
+        }
+        __syncwarp();
+    }
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(128)
+pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __restrict__ x0,
+               const double* __restrict__ mass, const double* __restrict__ params,
+               const int32_t* __restrict__ fixed_modes, double* __restrict__ u, double* __restrict__ x,
+               double* __restrict__ extra, int32_t* __restrict__ modes, double* __restrict__ obj,
+               int32_t* __restrict__ status, int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
+    extern __shared__ double pm_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
+    Warp W(S, base, lane);
+    const int64_t stride = (int64_t)gridDim.x * wpb;
+    const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
+    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < batch; i += stride) {
+        W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar,
+                fixed_modes ? fixed_modes + su * i : nullptr);
+        W.solve();
+        W.finish(u + su * i, x + sx * i, extra ? extra + (size_t)S.ne * i : nullptr, modes + su * i, obj + i,
+                 status + i, nodes + i, qp_iters ? qp_iters + i : nullptr);
+    }
+}
+
+// per-warp shared-memory carve-up
+void pm_layout(PmDev& S) {
+    const int nv = S.nv, D = S.depth;
+    S.ld = nv | 1;
+    int o = 0;
+    S.o_hinv = o; o += nv * S.ld;
+    S.o_ginv = o; o += nv * S.ld;
+    S.o_nact = o; o += nv * S.ld;
+    S.o_vec = o; o += 11 * nv;
+    S.o_cres = o; o += S.nres + S.nlin;
+    S.o_bgen = o; o += S.ng;
+    S.o_pvec = o; o += S.npv;
+    S.o_misc = o; o += 3 * S.nl + (D + 1) + 2 * S.nl * (S.N + 1) + 3 * D;
+    S.smem_doubles = o;
+    const int ints = nv + (D + 1) + 3 * D + S.ng;
+    S.o_int = o;
+    S.smem_bytes = (o * 8 + ints * 4 + 15) / 16 * 16;
+}
+
+cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
+                           const double* params, const int32_t* fixed_modes, double* u, double* x,
+                           double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
+                           int32_t* qp_iters, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    int wpb = 4;
+    while (wpb > 1 && (size_t)wpb * S.smem_bytes > 200 * 1024) wpb >>= 1;
+    const size_t smem = (size_t)wpb * S.smem_bytes;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = smem;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16 / wpb * 4) per_sm = 16 / wpb * 4;
+    int64_t blocks = (batch + wpb - 1) / wpb;
+    const int64_t cap = (int64_t)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, u, x,
+                                                                 extra, modes, obj, status, nodes, qp_iters);
+    return cudaGetLastError();
+}
+
+}  // namespace hvp

@@ -1,0 +1,56 @@
+// pm_types.h -- data shared by the host-side problem compiler (pm_build.cu) and the platoon-MIQP
+// kernel (pm_kernel.cu): the "compiled structure" of one MPC formulation.
+//
+// A formulation (centralized cent_mld.py:48-177, event-based fleet_event_based.py:72-291, naive ADMM
+// fleet_naive_admm.py:63-237, g-ADMM fleet_g_admm.py:55-158, local fleet_decent_mld.py:61-208) is
+// compiled ONCE -- like the reference builds its Gurobi model once -- into dense matrices over the
+// decision vector
+//     z = [ v_{i,k}  (i = 0..nl-1 vehicles, k = 1..N) ,  extras (free copies) ]
+// and the per-solve parameter vector
+//     pvec = [ x0 (2 nl) , params (npar) , 1 ].
+// Everything that differs between the problems of a batch is pvec, the masses and the result.
+#pragma once
+#include <stdint.h>
+
+namespace hvp {
+
+constexpr int PM_MAXMODES = 12;
+
+struct PmModel {                 // PWA modes of one vehicle: v+ = a v + b u + c for lo <= v <= hi
+    int R;                       // number of modes (7: pwa_gear, 12: friction x gear)
+    double cf[PM_MAXMODES];      // a = 1 - cf/m
+    double bg[PM_MAXMODES];      // b = bg/m
+    double dd[PM_MAXMODES];      // c = -mu g - dd/m
+    double lo[PM_MAXMODES], hi[PM_MAXMODES];
+    int gear[PM_MAXMODES];       // gear (1..6) reported for the mode
+    double mug;
+};
+
+struct PmDev {                   // kernel argument
+    int nl, N, ne, nv, ld;       // vehicles, horizon, extras, variables, padded (odd) leading dimension
+    int npar, npv;               // params per problem; npv = 2 nl + npar + 1
+    int nres, nlin, ng, n0;      // residuals, param-linear cost terms, generic rows, constant rows
+    int depth;                   // nl * N branching decisions (stage-major: d = k nl + i)
+    int max_nodes;
+    PmModel M;
+    double qu, w, vmin, vmax, pmin, pmax, umin, umax, a_acc, a_dec, tight;
+    // device arrays (shared by all problems; read-only, L1/L2 resident)
+    const double* H0;            // [nv][nv]      2 R'WR
+    const double* H0inv;         // [nv][nv]
+    const double* Cres;          // [nres][npv]   residual constants c_r = Cres[r] . pvec
+    const double* wres;          // [nres]
+    const double* RW2;           // [nv][nres]    2 w_r R[r][j]
+    const double* La;            // [nlin][npv]   cost += (La.pvec) * (Lz.z + Lp.pvec)
+    const double* Lz;            // [nlin][nv]
+    const double* Lp;            // [nlin][npv]
+    const double* AT;            // [nv][ng]      generic rows, column-major: row r is sum_j AT[j][r] z_j <= BR[r].pvec
+    const double* BR;            // [ng][npv]
+    const double* wmax;          // [ng]          L1 penalty weight (soft) or +inf (hard)
+    const double* B0;            // [n0][npv]     constant rows: B0[r].pvec <= 0
+    const double* w0;            // [n0]
+    // shared-memory carve-up (offsets in doubles / ints), filled by pm_layout()
+    int o_hinv, o_ginv, o_nact, o_vec, o_cres, o_bgen, o_pvec, o_misc, smem_doubles;
+    int o_int, smem_bytes;
+};
+
+}  // namespace hvp

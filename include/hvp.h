@@ -126,6 +126,71 @@ int hvp_local_miqp_host(hvp_ctx* ctx, const hvp_local_desc* desc, int64_t batch,
                         const double* xl, double* u, double* x, int32_t* modes, double* obj,
                         int32_t* status, int32_t* nodes, int32_t* qp_iters);
 
+/* ---- (a) compiled MPC formulations: centralized, event-based, ADMM, discrete gears --------------
+ * One handle = one MPC model, built once (the reference builds its Gurobi model once per controller)
+ * and solved for batches of (initial state, parameters).  Replaces
+ *   HVP_MPC_CENT   MpcMldCent(...).solve_mpc            mpcs/cent_mld.py:9-182      (+ set_leader_traj)
+ *   HVP_MPC_LOCAL  LocalMpcMld / LocalMpcGear            fleet_decent_mld.py:21-253, fleet_seq_mld.py:21-264
+ *   HVP_MPC_EVENT  event-based LocalMpc / LocalMpcGear   fleet_event_based.py:26-376  (solve_mpc)
+ *   HVP_MPC_ADMM   LocalMpcADMM / LocalMpcGear           fleet_naive_admm.py:24-290
+ *   HVP_MPC_GADMM  fixed-sequence LocalMpc(MpcSwitching) fleet_g_admm.py:22-205       (pass fixed_modes)
+ * on model HVP_MODEL_PWA_GEAR (7 PWA regions, models.py:397-492) or HVP_MODEL_FRICTION_GEAR (2 friction
+ * regions x 6 discrete gears = MpcGear.setup_gears on pwa_friction, mpcs/mpc_gear.py:30-114,
+ * models.py:288-332; the penalised/limited input is the throttle u_g).
+ *
+ * Parameter vector of one problem, params[npar]: blocks of (2, N+1) row-major [p_0..p_N, v_0..v_N]:
+ *   CENT : leader_traj
+ *   LOCAL: x_front, x_back, leader_x                     (set_x_front / set_x_back / set_leader_x)
+ *   EVENT: leader_x, x_f2, x_b2                          (set_leader_x / set_x_f2 / set_x_b2)
+ *   ADMM : leader_x, y_front, z_front, y_back, z_back    (set_leader_x / set_front_vars / set_back_vars)
+ *   GADMM: x_ref, then y and z, each (2 (1 + n_front + n_behind), N+1) in augmented order
+ *          [copies in front..., own state, copies behind...]
+ * Unused blocks must still be present (any finite values).  Extra decision variables returned in
+ * extra[n_extra]: ADMM [x_front if not FRONT][x_back if not TRAILER]; GADMM the neighbour copies in
+ * augmented order; others none.
+ * Local vehicles are ordered front to back: x0 [batch][n_local][2], mass [batch][n_local]. */
+#define HVP_MPC_CENT 1
+#define HVP_MPC_LOCAL 2
+#define HVP_MPC_EVENT 3
+#define HVP_MPC_ADMM 4
+#define HVP_MPC_GADMM 5
+#define HVP_MODEL_PWA_GEAR 0
+#define HVP_MODEL_FRICTION_GEAR 1
+#define HVP_REAL_VEHICLE_REF 8 /* flags bit: real_vehicle_as_reference (cent_mld.py:31, fleet_seq_mld.py:211-219) */
+#define HVP_NO_LEADER (-100)   /* EVENT: rel_leader_index = None */
+typedef struct {
+    int32_t kind;         /* HVP_MPC_* */
+    int32_t model;        /* HVP_MODEL_* */
+    int32_t n_local;      /* vehicles whose inputs are decided (CENT: n; EVENT: 2-3; others: 1) */
+    int32_t N;            /* horizon */
+    int32_t flags;        /* HVP_FRONT|HVP_LEADER|HVP_TRAILER (LOCAL, ADMM, GADMM: HVP_LEADER) | HVP_REAL_VEHICLE_REF */
+    int32_t leader_index; /* CENT: leader_index; EVENT: rel_leader_index in {-1,0,1} or HVP_NO_LEADER */
+    int32_t n_front;      /* EVENT: num_vehicles_in_front (0..2); GADMM: copies in front of own state */
+    int32_t n_behind;     /* EVENT: num_vehicles_behind (0..2);   GADMM: copies behind own state */
+    int32_t max_nodes;    /* per problem; 0 = unlimited */
+    int32_t reserved;
+    double d0, t0;        /* spacing policy */
+    double tight;         /* accel_cnstr_tightening */
+    double rho;           /* ADMM / GADMM penalty */
+} hvp_mpc_desc;
+typedef struct hvp_mpc hvp_mpc;
+int hvp_mpc_create(hvp_ctx* ctx, const hvp_mpc_desc* desc, hvp_mpc** out);
+int hvp_mpc_destroy(hvp_mpc* mpc);
+/* info[8] = { n_var, n_extra, n_param, n_modes, n_local, N, n_rows (coupling), smem bytes per warp } */
+int hvp_mpc_info(const hvp_mpc* mpc, int32_t* info);
+/* PWA mode table of the model: lo/hi velocity interval and the gear (1..6) of each of n_modes modes */
+int hvp_mpc_mode_table(const hvp_mpc* mpc, double* lo, double* hi, int32_t* gear);
+/* x0 [batch][n_local][2], mass [batch][n_local], params [batch][n_param], fixed_modes [batch][n_local][N]
+ * int32 or NULL (NULL: branch and bound over the modes; given: the single fixed-mode QP).
+ * Outputs: u [batch][n_local][N], x [batch][n_local][2][N+1], extra [batch][n_extra] or NULL,
+ * modes [batch][n_local][N] int32, obj, status, nodes [batch], qp_iters [batch] or NULL. */
+int hvp_mpc_solve_dev(hvp_mpc* mpc, int64_t batch, const double* x0, const double* mass, const double* params,
+                      const int32_t* fixed_modes, double* u, double* x, double* extra, int32_t* modes,
+                      double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters, void* stream);
+int hvp_mpc_solve_host(hvp_mpc* mpc, int64_t batch, const double* x0, const double* mass, const double* params,
+                       const int32_t* fixed_modes, double* u, double* x, double* extra, int32_t* modes,
+                       double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------
  * FP64 FMA issue peak of the device: `iters` dependent-chain FMAs x 8 independent chains per
  * thread over a full grid; returns achieved TFLOP/s (2 flop per FMA) in *tflops. */

@@ -23,8 +23,8 @@ _bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "hvp_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("hvp_oracle.c", "hvp_oracle_mpc.c")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libhvp_oracle.so"])
     return _LIB_PATH
 
@@ -59,6 +59,14 @@ def lib():
                                             C.POINTER(C.c_double), _dp, _dp, _dp]
         L.hvo_local_build_qp_py.restype = C.c_int
         L.hvo_max_threads.restype = C.c_int
+        hdr = [C.c_int] * 8 + [C.c_double] * 4
+        L.hvo_mpc_solve_batch.argtypes = [C.c_int] + hdr + [C.c_int, C.c_int, _dp, _dp, _dp, C.c_void_p, C.c_int,
+                                                          _dp, _dp, _dp, _ip, _dp, _dp, _ip, _lp, _lp]
+        L.hvo_mpc_solve_batch.restype = None
+        L.hvo_mpc_build_qp_py.argtypes = hdr + [_dp, _dp, _dp, _ip, _dp, _dp, C.POINTER(C.c_double), _dp, _dp, _dp]
+        L.hvo_mpc_build_qp_py.restype = C.c_int
+        L.hvo_mode_table.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp, _ip]
+        L.hvo_mode_table.restype = C.c_int
         _lib = L
     return _lib
 
@@ -165,6 +173,76 @@ def local_build_qp(N, flags, mass, x0, xf, xb, xl, modes, d0=50.0, t0=0.0, tight
         np.ascontiguousarray(z if xl is None else xl, dtype=np.float64),
         np.ascontiguousarray(modes, dtype=np.int32), H, g, C.byref(c0), A, b, w)
     return H, g, c0.value, A[: m * N].reshape(m, N), b[:m], w[:m]
+
+
+CENT, LOCAL, EVENT, ADMM, GADMM = 1, 2, 3, 4, 5
+PWA_GEAR, FRICTION_GEAR = 0, 1
+REAL_REF, NO_LEADER = 8, -100
+
+
+def mpc_dims(kind, nl, N, flags=0, n_front=0, n_behind=0):
+    """(n_param, n_extra) of a formulation (layout: include/hvp.h)."""
+    blk = 2 * (N + 1)
+    if kind == CENT:
+        return blk, 0
+    if kind in (LOCAL, EVENT):
+        return 3 * blk, 0
+    if kind == ADMM:
+        return 5 * blk, (0 if flags & FRONT else blk) + (0 if flags & TRAILER else blk)
+    if kind == GADMM:
+        na = n_front + n_behind + 1
+        return (1 + 2 * na) * blk, (n_front + n_behind) * blk
+    raise ValueError(kind)
+
+
+def mode_table(model, mass=800.0):
+    a, b, c, lo, hi = (np.zeros(12) for _ in range(5))
+    gear = np.zeros(12, np.int32)
+    R = lib().hvo_mode_table(int(model), float(mass), a, b, c, lo, hi, gear)
+    return a[:R], b[:R], c[:R], lo[:R], hi[:R], gear[:R]
+
+
+def mpc_solve(kind, nl, N, x0, mass, params, *, model=PWA_GEAR, flags=0, leader_index=0, n_front=0,
+              n_behind=0, d0=50.0, t0=0.0, tight=0.0, rho=0.5, fixed_modes=None, method=1):
+    """Batched exact solve of the compiled MPC formulations (hvp_oracle_mpc.c).
+    x0 (B,nl,2), mass (B,nl), params (B,npar); method 0 = exhaustive enumeration, 1 = branch and bound."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, nl, 2)
+    B = x0.shape[0]
+    npar, ne = mpc_dims(kind, nl, N, flags, n_front, n_behind)
+    mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, dtype=np.float64), (B, nl)))
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(B, npar)
+    fm = None
+    if fixed_modes is not None:
+        fixed_modes = np.ascontiguousarray(fixed_modes, dtype=np.int32).reshape(B, nl, N)
+        fm = fixed_modes.ctypes.data_as(C.c_void_p)
+    u = np.zeros((B, nl, N)); xt = np.zeros((B, nl, 2, N + 1)); extra = np.zeros((B, max(ne, 1)))
+    modes = np.zeros((B, nl, N), np.int32); obj = np.zeros(B); second = np.zeros(B)
+    status = np.zeros(B, np.int32); leaves = np.zeros(B, np.int64); nodes = np.zeros(B, np.int64)
+    lib().hvo_mpc_solve_batch(B, int(kind), int(model), int(nl), int(N), int(flags), int(leader_index),
+                              int(n_front), int(n_behind), float(d0), float(t0), float(tight), float(rho),
+                              int(npar), int(max(ne, 1)), x0, mass, params, fm, int(method), u, xt, extra, modes,
+                              obj, second, status, leaves, nodes)
+    return dict(u=u, x=xt, extra=extra[:, :ne], modes=modes, obj=obj, second=second, status=status,
+                leaves=leaves, nodes=nodes)
+
+
+def mpc_build_qp(kind, nl, N, x0, mass, params, modes, *, model=PWA_GEAR, flags=0, leader_index=0, n_front=0,
+                 n_behind=0, d0=50.0, t0=0.0, tight=0.0, rho=0.5):
+    """Dense fixed-mode QP (H,g,c0,A,b,wmax) of one problem in input space, for certification."""
+    npar, ne = mpc_dims(kind, nl, N, flags, n_front, n_behind)
+    n = nl * N + ne
+    maxrows = 2400
+    H = np.zeros((n, n)); g = np.zeros(n); A = np.zeros(maxrows * n); b = np.zeros(maxrows); w = np.zeros(maxrows)
+    c0 = C.c_double(0)
+    m = lib().hvo_mpc_build_qp_py(int(kind), int(model), int(nl), int(N), int(flags), int(leader_index),
+                                  int(n_front), int(n_behind), float(d0), float(t0), float(tight), float(rho),
+                                  np.ascontiguousarray(x0, dtype=np.float64).reshape(-1),
+                                  np.ascontiguousarray(np.broadcast_to(np.asarray(mass, dtype=np.float64), (nl,))),
+                                  np.ascontiguousarray(params, dtype=np.float64).reshape(-1),
+                                  np.ascontiguousarray(modes, dtype=np.int32).reshape(-1), H, g, C.byref(c0), A, b, w)
+    if m < 0:
+        return None
+    return H, g, c0.value, A[: m * n].reshape(m, n), b[:m], w[:m]
 
 
 def max_threads() -> int:
