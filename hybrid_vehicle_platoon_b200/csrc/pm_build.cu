@@ -32,6 +32,7 @@ struct hvp_mpc {
     hvp_mpc_desc desc;
     PmDev S;
     std::vector<void*> dev;     // device allocations owned by the handle
+    unsigned long long* counter; // work-distribution counter of the kernel
 };
 
 namespace {
@@ -415,6 +416,7 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     if (!rc) rc = upload(m, La, &S.La); if (!rc) rc = upload(m, Lz, &S.Lz); if (!rc) rc = upload(m, Lp, &S.Lp);
     if (!rc) rc = upload(m, AT, &S.AT); if (!rc) rc = upload(m, BR, &S.BR); if (!rc) rc = upload(m, wmax, &S.wmax);
     if (!rc) rc = upload(m, B0, &S.B0); if (!rc) rc = upload(m, w0, &S.w0);
+    if (!rc) { const double* cn = nullptr; rc = upload(m, std::vector<double>(2, 0.0), &cn); m->counter = (unsigned long long*)cn; }
     if (rc) { hvp_mpc_destroy(m); return rc; }
     *out = m;
     return 0;
@@ -452,7 +454,7 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_TRY(cudaEventRecord(c->ev0, st));
     CUDA_TRY(launch_pm_miqp(m->S, batch, x0, mass, params, fixed_modes, u, x, extra, modes, obj, status, nodes,
-                            qp_iters, st));
+                            qp_iters, m->counter, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     c->launches += 1;

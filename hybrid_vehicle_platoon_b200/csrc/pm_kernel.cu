@@ -38,8 +38,29 @@ constexpr unsigned FULL = 0xffffffffu;
 enum : int { PT_UB = 0, PT_LB, PT_UHI, PT_ULO, PT_ACC, PT_DEC, PT_PHI, PT_PLO, PT_GEN };
 enum : int { PS_NEXT = 0, PS_BUILD, PS_SELECT, PS_STEP, PS_DONE };
 #define PM_ID(t, idx) ((t) * 4096 + (idx))
-#define LANES(j, n) for (int j = lane; j < (n); j += 32)
+#define LANES(j, n) _Pragma("unroll 1") for (int j = lane; j < (n); j += 32)
 
+// reciprocal to ~1 ulp without the slow paths / code size of the IEEE division sequence
+__device__ __forceinline__ double rcp(double v) {
+    double r = (double)__frcp_rn((float)v);
+    r = r * (2.0 - v * r);
+    r = r * (2.0 - v * r);
+    r = r * (2.0 - v * r);
+    return r;
+}
+// dot product with two independent accumulation chains (the solver is latency bound);
+// `sa` = stride of a in doubles
+__device__ __forceinline__ double dot2(const double* a, int sa, const double* b, int n) {
+    double s0 = 0.0, s1 = 0.0;
+    int c = 0;
+#pragma unroll 2
+    for (; c + 1 < n; c += 2) {
+        s0 += a[(size_t)c * sa] * b[c];
+        s1 += a[(size_t)(c + 1) * sa] * b[c + 1];
+    }
+    if (c < n) s0 += a[(size_t)c * sa] * b[c];
+    return s0 + s1;
+}
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -70,11 +91,11 @@ struct Warp {
     double *Hinv, *Ginv, *Nact;
     double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best;
     double *cres, *bgen, *pvec;
-    double *inv_m, *pc, *v0, *xstar, *rlo, *rhi, *am, *bm, *cm;
+    double *inv_m, *pc, *v0, *xstar, *rlo, *rhi, *am, *bm, *cm, *amax, *amin;
     int *act, *cand, *modes, *bmodes, *built, *orient;
     // warp-uniform scalars (replicated in registers)
     int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
-    double inc, c0, cp, nHn, lam_p;
+    double inc, c0, cp, nHn, lam_p, dual;
     bool p_soft, trouble, limit;
 
     __device__ Warp(const PmDev& S_, double* base, int lane_) : S(S_), lane(lane_) {
@@ -88,6 +109,7 @@ struct Warp {
         const int nl = S.nl, N = S.N, D = S.depth;
         inv_m = m; pc = m + nl; v0 = m + 2 * nl; xstar = m + 3 * nl; rlo = xstar + D + 1;
         rhi = rlo + nl * (N + 1); am = rhi + nl * (N + 1); bm = am + D; cm = bm + D;
+        amax = cm + D; amin = amax + D;
         int* ib = reinterpret_cast<int*>(base + S.smem_doubles);
         act = ib; cand = ib + nv; modes = cand + D + 1; bmodes = modes + D; built = bmodes + D;
         orient = built + D;
@@ -105,7 +127,7 @@ struct Warp {
         LANES(t, S.npar) pvec[2 * nl + t] = params[t];
         if (lane == 0) pvec[npv - 1] = 1.0;
         LANES(i, nl) {
-            inv_m[i] = 1.0 / mass[i];
+            inv_m[i] = rcp(mass[i]);
             v0[i] = x0[2 * i + 1];
             pc[i] = x0[2 * i] + x0[2 * i + 1];
             rlo[i * (N + 1)] = x0[2 * i + 1];
@@ -117,12 +139,14 @@ struct Warp {
         bool infeas = false;
         LANES(r, S.nres) {
             double s = 0.0;
+            _Pragma("unroll 1")
             for (int t = 0; t < npv; ++t) s += S.Cres[(size_t)r * npv + t] * pvec[t];
             cres[r] = s;
             c += S.wres[r] * s * s;
         }
         LANES(l, S.nlin) {
             double a = 0.0, p = 0.0;
+            _Pragma("unroll 1")
             for (int t = 0; t < npv; ++t) {
                 a += S.La[(size_t)l * npv + t] * pvec[t];
                 p += S.Lp[(size_t)l * npv + t] * pvec[t];
@@ -132,11 +156,13 @@ struct Warp {
         }
         LANES(r, S.ng) {
             double s = 0.0;
+            _Pragma("unroll 1")
             for (int t = 0; t < npv; ++t) s += S.BR[(size_t)r * npv + t] * pvec[t];
             bgen[r] = s;
         }
         LANES(r, S.n0) {
             double s = 0.0;
+            _Pragma("unroll 1")
             for (int t = 0; t < npv; ++t) s += S.B0[(size_t)r * npv + t] * pvec[t];
             if (s > 0.0) {
                 if (isfinite(S.w0[r])) c += S.w0[r] * s;
@@ -151,7 +177,9 @@ struct Warp {
         infeas = __any_sync(FULL, infeas);
         LANES(j, nv) {
             double s = 0.0;
+            _Pragma("unroll 1")
             for (int r = 0; r < S.nres; ++r) s += S.RW2[(size_t)j * S.nres + r] * cres[r];
+            _Pragma("unroll 1")
             for (int l = 0; l < S.nlin; ++l) s += S.Lz[(size_t)l * nv + j] * cres[S.nres + l];
             g0[j] = s;
         }
@@ -184,6 +212,7 @@ struct Warp {
         const int i = lv % nl, k = lv / nl;
         const double lo = rlo[i * (N + 1) + k], hi = rhi[i * (N + 1) + k];
         int cn = 0;
+        _Pragma("unroll 1")
         for (int r = 0; r < S.M.R; ++r)
             if (S.M.lo[r] <= hi && S.M.hi[r] >= lo && S.M.lo[r] <= S.M.hi[r]) cn |= (1 << r);
         cand[lv] = cn;
@@ -196,6 +225,7 @@ struct Warp {
         if (lane == 0) {
             const double eps = 1e-9;
             const int nl = S.nl, N = S.N;
+            _Pragma("unroll 1")
             for (;;) {
                 const int cset = cand[nlev];
                 if (cset == 0) {
@@ -206,6 +236,7 @@ struct Warp {
                 const int i = nlev % nl, k = nlev / nl;
                 int rg = -1; double bd = HUGE_VAL;
                 const double xs = xstar[nlev];
+                _Pragma("unroll 1")
                 for (int c = 0; c < S.M.R; ++c) {
                     if (!((cset >> c) & 1)) continue;
                     const double lo = S.M.lo[c], hi = S.M.hi[c];
@@ -231,6 +262,43 @@ struct Warp {
         state = __shfl_sync(FULL, st, 0);
         lev = __shfl_sync(FULL, nlev, 0);
         L = __shfl_sync(FULL, nL, 0);
+        if (state == PS_BUILD) hull();
+    }
+
+    // Interval reachability of the NOT yet fixed stages (lane v = vehicle v): from the velocity interval
+    // at a vehicle's first unfixed stage, the hull over all PWA modes it can be in gives, stage by stage,
+    // a velocity interval and the acceleration range its traction / braking allows.  Every completion of
+    // the node's mode prefix satisfies them, so the node relaxation may impose them (they replace the
+    // constant a_dec / a_acc rows of the unfixed stages) and stays a valid lower bound.
+    __device__ void hull() {
+        const int nl = S.nl, N = S.N;
+        const double eps = 1e-9;
+        LANES(v, nl) {
+            int kf = (L - v + nl - 1) / nl;              // stages 0..kf-1 of vehicle v are fixed
+            if (kf < 0) kf = 0;
+            double lo = rlo[v * (N + 1) + kf], hi = rhi[v * (N + 1) + kf];
+            _Pragma("unroll 1")
+            for (int s = kf; s < N; ++s) {
+                double nlo = HUGE_VAL, nhi = -HUGE_VAL, dmax = -HUGE_VAL, dmin = HUGE_VAL;
+                _Pragma("unroll 1")
+                for (int r = 0; r < S.M.R; ++r) {
+                    const double jlo = fmax(lo, S.M.lo[r]), jhi = fmin(hi, S.M.hi[r]);
+                    if (jlo > jhi + eps) continue;
+                    const double a = ma(v, r), b = mb(v, r), c = mc(v, r);
+                    nlo = fmin(nlo, a * jlo + c + b * S.umin);
+                    nhi = fmax(nhi, a * jhi + c + b * S.umax);
+                    dmax = fmax(dmax, (a - 1.0) * jlo + c + b * S.umax);     // a < 1: largest at the low end
+                    dmin = fmin(dmin, (a - 1.0) * jhi + c + b * S.umin);
+                }
+                const double acc = S.a_acc - s * S.tight, dec = S.a_dec + s * S.tight;
+                dmax = fmin(dmax + eps, acc); dmin = fmax(dmin - eps, dec);
+                nlo = fmax(fmax(nlo, lo + dec), S.vmin); nhi = fmin(fmin(nhi, hi + acc), S.vmax);
+                amax[v * N + s] = dmax; amin[v * N + s] = dmin;
+                lo = nlo - eps; hi = nhi + eps;
+                rlo[v * (N + 1) + s + 1] = lo; rhi[v * (N + 1) + s + 1] = hi;
+            }
+        }
+        __syncwarp();
     }
 
     // st: 0 solved, 1 infeasible, 2 numerical trouble
@@ -258,7 +326,7 @@ struct Warp {
     __device__ void rank1(int d, int rg, double s) {
         const int nl = S.nl, N = S.N, nv = S.nv, ld = S.ld;
         const int i = d % nl, k = d / nl, jk = i * N + k, jm = jk - 1;
-        const double ib = 1.0 / mb(i, rg), ea = (k >= 1) ? -ma(i, rg) * ib : 0.0;
+        const double ib = rcp(mb(i, rg)), ea = (k >= 1) ? -ma(i, rg) * ib : 0.0;
         LANES(j, nv) {
             double v = ib * Hinv[j * ld + jk];
             if (k >= 1) v += ea * Hinv[j * ld + jm];
@@ -266,9 +334,10 @@ struct Warp {
         }
         __syncwarp();
         const double ev = ib * wv[jk] + ((k >= 1) ? ea * wv[jm] : 0.0);
-        const double den = 1.0 / (s / (2.0 * S.qu) + ev);
+        const double den = rcp(s * (0.5 / S.qu) + ev);
         LANES(j, nv) {
             const double vj = wv[j] * den;
+            _Pragma("unroll 1")
             for (int c = 0; c < nv; ++c) Hinv[j * ld + c] -= vj * wv[c];
         }
         __syncwarp();
@@ -283,11 +352,14 @@ struct Warp {
         const bool reload = built_L < 0 || c == 0 || (built_L - c > c);
         __syncwarp();
         if (reload) {
+            _Pragma("unroll 1")
             for (int e = lane; e < nv * nv; e += 32) Hinv[(e / nv) * ld + (e % nv)] = S.H0inv[e];
             c = 0; built_L = 0;
             __syncwarp();
         }
+        _Pragma("unroll 1")
         for (int d = built_L - 1; d >= c; --d) rank1(d, built[d], -1.0);
+        _Pragma("unroll 1")
         for (int d = c; d < L; ++d) rank1(d, modes[d], 1.0);
         LANES(d, L) {
             built[d] = modes[d];
@@ -303,23 +375,31 @@ struct Warp {
                 const int i = j / N, kk = j % N;
                 const int d0 = kk * nl + i, d1 = d0 + nl;
                 if (d0 < L) {
-                    const double ib = 1.0 / bm[d0];
+                    const double ib = rcp(bm[d0]);
                     const double kc = (kk == 0) ? -(am[d0] * v0[i] + cm[d0]) * ib : -cm[d0] * ib;
                     g += 2.0 * qu * kc * ib;
                 }
                 if (kk + 1 < N && d1 < L) {
-                    const double ib = 1.0 / bm[d1];
+                    const double ib = rcp(bm[d1]);
                     g += 2.0 * qu * (-cm[d1] * ib) * (-am[d1] * ib);
                 }
             }
             gn[j] = g;
         }
         __syncwarp();
+        double dpart = 0.0;
         LANES(j, nv) {
-            double s = 0.0;
-            for (int c2 = 0; c2 < nv; ++c2) s += Hinv[j * ld + c2] * gn[c2];
+            const double s = dot2(Hinv + j * ld, 1, gn, nv);
             x[j] = -s;
+            dpart -= 0.5 * gn[j] * s;
         }
+        LANES(d, L) {
+            const int i = d % nl, k = d / nl;
+            const double kc = ((k == 0) ? -(am[d] * v0[i] + cm[d]) : -cm[d]) * rcp(bm[d]);
+            dpart += qu * kc * kc;
+        }
+        // value of the node's dual function at the unconstrained minimiser; it only grows from here
+        dual = c0 + wsum(dpart);
         LANES(r, S.ng) orient[r] = 1;
         it = 0; q = 0;
         state = PS_SELECT;
@@ -345,6 +425,9 @@ struct Warp {
                 const int r = modes[d1];
                 lo = fmax(lo, S.M.lo[r]); hi = fmin(hi, S.M.hi[r]);
             }
+            if (d0 >= L) {       // stage kk not fixed: reachable interval of v_{kk+1}
+                lo = fmax(lo, rlo[i * (N + 1) + kk + 1]); hi = fmin(hi, rhi[i * (N + 1) + kk + 1]);
+            }
             if (kk == 0) {
                 lo = fmax(lo, v0[i] + S.a_dec); hi = fmin(hi, v0[i] + S.a_acc);
                 if (d0 < L) {
@@ -353,14 +436,17 @@ struct Warp {
                 }
             } else {
                 const double xm = x[j - 1];
+                double acc = S.a_acc - kk * S.tight, dec = S.a_dec + kk * S.tight;
                 if (d0 < L) {
                     const double du = xv - am[d0] * xm - cm[d0];
                     PM_CAND(PT_UHI, j, du - bm[d0] * S.umax);
                     PM_CAND(PT_ULO, j, bm[d0] * S.umin - du);
+                } else {
+                    acc = amax[j]; dec = amin[j];
                 }
                 const double dvv = xv - xm;
-                PM_CAND(PT_ACC, j, dvv - (S.a_acc - kk * S.tight));
-                PM_CAND(PT_DEC, j, (S.a_dec + kk * S.tight) - dvv);
+                PM_CAND(PT_ACC, j, dvv - acc);
+                PM_CAND(PT_DEC, j, dec - dvv);
             }
             PM_CAND(PT_UB, j, xv - hi);
             PM_CAND(PT_LB, j, lo - xv);
@@ -369,13 +455,13 @@ struct Warp {
             LANES(i, nl) {
                 double ps = pc[i];
                 PM_CAND(PT_PLO, i, S.pmin - (ps + x[i * N]));
+                _Pragma("unroll 1")
                 for (int kk = 0; kk + 1 < N; ++kk) ps += x[i * N + kk];
                 PM_CAND(PT_PHI, i, ps - S.pmax);
             }
         }
         LANES(r, ng) {
-            double s = -bgen[r];
-            for (int j = 0; j < nv; ++j) s += S.AT[(size_t)j * ng + r] * x[j];
+            const double s = dot2(S.AT + r, ng, x, nv) - bgen[r];
             PM_CAND(PT_GEN, r, orient[r] > 0 ? s : -s);
         }
 #undef PM_CAND
@@ -384,21 +470,19 @@ struct Warp {
             // ---- node solved: objective ----
             double f = 0.0;
             LANES(j, nv) {
-                double s = 0.0;
-                for (int c = 0; c < nv; ++c) s += S.H0[(size_t)j * nv + c] * x[c];
+                const double s = dot2(S.H0 + (size_t)j * nv, 1, x, nv);
                 f += x[j] * (g0[j] + 0.5 * s);
             }
             LANES(d, L) {
                 const int i = d % nl, k = d / nl, jk = i * N + k;
                 const double xp = (k >= 1) ? x[jk - 1] : v0[i];
-                const double uu = (x[jk] - am[d] * xp - cm[d]) / bm[d];
+                const double uu = (x[jk] - am[d] * xp - cm[d]) * rcp(bm[d]);
                 f += S.qu * uu * uu;
             }
             LANES(r, ng) {
                 const double wm = S.wmax[r];
                 if (isfinite(wm)) {
-                    double s = -bgen[r];
-                    for (int j = 0; j < nv; ++j) s += S.AT[(size_t)j * ng + r] * x[j];
+                    const double s = dot2(S.AT + r, ng, x, nv) - bgen[r];
                     if (s > 0.0) f += wm * s;
                 }
             }
@@ -437,8 +521,7 @@ struct Warp {
         // yp = H^-1 n_p, nHn = n_p' yp
         double acc = 0.0;
         LANES(j, nv) {
-            double s = 0.0;
-            for (int c = 0; c < nv; ++c) s += Hinv[j * S.ld + c] * np_[c];
+            const double s = dot2(Hinv + j * S.ld, 1, np_, nv);
             yp[j] = s;
             acc += s * np_[j];
         }
@@ -457,29 +540,26 @@ struct Warp {
         if (cp <= tol) { state = PS_SELECT; return; }
         // d = N' yp
         LANES(a, q) {
-            double s = 0.0;
-            for (int c = 0; c < nv; ++c) s += Nact[a * ld + c] * yp[c];
-            dv[a] = s;
+            dv[a] = dot2(Nact + a * ld, 1, yp, nv);
         }
         __syncwarp();
         // r = Ginv d ; nz = nHn - d'r ; ratio tests
         double part = 0.0, t1 = INF, t3 = INF;
         int k1 = 0x7fffffff, k3 = 0x7fffffff;
         LANES(a, q) {
-            double s = 0.0;
-            for (int b = 0; b < q; ++b) s += Ginv[a * ld + b] * dv[b];
+            const double s = dot2(Ginv + a * ld, 1, dv, q);
             rv[a] = s;
             part += s * dv[a];
             const double la = lam[a];
             if (s > 1e-14) {
-                const double t = la / s;
+                const double t = la * rcp(s);
                 if (t < t1) { t1 = t; k1 = a; }
             } else if (s < -1e-14) {
                 const int id = act[a];
                 if (id >= PM_ID(PT_GEN, 0)) {
                     const double wm = S.wmax[id - PM_ID(PT_GEN, 0)];
                     if (isfinite(wm)) {
-                        const double t = (wm - la) / (-s);
+                        const double t = (wm - la) * rcp(-s);
                         if (t < t3) { t3 = t; k3 = a; }
                     }
                 }
@@ -489,23 +569,22 @@ struct Warp {
         wargmin(t1, k1);
         wargmin(t3, k3);
         const bool dependent = (q == nv) || !(nz > 1e-11 * nHn);
-        const double t2 = dependent ? INF : cp / nz;
+        const double t2 = dependent ? INF : cp * rcp(nz);
         const double t3p = p_soft ? (S.wmax[pid - PM_ID(PT_GEN, 0)] - lam_p) : INF;
         const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
         if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
+        // d(dual)/dt = violation of p along the step: the dual value is a lower bound on the node optimum
+        dual += t * cp - (dependent ? 0.0 : 0.5 * t * t * nz);
+        if (dual > inc) { node_done(1, 0.0); return; }          // the node cannot beat the incumbent
         __syncwarp();
         if (!dependent) {
             // w = n_p - N r ;  x -= t H^-1 w ;  the violation of p shrinks by t nz
             LANES(j, nv) {
-                double s = np_[j];
-                for (int a = 0; a < q; ++a) s -= rv[a] * Nact[a * ld + j];
-                wv[j] = s;
+                wv[j] = np_[j] - dot2(Nact + j, ld, rv, q);
             }
             __syncwarp();
             LANES(j, nv) {
-                double s = 0.0;
-                for (int c = 0; c < nv; ++c) s += Hinv[j * ld + c] * wv[c];
-                x[j] -= t * s;
+                x[j] -= t * dot2(Hinv + j * ld, 1, wv, nv);
             }
             cp -= t * nz;
         }
@@ -513,9 +592,10 @@ struct Warp {
         lam_p += t;
         if (t == t2) {
             // p becomes slot q: bordering update of Ginv with Schur complement nz
-            const double is = 1.0 / nz;
+            const double is = rcp(nz);
             LANES(a, q) {
                 const double ra = rv[a] * is;
+                _Pragma("unroll 1")
                 for (int b = 0; b < q; ++b) Ginv[a * ld + b] += ra * rv[b];
                 Ginv[a * ld + q] = -ra;
                 Ginv[q * ld + a] = -ra;
@@ -545,11 +625,12 @@ struct Warp {
         }
         __syncwarp();
         {   // Ginv <- Ginv - g g'/g_dd on the remaining slots, then move the last slot into `drop`
-            const double idd = 1.0 / Ginv[drop * ld + drop];
+            const double idd = rcp(Ginv[drop * ld + drop]);
             LANES(a, q) dv[a] = Ginv[a * ld + drop];
             __syncwarp();
             LANES(a, q) {
                 const double da = dv[a] * idd;
+                _Pragma("unroll 1")
                 for (int b = 0; b < q; ++b) Ginv[a * ld + b] -= da * dv[b];
             }
             __syncwarp();
@@ -593,6 +674,7 @@ struct Warp {
             if (ok) {
                 double p = pvec[2 * i], v = v0[i];
                 xo[0] = p; xo[np1] = v;
+                _Pragma("unroll 1")
                 for (int k = 0; k < N; ++k) {
                     const int r = bmodes[k * nl + i];
                     const double vn = best[i * N + k];
@@ -602,7 +684,9 @@ struct Warp {
                     xo[k + 1] = p; xo[np1 + k + 1] = v;
                 }
             } else {
+                _Pragma("unroll 1")
                 for (int k = 0; k < N; ++k) { uo[k] = 0.0; mo[k] = -1; }
+                _Pragma("unroll 1")
                 for (int k = 0; k <= N; ++k) { xo[k] = 0.0; xo[np1 + k] = 0.0; }
             }
         }
@@ -625,14 +709,20 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
                const double* __restrict__ mass, const double* __restrict__ params,
                const int32_t* __restrict__ fixed_modes, double* __restrict__ u, double* __restrict__ x,
                double* __restrict__ extra, int32_t* __restrict__ modes, double* __restrict__ obj,
-               int32_t* __restrict__ status, int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
+               int32_t* __restrict__ status, int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters,
+               unsigned long long* __restrict__ counter) {
     extern __shared__ double pm_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
     Warp W(S, base, lane);
-    const int64_t stride = (int64_t)gridDim.x * wpb;
     const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
-    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < batch; i += stride) {
+    // problems are handed out one at a time (tree sizes vary by orders of magnitude)
+    _Pragma("unroll 1")
+    for (;;) {
+        unsigned long long nxt = 0;
+        if (lane == 0) nxt = atomicAdd(counter, 1ull);
+        const int64_t i = (int64_t)__shfl_sync(FULL, nxt, 0);
+        if (i >= batch) break;
         W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar,
                 fixed_modes ? fixed_modes + su * i : nullptr);
         W.solve();
@@ -653,7 +743,7 @@ void pm_layout(PmDev& S) {
     S.o_cres = o; o += S.nres + S.nlin;
     S.o_bgen = o; o += S.ng;
     S.o_pvec = o; o += S.npv;
-    S.o_misc = o; o += 3 * S.nl + (D + 1) + 2 * S.nl * (S.N + 1) + 3 * D;
+    S.o_misc = o; o += 3 * S.nl + (D + 1) + 2 * S.nl * (S.N + 1) + 5 * D;
     S.smem_doubles = o;
     const int ints = nv + (D + 1) + 3 * D + S.ng;
     S.o_int = o;
@@ -663,7 +753,7 @@ void pm_layout(PmDev& S) {
 cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
                            const double* params, const int32_t* fixed_modes, double* u, double* x,
                            double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
-                           int32_t* qp_iters, cudaStream_t stream) {
+                           int32_t* qp_iters, unsigned long long* counter, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     int wpb = 4;
     while (wpb > 1 && (size_t)wpb * S.smem_bytes > 200 * 1024) wpb >>= 1;
@@ -684,8 +774,10 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
     int64_t blocks = (batch + wpb - 1) / wpb;
     const int64_t cap = (int64_t)sms * per_sm;
     if (blocks > cap) blocks = cap;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
     pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, u, x,
-                                                                 extra, modes, obj, status, nodes, qp_iters);
+                                                                 extra, modes, obj, status, nodes, qp_iters, counter);
     return cudaGetLastError();
 }
 

@@ -87,6 +87,74 @@ class PwaGearVehicle(Vehicle):
         raise RuntimeError("Didn't find any PWA region for the given speed!")
 
 
+class PwaFrictionVehicle(Vehicle):
+    """PWA approximation of the friction only: 2 velocity regions, input = traction force with
+    B = 1/m; used with the discrete gears of MpcGear (models.py:272-387)."""
+
+    beta, alpha, c1, c2, d = PwaGearVehicle.beta, PwaGearVehicle.alpha, PwaGearVehicle.c1, PwaGearVehicle.c2, PwaGearVehicle.d
+
+    def __init__(self, m: float = 800) -> None:
+        super().__init__(m)
+        self.system = self._build(m)
+
+    def _build(self, mass):
+        S = [np.array([[0, 1], [0, 0]]), np.array([[0, 0], [0, -1]])]
+        T = [np.array([[self.alpha], [0]]), np.array([[0], [-self.alpha]])]
+        R = [np.zeros((2, 1)), np.zeros((2, 1))]
+        A = [np.array([[0, 1], [0, -self.c1 / mass]]), np.array([[0, 1], [0, -self.c2 / mass]])]
+        B = [np.array([[0], [1 / mass]]), np.array([[0], [1 / mass]])]
+        c = [np.array([[0], [-self.mu * self.grav]]), np.array([[0], [-self.mu * self.grav - self.d / mass]])]
+        D = np.array([[1, 0], [-1, 0], [0, 1], [0, -1]])
+        E = np.array([[self.p_max], [-self.p_min], [self.v_max], [-self.v_min]])
+        F = np.array([[1], [-1]])
+        G = np.array([[self.u_max], [-self.u_min]])
+        return {"S": S, "R": R, "T": T, "A": A, "B": B, "c": c, "D": D, "E": E, "F": F, "G": G}
+
+    get_discrete_system = PwaGearVehicle.get_discrete_system
+
+    def get_gear_from_velocity(self, v: float) -> int:
+        """Vehicle.get_gear_from_velocity (models.py:161-174): first gear whose OPEN window contains v."""
+        if v < self.v_min or v > self.v_max:
+            warnings.warn(f"Velocity {v} is not within bounds {self.v_min}/{self.v_max}")
+            if v < self.v_min:
+                return 1
+            if v > self.v_max:
+                return 6
+        for i in range(len(self.b)):
+            if self.vl[i] < v < self.vh[i]:
+                return i + 1
+        raise ValueError(f"No gear found for velocity {v}")
+
+    def get_u_for_constant_vel(self, v: float, j: int) -> float:
+        """Throttle keeping v constant in gear j under the PWA-friction dynamics (models.py:334-368)."""
+        if j < 1 or j > 6:
+            raise ValueError(f"{j} is not a valid gear.")
+        j -= 1
+        if not ((v < self.v_min and j == 0) or (v > self.v_max and j == 5)) and (v < self.vl[j] or v > self.vh[j]):
+            raise ValueError(f"Velocity {v} is not valid for gear {j + 1}")
+        for i in range(2):
+            S, T = self.system["S"][i], self.system["T"][i]
+            if all(S @ np.array([[0], [v]]) <= T + np.array([[0], [1e-4]])):
+                return (1 / (self.b[j] * self.system["B"][i][1, 0])) * (
+                    -self.system["A"][i][1, 1] * v - self.system["c"][i][1, 0])
+        raise RuntimeError("Didn't find any PWA region for the given speed!")
+
+
+def model_of_pwa_system(system: dict):
+    """(model id, mass) of a system dict (ours or the reference's): 0 = pwa_gear (7 regions),
+    1 = pwa_friction (2 regions; solved with the six discrete gears of MpcGear)."""
+    nreg = len(system["A"])
+    if nreg == 7:
+        return 0, mass_of_pwa_system(system)
+    if nreg == 2:
+        m = 1.0 / float(system["B"][0][1, 0])
+        ref = PwaFrictionVehicle(m).get_discrete_system(1.0)
+        if not all(np.allclose(system[k][r], ref[k][r], rtol=1e-9, atol=1e-12) for k in ("A", "B", "c", "T") for r in range(2)):
+            raise NotImplementedError("only the pwa_friction model with ts = 1 is implemented on the GPU path")
+        return 1, m
+    raise NotImplementedError("GPU MPC needs a pwa_gear (7 regions) or pwa_friction (2 regions) system dict")
+
+
 def mass_of_pwa_system(system: dict) -> float:
     """Recover the vehicle mass from a pwa_gear system dict (ours or the reference's) and check
     that the dict really is that model (the GPU path implements pwa_gear only)."""
@@ -109,12 +177,14 @@ class Platoon:
     nu_l = Vehicle.nu_l
 
     def __init__(self, n: int, vehicle_type: str = "pwa_gear", masses=None) -> None:
-        if vehicle_type != "pwa_gear":
-            raise NotImplementedError(f"vehicle_type {vehicle_type!r}: only 'pwa_gear' is implemented")
+        cls = {"pwa_gear": PwaGearVehicle, "pwa_friction": PwaFrictionVehicle}.get(vehicle_type)
+        if cls is None:
+            raise NotImplementedError(f"vehicle_type {vehicle_type!r}: 'pwa_gear' and 'pwa_friction' are implemented "
+                                      "(the non-convex 'nonlinear' MPC model is SURVEY.md 8f rank 4)")
         if masses is not None and len(masses) != n:
             raise ValueError(f"Required {n} vehicles masses. Got {len(masses)}.")
         self.n = n
-        self.vehicles = [PwaGearVehicle(m=masses[i]) if masses is not None else PwaGearVehicle() for i in range(n)]
+        self.vehicles = [cls(m=masses[i]) if masses is not None else cls() for i in range(n)]
 
     @property
     def masses(self) -> np.ndarray:

@@ -340,6 +340,9 @@ static int solve_modes(search* S, const int* modes, double* z, double* obj) {
     return st;
 }
 
+static double g_margin_rel = 1e-6;
+void hvo_set_margin(double m) { g_margin_rel = m; }
+
 static void search_rec(search* S, int d) {
     const mpc_prob* P = S->P;
     const int nl = P->nl, N = P->N, D = nl * N;
@@ -367,7 +370,7 @@ static void search_rec(search* S, int d) {
         S->nodes++;
         if (st == 1) return;
         if (st == 0) {
-            double margin = 1e-6 * fmax(1.0, fabs(S->best));
+            double margin = g_margin_rel * fmax(1.0, fabs(S->best));
             if (isfinite(S->best) && obj > S->best + margin) return;
             /* relaxed velocity of the branching stage, to order the children */
             const aff* e = &S->Q.v[i][k];

@@ -41,3 +41,112 @@ def test_cent_vs_oracle(hvp, n, N, stress, t0):
     ro = O.mpc_solve(O.CENT, n, N, x0, 800.0, params, d0=d0, t0=t0, method=0 if exhaustive else 1)
     _compare(r, ro, f"cent n={n} N={N}")
     assert (r["nodes"] > 0).all()
+
+
+@pytest.mark.parametrize("nf,nb,rl,N,t0", [(0, 1, 0, 4, 0.0), (1, 1, 1, 3, 0.0), (2, 2, O.NO_LEADER, 3, 3.0),
+                                           (2, 0, -1 + 1, 4, 0.0), (1, 2, -1, 3, 0.0)])
+def test_event_vs_oracle(hvp, nf, nb, rl, N, t0):
+    rng = np.random.default_rng(200 + nf * 7 + nb * 3 + N)
+    B = 24
+    nl = (nf > 0) + 1 + (nb > 0)
+    x0, params = G.event_cases(rng, B, nf, nb, N, stress=True)
+    d0 = 10.0 if t0 else 50.0
+    mpc = hvp.api.CompiledMpc(G.EVENT, N, n_local=nl, leader_index=rl, n_front=nf, n_behind=nb, d0=d0, t0=t0)
+    r = mpc.solve(x0, 800.0, params)
+    ro = O.mpc_solve(O.EVENT, nl, N, x0, 800.0, params, leader_index=rl, n_front=nf, n_behind=nb, d0=d0, t0=t0,
+                     method=0 if nl * N <= 9 else 1)
+    _compare(r, ro, f"event nf={nf} nb={nb}")
+
+
+@pytest.mark.parametrize("flags,N", [(0, 4), (G.FRONT | G.LEADER, 4), (G.TRAILER, 5), (G.LEADER, 3), (0, 8)])
+def test_admm_vs_oracle(hvp, flags, N):
+    rng = np.random.default_rng(300 + flags * 5 + N)
+    B = 16
+    x0, params = G.admm_cases(rng, B, N, stress=True)
+    mass = rng.uniform(700, 1000, (B, 1))
+    mpc = hvp.api.CompiledMpc(G.ADMM, N, flags=flags, rho=0.5)
+    r = mpc.solve(x0, mass, params)
+    ro = O.mpc_solve(O.ADMM, 1, N, x0, mass, params, flags=flags, rho=0.5, method=0 if N <= 5 else 1)
+    _compare(r, ro, f"admm flags={flags} N={N}")
+
+
+@pytest.mark.parametrize("nf,nb,leader,N", [(0, 1, True, 6), (1, 1, False, 8), (1, 0, False, 5)])
+def test_gadmm_fixed_mode_qp_vs_oracle(hvp, nf, nb, leader, N):
+    rng = np.random.default_rng(400 + nf + 2 * nb + N)
+    B = 32
+    x0, params, modes = G.gadmm_cases(rng, B, nf, nb, N)
+    flags = G.LEADER if leader else 0
+    mpc = hvp.api.CompiledMpc(G.GADMM, N, flags=flags, n_front=nf, n_behind=nb, rho=0.5)
+    r = mpc.solve(x0, 800.0, params, fixed_modes=modes)
+    ro = O.mpc_solve(O.GADMM, 1, N, x0, 800.0, params, flags=flags, n_front=nf, n_behind=nb, rho=0.5,
+                     fixed_modes=modes)
+    _compare(r, ro, f"gadmm nf={nf} nb={nb}", check_modes=False)
+    assert (r["nodes"][r["status"] == 2] == 1).all()
+    assert (ro["status"] == 2).sum() >= B // 2
+
+
+@pytest.mark.parametrize("kind,nl,N", [(G.LOCAL, 1, 5), (G.CENT, 2, 3), (G.ADMM, 1, 4)])
+def test_friction_gear_model_vs_oracle(hvp, kind, nl, N):
+    """MpcGear variants: pwa_friction model with six discrete gears (mpcs/mpc_gear.py:30-135)."""
+    rng = np.random.default_rng(500 + kind * 3 + N)
+    B = 24
+    if kind == G.CENT:
+        x0, params = G.cent_cases(rng, B, nl, N, stress=True)
+        flags = 0
+    elif kind == G.ADMM:
+        x0, params = G.admm_cases(rng, B, N, stress=True)
+        flags = 0
+    else:
+        full = G.platoon_states(rng, B, 3, stress=True)
+        x0 = full[:, 1:2]
+        lead = x0[:, 0] + [30.0, 2.0]
+        params = np.concatenate([G.const_vel(a, N).reshape(B, -1) for a in (full[:, 0], full[:, 2], lead)], axis=1)
+        flags = 0
+    mpc = hvp.api.CompiledMpc(kind, N, n_local=nl, model=1, flags=flags)
+    assert mpc.n_modes == 12
+    r = mpc.solve(x0, 800.0, params)
+    ro = O.mpc_solve(kind, nl, N, x0, 800.0, params, model=1, flags=flags, method=0 if nl * N <= 6 else 1)
+    _compare(r, ro, f"gear kind={kind}")
+    ok = ro["status"] == 2
+    gears = mpc.gears(r["modes"])
+    assert ((gears[ok] >= 1) & (gears[ok] <= 6)).all()
+    # the chosen gear's window contains the predicted velocity (mpc_gear.py:101-110)
+    vl = np.array([3.94, 5.43, 7.56, 9.96, 13.70, 19.10]); vh = np.array([9.46, 13.04, 18.15, 23.90, 32.93, 45.84])
+    v = r["x"][:, :, 1, :N]
+    assert (v[ok] >= vl[gears[ok] - 1] - 1e-6).all() and (v[ok] <= vh[gears[ok] - 1] + 1e-6).all()
+
+
+def test_local_kind_matches_local_kernel(hvp):
+    """The compiled LOCAL formulation and the specialised per-vehicle kernel solve the same problem."""
+    from gen_cases import platoon_local_problems
+    rng = np.random.default_rng(77)
+    N, n = 6, 10
+    cs = platoon_local_problems(rng, 4, n, N, stress=True, hetero=True)
+    r = hvp.local_miqp(N, cs["flags"], cs["mass"], cs["x0"], cs["xf"], cs["xb"], cs["xl"])
+    for fl in np.unique(cs["flags"]):
+        sel = cs["flags"] == fl
+        mpc = hvp.api.CompiledMpc(G.LOCAL, N, flags=int(fl))
+        params = np.concatenate([cs[k][sel].reshape(sel.sum(), -1) for k in ("xf", "xb", "xl")], axis=1)
+        g = mpc.solve(cs["x0"][sel][:, None, :], cs["mass"][sel][:, None], params)
+        assert (g["status"] == r["status"][sel]).all()
+        ok = g["status"] == 2
+        assert np.allclose(g["obj"][ok], r["obj"][sel][ok], rtol=1e-9)
+        assert np.abs(g["u"][ok][:, 0] - r["u"][sel][ok]).max() < 1e-7
+
+
+def test_mpc_edge_cases(hvp):
+    mpc = hvp.api.CompiledMpc(G.CENT, 3, n_local=2)
+    # empty batch
+    r = mpc.solve(np.zeros((0, 2, 2)), np.zeros((0, 2)), np.zeros((0, mpc.n_param)))
+    assert r["obj"].shape == (0,)
+    # infeasible: initial velocity outside every region-reachable box
+    x0 = np.array([[[3000.0, 60.0], [2900.0, 20.0]]])
+    r = mpc.solve(x0, 800.0, np.zeros((1, mpc.n_param)))
+    assert r["status"][0] == 3 and np.isinf(r["obj"][0])
+    # bad descriptors
+    with pytest.raises(RuntimeError):
+        hvp.api.CompiledMpc(G.CENT, 3, n_local=2, leader_index=5)
+    with pytest.raises(RuntimeError):
+        hvp.api.CompiledMpc(G.EVENT, 3, n_local=3, n_front=1, n_behind=0)
+    with pytest.raises(RuntimeError):
+        hvp.api.CompiledMpc(99, 3)
