@@ -144,6 +144,18 @@ class CompiledMpc:
                                       p(extra), p(modes), p(obj), p(status), p(nodes), p(qp_iters),
                                       _stream_arg(stream)))
 
+    def eval_cost(self, mass, params, xg, ug):
+        """Cost of pinned guesses (fleet_event_based.py:308-327): xg (B,nl,2,N+1), ug (B,nl,N) -> (B,)."""
+        nl, N = self.n_local, self.N
+        xg = _c(xg, np.float64).reshape(-1, nl, 2, N + 1)
+        B = xg.shape[0]
+        ug = _c(ug, np.float64).reshape(B, nl, N)
+        mass = _c(np.broadcast_to(np.asarray(mass, dtype=np.float64), (B, nl)), np.float64)
+        params = _c(params, np.float64).reshape(B, self.n_param)
+        cost = np.empty(B)
+        check(lib().hvp_mpc_eval_host(self._h, B, _hp(mass), _hp(params), _hp(xg), _hp(ug), _hp(cost)))
+        return cost
+
     def gears(self, modes):
         """Gear (1..6) of each mode index (MpcGear.solve_mpc: argmax sigma + 1, mpc_gear.py:120-125)."""
         return self.mode_gear[np.clip(modes, 0, self.n_modes - 1)]

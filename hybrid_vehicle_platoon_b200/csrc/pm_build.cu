@@ -33,6 +33,8 @@ struct hvp_mpc {
     PmDev S;
     std::vector<void*> dev;     // device allocations owned by the handle
     unsigned long long* counter; // work-distribution counter of the kernel
+    double* x0buf = nullptr;     // scratch of hvp_mpc_eval_dev
+    size_t x0cap = 0;
 };
 
 namespace {
@@ -340,6 +342,7 @@ extern "C" int hvp_mpc_destroy(hvp_mpc* m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     for (void* p : m->dev) cudaFree(p);
+    if (m->x0buf) cudaFree(m->x0buf);
     delete m;
     return 0;
 }
@@ -511,6 +514,69 @@ extern "C" int hvp_mpc_solve_host(hvp_mpc* m, int64_t batch, const double* x0, c
     CUDA_TRY(cudaMemcpyAsync(status, dst, B * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(nodes, dno, B * 4, cudaMemcpyDeviceToHost, st));
     if (qp_iters) CUDA_TRY(cudaMemcpyAsync(qp_iters, dit, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// gathers the initial condition x0[b][i] = (xg[b][i][0][0], xg[b][i][1][0]) of an eval_cost guess
+__global__ void pm_gather_x0(int64_t total, int np1, const double* __restrict__ xg, double* __restrict__ x0) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // t = (b * nl + i) * 2 + row
+    if (t < total) x0[t] = xg[(size_t)t * np1];
+}
+
+extern "C" int hvp_mpc_eval_dev(hvp_mpc* m, int64_t batch, const double* mass, const double* params,
+                                const double* xg, const double* ug, double* cost, void* stream) {
+    if (!m) return fail(-1, "mpc_eval: handle is NULL");
+    if (batch < 0) return fail(-4, "mpc_eval: negative batch");
+    if (batch == 0) return 0;
+    if (!mass || !params || !xg || !ug || !cost) return fail(-1, "mpc_eval: NULL array argument");
+    hvp_ctx* c = m->ctx;
+    const PmDev& S = m->S;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    // scratch for the gathered initial conditions lives behind the handle (grow-only)
+    const size_t need = (size_t)batch * S.nl * 2 * sizeof(double);
+    if (need > m->x0cap) {
+        if (m->x0buf) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->x0buf)); m->x0buf = nullptr; m->x0cap = 0; }
+        CUDA_TRY(cudaMalloc(&m->x0buf, need + need / 2));
+        m->x0cap = need + need / 2;
+    }
+    const int64_t total = batch * S.nl * 2;
+    pm_gather_x0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, S.N + 1, xg, m->x0buf);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pm_eval(S, batch, m->x0buf, mass, params, xg, ug, cost, st));
+    c->launches += 2;
+    return 0;
+}
+
+extern "C" int hvp_mpc_eval_host(hvp_mpc* m, int64_t batch, const double* mass, const double* params,
+                                 const double* xg, const double* ug, double* cost) {
+    if (!m) return fail(-1, "mpc_eval: handle is NULL");
+    if (batch < 0) return fail(-4, "mpc_eval: negative batch");
+    if (batch == 0) return 0;
+    if (!mass || !params || !xg || !ug || !cost) return fail(-1, "mpc_eval: NULL array argument");
+    hvp_ctx* c = m->ctx;
+    const PmDev& S = m->S;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t B = (size_t)batch, nl = S.nl, N = S.N;
+    const size_t b_m = al256(B * nl * 8), b_p = al256(B * S.npar * 8), b_x = al256(B * nl * 2 * (N + 1) * 8);
+    const size_t b_u = al256(B * nl * N * 8), b_c = al256(B * 8);
+    int rc = hvp_ensure_dbuf(c, b_m + b_p + b_x + b_u + b_c);
+    if (rc) return rc;
+    char* q = c->dbuf;
+    double* dm = (double*)q; q += b_m;
+    double* dp = (double*)q; q += b_p;
+    double* dx = (double*)q; q += b_x;
+    double* du = (double*)q; q += b_u;
+    double* dc = (double*)q;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(dm, mass, B * nl * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dp, params, B * S.npar * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dx, xg, B * nl * 2 * (N + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(du, ug, B * nl * N * 8, cudaMemcpyHostToDevice, st));
+    rc = hvp_mpc_eval_dev(m, batch, dm, dp, dx, du, dc, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(cost, dc, B * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }

@@ -406,11 +406,11 @@ struct Warp {
         __syncwarp();
     }
 
-    // ---- SELECT: most violated row, or the node is solved --------------------------------------
-    __device__ void do_select() {
+    // most violated row of the node QP at x (rows already active have residual ~0); `soft` = also
+    // consider the L1-penalised rows (in their current orientation)
+    __device__ void scan(double& best_v, int& bid, double tol, bool soft) {
         const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
-        const double tol = 1e-9;
-        double best_v = tol; int bid = 0x7fffffff;
+        best_v = tol; bid = 0x7fffffff;
 #define PM_CAND(T, IDX, SV)                                                        \
     {                                                                              \
         const double s__ = (SV);                                                   \
@@ -461,33 +461,45 @@ struct Warp {
             }
         }
         LANES(r, ng) {
+            if (!soft && isfinite(S.wmax[r])) continue;
             const double s = dot2(S.AT + r, ng, x, nv) - bgen[r];
             PM_CAND(PT_GEN, r, orient[r] > 0 ? s : -s);
         }
 #undef PM_CAND
         wargmax(best_v, bid);
+    }
+
+    // objective of the node QP at x (tracking + input cost of the fixed stages + L1 penalties)
+    __device__ double objective() {
+        const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
+        double f = 0.0;
+        LANES(j, nv) {
+            const double s = dot2(S.H0 + (size_t)j * nv, 1, x, nv);
+            f += x[j] * (g0[j] + 0.5 * s);
+        }
+        LANES(d, L) {
+            const int i = d % nl, k = d / nl, jk = i * N + k;
+            const double xp = (k >= 1) ? x[jk - 1] : v0[i];
+            const double uu = (x[jk] - am[d] * xp - cm[d]) * rcp(bm[d]);
+            f += S.qu * uu * uu;
+        }
+        LANES(r, ng) {
+            const double wm = S.wmax[r];
+            if (isfinite(wm)) {
+                const double s = dot2(S.AT + r, ng, x, nv) - bgen[r];
+                if (s > 0.0) f += wm * s;
+            }
+        }
+        return c0 + wsum(f);
+    }
+
+    // ---- SELECT: most violated row, or the node is solved --------------------------------------
+    __device__ void do_select() {
+        const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
+        double best_v; int bid;
+        scan(best_v, bid, 1e-9, true);
         if (bid == 0x7fffffff) {
-            // ---- node solved: objective ----
-            double f = 0.0;
-            LANES(j, nv) {
-                const double s = dot2(S.H0 + (size_t)j * nv, 1, x, nv);
-                f += x[j] * (g0[j] + 0.5 * s);
-            }
-            LANES(d, L) {
-                const int i = d % nl, k = d / nl, jk = i * N + k;
-                const double xp = (k >= 1) ? x[jk - 1] : v0[i];
-                const double uu = (x[jk] - am[d] * xp - cm[d]) * rcp(bm[d]);
-                f += S.qu * uu * uu;
-            }
-            LANES(r, ng) {
-                const double wm = S.wmax[r];
-                if (isfinite(wm)) {
-                    const double s = dot2(S.AT + r, ng, x, nv) - bgen[r];
-                    if (s > 0.0) f += wm * s;
-                }
-            }
-            f = c0 + wsum(f);
-            node_done(0, f);
+            node_done(0, objective());
             return;
         }
         // a selected row can never already be active (active rows have residual ~1e-13 << tol)
@@ -662,6 +674,67 @@ struct Warp {
         }
     }
 
+    // ---- eval_cost: objective of a pinned (x[:, :N], u) guess, +inf if it is not feasible for the
+    // MLD model within Gurobi's feasibility tolerance (fleet_event_based.py:308-327).  The modes are
+    // whatever makes the pinned data consistent; the free last state follows from the dynamics, with
+    // the cheaper mode when the last pinned velocity sits on a region boundary.
+    __device__ double eval(const double* xg, const double* ug) {
+        const int nl = S.nl, N = S.N, np1 = N + 1;
+        const double tol = 1e-6;
+        if (state == PS_DONE) return HUGE_VAL;                    // constant rows already infeasible
+        bool bad = false;
+        int c0m = -1, c1m = -1;                                   // candidate modes of the last stage (lane = vehicle)
+        LANES(i, nl) {
+            const double* xp = xg + (size_t)i * 2 * np1;
+            const double* xv = xp + np1;
+            _Pragma("unroll 1")
+            for (int k = 0; k < N; ++k) {
+                const double v = xv[k], uu = ug[i * N + k];
+                if (k + 1 < N && fabs(xp[k + 1] - (xp[k] + v)) > tol) bad = true;
+                int found = -1, found2 = -1;
+                _Pragma("unroll 1")
+                for (int r = 0; r < S.M.R; ++r) {
+                    if (!(v >= S.M.lo[r] - tol && v <= S.M.hi[r] + tol)) continue;
+                    if (k + 1 < N && fabs(xv[k + 1] - (ma(i, r) * v + mc(i, r) + mb(i, r) * uu)) > tol) continue;
+                    if (found < 0) found = r; else if (found2 < 0) found2 = r;
+                }
+                if (found < 0) { bad = true; found = 0; }
+                modes[k * nl + i] = found;
+                if (k + 1 < N) x[i * N + k] = xv[k + 1];
+                else { c0m = found; c1m = found2; }
+            }
+        }
+        if (__any_sync(FULL, bad)) return HUGE_VAL;
+        L = S.depth;
+        LANES(r, S.ng) orient[r] = 1;
+        double bestf = HUGE_VAL;
+        _Pragma("unroll 1")
+        for (int mask = 0; mask < (1 << nl); ++mask) {
+            bool skip = false;
+            LANES(i, nl) {
+                const int r = ((mask >> i) & 1) ? c1m : c0m;
+                if (r < 0) skip = true;
+                else {
+                    const double v = xg[(size_t)i * 2 * np1 + np1 + N - 1], uu = ug[i * N + N - 1];
+                    modes[(N - 1) * nl + i] = r;
+                    x[i * N + N - 1] = ma(i, r) * v + mc(i, r) + mb(i, r) * uu;
+                }
+            }
+            if (__any_sync(FULL, skip)) continue;
+            __syncwarp();
+            LANES(d, L) {
+                const int i = d % nl, r = modes[d];
+                am[d] = ma(i, r); bm[d] = mb(i, r); cm[d] = mc(i, r);
+            }
+            __syncwarp();
+            double bv; int bid;
+            scan(bv, bid, tol, false);
+            if (bid == 0x7fffffff) bestf = fmin(bestf, objective());
+            __syncwarp();
+        }
+        return bestf;
+    }
+
     __device__ void finish(double* u_out, double* x_out, double* e_out, int32_t* m_out, double* obj,
                            int32_t* status, int32_t* nodes_out, int32_t* iters_out) {
         const int nl = S.nl, N = S.N, np1 = N + 1;
@@ -731,6 +804,23 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
     }
 }
 
+__global__ void __launch_bounds__(128)
+pm_eval_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __restrict__ x0,
+               const double* __restrict__ mass, const double* __restrict__ params,
+               const double* __restrict__ xg, const double* __restrict__ ug, double* __restrict__ cost) {
+    extern __shared__ double pm_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
+    Warp W(S, base, lane);
+    const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
+    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < batch; i += (int64_t)gridDim.x * wpb) {
+        W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar, nullptr);
+        const double f = W.eval(xg + sx * i, ug + su * i);
+        if (lane == 0) cost[i] = f;
+        __syncwarp();
+    }
+}
+
 // per-warp shared-memory carve-up
 void pm_layout(PmDev& S) {
     const int nv = S.nv, D = S.depth;
@@ -778,6 +868,25 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
     if (e != cudaSuccess) return e;
     pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, u, x,
                                                                  extra, modes, obj, status, nodes, qp_iters, counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pm_eval(const PmDev& S, int64_t batch, const double* x0, const double* mass,
+                           const double* params, const double* xg, const double* ug, double* cost,
+                           cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    int wpb = 4;
+    while (wpb > 1 && (size_t)wpb * S.smem_bytes > 200 * 1024) wpb >>= 1;
+    const size_t smem = (size_t)wpb * S.smem_bytes;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(pm_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = smem;
+    }
+    int64_t blocks = (batch + wpb - 1) / wpb;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pm_eval_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, xg, ug, cost);
     return cudaGetLastError();
 }
 

@@ -191,6 +191,15 @@ int hvp_mpc_solve_host(hvp_mpc* mpc, int64_t batch, const double* x0, const doub
                        const int32_t* fixed_modes, double* u, double* x, double* extra, int32_t* modes,
                        double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters);
 
+/* eval_cost of the event-based LocalMpc (fleet_event_based.py:308-327): cost of a guess with x[:, :N]
+ * and u pinned -- xg [batch][n_local][2][N+1] (column N is ignored: the last state is free),
+ * ug [batch][n_local][N]; the initial condition is xg[..., 0].  cost [batch] = objVal, +inf if the guess
+ * is infeasible for the MLD model (tolerance 1e-6 = Gurobi's FeasibilityTol). */
+int hvp_mpc_eval_dev(hvp_mpc* mpc, int64_t batch, const double* mass, const double* params, const double* xg,
+                     const double* ug, double* cost, void* stream);
+int hvp_mpc_eval_host(hvp_mpc* mpc, int64_t batch, const double* mass, const double* params, const double* xg,
+                      const double* ug, double* cost);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------
  * FP64 FMA issue peak of the device: `iters` dependent-chain FMAs x 8 independent chains per
  * thread over a full grid; returns achieved TFLOP/s (2 flop per FMA) in *tflops. */

@@ -150,3 +150,65 @@ def test_mpc_edge_cases(hvp):
         hvp.api.CompiledMpc(G.EVENT, 3, n_local=3, n_front=1, n_behind=0)
     with pytest.raises(RuntimeError):
         hvp.api.CompiledMpc(99, 3)
+
+
+def _oracle_eval(kind, nl, N, mass, params, xg, ug, tol=1e-6, **kw):
+    """Independent restatement of eval_cost (fleet_event_based.py:308-327) on the oracle's dense
+    input-space QP: modes from consistency of the pinned data, objective + L1 penalties at u."""
+    a, b, c, lo, hi, _ = O.mode_table(kw.get("model", 0), mass)
+    R = len(a)
+    cands = []
+    for i in range(nl):
+        row = []
+        for k in range(N):
+            v = xg[i, 1, k]
+            ok = [r for r in range(R) if lo[r] - tol <= v <= hi[r] + tol and
+                  (k == N - 1 or abs(xg[i, 1, k + 1] - (a[r] * v + b[r] * ug[i, k] + c[r])) <= tol)]
+            if k < N - 1 and abs(xg[i, 0, k + 1] - xg[i, 0, k] - v) > tol:
+                return np.inf
+            if not ok:
+                return np.inf
+            row.append(ok if k == N - 1 else ok[:1])
+        cands.append(row)
+    import itertools
+    best = np.inf
+    for last in itertools.product(*[cands[i][N - 1] for i in range(nl)]):
+        modes = np.array([[cands[i][k][0] for k in range(N - 1)] + [last[i]] for i in range(nl)], np.int32)
+        q = O.mpc_build_qp(kind, nl, N, xg[:, :, 0], mass, params, modes, **kw)
+        if q is None:
+            continue
+        H, g, c0, A, bb, w = q
+        z = ug.reshape(-1)
+        s = A @ z - bb
+        hard = ~np.isfinite(w)
+        if (s[hard] > tol).any():
+            continue
+        f = 0.5 * z @ H @ z + g @ z + c0 + (w[~hard] * np.maximum(s[~hard], 0)).sum()
+        best = min(best, f)
+    return best
+
+
+def test_event_eval_cost_vs_oracle(hvp):
+    rng = np.random.default_rng(600)
+    N, nf, nb, nl = 5, 2, 1, 3
+    B = 24
+    x0, params = G.event_cases(rng, B, nf, nb, N, stress=True)
+    mpc = hvp.api.CompiledMpc(G.EVENT, N, n_local=nl, leader_index=0, n_front=nf, n_behind=nb)
+    r = mpc.solve(x0, 800.0, params)
+    ok = r["status"] == 2
+    # (1) the optimal solution itself: eval_cost reproduces the optimal objective
+    c = mpc.eval_cost(800.0, params, r["x"], r["u"])
+    assert np.allclose(c[ok], r["obj"][ok], rtol=1e-9)
+    # (2) shifted guesses (drop column 0, repeat the last: fleet_event_based.py:591-603)
+    xs = np.concatenate([r["x"][..., 1:], r["x"][..., -1:]], axis=-1)
+    us = np.concatenate([r["u"][..., 1:], r["u"][..., -1:]], axis=-1)
+    c = mpc.eval_cost(800.0, params, xs, us)
+    co = np.array([_oracle_eval(O.EVENT, nl, N, 800.0, params[i], xs[i], us[i], leader_index=0, n_front=nf,
+                                n_behind=nb) if ok[i] else np.inf for i in range(B)])
+    fin = np.isfinite(co)
+    assert (np.isfinite(c[ok]) == fin[ok]).all()
+    assert np.allclose(c[ok & fin], co[ok & fin], rtol=1e-9)
+    assert fin.sum() >= 3
+    # (3) an inconsistent guess is infeasible
+    xbad = r["x"].copy(); xbad[:, 0, 1, 2] += 0.5
+    assert np.isinf(mpc.eval_cost(800.0, params, xbad, r["u"])).all()
