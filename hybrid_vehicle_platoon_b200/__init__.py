@@ -5,7 +5,7 @@ branch-and-bound kernel behind a C ABI (include/hvp.h), with reference-shaped Py
 from . import _lib  # noqa: F401
 from ._lib import FRONT, LEADER, TRAILER, Context, default_context  # noqa: F401
 from .api import (  # noqa: F401
-    env_desc, local_desc, local_miqp, local_miqp_device, microbench_fp64, rollout_step,
+    CompiledMpc, env_desc, local_desc, local_miqp, local_miqp_device, microbench_fp64, rollout_step,
     rollout_step_device,
 )
 
@@ -19,5 +19,11 @@ from .misc import (  # noqa: F401,E402
     ConstantSpacingPolicy, ConstantTimePolicy, ConstantVelocityLeaderTrajectory, Params, Sim, Sim_n_task_1,
     Sim_n_task_2, StopAndGoLeaderTrajectory,
 )
-from .models import Platoon, PwaGearVehicle, Vehicle  # noqa: F401,E402
-from .mpc import LocalMpcMld, solve_local_batch  # noqa: F401,E402
+from .models import Platoon, PwaFrictionVehicle, PwaGearVehicle, Vehicle  # noqa: F401,E402
+from .mpc import (  # noqa: F401,E402
+    EventLocalMpc, GAdmmLocalMpc, LocalMpcADMM, LocalMpcGear, LocalMpcMld, MpcGearCent, MpcMldCent,
+    eval_compiled_batch, solve_compiled_batch, solve_local_batch,
+)
+from . import (  # noqa: F401,E402
+    fleet_cent_mld, fleet_decent_mld, fleet_event_based, fleet_g_admm, fleet_naive_admm, fleet_seq_mld,
+)

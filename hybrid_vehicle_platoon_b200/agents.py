@@ -13,7 +13,7 @@ from collections import deque
 import numpy as np
 
 from .misc import Params
-from .mpc import LocalMpcMld, solve_local_batch
+from .mpc import LocalMpcGear, LocalMpcMld, _CompiledController, solve_compiled_batch, solve_local_batch
 
 
 # ---- env wrappers ---------------------------------------------------------------------------
@@ -137,6 +137,20 @@ class MldAgent:
     def on_episode_end(self, env, episode, rewards): pass
 
 
+def _solve_batch(mpcs, states):
+    """All local problems of one wave in as few launches as possible."""
+    if isinstance(mpcs[0], _CompiledController):
+        return solve_compiled_batch(mpcs, states)
+    return solve_local_batch(mpcs, states)
+
+
+def _stack_controls(u, nu_l=1):
+    """[u_g ; gear] per vehicle -> all throttles, then all gears (fleet_decent_mld.py:317-326)."""
+    if u[0].shape[0] > nu_l:
+        return np.vstack((np.vstack([ui[:nu_l, :] for ui in u]), np.vstack([ui[nu_l:, :] for ui in u])))
+    return np.vstack(u)
+
+
 def _extrapolate_constant_vel(p, v, N, ts):
     """fleet_decent_mld.py:421-428: p_{k+1} = p_k + ts*v_k (sequential sums), v constant."""
     x = np.zeros((2, N + 1))
@@ -174,10 +188,10 @@ class TrackingDecentMldCoordinator(MldAgent):
 
     def get_control(self, state):
         x_l = np.split(np.asarray(state, dtype=np.float64), self.n, axis=0)
-        res = solve_local_batch([a.mpc for a in self.agents], x_l)
+        res = _solve_batch([a.mpc for a in self.agents], x_l)
         for a, (_, info) in zip(self.agents, res):
             a._store(info)
-        return np.vstack([u for u, _ in res]), {}
+        return _stack_controls([u for u, _ in res]), {}
 
     def on_timestep_end(self, env, episode, timestep) -> None:
         self.agents[self.leader_index].mpc.set_leader_x(self.leader_x[:, timestep:timestep + self.N + 1])
@@ -255,7 +269,7 @@ class TrackingSequentialMldCoordinator(MldAgent):
                 if xb is not None:
                     ag[i].mpc.set_x_back(xb)
             u[i], _ = ag[i].get_control(x_l[i])
-        return np.vstack(u), {}
+        return _stack_controls(u), {}
 
     def on_timestep_end(self, env, episode, timestep) -> None:
         self.agents[self.leader_index].mpc.set_leader_x(self.leader_x[:, timestep:timestep + self.N + 1])
@@ -282,6 +296,8 @@ def simulate(sim, controller: str = "decent", seed: int = 2, leader_index: int =
     from .env import PlatoonEnv
     from .models import Platoon
     env_class = env_class or PlatoonEnv
+    if sim.vehicle_model_type == "pwa_friction" and mpc_class is LocalMpcMld:
+        mpc_class = LocalMpcGear              # fleet_decent_mld.py:497-505: the model type picks the MPC class
     n, N, ts = sim.n, sim.N, Params.ts
     ep_len = ep_len or sim.ep_len
     leader_x = sim.leader_trajectory.get_leader_trajectory()
