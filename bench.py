@@ -110,6 +110,69 @@ def cpu_reference_leg(scenarios_hint, budget_s=12.0):
             "leaves_per_solve": float(r["leaves"].mean())}, dt, scen
 
 
+def compiled_mpc_legs(hvp, torch, dev, stream, flush, steps=5, with_cpu=True):
+    """BASELINE.json configs[0] and configs[2] on the compiled-MPC kernel (pm_kernel.cu): centralized
+    MIQP n=3,N=5; naive-ADMM local MIQPs N=8; g-ADMM fixed-mode QPs N=8 -- device-timed, inputs in HBM."""
+    import gen_mpc_cases as G
+    from oracle import oracle as O
+    rng = np.random.default_rng(1234 + 2)
+    legs = {}
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+
+    def run(name, mpc, x0, params, fm=None, cpu=None):
+        B, nl, N = x0.shape[0], mpc.n_local, mpc.N
+        dx0, dm, dp = t(x0), t(np.full((B, nl), 800.0)), t(params)
+        dfm = None if fm is None else t(fm, torch.int32)
+        u = torch.empty(B, nl, N, dtype=torch.float64, device=dev)
+        x = torch.empty(B, nl, 2, N + 1, dtype=torch.float64, device=dev)
+        ex = torch.empty(B, max(mpc.n_extra, 1), dtype=torch.float64, device=dev)
+        mo = torch.empty(B, nl, N, dtype=torch.int32, device=dev)
+        ob = torch.empty(B, dtype=torch.float64, device=dev)
+        st = torch.empty(B, dtype=torch.int32, device=dev)
+        no = torch.empty(B, dtype=torch.int32, device=dev)
+        it = torch.empty(B, dtype=torch.int32, device=dev)
+        ms = []
+        for i in range(2 + steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            mpc.solve_device(B, dx0, dm, dp, dfm, u, x, ex, mo, ob, st, no, it, stream=stream)
+            b.record()
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(a.elapsed_time(b))
+        leg = {"value": B / (np.mean(ms) * 1e-3), "unit": "solves/s", "batch": B, "ms_per_launch": float(np.mean(ms)),
+               "variables": mpc.n_var, "nodes_per_solve": float(no.double().mean()),
+               "qp_iters_per_solve": float(it.double().mean()), "optimal_frac": float((st == 2).double().mean())}
+        if cpu is not None and with_cpu:
+            t0 = time.perf_counter()
+            cpu()
+            leg["cpu_port_solves_per_s"] = cpu.count / (time.perf_counter() - t0)
+            leg["cpu_port"] = f"oracle branch-and-bound + exact QP, OpenMP over {O.max_threads()} threads, {cpu.count} problems"
+        legs[name] = leg
+
+    class _Cpu:
+        def __init__(self, count, fn):
+            self.count, self.fn = count, fn
+
+        def __call__(self):
+            self.fn(self.count)
+
+    B = 16384
+    x0, params = G.cent_cases(rng, B, 3, 5)
+    run("cent_n3_N5 (configs[0]: MpcMldCent MIQP)", hvp.api.CompiledMpc(G.CENT, 5, n_local=3), x0, params,
+        cpu=_Cpu(512, lambda c: O.mpc_solve(O.CENT, 3, 5, x0[:c], 800.0, params[:c], method=1)))
+    x0, params = G.admm_cases(rng, B, 8)
+    run("naive_admm_local_N8 (configs[2]: LocalMpcADMM MIQP, interior vehicle)", hvp.api.CompiledMpc(G.ADMM, 8, rho=0.5),
+        x0, params, cpu=_Cpu(512, lambda c: O.mpc_solve(O.ADMM, 1, 8, x0[:c], 800.0, params[:c], rho=0.5, method=1)))
+    x0, params, fm = G.gadmm_cases(rng, 4 * B, 1, 1, 8)
+    run("g_admm_fixed_mode_qp_N8 (configs[2]: local fixed-mode QPs per ADMM round)",
+        hvp.api.CompiledMpc(G.GADMM, 8, n_front=1, n_behind=1, rho=0.5), x0, params, fm=fm,
+        cpu=_Cpu(4096, lambda c: O.mpc_solve(O.GADMM, 1, 8, x0[:c], 800.0, params[:c], n_front=1, n_behind=1, rho=0.5,
+                                             fixed_modes=fm[:c])))
+    return legs
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -338,6 +401,7 @@ def main():
         cpu = None
         if not args.no_cpu:
             cpu, _, _ = cpu_reference_leg(S, budget_s=12.0)
+        other = compiled_mpc_legs(hvp, torch, dev, stream, flush, with_cpu=not args.no_cpu)
 
         out = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
@@ -357,7 +421,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
                          "algorithmic_bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
-                         "kernel": "coop_miqp_kernel<8>",
+                         "kernel": "flat_miqp_kernel<6>",
                          "note": "on-chip FP64 branch-and-bound: HBM traffic is parameters in + solution "
                                  "out only, so the HBM fraction is small by construction; see fp64_pipe"},
             "fp64_pipe": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,
@@ -368,6 +432,7 @@ def main():
                         "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                         "samples": int(lat.size)},
             "rollout": rollout,
+            "other_configs": other,
             "cpu_baseline": cpu,
         }
     if world > 1:

@@ -73,7 +73,7 @@ struct FlatSolver {
     const double* xb_;
     double* best_;                      // incumbent velocities go straight to the output trajectory
     // cold per-problem arrays (touched once per node): thread-local memory
-    double gt[N], xstar[N], rlo[N + 1], rhi[N + 1];
+    double gt[N], xstar[N], rlo[N + 1], rhi[N + 1], amax[N], amin[N];
     double p0, v0, pc, inv_m, a_lo, a_hi, c_lo, c_hi, hw1, hw2, hd, ct;
     bool has_sf, has_sb;
     // branch and bound
@@ -89,6 +89,7 @@ struct FlatSolver {
     // constraint being added
     int pid, pkind, pj;
     double psgn, pcoef, nHn, lam_p, cp;
+    double dual;                                         // value of the node's dual function (lower bound)
     bool p_soft;
 
     HVP_HD double& w(int off, int i) const { return W[(size_t)(off + i) * ST]; }
@@ -226,8 +227,36 @@ struct FlatSolver {
             if (pc > P->pmax + eps || pc < P->pmin - eps) continue;
             rlo[lev + 1] = nlo - eps; rhi[lev + 1] = nhi + eps;
             L = lev + 1;
+            if (P->hull) hull();
             state = S_BUILD;
             return;
+        }
+    }
+
+    // Interval reachability of the stages that are not fixed yet: hull over the PWA regions of the
+    // velocity interval and of the acceleration the traction / braking allows, stage by stage.  Every
+    // completion of the node's region prefix satisfies these bounds, so the relaxation may impose them.
+    HVP_HD void hull() {
+        const double eps = 1e-9;
+        double lo = rlo[L], hi = rhi[L];
+        HVP_ROLL
+        for (int s = L; s < N; ++s) {
+            double nlo = HUGE_VAL, nhi = -HUGE_VAL, dmax = -HUGE_VAL, dmin = HUGE_VAL;
+            HVP_ROLL
+            for (int r = 0; r < NREG; ++r) {
+                const double jlo = fmax(lo, P->edge[r]), jhi = fmin(hi, P->edge[r + 1]);
+                if (jlo > jhi + eps) continue;
+                const double a = ra(r), b = rb(r), c = rc(r);
+                nlo = fmin(nlo, a * jlo + c + b * P->umin);
+                nhi = fmax(nhi, a * jhi + c + b * P->umax);
+                dmax = fmax(dmax, (a - 1.0) * jlo + c + b * P->umax);
+                dmin = fmin(dmin, (a - 1.0) * jhi + c + b * P->umin);
+            }
+            const double acc = P->a_acc - s * P->tight, dec = P->a_dec + s * P->tight;
+            amax[s] = fmin(dmax + eps, acc); amin[s] = fmax(dmin - eps, dec);
+            nlo = fmax(fmax(nlo, lo + dec), P->vmin); nhi = fmin(fmin(nhi, hi + acc), P->vmax);
+            lo = nlo - eps; hi = nhi + eps;
+            rlo[s + 1] = lo; rhi[s + 1] = hi;
         }
     }
 
@@ -289,6 +318,7 @@ struct FlatSolver {
         // gradient g = gt + input-cost terms (into O_D), then x = -H^-1 g
         HVP_ROLL
         for (int i = 0; i < N; ++i) w(LY::O_D, i) = gt[i];
+        dual = ct;
         HVP_ROLL
         for (int k = 0; k < L; ++k) {
             const int rg = mode(k);
@@ -296,6 +326,7 @@ struct FlatSolver {
             const double kc = (k == 0) ? -(ra(rg) * v0 + rc(rg)) * ib : -rc(rg) * ib;
             w(LY::O_D, k) += 2.0 * qu * kc * ib;
             if (k >= 1) w(LY::O_D, k - 1) += 2.0 * qu * kc * ea;
+            dual += qu * kc * kc;
         }
         HVP_ROLL
         for (int i = 0; i < N; ++i) {
@@ -303,6 +334,7 @@ struct FlatSolver {
             HVP_ROLL
             for (int j = 0; j < N; ++j) s -= w(LY::O_HINV, i * N + j) * w(LY::O_D, j);
             w(LY::O_X, i) = s;
+            dual += 0.5 * w(LY::O_D, i) * s;      // objective at the unconstrained minimiser: c + g'x/2
         }
         it = 0; q = 0; satf = 0; satb = 0; act_lo = act_hi = 0;
         state = S_SELECT;
@@ -311,6 +343,7 @@ struct FlatSolver {
     // merged simple bounds of x_j = v_{j+1}: state box, region of stage j+1 if fixed, stage-0 rows
     HVP_HD void bounds(int j, double& lo, double& hi) const {
         lo = P->vmin; hi = P->vmax;
+        if (P->hull && j >= L) { lo = fmax(lo, rlo[j + 1]); hi = fmin(hi, rhi[j + 1]); }
         if (j + 1 < L) {
             const int rg = mode(j + 1);
             lo = fmax(lo, P->edge[rg]); hi = fmin(hi, P->edge[rg + 1]);
@@ -349,8 +382,8 @@ struct FlatSolver {
                     HVP_CAND(T_ULO, j, bb * P->umin - du);
                 }
                 const double dv = xv - xm;
-                HVP_CAND(T_ACC, j, dv - (P->a_acc - j * P->tight));
-                HVP_CAND(T_DEC, j, (P->a_dec + j * P->tight) - dv);
+                HVP_CAND(T_ACC, j, dv - ((j < L || !P->hull) ? P->a_acc - j * P->tight : amax[j]));
+                HVP_CAND(T_DEC, j, ((j < L || !P->hull) ? P->a_dec + j * P->tight : amin[j]) - dv);
                 if (has_sf) {
                     const double s = PS - sf(j);
                     HVP_CAND(T_SF, j, ((satf >> j) & 1u) ? -s : s);
@@ -486,6 +519,10 @@ struct FlatSolver {
         const double t3p = p_soft ? (ww - lam_p) : INF;
         const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
         if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
+        // the dual value grows by the violation of p integrated along the step; it bounds the node
+        // optimum from below, so a node whose dual passes the incumbent is finished
+        dual += t * cp - (dependent ? 0.0 : 0.5 * t * t * nz);
+        if (dual > inc) { node_done(1, 0.0); return; }
         if (!dependent) {
             // w = n_p - N r ;  x -= t H^-1 w ;  the violation of p shrinks by t * nz
             HVP_ROLL

@@ -44,6 +44,7 @@ constexpr int NREG = 7;
 struct LocalParams {
     int N;
     int max_nodes;
+    int hull;                            // flat kernel: interval-hull tightening of the unfixed stages
     double d0, t0, tight;
     double qxp, qxv, qu, w;              // Params.Q_x, Q_u, w (common_controller_params.py:14-23)
     double a_acc, a_dec, d_safe;
