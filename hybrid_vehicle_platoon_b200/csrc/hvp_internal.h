@@ -52,8 +52,10 @@ cudaError_t launch_rollout(const RolloutParams& P, int64_t batch, const double* 
                            double* cost, uint8_t* viol, int32_t* err, cudaStream_t stream);
 
 void pm_layout(PmDev& S);
+cudaError_t launch_pm_precompute(const PmDev& S, int64_t batch, const double* x0, const double* params, double* Y,
+                                 cudaStream_t stream);
 cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
-                           const double* params, const int32_t* fixed_modes, double* u, double* x,
+                           const double* params, const int32_t* fixed_modes, const double* Y, double* u, double* x,
                            double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                            int32_t* qp_iters, unsigned long long* counter, cudaStream_t stream);
 cudaError_t launch_pm_eval(const PmDev& S, int64_t batch, const double* x0, const double* mass,

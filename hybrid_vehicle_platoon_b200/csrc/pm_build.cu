@@ -35,6 +35,8 @@ struct hvp_mpc {
     unsigned long long* counter; // work-distribution counter of the kernel
     double* x0buf = nullptr;     // scratch of hvp_mpc_eval_dev
     size_t x0cap = 0;
+    double* ybuf = nullptr;      // output of the tensor-core precompute, [batch][mw]
+    size_t ycap = 0;
 };
 
 namespace {
@@ -343,6 +345,7 @@ extern "C" int hvp_mpc_destroy(hvp_mpc* m) {
     cudaStreamSynchronize(m->ctx->stream);
     for (void* p : m->dev) cudaFree(p);
     if (m->x0buf) cudaFree(m->x0buf);
+    if (m->ybuf) cudaFree(m->ybuf);
     delete m;
     return 0;
 }
@@ -410,6 +413,33 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
         for (int t = 0; t < npv; ++t) B0[(size_t)g * npv + t] = e.p[t];
         w0[g] = B.wmax[cst[g]];
     }
+    // stacked matrix of the tensor-core precompute (pm_types.h)
+    {
+        const int nres = S.nres, nlin = S.nlin;
+        S.kw = (npv + 3) / 4 * 4;
+        S.mw = (nv + S.ng + S.n0 + npv + 7) / 8 * 8;
+        std::vector<double> Wm((size_t)S.mw * S.kw, 0.0);
+        for (int j = 0; j < nv; ++j)
+            for (int t = 0; t < npv; ++t) {
+                double s = 0.0;
+                for (int r = 0; r < nres; ++r) s += RW2[(size_t)j * nres + r] * Cres[(size_t)r * npv + t];
+                for (int l = 0; l < nlin; ++l) s += Lz[(size_t)l * nv + j] * La[(size_t)l * npv + t];
+                Wm[(size_t)j * S.kw + t] = s;
+            }
+        for (int g = 0; g < S.ng; ++g)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)(nv + g) * S.kw + t] = BR[(size_t)g * npv + t];
+        for (int g = 0; g < S.n0; ++g)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)(nv + S.ng + g) * S.kw + t] = B0[(size_t)g * npv + t];
+        for (int a = 0; a < npv; ++a)
+            for (int t = 0; t < npv; ++t) {
+                double s = 0.0;
+                for (int r = 0; r < nres; ++r) s += wres[r] * Cres[(size_t)r * npv + a] * Cres[(size_t)r * npv + t];
+                for (int l = 0; l < nlin; ++l) s += La[(size_t)l * npv + a] * Lp[(size_t)l * npv + t];
+                Wm[(size_t)(nv + S.ng + S.n0 + a) * S.kw + t] = s;
+            }
+        rc = upload(m, Wm, &S.W);
+        if (rc) { delete Bp; hvp_mpc_destroy(m); return rc; }
+    }
     delete Bp;
     pm_layout(S);
     if (S.smem_bytes > 220 * 1024) { delete m; return fail(-4, "mpc_create: problem needs %d bytes of shared memory per warp", S.smem_bytes); }
@@ -455,12 +485,19 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
     hvp_ctx* c = m->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const size_t need = (size_t)batch * m->S.mw * sizeof(double);
+    if (need > m->ycap) {
+        if (m->ybuf) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->ybuf)); m->ybuf = nullptr; m->ycap = 0; }
+        CUDA_TRY(cudaMalloc(&m->ybuf, need + need / 4));
+        m->ycap = need + need / 4;
+    }
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    CUDA_TRY(launch_pm_miqp(m->S, batch, x0, mass, params, fixed_modes, u, x, extra, modes, obj, status, nodes,
-                            qp_iters, m->counter, st));
+    CUDA_TRY(launch_pm_precompute(m->S, batch, x0, params, m->ybuf, st));
+    CUDA_TRY(launch_pm_miqp(m->S, batch, x0, mass, params, fixed_modes, m->ybuf, u, x, extra, modes, obj, status,
+                            nodes, qp_iters, m->counter, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
-    c->launches += 1;
+    c->launches += 2;
     return 0;
 }
 

@@ -121,7 +121,8 @@ struct Warp {
     __device__ __forceinline__ double mc(int i, int r) const { return -S.M.mug - S.M.dd[r] * inv_m[i]; }
 
     // ---- per-problem setup --------------------------------------------------------------------
-    __device__ void setup(const double* x0, const double* mass, const double* params, const int32_t* fm) {
+    __device__ void setup(const double* x0, const double* mass, const double* params, const int32_t* fm,
+                          const double* Y = nullptr) {
         const int nl = S.nl, N = S.N, nv = S.nv, npv = S.npv;
         LANES(t, 2 * nl) pvec[t] = x0[t];
         LANES(t, S.npar) pvec[2 * nl + t] = params[t];
@@ -134,39 +135,53 @@ struct Warp {
             rhi[i * (N + 1)] = x0[2 * i + 1];
         }
         __syncwarp();
-        // residual constants, param-linear factors, generic right-hand sides, constant rows
         double c = 0.0;
         bool infeas = false;
-        LANES(r, S.nres) {
-            double s = 0.0;
-            _Pragma("unroll 1")
-            for (int t = 0; t < npv; ++t) s += S.Cres[(size_t)r * npv + t] * pvec[t];
-            cres[r] = s;
-            c += S.wres[r] * s * s;
-        }
-        LANES(l, S.nlin) {
-            double a = 0.0, p = 0.0;
-            _Pragma("unroll 1")
-            for (int t = 0; t < npv; ++t) {
-                a += S.La[(size_t)l * npv + t] * pvec[t];
-                p += S.Lp[(size_t)l * npv + t] * pvec[t];
+        if (Y) {
+            // products with the shared structure matrices were done on the tensor cores (pm_precompute_kernel)
+            LANES(j, nv) g0[j] = Y[j];
+            LANES(r, S.ng) bgen[r] = Y[nv + r];
+            LANES(r, S.n0) {
+                const double s = Y[nv + S.ng + r];
+                if (s > 0.0) {
+                    if (isfinite(S.w0[r])) c += S.w0[r] * s;
+                    else if (s > 1e-9) infeas = true;
+                }
             }
-            cres[S.nres + l] = a;
-            c += a * p;
-        }
-        LANES(r, S.ng) {
-            double s = 0.0;
-            _Pragma("unroll 1")
-            for (int t = 0; t < npv; ++t) s += S.BR[(size_t)r * npv + t] * pvec[t];
-            bgen[r] = s;
-        }
-        LANES(r, S.n0) {
-            double s = 0.0;
-            _Pragma("unroll 1")
-            for (int t = 0; t < npv; ++t) s += S.B0[(size_t)r * npv + t] * pvec[t];
-            if (s > 0.0) {
-                if (isfinite(S.w0[r])) c += S.w0[r] * s;
-                else if (s > 1e-9) infeas = true;
+            LANES(t, npv) c += pvec[t] * Y[nv + S.ng + S.n0 + t];
+        } else {
+            // residual constants, param-linear factors, generic right-hand sides, constant rows
+            LANES(r, S.nres) {
+                double s = 0.0;
+                _Pragma("unroll 4")
+                for (int t = 0; t < npv; ++t) s += S.Cres[(size_t)r * npv + t] * pvec[t];
+                cres[r] = s;
+                c += S.wres[r] * s * s;
+            }
+            LANES(l, S.nlin) {
+                double a = 0.0, p = 0.0;
+                _Pragma("unroll 4")
+                for (int t = 0; t < npv; ++t) {
+                    a += S.La[(size_t)l * npv + t] * pvec[t];
+                    p += S.Lp[(size_t)l * npv + t] * pvec[t];
+                }
+                cres[S.nres + l] = a;
+                c += a * p;
+            }
+            LANES(r, S.ng) {
+                double s = 0.0;
+                _Pragma("unroll 4")
+                for (int t = 0; t < npv; ++t) s += S.BR[(size_t)r * npv + t] * pvec[t];
+                bgen[r] = s;
+            }
+            LANES(r, S.n0) {
+                double s = 0.0;
+                _Pragma("unroll 4")
+                for (int t = 0; t < npv; ++t) s += S.B0[(size_t)r * npv + t] * pvec[t];
+                if (s > 0.0) {
+                    if (isfinite(S.w0[r])) c += S.w0[r] * s;
+                    else if (s > 1e-9) infeas = true;
+                }
             }
         }
         LANES(i, nl) {   // state row k = 1 on the (constant) position p_1 = p_0 + v_0
@@ -175,13 +190,15 @@ struct Warp {
         __syncwarp();
         c0 = wsum(c);
         infeas = __any_sync(FULL, infeas);
-        LANES(j, nv) {
-            double s = 0.0;
-            _Pragma("unroll 1")
-            for (int r = 0; r < S.nres; ++r) s += S.RW2[(size_t)j * S.nres + r] * cres[r];
-            _Pragma("unroll 1")
-            for (int l = 0; l < S.nlin; ++l) s += S.Lz[(size_t)l * nv + j] * cres[S.nres + l];
-            g0[j] = s;
+        if (!Y) {
+            LANES(j, nv) {
+                double s = 0.0;
+                _Pragma("unroll 4")
+                for (int r = 0; r < S.nres; ++r) s += S.RW2[(size_t)j * S.nres + r] * cres[r];
+                _Pragma("unroll 4")
+                for (int l = 0; l < S.nlin; ++l) s += S.Lz[(size_t)l * nv + j] * cres[S.nres + l];
+                g0[j] = s;
+            }
         }
         built_L = -1;                      // H^-1 not loaded yet
         iters = nodes = it = q = 0;
@@ -780,8 +797,8 @@ struct Warp {
 __global__ void __launch_bounds__(128)
 pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __restrict__ x0,
                const double* __restrict__ mass, const double* __restrict__ params,
-               const int32_t* __restrict__ fixed_modes, double* __restrict__ u, double* __restrict__ x,
-               double* __restrict__ extra, int32_t* __restrict__ modes, double* __restrict__ obj,
+               const int32_t* __restrict__ fixed_modes, const double* __restrict__ Y, double* __restrict__ u,
+               double* __restrict__ x, double* __restrict__ extra, int32_t* __restrict__ modes, double* __restrict__ obj,
                int32_t* __restrict__ status, int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters,
                unsigned long long* __restrict__ counter) {
     extern __shared__ double pm_smem[];
@@ -797,7 +814,7 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
         const int64_t i = (int64_t)__shfl_sync(FULL, nxt, 0);
         if (i >= batch) break;
         W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar,
-                fixed_modes ? fixed_modes + su * i : nullptr);
+                fixed_modes ? fixed_modes + su * i : nullptr, Y ? Y + (size_t)S.mw * i : nullptr);
         W.solve();
         W.finish(u + su * i, x + sx * i, extra ? extra + (size_t)S.ne * i : nullptr, modes + su * i, obj + i,
                  status + i, nodes + i, qp_iters ? qp_iters + i : nullptr);
@@ -821,6 +838,74 @@ pm_eval_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
     }
 }
 
+// ---- shared-structure multi-RHS product on the FP64 tensor cores --------------------------------
+// Every problem of a batch shares the formulation matrices; only pvec = [x0 ; params ; 1] differs.
+// So gradient, right-hand sides and the constant term of ALL problems are one dense product
+//     Y [batch][mw] = P [batch][kw] . W' [kw][mw]
+// issued as mma.sync.m8n8k4 FP64 (DMMA): a warp owns 16 problems (two 8-row tiles of P) and walks the
+// output columns 32 at a time; fragments come straight from global memory / L1 (W is a few hundred KB
+// at most and shared by every warp; each P row is read once per 32-column sweep from L1).
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+pm_precompute_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __restrict__ x0,
+                     const double* __restrict__ params, double* __restrict__ Y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t b0 = warp * 16;
+    if (b0 >= batch) return;
+    const int row = lane >> 2, kk = lane & 3;
+    const int nx = 2 * S.nl, npv = S.npv, kw = S.kw, mw = S.mw;
+    auto P = [&](int64_t b, int k) -> double {        // element k of problem b's parameter vector
+        if (b >= batch || k >= npv) return 0.0;
+        if (k < nx) return x0[(size_t)b * nx + k];
+        if (k < npv - 1) return params[(size_t)b * S.npar + (k - nx)];
+        return 1.0;
+    };
+    for (int n0 = 0; n0 < mw; n0 += 32) {
+        double acc[2][4][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[a][t][0] = acc[a][t][1] = 0.0;
+        for (int k0 = 0; k0 < kw; k0 += 4) {
+            const double a0 = P(b0 + row, k0 + kk), a1 = P(b0 + 8 + row, k0 + kk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int n = n0 + t * 8 + row;
+                const double bf = (n < mw) ? S.W[(size_t)n * kw + k0 + kk] : 0.0;
+                dmma8x8x4(acc[0][t][0], acc[0][t][1], a0, bf);
+                dmma8x8x4(acc[1][t][0], acc[1][t][1], a1, bf);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int64_t b = b0 + a * 8 + row;
+            if (b >= batch) continue;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int n = n0 + t * 8 + 2 * kk;
+                if (n < mw) {
+                    double2 v; v.x = acc[a][t][0]; v.y = acc[a][t][1];
+                    *reinterpret_cast<double2*>(Y + (size_t)b * mw + n) = v;
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_pm_precompute(const PmDev& S, int64_t batch, const double* x0, const double* params, double* Y,
+                                 cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    const int64_t warps = (batch + 15) / 16;
+    const int64_t blocks = (warps + 3) / 4;
+    pm_precompute_kernel<<<(unsigned)blocks, 128, 0, stream>>>(S, batch, x0, params, Y);
+    return cudaGetLastError();
+}
+
 // per-warp shared-memory carve-up
 void pm_layout(PmDev& S) {
     const int nv = S.nv, D = S.depth;
@@ -841,7 +926,7 @@ void pm_layout(PmDev& S) {
 }
 
 cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
-                           const double* params, const int32_t* fixed_modes, double* u, double* x,
+                           const double* params, const int32_t* fixed_modes, const double* Y, double* u, double* x,
                            double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                            int32_t* qp_iters, unsigned long long* counter, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
@@ -866,7 +951,7 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
     if (blocks > cap) blocks = cap;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, u, x,
+    pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,
                                                                  extra, modes, obj, status, nodes, qp_iters, counter);
     return cudaGetLastError();
 }

@@ -48,6 +48,12 @@ struct PmDev {                   // kernel argument
     const double* wmax;          // [ng]          L1 penalty weight (soft) or +inf (hard)
     const double* B0;            // [n0][npv]     constant rows: B0[r].pvec <= 0
     const double* w0;            // [n0]
+    // shared-structure multi-RHS product (tensor-core precompute): Y[b] = W . pvec_b with
+    // W = [GC ; BR ; B0 ; CC] ([mw][kw], zero padded to multiples of 8 x 4):
+    //   GC = RW2.Cres + Lz'.La  -> g0 = GC.pvec      BR -> generic right-hand sides
+    //   B0 -> constant rows                           CC = Cres'W Cres + La'Lp -> c0 = pvec'.CC.pvec
+    const double* W;
+    int mw, kw;
     // shared-memory carve-up (offsets in doubles / ints), filled by pm_layout()
     int o_hinv, o_ginv, o_nact, o_vec, o_cres, o_bgen, o_pvec, o_misc, smem_doubles;
     int o_int, smem_bytes;
