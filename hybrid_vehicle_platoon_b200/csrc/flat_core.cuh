@@ -82,6 +82,7 @@ struct FlatSolver {
     uint64_t modes_pk, best_modes, cand_pk, built_pk;   // 3 bits / stage; 7 candidate bits / level
     int built_L;                                        // H^-1 currently holds stages 0..built_L-1 of built_pk
     bool trouble, limit;
+    bool dive;                                          // first descent: path nodes are not solved, only the leaf
     // active set
     int q;
     uint64_t act_lo, act_hi;                            // slot ids, 8 bits each
@@ -187,7 +188,7 @@ struct FlatSolver {
         built_L = 0; built_pk = 0;
         // ---- start of the search ----
         iters = 0; nodes = 0; it = 0; modes_pk = 0; best_modes = 0; cand_pk = 0;
-        inc = HUGE_VAL; trouble = limit = false; lev = 0;
+        inc = HUGE_VAL; trouble = limit = false; lev = 0; dive = P->dive != 0;
         int c0 = 0;
         HVP_ROLL
         for (int rg = 0; rg < NREG; ++rg)
@@ -227,6 +228,19 @@ struct FlatSolver {
             if (pc > P->pmax + eps || pc < P->pmin - eps) continue;
             rlo[lev + 1] = nlo - eps; rhi[lev + 1] = nhi + eps;
             L = lev + 1;
+            if (dive && nodes >= 1 && L < N) {
+                // First descent: no incumbent exists yet, so the relaxations along the path could not
+                // prune anything -- they only guide the choice of region.  Keep following the last
+                // relaxed trajectory and solve the LEAF directly; its objective is the first incumbent.
+                ++lev;
+                xstar[lev] = w(LY::O_X, lev - 1);
+                int cn = 0;
+                HVP_ROLL
+                for (int c = 0; c < NREG; ++c)
+                    if (P->edge[c] <= rhi[lev] && P->edge[c + 1] >= rlo[lev]) cn |= (1 << c);
+                set_cand(lev, cn);
+                continue;
+            }
             if (P->hull) hull();
             state = S_BUILD;
             return;
@@ -264,6 +278,7 @@ struct FlatSolver {
         iters += it;
         ++nodes;
         state = S_NEXT;
+        if (st != 0 || L == N) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
         if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
@@ -609,6 +624,17 @@ struct FlatSolver {
     HVP_HD void trip() {
         if (state == S_NEXT) do_next();
         if (state == S_BUILD) do_build();
+        if (state == S_SELECT) do_select();
+        if (state == S_STEP) do_step();
+    }
+    // the two halves of a trip, so that a warp can run the (expensive, once per node) node set-up for
+    // MANY lanes at once instead of for the one or two lanes that happen to need it on every trip
+    HVP_HD bool wants_node() const { return state == S_NEXT || state == S_BUILD; }
+    HVP_HD void trip_node() {
+        if (state == S_NEXT) do_next();
+        if (state == S_BUILD) do_build();
+    }
+    HVP_HD void trip_step() {
         if (state == S_SELECT) do_select();
         if (state == S_STEP) do_step();
     }

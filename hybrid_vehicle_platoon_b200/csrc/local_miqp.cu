@@ -92,24 +92,18 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
     Solver sol;
     bool have = false;
     int64_t i = 0;
+    // A lane is either stepping its node QP (SELECT/STEP: the common, cheap trip) or waiting for node
+    // work (store a finished problem, load the next one, NEXT + BUILD of a new node).  Node work is
+    // several times the cost of a step and only ~1 lane in 6 needs it on a given trip, so the warp
+    // lets waiting lanes accumulate and serves them together (r01d ncu: 7.7 of 32 lanes active when
+    // every trip served them immediately).
+    const int node_batch = P.node_batch;
     for (;;) {
         __syncwarp();
-        const unsigned need = __ballot_sync(0xffffffffu, !have);
-        if (need) {
-            if (!have) {
-                i = next + __popc(need & ((1u << lane) - 1u));
-                if (i < end) {
-                    sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
-                              xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 2));
-                    have = true;
-                }
-            }
-            next += __popc(need);
-        }
-        if (!__any_sync(0xffffffffu, have)) break;
-        if (have) {
-            sol.trip();
-            if (sol.state == Solver::S_DONE) {
+        const bool slow = !have || sol.state == Solver::S_DONE || sol.wants_node();
+        const unsigned ms = __ballot_sync(0xffffffffu, slow);
+        if (ms == 0xffffffffu || __popc(ms) >= node_batch) {
+            if (have && sol.state == Solver::S_DONE) {
                 const LocalResult R = sol.finish(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
                 obj[i] = R.obj;
                 status[i] = R.status;
@@ -117,8 +111,28 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                 if (qp_iters) qp_iters[i] = R.qp_iters;
                 have = false;
             }
+            const unsigned need = __ballot_sync(0xffffffffu, !have);
+            if (need) {
+                if (!have) {
+                    i = next + __popc(need & ((1u << lane) - 1u));
+                    if (i < end) {
+                        sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
+                                  xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 2));
+                        have = true;
+                    }
+                }
+                next += __popc(need);
+            }
+            if (!__any_sync(0xffffffffu, have)) break;
+            if (have) sol.trip_node();
         }
+        if (have) sol.trip_step();
     }
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 template <int N>
@@ -144,7 +158,12 @@ static cudaError_t launch_flat(const LocalParams& P, int64_t batch, const int32_
     // persistent grid: every resident warp slot, but never more warps than 32-problem shares
     int64_t g = (batch + 31) / 32;
     if (g > grid_full) g = grid_full;
-    flat_miqp_kernel<N><<<(unsigned)g, 32, smem, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
+    LocalParams Q = P;
+    static const int nb = env_int("HVP_NODE_BATCH", 0), hl = env_int("HVP_FLAT_HULL", -1), dv = env_int("HVP_FLAT_DIVE", -1);
+    if (nb > 0) Q.node_batch = nb;
+    if (hl >= 0) Q.hull = hl;
+    if (dv >= 0) Q.dive = dv;
+    flat_miqp_kernel<N><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
                                                           status, nodes, qp_iters);
     return cudaGetLastError();
 }
@@ -161,6 +180,7 @@ static int kernel_choice() {
     }
     return v;
 }
+
 static bool use_scalar_kernel() { return kernel_choice() == 1; }
 
 cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,

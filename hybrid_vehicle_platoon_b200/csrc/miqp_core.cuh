@@ -45,6 +45,8 @@ struct LocalParams {
     int N;
     int max_nodes;
     int hull;                            // flat kernel: interval-hull tightening of the unfixed stages
+    int dive;                            // flat kernel: first descent solves only the leaf
+    int node_batch;                      // flat kernel: lanes that must wait for node set-up before a warp runs it
     double d0, t0, tight;
     double qxp, qxv, qu, w;              // Params.Q_x, Q_u, w (common_controller_params.py:14-23)
     double a_acc, a_dec, d_safe;

@@ -14,9 +14,14 @@ def _check(r, ro):
     np.testing.assert_array_equal(r["status"], ro["status"])
     ok = ro["status"] == 2
     np.testing.assert_allclose(r["obj"][ok], ro["obj"][ok], rtol=1e-9)
-    assert np.abs(r["u"][ok] - ro["u"][ok]).max() < 1e-7
-    assert np.abs(r["x"][ok] - ro["x"][ok]).max() < 1e-6
-    uniq = ok & ((ro["second"] - ro["obj"]) > 1e-6 * np.abs(ro["obj"]))
+    # inputs / states / region sequences are compared wherever the optimum is unique (second-best leaf
+    # more than 1e-6 relative away -- BASELINE.json's own qualifier); two leaves whose objectives agree to
+    # 1e-9 are both "the optimum" at the solvers' tolerances
+    with np.errstate(invalid="ignore"):
+        uniq = ok & ((ro["second"] - ro["obj"]) > 1e-6 * np.abs(ro["obj"]))
+    assert uniq.sum() >= 0.9 * ok.sum()
+    assert np.abs(r["u"][uniq] - ro["u"][uniq]).max() < 1e-7
+    assert np.abs(r["x"][uniq] - ro["x"][uniq]).max() < 1e-6
     np.testing.assert_array_equal(r["modes"][uniq], ro["modes"][uniq])
     assert np.isinf(r["obj"][~ok]).all()
 
