@@ -96,7 +96,7 @@ struct Warp {
     // warp-uniform scalars (replicated in registers)
     int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
     double inc, c0, cp, nHn, lam_p, dual;
-    bool p_soft, trouble, limit;
+    bool p_soft, trouble, limit, dive;
 
     __device__ Warp(const PmDev& S_, double* base, int lane_) : S(S_), lane(lane_) {
         const int nv = S.nv, ld = S.ld;
@@ -202,7 +202,7 @@ struct Warp {
         }
         built_L = -1;                      // H^-1 not loaded yet
         iters = nodes = it = q = 0;
-        inc = HUGE_VAL; trouble = limit = false;
+        inc = HUGE_VAL; trouble = limit = false; dive = true;
         lev = 0; L = 0; fixed = (fm != nullptr);
         if (infeas) { state = PS_DONE; __syncwarp(); return; }
         if (fixed) {
@@ -271,6 +271,13 @@ struct Warp {
                 if (nlo > nhi + eps) continue;
                 rlo[i * (N + 1) + k + 1] = nlo - eps; rhi[i * (N + 1) + k + 1] = nhi + eps;
                 nL = nlev + 1;
+                if (dive && nodes >= 1 && nL < S.depth) {
+                    // first descent: without an incumbent the relaxations along the path cannot prune, they
+                    // only guide the region choice -- follow the last relaxed trajectory and solve the leaf
+                    ++nlev;
+                    open_level(nlev);
+                    continue;
+                }
                 st = PS_BUILD;
                 break;
             }
@@ -323,6 +330,7 @@ struct Warp {
         iters += it;
         ++nodes;
         state = fixed ? PS_DONE : PS_NEXT;
+        if (st != 0 || L == S.depth) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
         if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
