@@ -127,6 +127,7 @@ static int fill_rollout_params(RolloutParams& P, const hvp_env_desc* d) {
     M.gear_limits(P.lim);
     P.c_fric = M.c_fric; P.mug = M.mu * M.grav; P.default_mass = 800.0;
     { int ex; P.fric_pow2 = (frexp(M.c_fric, &ex) == 0.5) ? 1 : 0; }
+    P.inv_c_fric = 1.0 / M.c_fric;
     return 0;
 }
 

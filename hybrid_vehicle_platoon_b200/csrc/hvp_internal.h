@@ -36,6 +36,7 @@ struct RolloutParams {
     double inv_rise[6], inv_fall[6]; // RN(1/(v1-v0)), RN(1/(v3-v2)) per gear (exact-division helper)
     double lim[5];                  // gear-switch velocities (models.py:401-403)
     double c_fric, mug;             // friction, mu*g
+    double inv_c_fric;              // 1/c_fric (exact when c_fric is a power of two)
     int fric_pow2;                  // c_fric is a power of two (exact-scaling shortcut allowed)
     double default_mass;
 };

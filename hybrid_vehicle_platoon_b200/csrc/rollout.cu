@@ -118,13 +118,13 @@ rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const dou
         } else {
             const int j = g - 1;
             const double v1 = P.tr_v[j][1], v2 = P.tr_v[j][2];     // flat part of the traction curve
-            const double ym = 1.0 / m;                       // RN(1/m), once per vehicle-step
+            const double ym = __drcp_rn(m);                  // RN(1/m), once per vehicle-step
             const double Bv_flat = div_by(P.tr_t[j][1], m, ym);
             // (c_fric v^2)/m with c_fric a power of two equals v^2/(m/c_fric) bit for bit (scaling
             // by 2^k commutes with rounding), which saves the multiplication by c_fric
-            const double mf = P.fric_pow2 ? m / P.c_fric : m, ymf = P.fric_pow2 ? ym * P.c_fric : ym;
+            const double mf = P.fric_pow2 ? m * P.inv_c_fric : m, ymf = P.fric_pow2 ? ym * P.c_fric : ym;
             const double zu = 0.0 * ui;                      // the reference adds 0*u to v (models.py:124)
-            const bool zu_is_zero = (zu == 0.0);             // always, unless u is inf/nan
+            const double Bu_flat = Bv_flat * ui;             // loop invariant on the flat part of the curve
 #pragma unroll 1
             for (int s = 0; s < 10; ++s) {
                 // traction (models.py:43-51).  On the flat part of the curve -- where the PWA-derived
@@ -132,7 +132,7 @@ rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const dou
                 // v is inside the gear's range, so two comparisons guard everything; the sloped parts
                 // and the reference's exceptions (models.py:119-122, :39-42) take the rare branch, which
                 // fetches its constants on demand to keep the hot loop's register footprint small.
-                double Bv = Bv_flat;                                                 // models.py:109-112
+                double Bu = Bu_flat;                                                 // B(x) u, models.py:109-112
                 if (!(v >= v1 && v <= v2)) {
                     const double v0 = P.tr_v[j][0], v3 = P.tr_v[j][3];
                     if (!(v > v0 && v < v3)) {
@@ -140,13 +140,15 @@ rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const dou
                         break;
                     }
                     const double t0 = P.tr_t[j][0], t1 = P.tr_t[j][1], t2 = P.tr_t[j][2];
+                    double Bv;
                     if (v < v1) Bv = div_by(div_by(v - v0, v1 - v0, P.inv_rise[j]) * (t1 - t0) + t0, m, ym);
                     else Bv = div_by(t1 - div_by(v - v2, v3 - v2, P.inv_fall[j]) * (t1 - t2), m, ym);
+                    Bu = Bv * ui;
                 }
                 const double vv = P.fric_pow2 ? v * v : P.c_fric * (v * v);
                 const double Av = -div_by(vv, mf, ymf) - P.mug;                      // models.py:99-107
-                const double pn = p + DT * (zu_is_zero ? v : v + zu);
-                const double vn = v + DT * (Av + Bv * ui);
+                const double pn = p + DT * (v + zu);         // v + 0*u == v bit for bit unless u is inf/nan
+                const double vn = v + DT * (Av + Bu);
                 p = pn; v = vn;
             }
         }
