@@ -173,6 +173,28 @@ def compiled_mpc_legs(hvp, torch, dev, stream, flush, steps=5, with_cpu=True):
     return legs
 
 
+def closed_loop_leg(ctx, S=4096, T=20):
+    """Whole closed-loop episodes of the decentralized controller for S scenarios, state resident on the device
+    (sweep.BatchedDecentSweep): observe -> S*n MIQPs -> rollout per timestep, wall-clock incl. result read-back."""
+    from hybrid_vehicle_platoon_b200.sweep import BatchedDecentSweep
+    from hybrid_vehicle_platoon_b200.misc import StopAndGoLeaderTrajectory
+    rng = np.random.default_rng(1234 + 3)
+    v = np.floor(rng.uniform(5, 35, (S, N_VEH))); gaps = rng.uniform(60, 160, (S, N_VEH))
+    p = np.floor(3000.0 - np.cumsum(gaps, 1) + gaps[:, :1])
+    x0 = np.empty((S, 2 * N_VEH)); x0[:, 0::2] = p; x0[:, 1::2] = v
+    lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=10, vf=30, v_change_steps=[5, 12], trajectory_len=T + HORIZON + 10,
+                                   ts=1).get_leader_trajectory()
+    sw = BatchedDecentSweep(N_VEH, HORIZON, ctx=ctx)
+    sw.run(x0[:256], lx, 3)
+    t0 = time.perf_counter()
+    out = sw.run(x0, lx, T)
+    dt = time.perf_counter() - t0
+    return {"value": S * T / dt, "unit": "scenario-timesteps/s", "solves_per_s": S * T * N_VEH / dt, "scenarios": S,
+            "timesteps": T, "seconds": dt, "optimal_frac": float((out["status"] == 2).mean()),
+            "rollout_exceptions": int((out["errors"] != 0).any(0).sum()),
+            "mean_nodes": float(out["nodes"].mean())}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -402,6 +424,7 @@ def main():
         if not args.no_cpu:
             cpu, _, _ = cpu_reference_leg(S, budget_s=12.0)
         other = compiled_mpc_legs(hvp, torch, dev, stream, flush, with_cpu=not args.no_cpu)
+        other["closed_loop_decent_n10_N6 (configs[3] shape: 4096 scenarios, on-device episode)"] = closed_loop_leg(ctx)
 
         out = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,

@@ -1,0 +1,97 @@
+"""Whole-episode closed loops for MANY scenarios at once, state resident on the device (SURVEY.md 8f rank 1;
+the batched replacement of the serial loops in n_sweep*.py for the decentralized controller).
+
+One timestep of `BatchedDecentSweep.run` is, for all S scenarios together:
+  observe  -- constant-velocity extrapolation of every vehicle's neighbours (fleet_decent_mld.py:348-428)
+              and the leader-trajectory window leader_x[:, t:t+N+1] (:329-331), as a handful of torch ops;
+  solve    -- the S*n per-vehicle MIQPs in ONE launch of the local-MIQP kernel (hvp_local_miqp_dev);
+  step     -- PlatoonEnv.step for all scenarios in ONE launch of the rollout kernel (hvp_rollout_step_dev);
+nothing crosses PCIe until the episode's result tensors are read back.  Scenarios are independent, so
+multi-GPU runs shard them by rank with no collective."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+from ._lib import FRONT, LEADER, TRAILER, default_context
+from .misc import ConstantSpacingPolicy, Params, spacing_params
+
+
+class BatchedDecentSweep:
+    """S independent platoons of n vehicles under the decentralized MLD-MPC (TrackingDecentMldCoordinator
+    with the constant-velocity estimator), pwa_gear model, horizon N."""
+
+    def __init__(self, n: int, N: int, masses=None, spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0,
+                 d_safe: float = Params.d_safe, device: int = 0, ctx=None):
+        import torch
+        self.torch = torch
+        self.n, self.N, self.leader_index = n, N, leader_index
+        self.dev = torch.device("cuda", device)
+        self.ctx = ctx or default_context(device)
+        self.d0, self.t0 = spacing_params(spacing_policy)
+        self.d_safe = d_safe
+        self.masses = None if masses is None else np.asarray(masses, dtype=np.float64)   # (n,) or (S,n)
+        self.ldesc = api.local_desc(N, self.d0, self.t0)
+
+    def run(self, x0, leader_x, ep_len: int):
+        """x0 (S,2n) initial states (e.g. PlatoonEnv.reset of each scenario), leader_x (2,>=ep_len+N+1) shared
+        or (S,2,>=ep_len+N+1) per scenario.  Returns dict of numpy arrays: X (T+1,S,2n), U (T,S,n), R (T,S),
+        violations (T,S) uint8, errors (T,S) int32, nodes (T,S,n) int32, status (T,S,n) int32."""
+        torch, dev, n, N = self.torch, self.dev, self.n, self.N
+        f64 = torch.float64
+        x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
+        S = x.shape[0]
+        B = S * n
+        lx = torch.as_tensor(np.ascontiguousarray(leader_x, dtype=np.float64), device=dev)
+        if lx.ndim == 2:
+            lx = lx.unsqueeze(0).expand(S, -1, -1)
+        if lx.shape[2] < ep_len + N + 1:
+            raise ValueError("leader trajectory shorter than ep_len + N + 1")
+        flags = np.zeros((S, n), np.int32)
+        flags[:, 0] |= FRONT; flags[:, -1] |= TRAILER; flags[:, self.leader_index] |= LEADER
+        d_flags = torch.as_tensor(flags.reshape(B), device=dev)
+        m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
+        d_mass = torch.as_tensor(np.ascontiguousarray(m), device=dev)
+        edesc = api.env_desc(n, self.leader_index, self.d0, self.t0, self.d_safe, True, False, True)
+        # per-step work buffers
+        xf = torch.zeros((S, n, 2, N + 1), dtype=f64, device=dev)
+        xb = torch.zeros((S, n, 2, N + 1), dtype=f64, device=dev)
+        xl = torch.zeros((S, n, 2, N + 1), dtype=f64, device=dev)
+        pred = torch.empty((S, n, 2, N + 1), dtype=f64, device=dev)
+        u = torch.empty((B, N), dtype=f64, device=dev); xs = torch.empty((B, 2, N + 1), dtype=f64, device=dev)
+        modes = torch.empty((B, N), dtype=torch.int32, device=dev); obj = torch.empty(B, dtype=f64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev); nodes = torch.empty(B, dtype=torch.int32, device=dev)
+        X = torch.empty((ep_len + 1, S, 2 * n), dtype=f64, device=dev)
+        U = torch.empty((ep_len, S, n), dtype=f64, device=dev)
+        R = torch.empty((ep_len, S), dtype=f64, device=dev)
+        V = torch.empty((ep_len, S), dtype=torch.uint8, device=dev)
+        E = torch.empty((ep_len, S), dtype=torch.int32, device=dev)
+        ND = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
+        ST = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
+        X[0] = x
+        stream = torch.cuda.current_stream().cuda_stream
+        ts = float(Params.ts)
+        for t in range(ep_len):
+            # ---- observe: p_{k+1} = p_k + ts v_k (sequential sums, as the reference), v constant ----
+            xv = x.view(S, n, 2)
+            pred[:, :, 0, 0] = xv[:, :, 0]
+            pred[:, :, 1, :] = xv[:, :, 1:2]
+            for k in range(N):
+                pred[:, :, 0, k + 1] = pred[:, :, 0, k] + ts * pred[:, :, 1, k]
+            xf[:, 1:] = pred[:, :-1]
+            xb[:, :-1] = pred[:, 1:]
+            xl[:, self.leader_index] = lx[:, :, t:t + N + 1]
+            # ---- solve all S*n local MIQPs ----
+            api.local_miqp_device(self.ldesc, B, d_flags, d_mass.view(B), x.view(B, 2), xf.view(B, 2, N + 1),
+                                  xb.view(B, 2, N + 1), xl.view(B, 2, N + 1), u, xs, modes, obj, status, nodes,
+                                  None, ctx=self.ctx, stream=stream)
+            U[t] = u[:, 0].view(S, n)
+            ND[t] = nodes.view(S, n)
+            ST[t] = status.view(S, n)
+            # ---- step every platoon ----
+            api.rollout_step_device(edesc, S, x, U[t], None, d_mass, lx[:, :, t].contiguous(), X[t + 1], R[t], V[t],
+                                    E[t], ctx=self.ctx, stream=stream)
+            x = X[t + 1]
+        torch.cuda.synchronize()
+        return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
+                    errors=E.cpu().numpy(), nodes=ND.cpu().numpy(), status=ST.cpu().numpy())
