@@ -140,6 +140,8 @@ struct CoopSolver {
     // persistent across trips -------------------------------------------------------------
     int state, lev, it, nodes;
     double inc, nlo_cur, nhi_cur;
+    double dual;                 // value of the node's dual function: lower bound on the node optimum
+    bool dive;                   // first descent: path nodes are not solved, only the leaf
     uint64_t best_modes, cand_lo, cand_hi;
     bool trouble, limit;
     // constraint being added
@@ -160,7 +162,7 @@ struct CoopSolver {
 
     HVP_CD void begin() {
         iters = 0; modes_pk = 0; nodes = 0; it = 0;
-        inc = HUGE_VAL; best_modes = 0; cand_lo = cand_hi = 0; trouble = limit = false;
+        inc = HUGE_VAL; best_modes = 0; cand_lo = cand_hi = 0; trouble = limit = false; dive = P->dive != 0;
         best = bk.splat(0.0); xstar = bk.splat(v0); rlo = bk.splat(0.0); rhi = bk.splat(0.0);
         lev = 0;
         int c0 = 0;
@@ -205,6 +207,17 @@ struct CoopSolver {
             rlo = bk.sel(ln == lev, bk.splat(nlo - eps), rlo);
             rhi = bk.sel(ln == lev, bk.splat(nhi + eps), rhi);
             L = lev + 1;
+            if (dive && nodes >= 1 && L < N) {
+                // first descent (see flat_core.cuh): without an incumbent the relaxations along the path
+                // cannot prune; follow the last relaxed trajectory and solve the leaf directly
+                ++lev;
+                xstar = bk.sel(ln == lev, bk.splat(bk.bcast(x, lev - 1)), xstar);
+                int cn = 0;
+                for (int c = 0; c < NREG; ++c)
+                    if (P->edge[c] <= nhi_cur + eps && P->edge[c + 1] >= nlo_cur - eps) cn |= (1 << c);
+                cand_set(cand_lo, cand_hi, lev, cn);
+                continue;
+            }
             // merged simple bounds: state box, regions of fixed stages, stage-0 accel/input rows
             const I rgn = bk.bits3(modes_pk, ln + 1);
             const Bm fixed = (ln + 1) < L;
@@ -226,6 +239,7 @@ struct CoopSolver {
         iters += it;
         ++nodes;
         state = S_NEXT;
+        if (st != 0 || L == N) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
         if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
@@ -250,6 +264,7 @@ struct CoopSolver {
         const D hoff_l = hw1 * ((double)(N - 1) - lnd) + hw2;     // H_t[i][j], i<j, depends on j only
         const D hdiag_l = hw1 * ((double)(N - 1) - lnd) + hd;
         D g = gt;
+        double kc2 = 0.0;
 #pragma unroll
         for (int c = 0; c < G; ++c) {
             const double hoff_c = hw1 * (double)(N - 1 - c) + hw2;
@@ -267,6 +282,7 @@ struct CoopSolver {
                 const double kc = (k == 0) ? -(ra(rg) * v0 + rc(rg)) * ib : -rc(rg) * ib;
                 hinv[k] += bk.sel(ln == k, bk.splat(2.0 * qu * ib * ib), bk.splat(0.0));
                 g += bk.sel(ln == k, bk.splat(2.0 * qu * kc * ib), bk.splat(0.0));
+                kc2 += qu * kc * kc;
                 if (k >= 1) {
                     hinv[k] += bk.sel(ln == k - 1, bk.splat(2.0 * qu * ea * ib), bk.splat(0.0));
                     hinv[k - 1] += bk.sel(ln == k, bk.splat(2.0 * qu * ea * ib),
@@ -299,6 +315,7 @@ struct CoopSolver {
 #pragma unroll
         for (int c = 0; c < G; ++c) acc -= hinv[c] * bk.bcast(g, c);
         x = bk.sel(valid, acc, bk.splat(0.0));
+        dual = ct + kc2 + 0.5 * bk.gsum(bk.sel(valid, g * x, bk.splat(0.0)));   // objective at the unconstrained minimiser
         q = 0; satf = 0; satb = 0; am_lo = am_hi = 0;
         lam = bk.splat(0.0); s_sgn = bk.splat(0.0); s_coef = bk.splat(0.0);
         s_kind = bk.splati(0); s_j = bk.splati(0); s_id = bk.splati(0);
@@ -432,6 +449,8 @@ struct CoopSolver {
         const double t3p = p_soft ? (ww - lam_p) : INF;
         const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
         if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
+        dual += t * cp - (dependent ? 0.0 : 0.5 * t * t * nz);  // dD/dt = violation of p along the step
+        if (dual > inc) { node_done(1, 0.0); return; }          // the node cannot beat the incumbent
         double ru[G];
 #pragma unroll
         for (int a = 0; a < G; ++a) ru[a] = bk.bcast(r, a);

@@ -54,7 +54,7 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
     if (device < 0 || device >= n) return fail(-3, "hvp_ctx_create: device %d out of range [0,%d)", device, n);
     CUDA_TRY(cudaSetDevice(device));
     hvp_ctx* c = new hvp_ctx();
-    c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0;
+    c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0; c->hbuf = nullptr; c->hcap = 0;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -67,6 +67,7 @@ extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->dbuf) cudaFree(c->dbuf);
+    if (c->hbuf) cudaFreeHost(c->hbuf);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -262,6 +263,31 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
     int32_t* dno = (int32_t*)q; q += bs;
     int32_t* dit = qp_iters ? (int32_t*)q : nullptr;
     cudaStream_t st = c->stream;
+    const size_t in_bytes = (size_t)((char*)du - c->dbuf), all_bytes = (size_t)(q - c->dbuf) + bs;
+    if (all_bytes <= (256u << 10)) {
+        // latency path (one scenario-timestep = a handful of MIQPs): stage through a pinned mirror of the
+        // device buffer so the call costs ONE H2D and ONE D2H copy instead of 6 + 7 pageable ones
+        if (c->hcap < all_bytes) {
+            if (c->hbuf) { CUDA_TRY(cudaFreeHost(c->hbuf)); c->hbuf = nullptr; c->hcap = 0; }
+            CUDA_TRY(cudaMallocHost(&c->hbuf, 256u << 10));
+            c->hcap = 256u << 10;
+        }
+        char* h = c->hbuf;
+        auto off = [&](const void* d) { return (size_t)((const char*)d - c->dbuf); };
+        memcpy(h + off(dfl), flags, B * 4); memcpy(h + off(dma), mass, B * 8); memcpy(h + off(dx0), x0, B * 16);
+        if (xf) memcpy(h + off(dxf), xf, B * S * 8);
+        if (xb) memcpy(h + off(dxb), xb, B * S * 8);
+        if (xl) memcpy(h + off(dxl), xl, B * S * 8);
+        CUDA_TRY(cudaMemcpyAsync(c->dbuf, h, in_bytes, cudaMemcpyHostToDevice, st));
+        rc = hvp_local_miqp_dev(c, desc, batch, dfl, dma, dx0, dxf, dxb, dxl, du, dx, dmo, dob, dst, dno, dit, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h + in_bytes, c->dbuf + in_bytes, all_bytes - in_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        memcpy(u, h + off(du), B * N * 8); memcpy(x, h + off(dx), B * S * 8); memcpy(modes, h + off(dmo), B * N * 4);
+        memcpy(obj, h + off(dob), B * 8); memcpy(status, h + off(dst), B * 4); memcpy(nodes, h + off(dno), B * 4);
+        if (qp_iters) memcpy(qp_iters, h + off(dit), B * 4);
+        return 0;
+    }
     CUDA_TRY(cudaMemcpyAsync(dfl, flags, B * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dma, mass, B * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dx0, x0, B * 16, cudaMemcpyHostToDevice, st));

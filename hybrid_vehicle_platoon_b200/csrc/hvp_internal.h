@@ -16,6 +16,9 @@ struct hvp_ctx {
     // grow-only device staging for the *_host entry points
     char* dbuf;
     size_t dcap;
+    // pinned host mirror of dbuf for small calls: one H2D + one D2H instead of one copy per array
+    char* hbuf;
+    size_t hcap;
 };
 int hvp_fail(int code, const char* fmt, ...);          // records the thread's error text, returns code
 int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes);
