@@ -28,3 +28,10 @@ def sum_over_ranks(values, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [float(v) for v in t]
+
+
+def balanced_shards(costs, world: int):
+    """Load-balanced assignment for MIXED scenario sizes (n = 5..15, N = 4..10):
+    sort by the cost proxy (7 n N binaries per scenario) and deal round-robin.  Returns one index list per rank."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    return [sorted(order[r::world]) for r in range(world)]

@@ -95,3 +95,29 @@ class BatchedDecentSweep:
         torch.cuda.synchronize()
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
                     errors=E.cpu().numpy(), nodes=ND.cpu().numpy(), status=ST.cpu().numpy())
+
+
+def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, device: int = 0, ctx=None):
+    """Monte-Carlo sweep over scenarios of MIXED size (BASELINE.json configs[3]): `scenarios` is a list of dicts
+    {n, N, x0 (2n,), leader_x (2, >= ep_len+N+1), masses (n,) | None, spacing_policy | None}.  This rank takes
+    its load-balanced share (dist.balanced_shards), groups it by (n, N, spacing policy) and runs one
+    BatchedDecentSweep episode per group.  Returns {scenario index: dict(X (T+1,2n), U (T,n), R (T,), violations,
+    errors, nodes, status)} for the scenarios of this rank."""
+    from .dist import balanced_shards
+    mine = balanced_shards([7 * sc["n"] * sc["N"] for sc in scenarios], world)[rank]
+    groups: dict = {}
+    for i in mine:
+        sc = scenarios[i]
+        pol = sc.get("spacing_policy") or ConstantSpacingPolicy(50)
+        groups.setdefault((sc["n"], sc["N"], spacing_params(pol)), []).append(i)
+    out = {}
+    for (n, N, _), idx in sorted(groups.items()):
+        pol = scenarios[idx[0]].get("spacing_policy") or ConstantSpacingPolicy(50)
+        masses = np.stack([np.full(n, 800.0) if scenarios[i].get("masses") is None
+                           else np.asarray(scenarios[i]["masses"], dtype=np.float64) for i in idx])
+        sw = BatchedDecentSweep(n, N, masses=masses, spacing_policy=pol, device=device, ctx=ctx)
+        r = sw.run(np.stack([scenarios[i]["x0"] for i in idx]), np.stack([scenarios[i]["leader_x"] for i in idx]), ep_len)
+        for j, i in enumerate(idx):
+            out[i] = dict(X=r["X"][:, j], U=r["U"][:, j], R=r["R"][:, j], violations=r["violations"][:, j],
+                          errors=r["errors"][:, j], nodes=r["nodes"][:, j], status=r["status"][:, j])
+    return out

@@ -46,3 +46,15 @@ def test_shard_range_properties():
             assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_shards_partition_and_balance():
+    import numpy as np
+    from hybrid_vehicle_platoon_b200.dist import balanced_shards
+    rng = np.random.default_rng(3)
+    costs = [7 * int(rng.integers(5, 16)) * int(rng.integers(4, 11)) for _ in range(4096)]
+    for world in (1, 2, 4, 8):
+        sh = balanced_shards(costs, world)
+        assert sorted(i for s_ in sh for i in s_) == list(range(4096))
+        loads = [sum(costs[i] for i in s_) for s_ in sh]
+        assert max(loads) - min(loads) <= max(costs)

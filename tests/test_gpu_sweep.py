@@ -53,3 +53,32 @@ def test_batched_sweep_larger_batch_is_self_consistent():
     # the optimum is unique")
     d = np.abs(a["X"][:, :300][:, ok] - b["X"][:, ok]).max(axis=(0, 2))
     assert (d < 1e-6).mean() > 0.97 and d.max() < 1e-2
+
+
+def test_mixed_size_sweep_shards_cover_everything():
+    """configs[3] shape: scenarios with n in 5..9 and N in 4..7, two 'ranks' on one GPU: the shards partition the
+    scenario set, every MIQP is optimal and a scenario's result does not depend on which rank ran it."""
+    from hybrid_vehicle_platoon_b200.sweep import run_mixed_sweep
+    from hybrid_vehicle_platoon_b200.misc import ConstantTimePolicy, StopAndGoLeaderTrajectory
+    rng = np.random.default_rng(21)
+    T, scen = 4, []
+    for i in range(60):
+        n, N = int(rng.integers(5, 10)), int(rng.integers(4, 8))
+        v = np.floor(rng.uniform(8, 30, n)); gaps = rng.uniform(60, 140, n)
+        p = np.floor(3000.0 - np.cumsum(gaps) + gaps[0])
+        x0 = np.empty(2 * n); x0[0::2] = p; x0[1::2] = v
+        lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=float(rng.uniform(8, 14)), vf=float(rng.uniform(22, 32)),
+                                       v_change_steps=[2, 3], trajectory_len=T + N + 5, ts=1).get_leader_trajectory()
+        scen.append(dict(n=n, N=N, x0=x0, leader_x=lx[:, :T + 7 + 1 + 3], masses=rng.uniform(700, 1000, n),
+                         spacing_policy=ConstantTimePolicy(10, 3) if i % 2 else None))
+    for sc in scen:   # pad leader windows to a common usable length per scenario
+        assert sc["leader_x"].shape[1] >= T + sc["N"] + 1
+    a0, a1 = run_mixed_sweep(scen, T, rank=0, world=2), run_mixed_sweep(scen, T, rank=1, world=2)
+    assert set(a0) | set(a1) == set(range(60)) and not (set(a0) & set(a1))
+    full = run_mixed_sweep(scen, T)
+    for part in (a0, a1):
+        for i, r in part.items():
+            assert (r["status"] == 2).all()
+            if (r["errors"] == 0).all() and (full[i]["errors"] == 0).all():
+                assert np.abs(r["X"] - full[i]["X"]).max() < 1e-2
+            assert r["X"].shape == (T + 1, 2 * scen[i]["n"])
