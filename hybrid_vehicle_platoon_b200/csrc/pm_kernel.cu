@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "hvp_internal.h"
 #include "pm_types.h"
@@ -84,6 +85,16 @@ __device__ __forceinline__ void wargmin(double& v, int& id) {
     }
 }
 
+// order-preserving map double -> uint64 (so that atomicMin orders objectives)
+__device__ __forceinline__ unsigned long long dkey(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dval(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
 struct Warp {
     const PmDev& S;
     int lane;
@@ -97,6 +108,12 @@ struct Warp {
     int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
     double inc, c0, cp, nHn, lam_p, dual;
     bool p_soft, trouble, limit, dive;
+    // tree splitting (PmSplit)
+    int sub_M, sub_D, sub_code, sub_ord, budget;
+    double own;                        // objective of this warp's own best leaf
+    unsigned long long* shared;        // incumbent shared by the warps working on one problem
+    const PmSplit* sp;
+    int64_t prob;
 
     __device__ Warp(const PmDev& S_, double* base, int lane_) : S(S_), lane(lane_) {
         const int nv = S.nv, ld = S.ld;
@@ -114,6 +131,7 @@ struct Warp {
         act = ib; cand = ib + nv; modes = cand + D + 1; bmodes = modes + D; built = bmodes + D;
         orient = built + D;
         (void)ld;
+        sub_M = sub_D = sub_code = sub_ord = budget = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
     }
 
     __device__ __forceinline__ double ma(int i, int r) const { return 1.0 - S.M.cf[r] * inv_m[i]; }
@@ -202,7 +220,7 @@ struct Warp {
         }
         built_L = -1;                      // H^-1 not loaded yet
         iters = nodes = it = q = 0;
-        inc = HUGE_VAL; trouble = limit = false; dive = true;
+        inc = HUGE_VAL; own = HUGE_VAL; trouble = limit = false; dive = true; sub_ord = 0;
         lev = 0; L = 0; fixed = (fm != nullptr);
         if (infeas) { state = PS_DONE; __syncwarp(); return; }
         if (fixed) {
@@ -253,12 +271,16 @@ struct Warp {
                 const int i = nlev % nl, k = nlev / nl;
                 int rg = -1; double bd = HUGE_VAL;
                 const double xs = xstar[nlev];
-                _Pragma("unroll 1")
-                for (int c = 0; c < S.M.R; ++c) {
-                    if (!((cset >> c) & 1)) continue;
-                    const double lo = S.M.lo[c], hi = S.M.hi[c];
-                    const double dist = xs < lo ? lo - xs : (xs > hi ? xs - hi : 0.0);
-                    if (dist < bd) { bd = dist; rg = c; }
+                if (sub_M > 0 && nlev < sub_D) {
+                    rg = __ffs(cset) - 1;      // prefix levels: a fixed order, identical in every warp of the problem
+                } else {
+                    _Pragma("unroll 1")
+                    for (int c = 0; c < S.M.R; ++c) {
+                        if (!((cset >> c) & 1)) continue;
+                        const double lo = S.M.lo[c], hi = S.M.hi[c];
+                        const double dist = xs < lo ? lo - xs : (xs > hi ? xs - hi : 0.0);
+                        if (dist < bd) { bd = dist; rg = c; }
+                    }
                 }
                 cand[nlev] = cset & ~(1 << rg);
                 modes[nlev] = rg;
@@ -271,6 +293,14 @@ struct Warp {
                 if (nlo > nhi + eps) continue;
                 rlo[i * (N + 1) + k + 1] = nlo - eps; rhi[i * (N + 1) + k + 1] = nhi + eps;
                 nL = nlev + 1;
+                if (sub_M > 0) {
+                    if (nL < sub_D) {          // mode prefix not complete yet: descend without solving
+                        ++nlev;
+                        open_level(nlev);
+                        continue;
+                    }
+                    if (nL == sub_D && (sub_ord++ % sub_M) != sub_code) continue;   // another warp's sub-tree
+                }
                 if (dive && nodes >= 1 && nL < S.depth) {
                     // first descent: without an incumbent the relaxations along the path cannot prune, they
                     // only guide the region choice -- follow the last relaxed trajectory and solve the leaf
@@ -335,13 +365,26 @@ struct Warp {
         if (st == 1) return;
         if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
         if (L == S.depth) {                                                           // leaf
-            inc = obj;
+            inc = obj; own = obj;
             LANES(j, S.nv) best[j] = x[j];
             LANES(d, S.depth) bmodes[d] = modes[d];
+            if (shared && lane == 0) atomicMin(shared, dkey(obj));
             __syncwarp();
             return;
         }
         if (S.max_nodes > 0 && nodes >= S.max_nodes) { limit = true; state = PS_DONE; return; }
+        if (budget > 0 && nodes >= budget) {
+            // heavy tree: hand it to the sub-tree pass if the list has room, else finish it here
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(sp->nflag, 1);
+            slot = __shfl_sync(FULL, slot, 0);
+            if (slot < sp->cap) {
+                if (lane == 0) { sp->flagged[slot] = (int)prob; sp->inc_shared[slot] = dkey(inc); }
+                limit = true; state = PS_DONE;
+                return;
+            }
+            budget = 0;
+        }
         ++lev;
         if (lane == 0) open_level(lev);
         __syncwarp();
@@ -371,6 +414,12 @@ struct Warp {
     // ---- BUILD: bring H^-1 to this node, gradient, unconstrained minimiser ----------------------
     __device__ void do_build() {
         const int nl = S.nl, N = S.N, nv = S.nv, ld = S.ld;
+        if (shared) {       // best objective found by ANY warp working on this problem
+            double g = 0.0;
+            if (lane == 0) g = dval(*reinterpret_cast<volatile unsigned long long*>(shared));
+            g = __shfl_sync(FULL, g, 0);
+            if (g < inc) inc = g;
+        }
         int c = 0;
         if (built_L > 0)
             while (c < built_L && c < L && built[c] == modes[c]) ++c;
@@ -763,7 +812,7 @@ struct Warp {
     __device__ void finish(double* u_out, double* x_out, double* e_out, int32_t* m_out, double* obj,
                            int32_t* status, int32_t* nodes_out, int32_t* iters_out) {
         const int nl = S.nl, N = S.N, np1 = N + 1;
-        const bool ok = inc < HUGE_VAL;
+        const bool ok = own < HUGE_VAL;
         __syncwarp();
         LANES(i, nl) {
             double* xo = x_out + (size_t)i * 2 * np1;
@@ -790,7 +839,7 @@ struct Warp {
         }
         if (e_out) LANES(e, S.ne) e_out[e] = ok ? best[nl * N + e] : 0.0;
         if (lane == 0) {
-            *obj = ok ? inc : HUGE_VAL;
+            *obj = ok ? own : HUGE_VAL;
             *status = limit ? HVP_ST_NODE_LIMIT
                             : (trouble ? HVP_ST_NUMERIC : (ok ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE));
             *nodes_out = nodes;
@@ -808,24 +857,74 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
                const int32_t* __restrict__ fixed_modes, const double* __restrict__ Y, double* __restrict__ u,
                double* __restrict__ x, double* __restrict__ extra, int32_t* __restrict__ modes, double* __restrict__ obj,
                int32_t* __restrict__ status, int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters,
-               unsigned long long* __restrict__ counter) {
+               unsigned long long* __restrict__ counter, const __grid_constant__ PmSplit sp) {
     extern __shared__ double pm_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
     Warp W(S, base, lane);
     const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
     // problems are handed out one at a time (tree sizes vary by orders of magnitude)
-    _Pragma("unroll 1")
+    W.sp = &sp;
     for (;;) {
         unsigned long long nxt = 0;
         if (lane == 0) nxt = atomicAdd(counter, 1ull);
-        const int64_t i = (int64_t)__shfl_sync(FULL, nxt, 0);
-        if (i >= batch) break;
+        const int64_t w = (int64_t)__shfl_sync(FULL, nxt, 0);
+        int64_t i = w, o = w;                    // problem (input) index, output index
+        W.sub_M = 0; W.sub_D = 0; W.sub_code = 0; W.shared = nullptr;
+        W.budget = (sp.mode == 1 && !fixed_modes) ? sp.budget : 0;
+        if (sp.mode == 2) {
+            int nf = *reinterpret_cast<volatile int*>(sp.nflag);
+            if (nf > sp.cap) nf = sp.cap;
+            if (w >= (int64_t)nf * sp.M) break;
+            const int f = (int)(w / sp.M);
+            i = sp.flagged[f];
+            W.sub_M = sp.M; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M); W.shared = sp.inc_shared + f;
+        } else if (w >= batch) break;
+        W.prob = i;
         W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar,
                 fixed_modes ? fixed_modes + su * i : nullptr, Y ? Y + (size_t)S.mw * i : nullptr);
         W.solve();
-        W.finish(u + su * i, x + sx * i, extra ? extra + (size_t)S.ne * i : nullptr, modes + su * i, obj + i,
-                 status + i, nodes + i, qp_iters ? qp_iters + i : nullptr);
+        W.finish(u + su * o, x + sx * o, extra ? extra + (size_t)S.ne * o : nullptr, modes + su * o, obj + o,
+                 status + o, nodes + o, qp_iters ? qp_iters + o : nullptr);
+    }
+}
+
+// pass 3 of the tree split: one warp per flagged problem keeps the best of its M sub-results (or the pass-1
+// incumbent when no sub-tree improved on it) and adds up the work counters
+__global__ void __launch_bounds__(128)
+pm_merge_kernel(const __grid_constant__ PmDev S, const __grid_constant__ PmSplit sp, const double* __restrict__ su_,
+                const double* __restrict__ sx_, const double* __restrict__ se_, const int32_t* __restrict__ sm_,
+                const double* __restrict__ sobj, const int32_t* __restrict__ sst, const int32_t* __restrict__ sno,
+                const int32_t* __restrict__ sit, double* __restrict__ u, double* __restrict__ x,
+                double* __restrict__ extra, int32_t* __restrict__ modes, double* __restrict__ obj,
+                int32_t* __restrict__ status, int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
+    const int lane = threadIdx.x & 31;
+    const int f = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int nf = *sp.nflag;
+    if (nf > sp.cap) nf = sp.cap;
+    if (f >= nf) return;
+    const int i = sp.flagged[f];
+    const size_t nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
+    double bestv = obj[i];                       // incumbent of the budgeted pass (+inf if it had none)
+    int bw = -1, nsum = 0, isum = 0;
+    bool numeric = false;
+    for (int c = 0; c < sp.M; ++c) {
+        const size_t w = (size_t)f * sp.M + c;
+        if (sobj[w] < bestv) { bestv = sobj[w]; bw = (int)w; }
+        nsum += sno[w];
+        if (sit) isum += sit[w];
+        if (sst[w] == HVP_ST_NUMERIC) numeric = true;
+    }
+    if (bw >= 0) {
+        for (size_t e = lane; e < nu; e += 32) { u[nu * i + e] = su_[nu * bw + e]; modes[nu * i + e] = sm_[nu * bw + e]; }
+        for (size_t e = lane; e < nx; e += 32) x[nx * i + e] = sx_[nx * bw + e];
+        if (extra) for (int e = lane; e < S.ne; e += 32) extra[(size_t)S.ne * i + e] = se_[(size_t)S.ne * bw + e];
+    }
+    if (lane == 0) {
+        obj[i] = bestv;
+        status[i] = numeric ? HVP_ST_NUMERIC : (bestv < HUGE_VAL ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE);
+        nodes[i] += nsum;
+        if (qp_iters) qp_iters[i] += isum;
     }
 }
 
@@ -936,7 +1035,7 @@ void pm_layout(PmDev& S) {
 cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
                            const double* params, const int32_t* fixed_modes, const double* Y, double* u, double* x,
                            double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
-                           int32_t* qp_iters, unsigned long long* counter, cudaStream_t stream) {
+                           int32_t* qp_iters, unsigned long long* counter, const PmScratch* sc, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     int wpb = 4;
     while (wpb > 1 && (size_t)wpb * S.smem_bytes > 200 * 1024) wpb >>= 1;
@@ -954,13 +1053,39 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
     int per_sm = (int)((220 * 1024) / smem);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 16 / wpb * 4) per_sm = 16 / wpb * 4;
+    const int64_t full = (int64_t)sms * per_sm;
     int64_t blocks = (batch + wpb - 1) / wpb;
-    const int64_t cap = (int64_t)sms * per_sm;
-    if (blocks > cap) blocks = cap;
+    if (blocks > full) blocks = full;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,
-                                                                 extra, modes, obj, status, nodes, qp_iters, counter);
+    const bool split = sc && !fixed_modes && S.max_nodes == 0 && sc->sp.D >= 1;
+    PmSplit sp;
+    memset(&sp, 0, sizeof sp);
+    if (!split) {
+        pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,
+                                                                     extra, modes, obj, status, nodes, qp_iters, counter, sp);
+        return cudaGetLastError();
+    }
+    // pass 1: every problem under a node budget; heavy trees are appended to the flagged list
+    sp = sc->sp;
+    sp.mode = 1;
+    e = cudaMemsetAsync(sp.nflag, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, u, x, extra,
+                                                                 modes, obj, status, nodes, qp_iters, counter, sp);
+    // pass 2: M warps per flagged problem, sub-trees by prefix ordinal, incumbent shared through global memory
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    sp.mode = 2;
+    int64_t b2 = ((int64_t)sp.cap * sp.M + wpb - 1) / wpb;
+    if (b2 > full) b2 = full;
+    pm_miqp_kernel<<<(unsigned)b2, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
+                                                             sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
+                                                             sc->iters, counter, sp);
+    // pass 3: keep the best sub-result of every flagged problem
+    pm_merge_kernel<<<(unsigned)((sp.cap + 3) / 4), 128, 0, stream>>>(S, sp, sc->u, sc->x, sc->extra, sc->modes, sc->obj,
+                                                                     sc->status, sc->nodes, sc->iters, u, x, extra,
+                                                                     modes, obj, status, nodes, qp_iters);
     return cudaGetLastError();
 }
 

@@ -59,4 +59,23 @@ struct PmDev {                   // kernel argument
     int o_int, smem_bytes;
 };
 
+// Tree splitting of heavy problems (pm_kernel.cu): pass 1 solves every problem under a node budget and
+// appends the ones that exceed it to `flagged`; pass 2 gives each flagged problem `M` warps, which share the
+// work by the ordinal of the depth-`D` mode prefix (ordinal mod M) and exchange the incumbent through
+// `inc_shared` (atomicMin on an order-preserving key); pass 3 keeps the best sub-result.
+struct PmSplit {
+    int mode;                          // 0 plain, 1 budgeted pass, 2 sub-tree pass
+    int budget, cap, M, D;
+    int* nflag;                        // [1] flagged problems so far
+    int* flagged;                      // [cap] their batch indices
+    unsigned long long* inc_shared;    // [cap] best objective known for each (order-preserving key)
+};
+
+// device scratch of the sub-tree pass: outputs of cap * M work items, same layout as the real outputs
+struct PmScratch {
+    PmSplit sp;
+    double *u, *x, *extra, *obj;
+    int32_t *modes, *status, *nodes, *iters;
+};
+
 }  // namespace hvp

@@ -212,3 +212,28 @@ def test_event_eval_cost_vs_oracle(hvp):
     # (3) an inconsistent guess is infeasible
     xbad = r["x"].copy(); xbad[:, 0, 1, 2] += 0.5
     assert np.isinf(mpc.eval_cost(800.0, params, xbad, r["u"])).all()
+
+
+@pytest.mark.parametrize("budget", ["3", "12"])
+def test_tree_split_matches_oracle(hvp, monkeypatch, budget):
+    """Heavy trees are split over 32 warps that share the incumbent (pm_kernel.cu pass 1-3).  With a tiny node
+    budget almost every problem takes that path; the result must not change."""
+    monkeypatch.setenv("HVP_MPC_BUDGET", budget)
+    rng = np.random.default_rng(700)
+    B, n, N = 48, 3, 4
+    x0, params = G.cent_cases(rng, B, n, N, stress=True)
+    mpc = hvp.api.CompiledMpc(G.CENT, N, n_local=n)
+    r = mpc.solve(x0, 800.0, params)
+    ro = O.mpc_solve(O.CENT, n, N, x0, 800.0, params, method=1)
+    _compare(r, ro, "cent split")
+    monkeypatch.setenv("HVP_MPC_SPLIT", "0")
+    r0 = hvp.api.CompiledMpc(G.CENT, N, n_local=n).solve(x0, 800.0, params)
+    assert np.allclose(r0["obj"], r["obj"], rtol=1e-9, equal_nan=True)
+    assert (r["nodes"] >= 1).all()
+    # ADMM formulation with extras, N = 6
+    x0, params = G.admm_cases(rng, 32, 6, stress=True)
+    monkeypatch.setenv("HVP_MPC_SPLIT", "1")
+    mpc = hvp.api.CompiledMpc(G.ADMM, 6, rho=0.5)
+    r = mpc.solve(x0, 800.0, params)
+    ro = O.mpc_solve(O.ADMM, 1, 6, x0, 800.0, params, rho=0.5, method=1)
+    _compare(r, ro, "admm split")
