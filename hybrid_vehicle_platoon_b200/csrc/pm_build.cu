@@ -40,6 +40,8 @@ struct hvp_mpc {
     size_t ycap = 0;
     PmScratch scratch;           // tree-split scratch (pm_types.h); scratch.sp.D == 0: disabled
     void* scratch_mem = nullptr;
+    size_t scratch_cap = 0;      // flagged-list capacity the scratch was sized for
+    int split_D = 0;
 };
 
 namespace {
@@ -455,36 +457,14 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     if (!rc) rc = upload(m, B0, &S.B0); if (!rc) rc = upload(m, w0, &S.w0);
     if (!rc) { const double* cn = nullptr; rc = upload(m, std::vector<double>(2, 0.0), &cn); m->counter = (unsigned long long*)cn; }
     if (rc) { hvp_mpc_destroy(m); return rc; }
-    // tree-split scratch: cap heavy problems x M warps each (see PmSplit)
+    // tree splitting of heavy problems (PmSplit): prefix depth of the split; the scratch is sized per batch
     memset(&m->scratch, 0, sizeof m->scratch);
     {
         const char* env = getenv("HVP_MPC_SPLIT");
-        const int depth = S.depth;
         int D = 3 * S.nl > 5 ? 3 * S.nl : 5;
-        if (D > depth - 1) D = depth - 1;
+        if (D > S.depth - 1) D = S.depth - 1;
         if (env && atoi(env) == 0) D = 0;
-        if (D >= 1) {
-            const char* em = getenv("HVP_MPC_SPLIT_M");
-            const int cap = 1024, M = em ? atoi(em) : 32;
-            const size_t items = (size_t)cap * M, nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
-            const size_t ne = S.ne > 0 ? (size_t)S.ne : 1;
-            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + (size_t)cap * (4 + 8) + 64 + 8 * 256;
-            void* p = nullptr;
-            cudaError_t ce = cudaMalloc(&p, bytes);
-            if (ce != cudaSuccess) { hvp_mpc_destroy(m); return fail(-100 - (int)ce, "mpc_create: scratch allocation failed: %s", cudaGetErrorString(ce)); }
-            m->scratch_mem = p;
-            char* q = (char*)p;
-            auto take = [&](size_t b) { char* r = q; q += (b + 255) & ~(size_t)255; return r; };
-            PmScratch& sc = m->scratch;
-            sc.u = (double*)take(items * nu * 8); sc.x = (double*)take(items * nx * 8); sc.extra = (double*)take(items * ne * 8);
-            sc.obj = (double*)take(items * 8); sc.modes = (int32_t*)take(items * nu * 4); sc.status = (int32_t*)take(items * 4);
-            sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
-            sc.sp.inc_shared = (unsigned long long*)take((size_t)cap * 8); sc.sp.flagged = (int*)take((size_t)cap * 4);
-            sc.sp.nflag = (int*)take(4);
-            sc.sp.cap = cap; sc.sp.M = M; sc.sp.D = D;
-            const char* eb = getenv("HVP_MPC_BUDGET");
-            sc.sp.budget = eb ? atoi(eb) : 256;
-        }
+        m->split_D = D;
     }
     *out = m;
     return 0;
@@ -526,10 +506,40 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
         CUDA_TRY(cudaMalloc(&m->ybuf, need + need / 4));
         m->ycap = need + need / 4;
     }
+    if (m->split_D >= 1 && !fixed_modes && m->S.max_nodes == 0) {
+        // cap heavy problems x M warps each; sized from the batch (grow-only)
+        static const int envM = getenv("HVP_MPC_SPLIT_M") ? atoi(getenv("HVP_MPC_SPLIT_M")) : 64;
+        static const int envB = getenv("HVP_MPC_BUDGET") ? atoi(getenv("HVP_MPC_BUDGET")) : 128;
+        size_t cap = (size_t)batch / 8;
+        if (cap < 256) cap = 256;
+        if (cap > 4096) cap = 4096;
+        if (cap > m->scratch_cap || m->scratch.sp.M != envM) {
+            if (m->scratch_mem) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->scratch_mem)); m->scratch_mem = nullptr; }
+            const PmDev& S = m->S;
+            const size_t items = cap * (size_t)envM, nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
+            const size_t ne = S.ne > 0 ? (size_t)S.ne : 1;
+            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + cap * (4 + 8) + 64 + 12 * 256;
+            void* p = nullptr;
+            CUDA_TRY(cudaMalloc(&p, bytes));
+            m->scratch_mem = p;
+            char* q = (char*)p;
+            auto take = [&](size_t b) { char* r = q; q += (b + 255) & ~(size_t)255; return r; };
+            PmScratch& sc = m->scratch;
+            sc.u = (double*)take(items * nu * 8); sc.x = (double*)take(items * nx * 8); sc.extra = (double*)take(items * ne * 8);
+            sc.obj = (double*)take(items * 8); sc.modes = (int32_t*)take(items * nu * 4); sc.status = (int32_t*)take(items * 4);
+            sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
+            sc.sp.inc_shared = (unsigned long long*)take(cap * 8); sc.sp.flagged = (int*)take(cap * 4);
+            sc.sp.nflag = (int*)take(4);
+            sc.sp.M = envM; sc.sp.D = m->split_D;
+            m->scratch_cap = cap;
+        }
+        m->scratch.sp.cap = (int)cap;
+        m->scratch.sp.budget = envB;
+    }
     CUDA_TRY(cudaEventRecord(c->ev0, st));
     CUDA_TRY(launch_pm_precompute(m->S, batch, x0, params, m->ybuf, st));
     CUDA_TRY(launch_pm_miqp(m->S, batch, x0, mass, params, fixed_modes, m->ybuf, u, x, extra, modes, obj, status,
-                            nodes, qp_iters, m->counter, m->scratch.sp.D >= 1 ? &m->scratch : nullptr, st));
+                            nodes, qp_iters, m->counter, (m->split_D >= 1 && m->scratch_mem) ? &m->scratch : nullptr, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     c->launches += 2;
