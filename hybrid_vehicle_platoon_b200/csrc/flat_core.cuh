@@ -33,6 +33,14 @@
 
 namespace hvp {
 
+#if defined(__CUDA_ARCH__)
+// The flat kernel runs one warp per CTA and its whole dynamic shared memory is the warp's work slab.
+// Indexing this symbol (instead of a generic double*) tells the compiler the address space: LDS/STS with
+// 32-bit address arithmetic instead of generic LD/ST with 64-bit pointer math (r01h ncu: 8.5 % of the
+// issued instructions were generic loads and a quarter were IMAD/LEA address arithmetic).
+extern __shared__ double hvp_flat_slab[];
+#endif
+
 // reciprocal to ~1 ulp without the slow paths of the IEEE division sequence
 HVP_HD double hvp_rcp(double v) {
 #if defined(__CUDA_ARCH__)
@@ -53,13 +61,11 @@ struct FlatLayout {
     static constexpr int O_GINV = N * N;          // packed lower (N'H^-1N)^-1, slots a >= b
     static constexpr int O_X = O_GINV + TRI;
     static constexpr int O_LAM = O_X + N;
-    static constexpr int O_SSGN = O_LAM + N;      // sign (incl. soft orientation) of slot a's row
-    static constexpr int O_SCOEF = O_SSGN + N;    // difference coefficient of slot a's row
-    static constexpr int O_YP = O_SCOEF + N;      // H^-1 n_p
-    static constexpr int O_WV = O_YP + N;         // n_p - N r ; scratch
-    static constexpr int O_D = O_WV + N;
+    static constexpr int O_YP = O_LAM + N;        // H^-1 n_p
+    static constexpr int O_D = O_YP + N;          // d = N'yp (dead once r is known) ...
+    static constexpr int O_WV = O_D;              // ... then w = n_p - N r and other scratch
     static constexpr int O_R = O_D + N;
-    static constexpr int SIZE = O_R + N;          // doubles per thread (105 at N = 6)
+    static constexpr int SIZE = O_R + N;          // doubles per thread (87 at N = 6: 10 warps / SM)
 };
 
 template <int N, int ST>
@@ -93,7 +99,14 @@ struct FlatSolver {
     double dual;                                         // value of the node's dual function (lower bound)
     bool p_soft;
 
-    HVP_HD double& w(int off, int i) const { return W[(size_t)(off + i) * ST]; }
+    int lane_;                          // lane of this problem within the warp (device)
+    HVP_HD double& w(int off, int i) const {
+#if defined(__CUDA_ARCH__)
+        return hvp_flat_slab[(off + i) * ST + lane_];
+#else
+        return W[(size_t)(off + i) * ST];
+#endif
+    }
     HVP_HD static int tri(int a, int b) { return a * (a + 1) / 2 + b; }          // a >= b
     HVP_HD double ra(int rg) const { return rg < 4 ? a_lo : a_hi; }
     HVP_HD double rc(int rg) const { return rg < 4 ? c_lo : c_hi; }
@@ -103,7 +116,15 @@ struct FlatSolver {
     HVP_HD void set_mode(int k, int rg) { modes_pk = (modes_pk & ~(7ull << (3 * k))) | ((uint64_t)rg << (3 * k)); }
     HVP_HD int cand(int lv) const { return (int)((cand_pk >> (7 * lv)) & 0x7fu); }
     HVP_HD void set_cand(int lv, int v) { cand_pk = (cand_pk & ~(0x7full << (7 * lv))) | ((uint64_t)v << (7 * lv)); }
-    HVP_HD int act(int a) const { return (int)(((a < 8 ? act_lo >> (8 * a) : act_hi >> (8 * (a - 8)))) & 0xffu); }
+    // slot a's row: id = type * 12 + stage in the low 7 bits, bit 7 = the row enters with sign -1 (the sign
+    // includes a soft row's orientation at the time it became active; it cannot flip while active)
+    HVP_HD int act_raw(int a) const { return (int)(((a < 8 ? act_lo >> (8 * a) : act_hi >> (8 * (a - 8)))) & 0xffu); }
+    HVP_HD int act(int a) const { return act_raw(a) & 0x7f; }
+    HVP_HD double slot_sgn(int a) const { return (act_raw(a) & 0x80) ? -1.0 : 1.0; }
+    HVP_HD double slot_coef(int a) const {           // difference coefficient: a_r of the stage for input-limit rows
+        const int id = act(a), t = id / 12;
+        return (t == T_UHI || t == T_ULO) ? ra(mode(id - 12 * t)) : 1.0;
+    }
     HVP_HD void set_act(int a, int id) {
         if (a < 8) act_lo = (act_lo & ~(0xffull << (8 * a))) | ((uint64_t)id << (8 * a));
         else act_hi = (act_hi & ~(0xffull << (8 * (a - 8)))) | ((uint64_t)id << (8 * (a - 8)));
@@ -480,19 +501,19 @@ struct FlatSolver {
         const int id = act(a), t = id / 12, j = id - 12 * t;
         double s;
         if (t < T_ACC) s = w(off, j);
-        else if (t < T_PHI) s = w(off, j) - w(LY::O_SCOEF, a) * w(off, j - 1);
+        else if (t < T_PHI) s = w(off, j) - slot_coef(a) * w(off, j - 1);
         else {
             s = 0.0;
             HVP_ROLL
             for (int i = 0; i < j; ++i) s += w(off, i);
         }
-        return w(LY::O_SSGN, a) * s;
+        return slot_sgn(a) * s;
     }
     HVP_HD void slot_axpy(int a, double c0, int off) const {
         const int id = act(a), t = id / 12, j = id - 12 * t;
-        const double c = c0 * w(LY::O_SSGN, a);
+        const double c = c0 * slot_sgn(a);
         if (t < T_ACC) w(off, j) += c;
-        else if (t < T_PHI) { w(off, j) += c; w(off, j - 1) -= c * w(LY::O_SCOEF, a); }
+        else if (t < T_PHI) { w(off, j) += c; w(off, j - 1) -= c * slot_coef(a); }
         else {
             HVP_ROLL
             for (int i = 0; i < j; ++i) w(off, i) += c;
@@ -573,10 +594,8 @@ struct FlatSolver {
                 w(LY::O_GINV, tri(q, a)) = -ra_;
             }
             w(LY::O_GINV, tri(q, q)) = is;
-            set_act(q, pid);
+            set_act(q, pid | (psgn < 0.0 ? 0x80 : 0));
             w(LY::O_LAM, q) = lam_p;
-            w(LY::O_SSGN, q) = psgn;
-            w(LY::O_SCOEF, q) = pcoef;
             ++q;
             state = S_SELECT;
             return;
@@ -612,10 +631,8 @@ struct FlatSolver {
         }
         HVP_ROLL
         for (int a = drop; a + 1 < q; ++a) {
-            set_act(a, act(a + 1));
+            set_act(a, act_raw(a + 1));
             w(LY::O_LAM, a) = w(LY::O_LAM, a + 1);
-            w(LY::O_SSGN, a) = w(LY::O_SSGN, a + 1);
-            w(LY::O_SCOEF, a) = w(LY::O_SCOEF, a + 1);
         }
         --q;
         // state stays S_STEP: continue with the same p

@@ -90,6 +90,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
     int64_t next = (int64_t)blockIdx.x * chunk;                   // warp-uniform
     const int64_t end = next + chunk < batch ? next + chunk : batch;
     Solver sol;
+    sol.lane_ = lane;
     bool have = false;
     int64_t i = 0;
     // A lane is either stepping its node QP (SELECT/STEP: the common, cheap trip) or waiting for node
@@ -157,7 +158,8 @@ static cudaError_t launch_flat(const LocalParams& P, int64_t batch, const int32_
     }
     // persistent grid: every resident warp slot, but never more warps than 32-problem shares
     int64_t g = (batch + 31) / 32;
-    if (g > grid_full) g = grid_full;
+    static const int gdiv = env_int("HVP_FLAT_GRID_DIV", 1);
+    if (g > grid_full / gdiv) g = grid_full / gdiv;
     LocalParams Q = P;
     static const int nb = env_int("HVP_NODE_BATCH", 0), hl = env_int("HVP_FLAT_HULL", -1), dv = env_int("HVP_FLAT_DIVE", -1);
     if (nb > 0) Q.node_batch = nb;
