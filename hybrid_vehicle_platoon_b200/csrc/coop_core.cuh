@@ -421,7 +421,10 @@ struct CoopSolver {
         const I ln = bk.lane();
         if (++it > 40 * N + 60) { node_done(2, 0.0); return; }
         const double cp = bk.gsum(np * x) - prhs;
-        if (cp <= tol) { state = S_SELECT; return; }
+        // see flat_core.cuh: a row that reaches its boundary at the end of a partial step joins the active
+        // set with its accumulated multiplier (zero-length full step)
+        const bool zero_step = (cp <= tol);
+        if (zero_step && !(lam_p > 0.0)) { state = S_SELECT; return; }
         // d_a = n_a' yp for slot a (lane a owns its row description);  r = Ginv d
         D d;
         {
@@ -435,7 +438,8 @@ struct CoopSolver {
         const double nz = nHn - bk.gsum(d * r);
         const bool dependent = (q == N) || !(nz > 1e-11 * nHn);
         const double INF = HUGE_VAL;
-        const double t2 = dependent ? INF : cp / nz;
+        if (zero_step && dependent) { node_done(2, 0.0); return; }
+        const double t2 = dependent ? INF : (zero_step ? 0.0 : cp / nz);
         double t1, t3; int k1, k3;
         {
             const Bm act_ok = ln < q;

@@ -436,6 +436,17 @@ struct FlatSolver {
             PS += xv; xm = xv;
         }
 #undef HVP_CAND
+        if (bid >= 0) {
+            // The most violated row is already active: its residual is round-off drift (ill-conditioned,
+            // heavily constrained node) and every other row is violated by even less -> converged.
+            bool dup = false;
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) dup = dup || (act(a) == bid);
+            if (dup) {
+                if (best < 1e-6) bid = -1;
+                else { node_done(2, 0.0); return; }
+            }
+        }
         if (bid < 0) {
             // ---- node solved: objective = tracking closed form + input cost + L1 penalties ----
             double f = ct;
@@ -458,10 +469,6 @@ struct FlatSolver {
             node_done(0, f);
             return;
         }
-        // a selected row can never already be active (active rows have residual ~1e-13 << tol)
-        HVP_ROLL
-        for (int a = 0; a < q; ++a)
-            if (act(a) == bid) { node_done(2, 0.0); return; }
         pid = bid;
         const int pt = pid / 12;
         pj = pid - 12 * pt;
@@ -524,7 +531,11 @@ struct FlatSolver {
     HVP_HD void do_step() {
         const double tol = 1e-9, ww = P->w;
         if (++it > 40 * N + 60) { node_done(2, 0.0); return; }
-        if (cp <= tol) { state = S_SELECT; return; }
+        // p can reach its boundary exactly at the end of a PARTIAL step (t1 = t2 tie): it then joins the
+        // active set with the multiplier it has accumulated (a full step of length zero) -- returning to
+        // SELECT here would drop lam_p * n_p from the stationarity condition
+        const bool zero_step = (cp <= tol);
+        if (zero_step && !(lam_p > 0.0)) { state = S_SELECT; return; }
         // d = N' yp ; r = Ginv d ; nz = nHn - d'r
         HVP_ROLL
         for (int a = 0; a < q; ++a) w(LY::O_D, a) = slot_dot(a, LY::O_YP);
@@ -549,7 +560,8 @@ struct FlatSolver {
         }
         const bool dependent = (q == N) || !(nz > 1e-11 * nHn);
         const double INF = HUGE_VAL;
-        const double t2 = dependent ? INF : cp * hvp_rcp(nz);
+        if (zero_step && dependent) { node_done(2, 0.0); return; }
+        const double t2 = dependent ? INF : (zero_step ? 0.0 : cp * hvp_rcp(nz));
         const double t1 = k1 >= 0 ? n1 * hvp_rcp(d1) : INF;
         const double t3 = k3 >= 0 ? n3 * hvp_rcp(d3) : INF;
         const double t3p = p_soft ? (ww - lam_p) : INF;

@@ -356,7 +356,8 @@ struct LocalSolver {
                 if (++it > maxit) { iters += it; return 2; }
                 const Row rp = decode(pid);
                 const double cp = row_dot(rp, LY::O_X) - rp.rhs;
-                if (cp <= tol) break;
+                const bool zero_step = (cp <= tol);             // see flat_core.cuh: zero-length full step
+                if (zero_step && !(lam_p > 0.0)) break;
                 hinv_row(rp, LY::O_YP);                         // yp = H^-1 n_p
                 const double nHn = row_dot(rp, LY::O_YP);
                 // d = N' yp ; r = Ginv d ; nz = nHn - d'r
@@ -370,7 +371,8 @@ struct LocalSolver {
                 }
                 const bool dependent = (q == N) || !(nz > 1e-11 * nHn);
                 const double INF = HUGE_VAL;
-                const double t2 = dependent ? INF : cp / nz;
+                if (zero_step && dependent) { iters += it; return 2; }
+                const double t2 = dependent ? INF : (zero_step ? 0.0 : cp / nz);
                 double t1 = INF, t3 = INF;
                 int k1 = -1, k3 = -1;
                 for (int a = 0; a < q; ++a) {

@@ -423,7 +423,7 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     {
         const int nres = S.nres, nlin = S.nlin;
         S.kw = (npv + 3) / 4 * 4;
-        S.mw = (nv + S.ng + S.n0 + npv + 7) / 8 * 8;
+        S.mw = (nv + S.ng + S.n0 + nres + 2 * nlin + 7) / 8 * 8;
         std::vector<double> Wm((size_t)S.mw * S.kw, 0.0);
         for (int j = 0; j < nv; ++j)
             for (int t = 0; t < npv; ++t) {
@@ -432,17 +432,19 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
                 for (int l = 0; l < nlin; ++l) s += Lz[(size_t)l * nv + j] * La[(size_t)l * npv + t];
                 Wm[(size_t)j * S.kw + t] = s;
             }
-        for (int g = 0; g < S.ng; ++g)
-            for (int t = 0; t < npv; ++t) Wm[(size_t)(nv + g) * S.kw + t] = BR[(size_t)g * npv + t];
-        for (int g = 0; g < S.n0; ++g)
-            for (int t = 0; t < npv; ++t) Wm[(size_t)(nv + S.ng + g) * S.kw + t] = B0[(size_t)g * npv + t];
-        for (int a = 0; a < npv; ++a)
-            for (int t = 0; t < npv; ++t) {
-                double s = 0.0;
-                for (int r = 0; r < nres; ++r) s += wres[r] * Cres[(size_t)r * npv + a] * Cres[(size_t)r * npv + t];
-                for (int l = 0; l < nlin; ++l) s += La[(size_t)l * npv + a] * Lp[(size_t)l * npv + t];
-                Wm[(size_t)(nv + S.ng + S.n0 + a) * S.kw + t] = s;
-            }
+        int row = nv;
+        for (int g = 0; g < S.ng; ++g, ++row)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = BR[(size_t)g * npv + t];
+        for (int g = 0; g < S.n0; ++g, ++row)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = B0[(size_t)g * npv + t];
+        // the constant term is summed from the residuals themselves (c0 = sum w_r c_r^2 + sum a_l p_l): the
+        // residuals are small numbers, whereas the quadratic form pvec' CC pvec cancels terms of size p^2 ~ 1e7
+        for (int r = 0; r < nres; ++r, ++row)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = Cres[(size_t)r * npv + t];
+        for (int l = 0; l < nlin; ++l, ++row)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = La[(size_t)l * npv + t];
+        for (int l = 0; l < nlin; ++l, ++row)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = Lp[(size_t)l * npv + t];
         rc = upload(m, Wm, &S.W);
         if (rc) { delete Bp; hvp_mpc_destroy(m); return rc; }
     }

@@ -103,7 +103,7 @@ struct Warp {
     double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best;
     double *cres, *bgen, *pvec;
     double *inv_m, *pc, *v0, *xstar, *rlo, *rhi, *am, *bm, *cm, *amax, *amin;
-    int *act, *cand, *modes, *bmodes, *built, *orient;
+    int *act, *cand, *modes, *bmodes, *built, *orient, *aflag, *agen;
     // warp-uniform scalars (replicated in registers)
     int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
     double inc, c0, cp, nHn, lam_p, dual;
@@ -129,7 +129,7 @@ struct Warp {
         amax = cm + D; amin = amax + D;
         int* ib = reinterpret_cast<int*>(base + S.smem_doubles);
         act = ib; cand = ib + nv; modes = cand + D + 1; bmodes = modes + D; built = bmodes + D;
-        orient = built + D;
+        orient = built + D; aflag = orient + S.ng; agen = aflag + nv;
         (void)ld;
         sub_M = sub_D = sub_code = sub_ord = budget = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
     }
@@ -166,7 +166,11 @@ struct Warp {
                     else if (s > 1e-9) infeas = true;
                 }
             }
-            LANES(t, npv) c += pvec[t] * Y[nv + S.ng + S.n0 + t];
+            {
+                const double* yr = Y + nv + S.ng + S.n0;
+                LANES(r, S.nres) c += S.wres[r] * yr[r] * yr[r];
+                LANES(l, S.nlin) c += yr[S.nres + l] * yr[S.nres + S.nlin + l];
+            }
         } else {
             // residual constants, param-linear factors, generic right-hand sides, constant rows
             LANES(r, S.nres) {
@@ -474,7 +478,8 @@ struct Warp {
         }
         // value of the node's dual function at the unconstrained minimiser; it only grows from here
         dual = c0 + wsum(dpart);
-        LANES(r, S.ng) orient[r] = 1;
+        LANES(r, S.ng) { orient[r] = 1; agen[r] = 0; }
+        LANES(j, nv) aflag[j] = 0;
         it = 0; q = 0;
         state = PS_SELECT;
         __syncwarp();
@@ -485,12 +490,15 @@ struct Warp {
     __device__ void scan(double& best_v, int& bid, double tol, bool soft) {
         const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
         best_v = tol; bid = 0x7fffffff;
+        // rows that are in the active set are skipped: their residual is zero up to round-off, which in
+        // heavily constrained, ill-conditioned nodes can exceed `tol` and must not be re-selected
 #define PM_CAND(T, IDX, SV)                                                        \
     {                                                                              \
         const double s__ = (SV);                                                   \
-        if (s__ > best_v) { best_v = s__; bid = PM_ID(T, IDX); }                   \
+        if (s__ > best_v && !((af__ >> (T)) & 1)) { best_v = s__; bid = PM_ID(T, IDX); } \
     }
         LANES(j, nl * N) {
+            const int af__ = aflag[j];
             const int i = j / N, kk = j % N;
             const int d0 = kk * nl + i, d1 = d0 + nl;
             const double xv = x[j];
@@ -527,6 +535,7 @@ struct Warp {
         }
         if (N >= 2) {
             LANES(i, nl) {
+                const int af__ = aflag[i];
                 double ps = pc[i];
                 PM_CAND(PT_PLO, i, S.pmin - (ps + x[i * N]));
                 _Pragma("unroll 1")
@@ -536,6 +545,7 @@ struct Warp {
         }
         LANES(r, ng) {
             if (!soft && isfinite(S.wmax[r])) continue;
+            const int af__ = agen[r] << PT_GEN;
             const double s = dot2(S.AT + r, ng, x, nv) - bgen[r];
             PM_CAND(PT_GEN, r, orient[r] > 0 ? s : -s);
         }
@@ -576,10 +586,6 @@ struct Warp {
             node_done(0, objective());
             return;
         }
-        // a selected row can never already be active (active rows have residual ~1e-13 << tol)
-        bool dup = false;
-        LANES(a, q) if (act[a] == bid) dup = true;
-        if (__any_sync(FULL, dup)) { node_done(2, 0.0); return; }
         pid = bid;
         const int pt = pid / 4096, idx = pid % 4096;
         p_soft = false;
@@ -623,7 +629,11 @@ struct Warp {
         const int nv = S.nv, ld = S.ld;
         const double tol = 1e-9, INF = HUGE_VAL;
         if (++it > 40 * nv + 200) { node_done(2, 0.0); return; }
-        if (cp <= tol) { state = PS_SELECT; return; }
+        // p can reach its boundary exactly at the end of a PARTIAL step (t1 = t2 tie): it then joins the
+        // active set with the multiplier it has accumulated (a full step of length zero) -- returning to
+        // SELECT here would drop lam_p * n_p from the stationarity condition
+        const bool zero_step = (cp <= tol);
+        if (zero_step && !(lam_p > 0.0)) { state = PS_SELECT; return; }
         // d = N' yp
         LANES(a, q) {
             dv[a] = dot2(Nact + a * ld, 1, yp, nv);
@@ -655,7 +665,8 @@ struct Warp {
         wargmin(t1, k1);
         wargmin(t3, k3);
         const bool dependent = (q == nv) || !(nz > 1e-11 * nHn);
-        const double t2 = dependent ? INF : cp * rcp(nz);
+        if (zero_step && dependent) { node_done(2, 0.0); return; }
+        const double t2 = dependent ? INF : (zero_step ? 0.0 : cp * rcp(nz));
         const double t3p = p_soft ? (S.wmax[pid - PM_ID(PT_GEN, 0)] - lam_p) : INF;
         const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
         if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
@@ -691,6 +702,8 @@ struct Warp {
                 Ginv[q * ld + q] = is;
                 act[q] = pid;
                 lam[q] = lam_p;
+                const int pt_ = pid / 4096, ix_ = pid % 4096;
+                if (pt_ == PT_GEN) agen[ix_] = 1; else aflag[ix_] |= (1 << pt_);
             }
             ++q;
             state = PS_SELECT;
@@ -708,6 +721,10 @@ struct Warp {
         else {                                                   // active soft row saturates: flip + drop
             drop = k3;
             if (lane == 0) { const int r = act[drop] - PM_ID(PT_GEN, 0); orient[r] = -orient[r]; }
+        }
+        if (lane == 0) {
+            const int id_ = act[drop], pt_ = id_ / 4096, ix_ = id_ % 4096;
+            if (pt_ == PT_GEN) agen[ix_] = 0; else aflag[ix_] &= ~(1 << pt_);
         }
         __syncwarp();
         {   // Ginv <- Ginv - g g'/g_dd on the remaining slots, then move the last slot into `drop`
@@ -757,7 +774,8 @@ struct Warp {
         const double tol = 1e-6;
         if (state == PS_DONE) return HUGE_VAL;                    // constant rows already infeasible
         bool bad = false;
-        int c0m = -1, c1m = -1;                                   // candidate modes of the last stage (lane = vehicle)
+        int lastm[4] = {-1, -1, -1, -1};                             // candidate modes of the last stage (lane = vehicle)
+        int ncm = 0;
         LANES(i, nl) {
             const double* xp = xg + (size_t)i * 2 * np1;
             const double* xv = xp + np1;
@@ -765,28 +783,36 @@ struct Warp {
             for (int k = 0; k < N; ++k) {
                 const double v = xv[k], uu = ug[i * N + k];
                 if (k + 1 < N && fabs(xp[k + 1] - (xp[k] + v)) > tol) bad = true;
-                int found = -1, found2 = -1;
+                int found = -1;
                 _Pragma("unroll 1")
                 for (int r = 0; r < S.M.R; ++r) {
                     if (!(v >= S.M.lo[r] - tol && v <= S.M.hi[r] + tol)) continue;
                     if (k + 1 < N && fabs(xv[k + 1] - (ma(i, r) * v + mc(i, r) + mb(i, r) * uu)) > tol) continue;
-                    if (found < 0) found = r; else if (found2 < 0) found2 = r;
+                    if (found < 0) found = r;
+                    if (k + 1 == N && ncm < 4) {                  // free last state: every admissible mode counts
+                        if (ncm == 0) lastm[0] = r; else if (ncm == 1) lastm[1] = r; else if (ncm == 2) lastm[2] = r; else lastm[3] = r;
+                        ++ncm;
+                    }
                 }
                 if (found < 0) { bad = true; found = 0; }
                 modes[k * nl + i] = found;
                 if (k + 1 < N) x[i * N + k] = xv[k + 1];
-                else { c0m = found; c1m = found2; }
             }
         }
         if (__any_sync(FULL, bad)) return HUGE_VAL;
         L = S.depth;
-        LANES(r, S.ng) orient[r] = 1;
+        LANES(r, S.ng) { orient[r] = 1; agen[r] = 0; }
+        LANES(j, S.nv) aflag[j] = 0;
         double bestf = HUGE_VAL;
+        int total = 1;
         _Pragma("unroll 1")
-        for (int mask = 0; mask < (1 << nl); ++mask) {
+        for (int i = 0; i < nl; ++i) total *= 4;
+        _Pragma("unroll 1")
+        for (int mask = 0; mask < total; ++mask) {
             bool skip = false;
             LANES(i, nl) {
-                const int r = ((mask >> i) & 1) ? c1m : c0m;
+                const int dg = (mask >> (2 * i)) & 3;
+                const int r = dg == 0 ? lastm[0] : (dg == 1 ? lastm[1] : (dg == 2 ? lastm[2] : lastm[3]));
                 if (r < 0) skip = true;
                 else {
                     const double v = xg[(size_t)i * 2 * np1 + np1 + N - 1], uu = ug[i * N + N - 1];
@@ -1027,7 +1053,7 @@ void pm_layout(PmDev& S) {
     S.o_pvec = o; o += S.npv;
     S.o_misc = o; o += 3 * S.nl + (D + 1) + 2 * S.nl * (S.N + 1) + 5 * D;
     S.smem_doubles = o;
-    const int ints = nv + (D + 1) + 3 * D + S.ng;
+    const int ints = nv + (D + 1) + 3 * D + S.ng + nv + S.ng;
     S.o_int = o;
     S.smem_bytes = (o * 8 + ints * 4 + 15) / 16 * 16;
 }

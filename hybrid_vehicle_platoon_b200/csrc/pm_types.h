@@ -49,9 +49,10 @@ struct PmDev {                   // kernel argument
     const double* B0;            // [n0][npv]     constant rows: B0[r].pvec <= 0
     const double* w0;            // [n0]
     // shared-structure multi-RHS product (tensor-core precompute): Y[b] = W . pvec_b with
-    // W = [GC ; BR ; B0 ; CC] ([mw][kw], zero padded to multiples of 8 x 4):
-    //   GC = RW2.Cres + Lz'.La  -> g0 = GC.pvec      BR -> generic right-hand sides
-    //   B0 -> constant rows                           CC = Cres'W Cres + La'Lp -> c0 = pvec'.CC.pvec
+    // W = [GC ; BR ; B0 ; Cres ; La ; Lp] ([mw][kw], zero padded to multiples of 8 x 4):
+    //   GC = RW2.Cres + Lz'.La  -> g0 = GC.pvec      BR -> generic right-hand sides      B0 -> constant rows
+    //   Cres, La, Lp -> residual constants c_r and the factors of the param-linear terms:
+    //                   c0 = sum_r w_r c_r^2 + sum_l a_l p_l
     const double* W;
     int mw, kw;
     // shared-memory carve-up (offsets in doubles / ints), filled by pm_layout()

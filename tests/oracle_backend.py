@@ -42,7 +42,7 @@ def oracle_eval_cost(kind, nl, N, mass, params, xg, ug, tol=1e-6, **kw):
             row.append(ok if k == N - 1 else ok[:1])
         cands.append(row)
     best = np.inf
-    for last in itertools.product(*[cands[i][N - 1][:2] for i in range(nl)]):
+    for last in itertools.product(*[cands[i][N - 1][:4] for i in range(nl)]):
         modes = np.array([[cands[i][k][0] for k in range(N - 1)] + [last[i]] for i in range(nl)], np.int32)
         q = O.mpc_build_qp(kind, nl, N, xg[:, :, 0], mass, params, modes, **kw)
         if q is None:

@@ -140,3 +140,39 @@ def test_gear_mode_table(oracle):
     assert np.allclose(lo[6:], np.maximum(vl, alpha)) and np.allclose(hi[6:], vh)
     assert np.allclose(b[:6], np.array([4057, 2945, 2116, 1607, 1166, 838]) / 800.0)
     assert (lo[:3] <= hi[:3]).all() and lo[6] > hi[6]          # gear 1 never meets the upper friction region
+
+
+def test_qp_tie_between_partial_and_full_step_regression(oracle):
+    """A row that reaches its boundary exactly at the end of a PARTIAL dual step must join the active set with the
+    multiplier it accumulated; an earlier version left the loop and lost lam_p * n_p (non-stationary 'optimum',
+    a branch-and-bound miss found by scripts/stress_parity.py seed 1).  The node relaxations along the optimal
+    path of that problem must be non-decreasing and agree with HiGHS."""
+    rng = np.random.default_rng(1)
+    B = 192
+    for (n, N) in ((3, 5), (2, 6), (4, 4)):
+        rng.choice([0.0, 3.0]); li = int(rng.integers(0, n))
+        G.cent_cases(rng, B, n, N, stress=False, leader_index=li)
+        rng.uniform(700, 1000, (B, n))
+    for (nf, nb, rl, N) in ((2, 2, -100, 5), (1, 2, 1, 5), (0, 1, 0, 6)):
+        nl = (nf > 0) + 1 + (nb > 0)
+        x0, params = G.event_cases(rng, B, nf, nb, N, stress=False)
+        mass = rng.uniform(700, 1000, (B, nl))
+    w, N, nl = 158, 6, 2
+    kw = dict(leader_index=0, n_front=0, n_behind=1)
+    best = np.array([[3, 2, 2, 2, 2, 3], [0, 1, 1, 2, 2, 3]], np.int32)
+    prev = -np.inf
+    for depth in range(0, nl * N + 1):
+        fm = np.full((nl, N), -1, np.int32)
+        for d in range(depth):
+            fm[d % nl, d // nl] = best[d % nl, d // nl]
+        H, g, c0, A, b, wm = oracle.mpc_build_qp(G.EVENT, nl, N, x0[w], mass[w], params[w], fm, **kw)
+        st, x, lam, obj, it = oracle.qp_solve(H, g, c0, A, b, wm)
+        assert st == 0
+        assert max(kkt_residuals(H, g, A, b, wm, x, lam).values()) < 1e-7
+        ok, xh, oh = highs_qp(H, g, c0, A, b, wm)
+        assert ok and abs(oh - obj) <= 1e-6 * abs(obj)
+        assert obj >= prev - 1e-6
+        prev = obj
+    a = oracle.mpc_solve(G.EVENT, nl, N, x0[w][None], mass[w][None], params[w][None], method=1, **kw)
+    e = oracle.mpc_solve(G.EVENT, nl, N, x0[w][None], mass[w][None], params[w][None], method=0, **kw)
+    assert abs(a["obj"][0] - e["obj"][0]) <= 1e-9 * e["obj"][0] and (a["modes"] == e["modes"]).all()
