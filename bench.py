@@ -195,6 +195,26 @@ def closed_loop_leg(ctx, S=4096, T=20):
             "mean_nodes": float(out["nodes"].mean())}
 
 
+def admm_loop_leg(ctx, S=1024, T=2, n=15, N=8, iters=20):
+    """BASELINE.json configs[2]: naive-ADMM consensus rounds at n = 15, N = 8 for S scenarios on the device
+    (sweep.BatchedAdmmSweep): per round the S*n local MIQPs are three launches (front / interior / trailer)."""
+    from hybrid_vehicle_platoon_b200.sweep import BatchedAdmmSweep
+    from hybrid_vehicle_platoon_b200.misc import ConstantVelocityLeaderTrajectory
+    rng = np.random.default_rng(1234 + 2)
+    v = np.floor(rng.uniform(10, 30, (S, n))); gaps = rng.uniform(60, 140, (S, n))
+    p = np.floor(3000.0 - np.cumsum(gaps, 1) + gaps[:, :1])
+    x0 = np.empty((S, 2 * n)); x0[:, 0::2] = p; x0[:, 1::2] = v
+    lx = ConstantVelocityLeaderTrajectory(p=3000, v=20, trajectory_len=T + N + 10, ts=1).get_leader_trajectory()
+    sw = BatchedAdmmSweep(n, N, admm_iters=iters, rho=0.5, ctx=ctx)
+    sw.run(x0[:64], lx, 1)
+    t0 = time.perf_counter()
+    out = sw.run(x0, lx, T)
+    dt = time.perf_counter() - t0
+    return {"value": S * T * iters / dt, "unit": "scenario-ADMM-rounds/s", "solves_per_s": S * T * iters * n / dt,
+            "scenarios": S, "timesteps": T, "admm_iters": iters, "seconds": dt,
+            "optimal_frac": float((out["status"] == 2).mean()), "rollout_exceptions": int((out["errors"] != 0).any(0).sum())}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -428,6 +448,7 @@ def main():
             cpu, _, _ = cpu_reference_leg(S, budget_s=12.0)
         other = compiled_mpc_legs(hvp, torch, dev, stream, flush, with_cpu=not args.no_cpu)
         other["closed_loop_decent_n10_N6 (configs[3] shape: 4096 scenarios, on-device episode)"] = closed_loop_leg(ctx)
+        other["closed_loop_naive_admm_n15_N8 (configs[2]: 1024 scenarios x 20 ADMM rounds per timestep)"] = admm_loop_leg(ctx)
 
         out = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,

@@ -51,7 +51,7 @@ class BatchedDecentSweep:
         flags[:, 0] |= FRONT; flags[:, -1] |= TRAILER; flags[:, self.leader_index] |= LEADER
         d_flags = torch.as_tensor(flags.reshape(B), device=dev)
         m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
-        d_mass = torch.as_tensor(np.ascontiguousarray(m), device=dev)
+        d_mass = torch.as_tensor(np.array(m, dtype=np.float64), device=dev)
         edesc = api.env_desc(n, self.leader_index, self.d0, self.t0, self.d_safe, True, False, True)
         # per-step work buffers
         xf = torch.zeros((S, n, 2, N + 1), dtype=f64, device=dev)
@@ -121,3 +121,117 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
             out[i] = dict(X=r["X"][:, j], U=r["U"][:, j], R=r["R"][:, j], violations=r["violations"][:, j],
                           errors=r["errors"][:, j], nodes=r["nodes"][:, j], status=r["status"][:, j])
     return out
+
+
+class BatchedAdmmSweep:
+    """S independent platoons under the naive (non-convex) ADMM controller (fleet_naive_admm.py:320-587), all
+    state on the device.  One timestep = admm_iters rounds; one round = the x-update of all S*n vehicles (one launch
+    of the compiled-MPC kernel per distinct role: front / interior / trailer, leader where applicable) followed by
+    the z- and y-updates as a few torch ops over (S, n, 2, N+1) tensors; then one rollout launch."""
+
+    def __init__(self, n: int, N: int, admm_iters: int = 20, rho: float = 0.5, masses=None,
+                 spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0, d_safe: float = Params.d_safe,
+                 device: int = 0, ctx=None):
+        import torch
+        from ._lib import MPC_ADMM
+        if n < 2:
+            raise ValueError("the ADMM scheme needs at least two vehicles")
+        self.torch, self.n, self.N, self.iters, self.rho, self.leader_index = torch, n, N, admm_iters, rho, leader_index
+        self.dev = torch.device("cuda", device)
+        self.ctx = ctx or default_context(device)
+        self.d0, self.t0 = spacing_params(spacing_policy)
+        self.d_safe = d_safe
+        self.masses = None if masses is None else np.asarray(masses, dtype=np.float64)
+        # one compiled formulation per distinct role; vehicles with the same role batch together
+        self.role_of = []
+        roles: dict = {}
+        for i in range(n):
+            fl = (FRONT if i == 0 else 0) | (TRAILER if i == n - 1 else 0) | (LEADER if i == leader_index else 0)
+            if fl not in roles:
+                roles[fl] = api.CompiledMpc(MPC_ADMM, N, flags=fl, rho=rho, d0=self.d0, t0=self.t0, ctx=self.ctx)
+            self.role_of.append(fl)
+        self.roles = roles
+
+    def run(self, x0, leader_x, ep_len: int):
+        """Same contract as BatchedDecentSweep.run; additionally returns nothing about the consensus variables."""
+        torch, dev, n, N, rho = self.torch, self.dev, self.n, self.N, self.rho
+        f64, np1 = torch.float64, N + 1
+        x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
+        S = x.shape[0]
+        lx = torch.as_tensor(np.ascontiguousarray(leader_x, dtype=np.float64), device=dev)
+        if lx.ndim == 2:
+            lx = lx.unsqueeze(0).expand(S, -1, -1)
+        m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
+        d_mass = torch.as_tensor(np.array(m, dtype=np.float64), device=dev)
+        edesc = api.env_desc(n, self.leader_index, self.d0, self.t0, self.d_safe, True, False, True)
+        zeros = lambda *s: torch.zeros(s, dtype=f64, device=dev)
+        y_front, y_back, z = zeros(S, n, 2, np1), zeros(S, n, 2, np1), zeros(S, n, 2, np1)
+        zf, zb = zeros(S, n, 2, np1), zeros(S, n, 2, np1)        # the z each vehicle's copies are pulled towards
+        xs = zeros(S, n, 2, np1)                                  # own predictions of the last round
+        cf, cb = zeros(S, n, 2, np1), zeros(S, n, 2, np1)        # copies x_front / x_back of the last round
+        have_pred = False
+        # per-role gather indices and work buffers
+        groups = {}
+        for fl, cm in self.roles.items():
+            idx = torch.as_tensor([i for i in range(n) if self.role_of[i] == fl], device=dev)
+            k = len(idx); B = S * k
+            groups[fl] = dict(cm=cm, idx=idx, k=k, B=B,
+                              u=torch.empty((B, 1, N), dtype=f64, device=dev), x=torch.empty((B, 1, 2, np1), dtype=f64, device=dev),
+                              e=torch.empty((B, max(cm.n_extra, 1)), dtype=f64, device=dev),
+                              mo=torch.empty((B, 1, N), dtype=torch.int32, device=dev), ob=torch.empty(B, dtype=f64, device=dev),
+                              st=torch.empty(B, dtype=torch.int32, device=dev), no=torch.empty(B, dtype=torch.int32, device=dev))
+        X = torch.empty((ep_len + 1, S, 2 * n), dtype=f64, device=dev)
+        U = torch.empty((ep_len, S, n), dtype=f64, device=dev)
+        R = torch.empty((ep_len, S), dtype=f64, device=dev)
+        V = torch.empty((ep_len, S), dtype=torch.uint8, device=dev)
+        E = torch.empty((ep_len, S), dtype=torch.int32, device=dev)
+        ST = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
+        X[0] = x
+        stream = torch.cuda.current_stream().cuda_stream
+        u0 = torch.empty((S, n), dtype=f64, device=dev)
+        stat = torch.empty((S, n), dtype=torch.int32, device=dev)
+        for t in range(ep_len):
+            # coupling guesses from the previous step's predictions, shifted (fleet_naive_admm.py:392-402)
+            if have_pred:
+                sh = torch.cat((xs[..., 1:], xs[..., -1:]), dim=-1)
+                zf[:, 1:] = sh[:, :-1]
+                zb[:, :-1] = sh[:, 1:]
+            lwin = lx[:, :, t:t + np1].reshape(S, 1, 2 * np1)
+            for _ in range(self.iters):
+                # ---- x-update: all vehicles of a role in one launch ----
+                for fl, g in groups.items():
+                    idx, k, B = g["idx"], g["k"], g["B"]
+                    params = torch.cat((lwin.expand(S, k, -1), y_front[:, idx].reshape(S, k, -1), zf[:, idx].reshape(S, k, -1),
+                                        y_back[:, idx].reshape(S, k, -1), zb[:, idx].reshape(S, k, -1)), dim=2).reshape(B, -1).contiguous()
+                    x0g = x.view(S, n, 2)[:, idx].reshape(B, 1, 2).contiguous()
+                    mg = d_mass[:, idx].reshape(B, 1).contiguous()
+                    g["cm"].solve_device(B, x0g, mg, params, None, g["u"], g["x"], g["e"], g["mo"], g["ob"], g["st"],
+                                         g["no"], None, stream=stream)
+                    xs[:, idx] = g["x"].view(S, k, 2, np1)
+                    u0[:, idx] = g["u"].view(S, k, N)[:, :, 0]
+                    stat[:, idx] = g["st"].view(S, k)
+                    e = g["e"].view(S, k, -1)
+                    o = 0
+                    if not fl & FRONT:
+                        cf[:, idx] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1); o += 2 * np1
+                    if not fl & TRAILER:
+                        cb[:, idx] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1)
+                # ---- z-update: average of a vehicle's own prediction and its neighbours' copies of it (:421-447) ----
+                z[:, 0] = (xs[:, 0] + cf[:, 1]) / 2.0
+                z[:, n - 1] = (xs[:, n - 1] + cb[:, n - 2]) / 2.0
+                if n > 2:
+                    z[:, 1:n - 1] = (xs[:, 1:n - 1] + cf[:, 2:] + cb[:, :n - 2]) / 3.0
+                # ---- y-update and the z each copy is pulled towards in the next round (:426-468) ----
+                y_front[:, 1:] += rho * (cf[:, 1:] - z[:, :-1])
+                y_back[:, :-1] += rho * (cb[:, :-1] - z[:, 1:])
+                zf[:, 1:] = z[:, :-1]
+                zb[:, :-1] = z[:, 1:]
+            have_pred = True
+            U[t] = u0
+            ST[t] = stat
+            api.rollout_step_device(edesc, S, x, U[t], None, d_mass, lx[:, :, t].contiguous(), X[t + 1], R[t], V[t],
+                                    E[t], ctx=self.ctx, stream=stream)
+            x = X[t + 1]
+        torch.cuda.synchronize()
+        return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
+                    errors=E.cpu().numpy(), status=ST.cpu().numpy())

@@ -82,3 +82,23 @@ def test_mixed_size_sweep_shards_cover_everything():
             if (r["errors"] == 0).all() and (full[i]["errors"] == 0).all():
                 assert np.abs(r["X"] - full[i]["X"]).max() < 1e-2
             assert r["X"].shape == (T + 1, 2 * scen[i]["n"])
+
+
+def test_batched_admm_sweep_matches_single_scenarios():
+    """sweep.BatchedAdmmSweep == fleet_naive_admm.simulate scenario by scenario (which is checked against the
+    oracle backend in test_gpu_fleets.py)."""
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200.sweep import BatchedAdmmSweep
+    from test_host_fleets import SmallSim
+    n, N, T, iters = 4, 4, 5, 5
+    singles, x0s = [], []
+    for s in (2, 3, 5):
+        singles.append(hvp.fleet_naive_admm.simulate(SmallSim(n, N, T, headway=True), admm_iters=iters, seed=s))
+        x0s.append(singles[-1]["X"][0])
+    sim = SmallSim(n, N, T, headway=True)
+    sw = BatchedAdmmSweep(n, N, admm_iters=iters, rho=0.5, spacing_policy=sim.spacing_policy)
+    out = sw.run(np.stack(x0s), singles[0]["leader_x"], T)
+    assert (out["status"] == 2).all()
+    for j, one in enumerate(singles):
+        assert np.abs(out["X"][:, j] - one["X"]).max() < 1e-6, np.abs(out["X"][:, j] - one["X"]).max()
+        assert np.abs(out["U"][:, j] - one["U"]).max() < 1e-6
