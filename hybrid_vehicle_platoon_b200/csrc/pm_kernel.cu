@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "hvp_internal.h"
@@ -39,7 +40,7 @@ constexpr unsigned FULL = 0xffffffffu;
 enum : int { PT_UB = 0, PT_LB, PT_UHI, PT_ULO, PT_ACC, PT_DEC, PT_PHI, PT_PLO, PT_GEN };
 enum : int { PS_NEXT = 0, PS_BUILD, PS_SELECT, PS_STEP, PS_DONE };
 #define PM_ID(t, idx) ((t) * 4096 + (idx))
-#define LANES(j, n) _Pragma("unroll 1") for (int j = lane; j < (n); j += 32)
+#define LANES(j, n) _Pragma("unroll 1") for (int j = lane; j < (n); j += GW)
 
 // reciprocal to ~1 ulp without the slow paths / code size of the IEEE division sequence
 __device__ __forceinline__ double rcp(double v) {
@@ -62,25 +63,30 @@ __device__ __forceinline__ double dot2(const double* a, int sa, const double* b,
     if (c < n) s0 += a[(size_t)c * sa] * b[c];
     return s0 + s1;
 }
-__device__ __forceinline__ double wsum(double v) {
+// GW = lanes of the group that owns one problem (32, or 16 so that a warp carries two small problems);
+// gm = the group's lane mask.  Shuffles use width GW, so lane indices are relative to the group.
+template <int GW>
+__device__ __forceinline__ double wsum(unsigned gm, double v) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    for (int o = GW / 2; o; o >>= 1) v += __shfl_xor_sync(gm, v, o, GW);
     return v;
 }
 // arg-max over the warp with the smaller id winning ties (every lane gets the same answer)
-__device__ __forceinline__ void wargmax(double& v, int& id) {
+template <int GW>
+__device__ __forceinline__ void wargmax(unsigned gm, double& v, int& id) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const double ov = __shfl_xor_sync(FULL, v, o);
-        const int oid = __shfl_xor_sync(FULL, id, o);
+    for (int o = GW / 2; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(gm, v, o, GW);
+        const int oid = __shfl_xor_sync(gm, id, o, GW);
         if (ov > v || (ov == v && oid < id)) { v = ov; id = oid; }
     }
 }
-__device__ __forceinline__ void wargmin(double& v, int& id) {
+template <int GW>
+__device__ __forceinline__ void wargmin(unsigned gm, double& v, int& id) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const double ov = __shfl_xor_sync(FULL, v, o);
-        const int oid = __shfl_xor_sync(FULL, id, o);
+    for (int o = GW / 2; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(gm, v, o, GW);
+        const int oid = __shfl_xor_sync(gm, id, o, GW);
         if (ov < v || (ov == v && oid < id)) { v = ov; id = oid; }
     }
 }
@@ -95,9 +101,11 @@ __device__ __forceinline__ double dval(unsigned long long k) {
     return __longlong_as_double((long long)u);
 }
 
+template <int GW>
 struct Warp {
     const PmDev& S;
     int lane;
+    unsigned gm;                       // lane mask of this group
     // shared-memory views
     double *Hinv, *Ginv, *Nact;
     double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best;
@@ -115,7 +123,7 @@ struct Warp {
     const PmSplit* sp;
     int64_t prob;
 
-    __device__ Warp(const PmDev& S_, double* base, int lane_) : S(S_), lane(lane_) {
+    __device__ Warp(const PmDev& S_, double* base, int lane_, unsigned gm_) : S(S_), lane(lane_), gm(gm_) {
         const int nv = S.nv, ld = S.ld;
         Hinv = base + S.o_hinv; Ginv = base + S.o_ginv; Nact = base + S.o_nact;
         double* v = base + S.o_vec;
@@ -152,7 +160,7 @@ struct Warp {
             rlo[i * (N + 1)] = x0[2 * i + 1];
             rhi[i * (N + 1)] = x0[2 * i + 1];
         }
-        __syncwarp();
+        __syncwarp(gm);
         double c = 0.0;
         bool infeas = false;
         if (Y) {
@@ -209,9 +217,9 @@ struct Warp {
         LANES(i, nl) {   // state row k = 1 on the (constant) position p_1 = p_0 + v_0
             if (pc[i] > S.pmax + 1e-9 || pc[i] < S.pmin - 1e-9) infeas = true;
         }
-        __syncwarp();
-        c0 = wsum(c);
-        infeas = __any_sync(FULL, infeas);
+        __syncwarp(gm);
+        c0 = wsum<GW>(gm, c);
+        infeas = __any_sync(gm, infeas);
         if (!Y) {
             LANES(j, nv) {
                 double s = 0.0;
@@ -226,7 +234,7 @@ struct Warp {
         iters = nodes = it = q = 0;
         inc = HUGE_VAL; own = HUGE_VAL; trouble = limit = false; dive = true; sub_ord = 0;
         lev = 0; L = 0; fixed = (fm != nullptr);
-        if (infeas) { state = PS_DONE; __syncwarp(); return; }
+        if (infeas) { state = PS_DONE; __syncwarp(gm); return; }
         if (fixed) {
             bool bad = false;
             LANES(d, S.depth) {
@@ -235,14 +243,14 @@ struct Warp {
                 if (r < 0 || r >= S.M.R) bad = true;
                 else if (k == 0 && (v0[i] > S.M.hi[r] + 1e-9 || v0[i] < S.M.lo[r] - 1e-9)) bad = true;
             }
-            bad = __any_sync(FULL, bad);
+            bad = __any_sync(gm, bad);
             L = S.depth;
             state = bad ? PS_DONE : PS_BUILD;
         } else {
             if (lane == 0) { open_level(0); }
             state = PS_NEXT;
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 
     // candidates of decision `lv` (lane 0 only)
@@ -316,10 +324,10 @@ struct Warp {
                 break;
             }
         }
-        __syncwarp();
-        state = __shfl_sync(FULL, st, 0);
-        lev = __shfl_sync(FULL, nlev, 0);
-        L = __shfl_sync(FULL, nL, 0);
+        __syncwarp(gm);
+        state = __shfl_sync(gm, st, 0, GW);
+        lev = __shfl_sync(gm, nlev, 0, GW);
+        L = __shfl_sync(gm, nL, 0, GW);
         if (state == PS_BUILD) hull();
     }
 
@@ -356,7 +364,7 @@ struct Warp {
                 rlo[v * (N + 1) + s + 1] = lo; rhi[v * (N + 1) + s + 1] = hi;
             }
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 
     // st: 0 solved, 1 infeasible, 2 numerical trouble
@@ -373,7 +381,7 @@ struct Warp {
             LANES(j, S.nv) best[j] = x[j];
             LANES(d, S.depth) bmodes[d] = modes[d];
             if (shared && lane == 0) atomicMin(shared, dkey(obj));
-            __syncwarp();
+            __syncwarp(gm);
             return;
         }
         if (S.max_nodes > 0 && nodes >= S.max_nodes) { limit = true; state = PS_DONE; return; }
@@ -381,7 +389,7 @@ struct Warp {
             // heavy tree: hand it to the sub-tree pass if the list has room, else finish it here
             int slot = 0;
             if (lane == 0) slot = atomicAdd(sp->nflag, 1);
-            slot = __shfl_sync(FULL, slot, 0);
+            slot = __shfl_sync(gm, slot, 0, GW);
             if (slot < sp->cap) {
                 if (lane == 0) { sp->flagged[slot] = (int)prob; sp->inc_shared[slot] = dkey(inc); }
                 limit = true; state = PS_DONE;
@@ -391,7 +399,7 @@ struct Warp {
         }
         ++lev;
         if (lane == 0) open_level(lev);
-        __syncwarp();
+        __syncwarp(gm);
     }
 
     // H <- H + s * 2 qu e e',  e = (e_jk - a e_jm)/b  (decision d in mode rg): Sherman-Morrison on H^-1
@@ -404,7 +412,7 @@ struct Warp {
             if (k >= 1) v += ea * Hinv[j * ld + jm];
             wv[j] = v;
         }
-        __syncwarp();
+        __syncwarp(gm);
         const double ev = ib * wv[jk] + ((k >= 1) ? ea * wv[jm] : 0.0);
         const double den = rcp(s * (0.5 / S.qu) + ev);
         LANES(j, nv) {
@@ -412,7 +420,7 @@ struct Warp {
             _Pragma("unroll 1")
             for (int c = 0; c < nv; ++c) Hinv[j * ld + c] -= vj * wv[c];
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 
     // ---- BUILD: bring H^-1 to this node, gradient, unconstrained minimiser ----------------------
@@ -421,19 +429,19 @@ struct Warp {
         if (shared) {       // best objective found by ANY warp working on this problem
             double g = 0.0;
             if (lane == 0) g = dval(*reinterpret_cast<volatile unsigned long long*>(shared));
-            g = __shfl_sync(FULL, g, 0);
+            g = __shfl_sync(gm, g, 0, GW);
             if (g < inc) inc = g;
         }
         int c = 0;
         if (built_L > 0)
             while (c < built_L && c < L && built[c] == modes[c]) ++c;
         const bool reload = built_L < 0 || c == 0 || (built_L - c > c);
-        __syncwarp();
+        __syncwarp(gm);
         if (reload) {
             _Pragma("unroll 1")
-            for (int e = lane; e < nv * nv; e += 32) Hinv[(e / nv) * ld + (e % nv)] = S.H0inv[e];
+            for (int e = lane; e < nv * nv; e += GW) Hinv[(e / nv) * ld + (e % nv)] = S.H0inv[e];
             c = 0; built_L = 0;
-            __syncwarp();
+            __syncwarp(gm);
         }
         _Pragma("unroll 1")
         for (int d = built_L - 1; d >= c; --d) rank1(d, built[d], -1.0);
@@ -445,7 +453,7 @@ struct Warp {
             am[d] = ma(i, r); bm[d] = mb(i, r); cm[d] = mc(i, r);
         }
         built_L = L;
-        __syncwarp();
+        __syncwarp(gm);
         const double qu = S.qu;
         LANES(j, nv) {
             double g = g0[j];
@@ -464,7 +472,7 @@ struct Warp {
             }
             gn[j] = g;
         }
-        __syncwarp();
+        __syncwarp(gm);
         double dpart = 0.0;
         LANES(j, nv) {
             const double s = dot2(Hinv + j * ld, 1, gn, nv);
@@ -477,12 +485,12 @@ struct Warp {
             dpart += qu * kc * kc;
         }
         // value of the node's dual function at the unconstrained minimiser; it only grows from here
-        dual = c0 + wsum(dpart);
+        dual = c0 + wsum<GW>(gm, dpart);
         LANES(r, S.ng) { orient[r] = 1; agen[r] = 0; }
         LANES(j, nv) aflag[j] = 0;
         it = 0; q = 0;
         state = PS_SELECT;
-        __syncwarp();
+        __syncwarp(gm);
     }
 
     // most violated row of the node QP at x (rows already active have residual ~0); `soft` = also
@@ -550,7 +558,7 @@ struct Warp {
             PM_CAND(PT_GEN, r, orient[r] > 0 ? s : -s);
         }
 #undef PM_CAND
-        wargmax(best_v, bid);
+        wargmax<GW>(gm, best_v, bid);
     }
 
     // objective of the node QP at x (tracking + input cost of the fixed stages + L1 penalties)
@@ -574,7 +582,7 @@ struct Warp {
                 if (s > 0.0) f += wm * s;
             }
         }
-        return c0 + wsum(f);
+        return c0 + wsum<GW>(gm, f);
     }
 
     // ---- SELECT: most violated row, or the node is solved --------------------------------------
@@ -609,7 +617,7 @@ struct Warp {
             }
             np_[j] = v;
         }
-        __syncwarp();
+        __syncwarp(gm);
         // yp = H^-1 n_p, nHn = n_p' yp
         double acc = 0.0;
         LANES(j, nv) {
@@ -617,11 +625,11 @@ struct Warp {
             yp[j] = s;
             acc += s * np_[j];
         }
-        nHn = wsum(acc);
+        nHn = wsum<GW>(gm, acc);
         cp = best_v;
         lam_p = 0.0;
         state = PS_STEP;
-        __syncwarp();
+        __syncwarp(gm);
     }
 
     // ---- STEP: one primal-dual step towards adding p -------------------------------------------
@@ -638,7 +646,7 @@ struct Warp {
         LANES(a, q) {
             dv[a] = dot2(Nact + a * ld, 1, yp, nv);
         }
-        __syncwarp();
+        __syncwarp(gm);
         // r = Ginv d ; nz = nHn - d'r ; ratio tests
         double part = 0.0, t1 = INF, t3 = INF;
         int k1 = 0x7fffffff, k3 = 0x7fffffff;
@@ -661,9 +669,9 @@ struct Warp {
                 }
             }
         }
-        const double nz = nHn - wsum(part);
-        wargmin(t1, k1);
-        wargmin(t3, k3);
+        const double nz = nHn - wsum<GW>(gm, part);
+        wargmin<GW>(gm, t1, k1);
+        wargmin<GW>(gm, t3, k3);
         const bool dependent = (q == nv) || !(nz > 1e-11 * nHn);
         if (zero_step && dependent) { node_done(2, 0.0); return; }
         const double t2 = dependent ? INF : (zero_step ? 0.0 : cp * rcp(nz));
@@ -673,13 +681,13 @@ struct Warp {
         // d(dual)/dt = violation of p along the step: the dual value is a lower bound on the node optimum
         dual += t * cp - (dependent ? 0.0 : 0.5 * t * t * nz);
         if (dual > inc) { node_done(1, 0.0); return; }          // the node cannot beat the incumbent
-        __syncwarp();
+        __syncwarp(gm);
         if (!dependent) {
             // w = n_p - N r ;  x -= t H^-1 w ;  the violation of p shrinks by t nz
             LANES(j, nv) {
                 wv[j] = np_[j] - dot2(Nact + j, ld, rv, q);
             }
-            __syncwarp();
+            __syncwarp(gm);
             LANES(j, nv) {
                 x[j] -= t * dot2(Hinv + j * ld, 1, wv, nv);
             }
@@ -707,13 +715,13 @@ struct Warp {
             }
             ++q;
             state = PS_SELECT;
-            __syncwarp();
+            __syncwarp(gm);
             return;
         }
         if (t == t3p) {                                          // soft p saturates: flip, not added
             if (lane == 0) orient[pid - PM_ID(PT_GEN, 0)] = -orient[pid - PM_ID(PT_GEN, 0)];
             state = PS_SELECT;
-            __syncwarp();
+            __syncwarp(gm);
             return;
         }
         int drop;
@@ -726,23 +734,23 @@ struct Warp {
             const int id_ = act[drop], pt_ = id_ / 4096, ix_ = id_ % 4096;
             if (pt_ == PT_GEN) agen[ix_] = 0; else aflag[ix_] &= ~(1 << pt_);
         }
-        __syncwarp();
+        __syncwarp(gm);
         {   // Ginv <- Ginv - g g'/g_dd on the remaining slots, then move the last slot into `drop`
             const double idd = rcp(Ginv[drop * ld + drop]);
             LANES(a, q) dv[a] = Ginv[a * ld + drop];
-            __syncwarp();
+            __syncwarp(gm);
             LANES(a, q) {
                 const double da = dv[a] * idd;
                 _Pragma("unroll 1")
                 for (int b = 0; b < q; ++b) Ginv[a * ld + b] -= da * dv[b];
             }
-            __syncwarp();
+            __syncwarp(gm);
             const int last = q - 1;
             if (drop != last) {
                 LANES(b, q) Ginv[drop * ld + b] = Ginv[last * ld + b];
-                __syncwarp();
+                __syncwarp(gm);
                 LANES(a, q) Ginv[a * ld + drop] = Ginv[a * ld + last];
-                __syncwarp();
+                __syncwarp(gm);
                 if (lane == 0) {
                     Ginv[drop * ld + drop] = Ginv[last * ld + last];
                     act[drop] = act[last];
@@ -751,7 +759,7 @@ struct Warp {
                 LANES(j, nv) Nact[drop * ld + j] = Nact[last * ld + j];
             }
             --q;
-            __syncwarp();
+            __syncwarp(gm);
         }
         // state stays PS_STEP: continue with the same p
     }
@@ -799,7 +807,7 @@ struct Warp {
                 if (k + 1 < N) x[i * N + k] = xv[k + 1];
             }
         }
-        if (__any_sync(FULL, bad)) return HUGE_VAL;
+        if (__any_sync(gm, bad)) return HUGE_VAL;
         L = S.depth;
         LANES(r, S.ng) { orient[r] = 1; agen[r] = 0; }
         LANES(j, S.nv) aflag[j] = 0;
@@ -820,17 +828,17 @@ struct Warp {
                     x[i * N + N - 1] = ma(i, r) * v + mc(i, r) + mb(i, r) * uu;
                 }
             }
-            if (__any_sync(FULL, skip)) continue;
-            __syncwarp();
+            if (__any_sync(gm, skip)) continue;
+            __syncwarp(gm);
             LANES(d, L) {
                 const int i = d % nl, r = modes[d];
                 am[d] = ma(i, r); bm[d] = mb(i, r); cm[d] = mc(i, r);
             }
-            __syncwarp();
+            __syncwarp(gm);
             double bv; int bid;
             scan(bv, bid, tol, false);
             if (bid == 0x7fffffff) bestf = fmin(bestf, objective());
-            __syncwarp();
+            __syncwarp(gm);
         }
         return bestf;
     }
@@ -839,7 +847,7 @@ struct Warp {
                            int32_t* status, int32_t* nodes_out, int32_t* iters_out) {
         const int nl = S.nl, N = S.N, np1 = N + 1;
         const bool ok = own < HUGE_VAL;
-        __syncwarp();
+        __syncwarp(gm);
         LANES(i, nl) {
             double* xo = x_out + (size_t)i * 2 * np1;
             double* uo = u_out + (size_t)i * N;
@@ -871,12 +879,13 @@ struct Warp {
             *nodes_out = nodes;
             if (iters_out) *iters_out = iters;
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 };
 
 }  // namespace
 
+template <int GW>
 __global__ void __launch_bounds__(128)
 pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __restrict__ x0,
                const double* __restrict__ mass, const double* __restrict__ params,
@@ -885,16 +894,17 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
                int32_t* __restrict__ status, int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters,
                unsigned long long* __restrict__ counter, const __grid_constant__ PmSplit sp) {
     extern __shared__ double pm_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x % GW, wib = threadIdx.x / GW;       // lane within the group, group within the CTA
+    const unsigned gm = GW == 32 ? FULL : (0xffffu << (16 * ((threadIdx.x >> 4) & 1)));
     double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
-    Warp W(S, base, lane);
+    Warp<GW> W(S, base, lane, gm);
     const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
     // problems are handed out one at a time (tree sizes vary by orders of magnitude)
     W.sp = &sp;
     for (;;) {
         unsigned long long nxt = 0;
         if (lane == 0) nxt = atomicAdd(counter, 1ull);
-        const int64_t w = (int64_t)__shfl_sync(FULL, nxt, 0);
+        const int64_t w = (int64_t)__shfl_sync(gm, nxt, 0, GW);
         int64_t i = w, o = w;                    // problem (input) index, output index
         W.sub_M = 0; W.sub_D = 0; W.sub_code = 0; W.shared = nullptr;
         W.budget = (sp.mode == 1 && !fixed_modes) ? sp.budget : 0;
@@ -959,9 +969,10 @@ pm_eval_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
                const double* __restrict__ mass, const double* __restrict__ params,
                const double* __restrict__ xg, const double* __restrict__ ug, double* __restrict__ cost) {
     extern __shared__ double pm_smem[];
+    constexpr int GW = 32;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
-    Warp W(S, base, lane);
+    Warp<GW> W(S, base, lane, FULL);
     const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
     for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < batch; i += (int64_t)gridDim.x * wpb) {
         W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar, nullptr);
@@ -1058,29 +1069,32 @@ void pm_layout(PmDev& S) {
     S.smem_bytes = (o * 8 + ints * 4 + 15) / 16 * 16;
 }
 
-cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
-                           const double* params, const int32_t* fixed_modes, const double* Y, double* u, double* x,
-                           double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
-                           int32_t* qp_iters, unsigned long long* counter, const PmScratch* sc, cudaStream_t stream) {
-    if (batch <= 0) return cudaSuccess;
-    int wpb = 4;
-    while (wpb > 1 && (size_t)wpb * S.smem_bytes > 200 * 1024) wpb >>= 1;
-    const size_t smem = (size_t)wpb * S.smem_bytes;
+template <int GW>
+static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double* x0, const double* mass,
+                                    const double* params, const int32_t* fixed_modes, const double* Y, double* u,
+                                    double* x, double* extra, int32_t* modes, double* obj, int32_t* status,
+                                    int32_t* nodes, int32_t* qp_iters, unsigned long long* counter,
+                                    const PmScratch* sc, cudaStream_t stream) {
+    // gpb groups (= problems in flight) per CTA of gpb * GW threads
+    int gpb = 128 / GW;
+    while (gpb > 1 && (size_t)gpb * S.smem_bytes > 200 * 1024) gpb >>= 1;
+    const size_t smem = (size_t)gpb * S.smem_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     static size_t attr_set = 0;
     if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = smem;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int threads = gpb * GW;
     int per_sm = (int)((220 * 1024) / smem);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16 / wpb * 4) per_sm = 16 / wpb * 4;
+    if (per_sm * threads > 2048) per_sm = 2048 / threads;
     const int64_t full = (int64_t)sms * per_sm;
-    int64_t blocks = (batch + wpb - 1) / wpb;
+    int64_t blocks = (batch + gpb - 1) / gpb;
     if (blocks > full) blocks = full;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
@@ -1088,8 +1102,8 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
     PmSplit sp;
     memset(&sp, 0, sizeof sp);
     if (!split) {
-        pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,
-                                                                     extra, modes, obj, status, nodes, qp_iters, counter, sp);
+        pm_miqp_kernel<GW><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,
+                                                                        extra, modes, obj, status, nodes, qp_iters, counter, sp);
         return cudaGetLastError();
     }
     // pass 1: every problem under a node budget; heavy trees are appended to the flagged list
@@ -1097,22 +1111,37 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
     sp.mode = 1;
     e = cudaMemsetAsync(sp.nflag, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
-    pm_miqp_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, u, x, extra,
-                                                                 modes, obj, status, nodes, qp_iters, counter, sp);
-    // pass 2: M warps per flagged problem, sub-trees by prefix ordinal, incumbent shared through global memory
+    pm_miqp_kernel<GW><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, u, x, extra,
+                                                                    modes, obj, status, nodes, qp_iters, counter, sp);
+    // pass 2: M groups per flagged problem, sub-trees by prefix ordinal, incumbent shared through global memory
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     sp.mode = 2;
-    int64_t b2 = ((int64_t)sp.cap * sp.M + wpb - 1) / wpb;
+    int64_t b2 = ((int64_t)sp.cap * sp.M + gpb - 1) / gpb;
     if (b2 > full) b2 = full;
-    pm_miqp_kernel<<<(unsigned)b2, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
-                                                             sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
-                                                             sc->iters, counter, sp);
+    pm_miqp_kernel<GW><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
+                                                                sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
+                                                                sc->iters, counter, sp);
     // pass 3: keep the best sub-result of every flagged problem
     pm_merge_kernel<<<(unsigned)((sp.cap + 3) / 4), 128, 0, stream>>>(S, sp, sc->u, sc->x, sc->extra, sc->modes, sc->obj,
                                                                      sc->status, sc->nodes, sc->iters, u, x, extra,
                                                                      modes, obj, status, nodes, qp_iters);
     return cudaGetLastError();
+}
+
+cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
+                           const double* params, const int32_t* fixed_modes, const double* Y, double* u, double* x,
+                           double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
+                           int32_t* qp_iters, unsigned long long* counter, const PmScratch* sc, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    // problems with at most 16 variables (e.g. the centralized n = 3, N = 5 MIQP) get a 16-lane group: two per warp
+    static const int force = getenv("HVP_MPC_GROUP") ? atoi(getenv("HVP_MPC_GROUP")) : 0;
+    const bool half = force ? force == 16 : (S.nv <= 16);
+    if (half)
+        return launch_pm_miqp_t<16>(S, batch, x0, mass, params, fixed_modes, Y, u, x, extra, modes, obj, status, nodes,
+                                    qp_iters, counter, sc, stream);
+    return launch_pm_miqp_t<32>(S, batch, x0, mass, params, fixed_modes, Y, u, x, extra, modes, obj, status, nodes,
+                                qp_iters, counter, sc, stream);
 }
 
 cudaError_t launch_pm_eval(const PmDev& S, int64_t batch, const double* x0, const double* mass,

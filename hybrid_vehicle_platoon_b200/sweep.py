@@ -51,7 +51,7 @@ class BatchedDecentSweep:
         flags[:, 0] |= FRONT; flags[:, -1] |= TRAILER; flags[:, self.leader_index] |= LEADER
         d_flags = torch.as_tensor(flags.reshape(B), device=dev)
         m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
-        d_mass = torch.as_tensor(np.array(m, dtype=np.float64), device=dev)
+        d_mass = torch.as_tensor(np.array(m, dtype=np.float64, order="C"), device=dev)
         edesc = api.env_desc(n, self.leader_index, self.d0, self.t0, self.d_safe, True, False, True)
         # per-step work buffers
         xf = torch.zeros((S, n, 2, N + 1), dtype=f64, device=dev)
@@ -162,7 +162,7 @@ class BatchedAdmmSweep:
         if lx.ndim == 2:
             lx = lx.unsqueeze(0).expand(S, -1, -1)
         m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
-        d_mass = torch.as_tensor(np.array(m, dtype=np.float64), device=dev)
+        d_mass = torch.as_tensor(np.array(m, dtype=np.float64, order="C"), device=dev)
         edesc = api.env_desc(n, self.leader_index, self.d0, self.t0, self.d_safe, True, False, True)
         zeros = lambda *s: torch.zeros(s, dtype=f64, device=dev)
         y_front, y_back, z = zeros(S, n, 2, np1), zeros(S, n, 2, np1), zeros(S, n, 2, np1)
