@@ -235,3 +235,87 @@ class BatchedAdmmSweep:
         torch.cuda.synchronize()
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
                     errors=E.cpu().numpy(), status=ST.cpu().numpy())
+
+
+class BatchedSeqSweep(BatchedDecentSweep):
+    """S independent platoons under the SEQUENTIAL MLD-MPC (TrackingSequentialMldCoordinator,
+    fleet_seq_mld.py:296-440): per timestep the leader is solved first, then the vehicles in front of it
+    (nearest first), then the ones behind -- n waves of S local MIQPs, each wave using the FRESH prediction of
+    the neighbour already solved and the shifted previous prediction of the other one."""
+
+    def run(self, x0, leader_x, ep_len: int):
+        torch, dev, n, N, li = self.torch, self.dev, self.n, self.N, self.leader_index
+        f64, np1 = torch.float64, N + 1
+        x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
+        S = x.shape[0]
+        lx = torch.as_tensor(np.ascontiguousarray(leader_x, dtype=np.float64), device=dev)
+        if lx.ndim == 2:
+            lx = lx.unsqueeze(0).expand(S, -1, -1)
+        m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
+        d_mass = torch.as_tensor(np.array(m, dtype=np.float64, order="C"), device=dev)
+        edesc = api.env_desc(n, li, self.d0, self.t0, self.d_safe, True, False, True)
+        ts = float(Params.ts)
+        # parameters currently set in each vehicle's controller (persist until overwritten, like the setters)
+        xf = torch.zeros((S, n, 2, np1), dtype=f64, device=dev)
+        xb = torch.zeros((S, n, 2, np1), dtype=f64, device=dev)
+        xl = torch.zeros((S, 2, np1), dtype=f64, device=dev)
+        # on_episode_start: constant-velocity extrapolation of the neighbours (fleet_seq_mld.py:411-431)
+        xv = x.view(S, n, 2)
+        cv = torch.empty((S, n, 2, np1), dtype=f64, device=dev)
+        cv[:, :, 0, 0] = xv[:, :, 0]
+        cv[:, :, 1, :] = xv[:, :, 1:2]
+        for k in range(N):
+            cv[:, :, 0, k + 1] = cv[:, :, 0, k] + ts * cv[:, :, 1, k]
+        xf[:, 1:] = cv[:, :-1]
+        xb[:, :-1] = cv[:, 1:]
+        pred = torch.zeros((S, n, 2, np1), dtype=f64, device=dev)      # latest prediction of every vehicle
+        have_pred = False
+        flags = [(FRONT if i == 0 else 0) | (TRAILER if i == n - 1 else 0) | (LEADER if i == li else 0) for i in range(n)]
+        d_flags = [torch.full((S,), f, dtype=torch.int32, device=dev) for f in flags]
+        u = torch.empty((S, N), dtype=f64, device=dev); xs = torch.empty((S, 2, np1), dtype=f64, device=dev)
+        modes = torch.empty((S, N), dtype=torch.int32, device=dev); obj = torch.empty(S, dtype=f64, device=dev)
+        status = torch.empty(S, dtype=torch.int32, device=dev); nodes = torch.empty(S, dtype=torch.int32, device=dev)
+        X = torch.empty((ep_len + 1, S, 2 * n), dtype=f64, device=dev)
+        U = torch.empty((ep_len, S, n), dtype=f64, device=dev)
+        R = torch.empty((ep_len, S), dtype=f64, device=dev)
+        V = torch.empty((ep_len, S), dtype=torch.uint8, device=dev)
+        E = torch.empty((ep_len, S), dtype=torch.int32, device=dev)
+        ND = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
+        ST = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
+        X[0] = x
+        stream = torch.cuda.current_stream().cuda_stream
+        order = [li] + list(range(li - 1, -1, -1)) + list(range(li + 1, n))
+
+        def shifted(p):          # drop column 0, repeat the last, re-extrapolate the last position (:342-344)
+            s = torch.cat((p[..., 1:], p[..., -1:]), dim=-1).clone()
+            s[:, 0, -1] = s[:, 0, -2] + ts * s[:, 1, -1]
+            return s
+
+        for t in range(ep_len):
+            xl[:] = lx[:, :, t:t + np1]
+            prev = pred.clone()
+            for i in order:
+                if have_pred:
+                    if i != 0:      # front neighbour: fresh if it was solved before me in this step, else shifted
+                        xf[:, i] = pred[:, i - 1] if (i > li) else shifted(prev[:, i - 1])
+                    if i != n - 1:
+                        xb[:, i] = pred[:, i + 1] if (i < li) else shifted(prev[:, i + 1])
+                else:               # first step: only the fresh predictions exist (:341, :368, :375)
+                    if i > li:
+                        xf[:, i] = pred[:, i - 1]
+                    if i < li:
+                        xb[:, i] = pred[:, i + 1]
+                api.local_miqp_device(self.ldesc, S, d_flags[i], d_mass[:, i].contiguous(), x.view(S, n, 2)[:, i].contiguous(),
+                                      xf[:, i].contiguous(), xb[:, i].contiguous(), xl, u, xs, modes, obj, status, nodes,
+                                      None, ctx=self.ctx, stream=stream)
+                pred[:, i] = xs
+                U[t, :, i] = u[:, 0]
+                ND[t, :, i] = nodes
+                ST[t, :, i] = status
+            have_pred = True
+            api.rollout_step_device(edesc, S, x, U[t], None, d_mass, lx[:, :, t].contiguous(), X[t + 1], R[t], V[t],
+                                    E[t], ctx=self.ctx, stream=stream)
+            x = X[t + 1]
+        torch.cuda.synchronize()
+        return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
+                    errors=E.cpu().numpy(), nodes=ND.cpu().numpy(), status=ST.cpu().numpy())

@@ -102,3 +102,23 @@ def test_batched_admm_sweep_matches_single_scenarios():
     for j, one in enumerate(singles):
         assert np.abs(out["X"][:, j] - one["X"]).max() < 1e-6, np.abs(out["X"][:, j] - one["X"]).max()
         assert np.abs(out["U"][:, j] - one["U"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("li", [0, 2])
+def test_batched_seq_sweep_matches_single_scenarios(li):
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200.sweep import BatchedSeqSweep
+    from hybrid_vehicle_platoon_b200.misc import Sim_n_task_2
+    n, N, T = 4, 5, 10
+    singles, x0s = [], []
+    for s in (0, 1, 2, 3):
+        sim = Sim_n_task_2(n, seed=7, N=N)
+        sim.ep_len = T
+        singles.append(hvp.simulate(sim, "seq", seed=s, ep_len=T, leader_index=li))
+        x0s.append(singles[-1]["X"][0])
+    sw = BatchedSeqSweep(n, N, masses=np.asarray(sim.masses), spacing_policy=sim.spacing_policy, leader_index=li)
+    out = sw.run(np.stack(x0s), singles[0]["leader_x"], T)
+    assert (out["status"] == 2).all()
+    for j, one in enumerate(singles):
+        assert np.abs(out["X"][:, j] - one["X"]).max() < 1e-6, (j, np.abs(out["X"][:, j] - one["X"]).max())
+        assert np.abs(out["U"][:, j] - one["U"]).max() < 1e-6
