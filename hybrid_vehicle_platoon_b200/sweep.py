@@ -319,3 +319,173 @@ class BatchedSeqSweep(BatchedDecentSweep):
         torch.cuda.synchronize()
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
                     errors=E.cpu().numpy(), nodes=ND.cpu().numpy(), status=ST.cpu().numpy())
+
+
+class BatchedGAdmmSweep:
+    """S independent platoons under the switching ("g") ADMM controller (fleet_g_admm.py; round logic restated in
+    fleet_g_admm.GAdmmCoordinator -- UNVERIFIED-3P).  Every agent holds a fixed PWA region sequence, so a round is
+    S*n convex QPs: one launch of the compiled-MPC kernel (fixed_modes path, FP64 tensor-core precompute) per role
+    (leader / interior / last); sequences are re-identified from a PWA roll-out of the current inputs as torch ops."""
+
+    def __init__(self, n: int, N: int, admm_iters: int = 100, rho: float = 0.5, masses=None,
+                 spacing_policy=ConstantSpacingPolicy(50), d_safe: float = Params.d_safe, device: int = 0, ctx=None):
+        import torch
+        from ._lib import MPC_GADMM
+        from .models import PwaGearVehicle
+        if n < 2:
+            raise ValueError("the g-ADMM scheme needs at least two vehicles")
+        self.torch, self.n, self.N, self.iters, self.rho = torch, n, N, admm_iters, rho
+        self.dev = torch.device("cuda", device)
+        self.ctx = ctx or default_context(device)
+        self.d0, self.t0 = spacing_params(spacing_policy)
+        self.d_safe = d_safe
+        self.masses = None if masses is None else np.asarray(masses, dtype=np.float64)
+        mk = lambda nf, nb, lead: api.CompiledMpc(MPC_GADMM, N, flags=LEADER if lead else 0, n_front=nf, n_behind=nb, rho=rho,
+                                                  d0=self.d0, t0=self.t0, ctx=self.ctx)
+        self.cm_lead = mk(0, 1, True)
+        self.cm_mid = mk(1, 1, False) if n > 2 else None
+        self.cm_last = mk(1, 0, False)
+        v = PwaGearVehicle(800.0)
+        lim = v.v_gear_lim
+        f64 = torch.float64
+        self.edges = torch.tensor([lim[0], lim[1], lim[2], v.alpha, lim[3], lim[4]], dtype=f64, device=self.dev)
+        g = [0, 1, 2, 3, 3, 4, 5]
+        self.cf = torch.tensor([v.c1 if r < 4 else v.c2 for r in range(7)], dtype=f64, device=self.dev)
+        self.bg = torch.tensor([float(v.b[g[r]]) for r in range(7)], dtype=f64, device=self.dev)
+        self.dd = torch.tensor([0.0 if r < 4 else v.d for r in range(7)], dtype=f64, device=self.dev)
+        self.mug = v.mu * v.grav
+
+    def _region(self, vel):           # first region whose closed interval (+1e-9) contains v (fleet_g_admm._region_of)
+        return self.torch.bucketize(vel, self.edges + 1e-9, right=False)
+
+    def _rollout(self, x, u, mass):
+        """PWA roll-out of all vehicles under inputs u (S,n,N): trajectories (S,n,2,N+1), region sequences (S,n,N)."""
+        torch, N = self.torch, self.N
+        S, n = u.shape[0], u.shape[1]
+        tr = torch.empty((S, n, 2, N + 1), dtype=torch.float64, device=self.dev)
+        seq = torch.empty((S, n, N), dtype=torch.int64, device=self.dev)
+        p, v = x.view(S, n, 2)[:, :, 0].clone(), x.view(S, n, 2)[:, :, 1].clone()
+        tr[:, :, 0, 0], tr[:, :, 1, 0] = p, v
+        for k in range(N):
+            r = self._region(v)
+            seq[:, :, k] = r
+            a = 1.0 + (-(self.cf[r]) / mass)
+            b = self.bg[r] / mass
+            c = -self.mug - self.dd[r] / mass
+            p, v = p + v, a * v + b * u[:, :, k] + c
+            tr[:, :, 0, k + 1], tr[:, :, 1, k + 1] = p, v
+        return tr, seq
+
+    def _const_vel_u(self, x, mass):  # PwaGearVehicle.get_u_for_constant_vel (models.py:537-556), vectorised
+        S, n = mass.shape
+        v = x.view(S, n, 2)[:, :, 1]
+        r = self.torch.bucketize(v, self.edges + 1e-4, right=False)
+        return (1.0 / (self.bg[r] / mass)) * (-(-(self.cf[r]) / mass) * v - (-self.mug - self.dd[r] / mass))
+
+    def _admm(self, x, u, mass, lwin):
+        """One g_admm_control call for all scenarios.  Returns (u (S,n,N), cost (S,), ok (S,) bool)."""
+        torch, n, N, rho, dev = self.torch, self.n, self.N, self.rho, self.dev
+        f64, np1 = torch.float64, N + 1
+        S = u.shape[0]
+        zer = lambda *s: torch.zeros(s, dtype=f64, device=dev)
+        # augmented blocks per vehicle: [front copy (i > 0), own, back copy (i < n-1)], y and z alike
+        yF, yO, yB = zer(S, n, 2, np1), zer(S, n, 2, np1), zer(S, n, 2, np1)
+        tr, seq = self._rollout(x, u, mass)
+        zbar = tr.clone()
+        ok = torch.ones(S, dtype=torch.bool, device=dev)
+        cost = zer(S)
+        own, cF, cB = zer(S, n, 2, np1), zer(S, n, 2, np1), zer(S, n, 2, np1)
+        stream = torch.cuda.current_stream().cuda_stream
+        groups = [(self.cm_lead, [0]), (self.cm_last, [n - 1])] + ([(self.cm_mid, list(range(1, n - 1)))] if n > 2 else [])
+        for _ in range(self.iters):
+            cost.zero_()
+            for cm, idx in groups:
+                k = len(idx); B = S * k
+                ii = torch.as_tensor(idx, device=dev)
+                blocks_y, blocks_z = [], []
+                if idx[0] > 0:
+                    blocks_y.append(yF[:, ii]); blocks_z.append(zbar[:, ii - 1])
+                blocks_y.append(yO[:, ii]); blocks_z.append(zbar[:, ii])
+                if idx[-1] < n - 1:
+                    blocks_y.append(yB[:, ii]); blocks_z.append(zbar[:, ii + 1])
+                params = torch.cat([lwin.reshape(S, 1, 2 * np1).expand(S, k, -1)] + [b.reshape(S, k, -1) for b in blocks_y]
+                                   + [b.reshape(S, k, -1) for b in blocks_z], dim=2).reshape(B, -1).contiguous()
+                x0g = x.view(S, n, 2)[:, ii].reshape(B, 1, 2).contiguous()
+                mg = mass[:, ii].reshape(B, 1).contiguous()
+                fm = seq[:, ii].reshape(B, 1, N).to(torch.int32).contiguous()
+                uo = torch.empty((B, 1, N), dtype=f64, device=dev); xo = torch.empty((B, 1, 2, np1), dtype=f64, device=dev)
+                eo = torch.empty((B, max(cm.n_extra, 1)), dtype=f64, device=dev)
+                mo = torch.empty((B, 1, N), dtype=torch.int32, device=dev); ob = torch.empty(B, dtype=f64, device=dev)
+                st = torch.empty(B, dtype=torch.int32, device=dev); no = torch.empty(B, dtype=torch.int32, device=dev)
+                cm.solve_device(B, x0g, mg, params, fm, uo, xo, eo, mo, ob, st, no, None, stream=stream)
+                good = (st == 2).view(S, k)
+                ok &= good.all(dim=1)
+                cost += torch.where(good, ob.view(S, k), torch.zeros_like(ob.view(S, k))).sum(dim=1)
+                u[:, ii] = torch.where(good.unsqueeze(-1), uo.view(S, k, N), u[:, ii])
+                own[:, ii] = xo.view(S, k, 2, np1)
+                e = eo.view(S, k, -1)
+                o = 0
+                if idx[0] > 0:
+                    cF[:, ii] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1); o += 2 * np1
+                if idx[-1] < n - 1:
+                    cB[:, ii] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1)
+            # z-update: average of every copy of vehicle j's trajectory (own, the copy held by j+1, the one held by j-1)
+            cnt = torch.ones(n, dtype=f64, device=dev); cnt[:-1] += 1; cnt[1:] += 1
+            acc = own.clone()
+            acc[:, :-1] += cF[:, 1:]
+            acc[:, 1:] += cB[:, :-1]
+            zbar = acc / cnt.view(1, n, 1, 1)
+            # y-update on every block with the new z
+            yO += rho * (own - zbar)
+            yF[:, 1:] += rho * (cF[:, 1:] - zbar[:, :-1])
+            yB[:, :-1] += rho * (cB[:, :-1] - zbar[:, 1:])
+            tr, seq = self._rollout(x, u, mass)
+        infeas = ((tr[:, :, 1, 1:] > 45.84 + 1e-6) | (tr[:, :, 1, 1:] < 3.94 - 1e-6)).any(dim=2).any(dim=1)
+        return u, cost, ok & ~infeas
+
+    def run(self, x0, leader_x, ep_len: int):
+        torch, dev, n, N = self.torch, self.dev, self.n, self.N
+        f64, np1 = torch.float64, N + 1
+        x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
+        S = x.shape[0]
+        lx = torch.as_tensor(np.ascontiguousarray(leader_x, dtype=np.float64), device=dev)
+        if lx.ndim == 2:
+            lx = lx.unsqueeze(0).expand(S, -1, -1)
+        m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
+        mass = torch.as_tensor(np.array(m, dtype=np.float64, order="C"), device=dev)
+        edesc = api.env_desc(n, 0, self.d0, self.t0, self.d_safe, True, False, True)
+        X = torch.empty((ep_len + 1, S, 2 * n), dtype=f64, device=dev)
+        U = torch.empty((ep_len, S, n), dtype=f64, device=dev)
+        R = torch.empty((ep_len, S), dtype=f64, device=dev)
+        V = torch.empty((ep_len, S), dtype=torch.uint8, device=dev)
+        E = torch.empty((ep_len, S), dtype=torch.int32, device=dev)
+        OK = torch.empty((ep_len, S), dtype=torch.bool, device=dev)
+        WS = torch.empty((ep_len, S), dtype=torch.int32, device=dev)
+        X[0] = x
+        stream = torch.cuda.current_stream().cuda_stream
+        prev = None
+        for t in range(ep_len):
+            lwin = lx[:, :, t:t + np1].contiguous()
+            starts = [self._const_vel_u(x, mass).unsqueeze(-1).expand(S, n, N).clone()]
+            if prev is not None:        # shifted previous solution (fleet_g_admm.py:266-272)
+                starts.append(torch.cat((prev[..., 1:], prev[..., -1:]), dim=-1))
+            best_cost = torch.full((S,), float("inf"), dtype=f64, device=dev)
+            best_u = torch.zeros((S, n, N), dtype=f64, device=dev)
+            which = torch.zeros(S, dtype=torch.int32, device=dev)
+            for w, u in enumerate(starts):
+                uu, cost, ok = self._admm(x, u.clone(), mass, lwin)
+                cost = torch.where(ok, cost, torch.full_like(cost, float("inf")))
+                better = cost < best_cost
+                best_cost = torch.where(better, cost, best_cost)
+                best_u = torch.where(better.view(S, 1, 1), uu, best_u)
+                which = torch.where(better, torch.full_like(which, w + 1), which)
+            OK[t] = torch.isfinite(best_cost)
+            WS[t] = which
+            prev = best_u
+            U[t] = best_u[:, :, 0]
+            api.rollout_step_device(edesc, S, x, U[t], None, mass, lx[:, :, t].contiguous(), X[t + 1], R[t], V[t], E[t],
+                                    ctx=self.ctx, stream=stream)
+            x = X[t + 1]
+        torch.cuda.synchronize()
+        return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
+                    errors=E.cpu().numpy(), solved=OK.cpu().numpy(), best_warm_start=WS.cpu().numpy())

@@ -122,3 +122,20 @@ def test_batched_seq_sweep_matches_single_scenarios(li):
     for j, one in enumerate(singles):
         assert np.abs(out["X"][:, j] - one["X"]).max() < 1e-6, (j, np.abs(out["X"][:, j] - one["X"]).max())
         assert np.abs(out["U"][:, j] - one["U"]).max() < 1e-6
+
+
+def test_batched_gadmm_sweep_matches_single_scenarios():
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200.sweep import BatchedGAdmmSweep
+    from test_host_fleets import SmallSim
+    n, N, T, iters = 3, 5, 5, 10
+    singles, x0s = [], []
+    for s in (5, 6, 9):
+        singles.append(hvp.fleet_g_admm.simulate(SmallSim(n, N, T), admm_iters=iters, seed=s))
+        x0s.append(singles[-1]["X"][0])
+    sw = BatchedGAdmmSweep(n, N, admm_iters=iters, rho=0.5)
+    out = sw.run(np.stack(x0s), singles[0]["leader_x"], T)
+    assert out["solved"].all()
+    for j, one in enumerate(singles):
+        assert np.abs(out["X"][:, j] - one["X"]).max() < 1e-6, (j, np.abs(out["X"][:, j] - one["X"]).max())
+        assert np.abs(out["U"][:, j] - one["U"]).max() < 1e-6
