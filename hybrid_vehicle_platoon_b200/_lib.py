@@ -87,6 +87,7 @@ def lib():
     mpc = [_vp, C.c_int64] + [_vp] * 12
     L.hvp_mpc_solve_dev.argtypes = mpc + [_vp]
     L.hvp_mpc_solve_host.argtypes = mpc
+    L.hvp_mpc_solve_shard_dev.argtypes = [_vp, C.c_int64, _vp, _vp, _vp] + [C.c_int32] * 5 + [_vp] * 10
     L.hvp_mpc_eval_dev.argtypes = [_vp, C.c_int64] + [_vp] * 6
     L.hvp_mpc_eval_host.argtypes = [_vp, C.c_int64] + [_vp] * 5
     L.hvp_microbench_fp64.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]

@@ -144,6 +144,15 @@ class CompiledMpc:
                                       p(extra), p(modes), p(obj), p(status), p(nodes), p(qp_iters),
                                       _stream_arg(stream)))
 
+    def solve_shard_device(self, batch, x0, mass, params, rank, world, groups, prefix_depth, node_budget, incumbent,
+                           u, x, extra, modes, obj, status, nodes, qp_iters=None, *, stream=None):
+        """One device's share of split trees (hvp_mpc_solve_shard_dev, include/hvp.h); DEVICE buffers."""
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        check(lib().hvp_mpc_solve_shard_dev(self._h, int(batch), p(x0), p(mass), p(params), int(rank), int(world),
+                                            int(groups), int(prefix_depth), int(node_budget), p(incumbent), p(u), p(x),
+                                            p(extra), p(modes), p(obj), p(status), p(nodes), p(qp_iters),
+                                            _stream_arg(stream)))
+
     def eval_cost(self, mass, params, xg, ug):
         """Cost of pinned guesses (fleet_event_based.py:308-327): xg (B,nl,2,N+1), ug (B,nl,N) -> (B,)."""
         nl, N = self.n_local, self.N

@@ -62,6 +62,10 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
                            const double* params, const int32_t* fixed_modes, const double* Y, double* u, double* x,
                            double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                            int32_t* qp_iters, unsigned long long* counter, const PmScratch* scratch, cudaStream_t stream);
+cudaError_t launch_pm_shard(const PmDev& S, int64_t batch, const double* x0, const double* mass, const double* params,
+                            const double* Y, const double* incumbent, double* u, double* x, double* extra,
+                            int32_t* modes, double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters,
+                            unsigned long long* counter, const PmScratch* scratch, cudaStream_t stream);
 cudaError_t launch_pm_eval(const PmDev& S, int64_t batch, const double* x0, const double* mass,
                            const double* params, const double* xg, const double* ug, double* cost,
                            cudaStream_t stream);

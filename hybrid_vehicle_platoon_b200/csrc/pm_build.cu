@@ -42,6 +42,9 @@ struct hvp_mpc {
     void* scratch_mem = nullptr;
     size_t scratch_cap = 0;      // flagged-list capacity the scratch was sized for
     int split_D = 0;
+    PmScratch shard;             // scratch of hvp_mpc_solve_shard_dev: batch x groups work items
+    void* shard_mem = nullptr;
+    size_t shard_items = 0;
 };
 
 namespace {
@@ -352,6 +355,7 @@ extern "C" int hvp_mpc_destroy(hvp_mpc* m) {
     if (m->x0buf) cudaFree(m->x0buf);
     if (m->ybuf) cudaFree(m->ybuf);
     if (m->scratch_mem) cudaFree(m->scratch_mem);
+    if (m->shard_mem) cudaFree(m->shard_mem);
     delete m;
     return 0;
 }
@@ -461,6 +465,7 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     if (rc) { hvp_mpc_destroy(m); return rc; }
     // tree splitting of heavy problems (PmSplit): prefix depth of the split; the scratch is sized per batch
     memset(&m->scratch, 0, sizeof m->scratch);
+    memset(&m->shard, 0, sizeof m->shard);
     {
         const char* env = getenv("HVP_MPC_SPLIT");
         int D = 3 * S.nl > 5 ? 3 * S.nl : 5;
@@ -545,6 +550,66 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     c->launches += 2;
+    return 0;
+}
+
+extern "C" int hvp_mpc_solve_shard_dev(hvp_mpc* m, int64_t batch, const double* x0, const double* mass,
+                                       const double* params, int32_t rank, int32_t world, int32_t groups,
+                                       int32_t prefix_depth, int32_t node_budget, const double* incumbent, double* u,
+                                       double* x, double* extra, int32_t* modes, double* obj, int32_t* status,
+                                       int32_t* nodes, int32_t* qp_iters, void* stream) {
+    if (!m) return fail(-1, "mpc_solve_shard: handle is NULL");
+    if (batch < 0) return fail(-4, "mpc_solve_shard: negative batch");
+    if (world < 1 || rank < 0 || rank >= world) return fail(-4, "mpc_solve_shard: rank %d outside world %d", rank, world);
+    if (groups < 1 || groups > 4096) return fail(-4, "mpc_solve_shard: groups must be 1..4096");
+    if (node_budget < 0) return fail(-4, "mpc_solve_shard: negative node budget");
+    if (batch == 0) return 0;
+    if (!x0 || !mass || !params || !u || !x || !modes || !obj || !status || !nodes)
+        return fail(-1, "mpc_solve_shard: NULL array argument");
+    const PmDev& S = m->S;
+    if (S.max_nodes != 0) return fail(-4, "mpc_solve_shard: the handle was created with max_nodes");
+    int D = prefix_depth > 0 ? prefix_depth : m->split_D;
+    if (D > S.depth - 1) D = S.depth - 1;
+    if (D < 1) return fail(-4, "mpc_solve_shard: the formulation has no tree to split (depth %d)", S.depth);
+    if ((size_t)batch * (size_t)groups > ((size_t)1 << 24)) return fail(-4, "mpc_solve_shard: batch x groups too large");
+    hvp_ctx* c = m->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const size_t need = (size_t)batch * S.mw * sizeof(double);
+    if (need > m->ycap) {
+        if (m->ybuf) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->ybuf)); m->ybuf = nullptr; m->ycap = 0; }
+        CUDA_TRY(cudaMalloc(&m->ybuf, need + need / 4));
+        m->ycap = need + need / 4;
+    }
+    const size_t items = (size_t)batch * (size_t)groups;
+    if (items > m->shard_items || (size_t)batch > (size_t)m->shard.sp.cap) {
+        if (m->shard_mem) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->shard_mem)); m->shard_mem = nullptr; }
+        const size_t nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1), ne = S.ne > 0 ? (size_t)S.ne : 1;
+        const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + (size_t)batch * (4 + 8) + 64 + 12 * 256;
+        void* p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, bytes));
+        m->shard_mem = p;
+        char* q = (char*)p;
+        auto take = [&](size_t b) { char* r = q; q += (b + 255) & ~(size_t)255; return r; };
+        PmScratch& sc = m->shard;
+        sc.u = (double*)take(items * nu * 8); sc.x = (double*)take(items * nx * 8); sc.extra = (double*)take(items * ne * 8);
+        sc.obj = (double*)take(items * 8); sc.modes = (int32_t*)take(items * nu * 4); sc.status = (int32_t*)take(items * 4);
+        sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
+        sc.sp.inc_shared = (unsigned long long*)take((size_t)batch * 8); sc.sp.flagged = (int*)take((size_t)batch * 4);
+        sc.sp.nflag = (int*)take(4);
+        sc.sp.cap = (int)batch;
+        m->shard_items = items;
+    }
+    PmScratch sc = m->shard;
+    sc.sp.M = groups; sc.sp.D = D; sc.sp.cap = (int)batch; sc.sp.budget = node_budget;
+    sc.sp.rank = rank; sc.sp.world = world;
+    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(launch_pm_precompute(S, batch, x0, params, m->ybuf, st));
+    CUDA_TRY(launch_pm_shard(S, batch, x0, mass, params, m->ybuf, incumbent, u, x, extra, modes, obj, status, nodes,
+                             qp_iters, m->counter, &sc, st));
+    CUDA_TRY(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    c->launches += 4;
     return 0;
 }
 

@@ -117,7 +117,7 @@ struct Warp {
     double inc, c0, cp, nHn, lam_p, dual;
     bool p_soft, trouble, limit, dive;
     // tree splitting (PmSplit)
-    int sub_M, sub_D, sub_code, sub_ord, budget;
+    int sub_M, sub_D, sub_code, sub_ord, budget, stop_nodes;
     double own;                        // objective of this warp's own best leaf
     unsigned long long* shared;        // incumbent shared by the warps working on one problem
     const PmSplit* sp;
@@ -139,7 +139,7 @@ struct Warp {
         act = ib; cand = ib + nv; modes = cand + D + 1; bmodes = modes + D; built = bmodes + D;
         orient = built + D; aflag = orient + S.ng; agen = aflag + nv;
         (void)ld;
-        sub_M = sub_D = sub_code = sub_ord = budget = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
+        sub_M = sub_D = sub_code = sub_ord = budget = stop_nodes = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
     }
 
     __device__ __forceinline__ double ma(int i, int r) const { return 1.0 - S.M.cf[r] * inv_m[i]; }
@@ -385,6 +385,7 @@ struct Warp {
             return;
         }
         if (S.max_nodes > 0 && nodes >= S.max_nodes) { limit = true; state = PS_DONE; return; }
+        if (stop_nodes > 0 && nodes >= stop_nodes) { limit = true; state = PS_DONE; return; }
         if (budget > 0 && nodes >= budget) {
             // heavy tree: hand it to the sub-tree pass if the list has room, else finish it here
             int slot = 0;
@@ -906,9 +907,17 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
         if (lane == 0) nxt = atomicAdd(counter, 1ull);
         const int64_t w = (int64_t)__shfl_sync(gm, nxt, 0, GW);
         int64_t i = w, o = w;                    // problem (input) index, output index
-        W.sub_M = 0; W.sub_D = 0; W.sub_code = 0; W.shared = nullptr;
+        W.sub_M = 0; W.sub_D = 0; W.sub_code = 0; W.shared = nullptr; W.stop_nodes = 0;
         W.budget = (sp.mode == 1 && !fixed_modes) ? sp.budget : 0;
-        if (sp.mode == 2) {
+        if (sp.mode == 3) {
+            // sharded pass: M groups of THIS device per problem; the sub-trees of a problem are dealt to
+            // world * M groups over all devices by prefix ordinal; the incumbent slot was seeded by the caller
+            if (w >= batch * sp.M) break;
+            i = w / sp.M;
+            W.sub_M = sp.M * sp.world; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M) * sp.world + sp.rank;   // ordinal o -> rank o % world
+            W.shared = sp.inc_shared + i;
+            W.stop_nodes = sp.budget;
+        } else if (sp.mode == 2) {
             int nf = *reinterpret_cast<volatile int*>(sp.nflag);
             if (nf > sp.cap) nf = sp.cap;
             if (w >= (int64_t)nf * sp.M) break;
@@ -943,22 +952,28 @@ pm_merge_kernel(const __grid_constant__ PmDev S, const __grid_constant__ PmSplit
     const size_t nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
     double bestv = obj[i];                       // incumbent of the budgeted pass (+inf if it had none)
     int bw = -1, nsum = 0, isum = 0;
-    bool numeric = false;
+    bool numeric = false, limited = false;
     for (int c = 0; c < sp.M; ++c) {
         const size_t w = (size_t)f * sp.M + c;
         if (sobj[w] < bestv) { bestv = sobj[w]; bw = (int)w; }
         nsum += sno[w];
         if (sit) isum += sit[w];
         if (sst[w] == HVP_ST_NUMERIC) numeric = true;
+        if (sst[w] == HVP_ST_NODE_LIMIT) limited = true;
     }
     if (bw >= 0) {
         for (size_t e = lane; e < nu; e += 32) { u[nu * i + e] = su_[nu * bw + e]; modes[nu * i + e] = sm_[nu * bw + e]; }
         for (size_t e = lane; e < nx; e += 32) x[nx * i + e] = sx_[nx * bw + e];
         if (extra) for (int e = lane; e < S.ne; e += 32) extra[(size_t)S.ne * i + e] = se_[(size_t)S.ne * bw + e];
+    } else if (sp.mode == 3) {                   // sharded pass: this device's share held nothing better
+        for (size_t e = lane; e < nu; e += 32) { u[nu * i + e] = 0.0; modes[nu * i + e] = -1; }
+        for (size_t e = lane; e < nx; e += 32) x[nx * i + e] = 0.0;
+        if (extra) for (int e = lane; e < S.ne; e += 32) extra[(size_t)S.ne * i + e] = 0.0;
     }
     if (lane == 0) {
         obj[i] = bestv;
-        status[i] = numeric ? HVP_ST_NUMERIC : (bestv < HUGE_VAL ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE);
+        status[i] = limited ? HVP_ST_NODE_LIMIT
+                            : (numeric ? HVP_ST_NUMERIC : (bestv < HUGE_VAL ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE));
         nodes[i] += nsum;
         if (qp_iters) qp_iters[i] += isum;
     }
@@ -1127,6 +1142,69 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
                                                                      sc->status, sc->nodes, sc->iters, u, x, extra,
                                                                      modes, obj, status, nodes, qp_iters);
     return cudaGetLastError();
+}
+
+// ---- one device's share of split trees (multi-GPU tree split; the incumbent exchange between the devices is the
+// caller's allreduce(min), hvp.h: hvp_mpc_solve_shard_dev) -------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pm_shard_init_kernel(int64_t batch, const double* __restrict__ incumbent, PmSplit sp, double* __restrict__ obj,
+                     int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *sp.nflag = (int)batch;
+    if (i >= batch) return;
+    sp.flagged[i] = (int)i;
+    sp.inc_shared[i] = dkey(incumbent ? incumbent[i] : HUGE_VAL);
+    obj[i] = HUGE_VAL;
+    nodes[i] = 0;
+    if (qp_iters) qp_iters[i] = 0;
+}
+
+template <int GW>
+static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double* x0, const double* mass,
+                                     const double* params, const double* Y, const double* incumbent, double* u,
+                                     double* x, double* extra, int32_t* modes, double* obj, int32_t* status,
+                                     int32_t* nodes, int32_t* qp_iters, unsigned long long* counter,
+                                     const PmScratch* sc, cudaStream_t stream) {
+    int gpb = 128 / GW;
+    while (gpb > 1 && (size_t)gpb * S.smem_bytes > 200 * 1024) gpb >>= 1;
+    const size_t smem = (size_t)gpb * S.smem_bytes;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int threads = gpb * GW;
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * threads > 2048) per_sm = 2048 / threads;
+    const int64_t full = (int64_t)sms * per_sm;
+    PmSplit sp = sc->sp;
+    sp.mode = 3;
+    int64_t blocks = (batch * sp.M + gpb - 1) / gpb;
+    if (blocks > full) blocks = full;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    pm_shard_init_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(batch, incumbent, sp, obj, nodes, qp_iters);
+    pm_miqp_kernel<GW><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
+                                                                    sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
+                                                                    sc->iters, counter, sp);
+    pm_merge_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, stream>>>(S, sp, sc->u, sc->x, sc->extra, sc->modes, sc->obj,
+                                                                    sc->status, sc->nodes, sc->iters, u, x, extra, modes,
+                                                                    obj, status, nodes, qp_iters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pm_shard(const PmDev& S, int64_t batch, const double* x0, const double* mass, const double* params,
+                            const double* Y, const double* incumbent, double* u, double* x, double* extra,
+                            int32_t* modes, double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters,
+                            unsigned long long* counter, const PmScratch* sc, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    if (S.nv <= 16)
+        return launch_pm_shard_t<16>(S, batch, x0, mass, params, Y, incumbent, u, x, extra, modes, obj, status, nodes,
+                                     qp_iters, counter, sc, stream);
+    return launch_pm_shard_t<32>(S, batch, x0, mass, params, Y, incumbent, u, x, extra, modes, obj, status, nodes,
+                                 qp_iters, counter, sc, stream);
 }
 
 cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,

@@ -65,8 +65,9 @@ struct PmDev {                   // kernel argument
 // work by the ordinal of the depth-`D` mode prefix (ordinal mod M) and exchange the incumbent through
 // `inc_shared` (atomicMin on an order-preserving key); pass 3 keeps the best sub-result.
 struct PmSplit {
-    int mode;                          // 0 plain, 1 budgeted pass, 2 sub-tree pass
+    int mode;                          // 0 plain, 1 budgeted pass, 2 sub-tree pass, 3 sharded pass (one rank's share)
     int budget, cap, M, D;
+    int rank, world;                   // mode 3: this device takes the prefix ordinals o with o % world == rank
     int* nflag;                        // [1] flagged problems so far
     int* flagged;                      // [cap] their batch indices
     unsigned long long* inc_shared;    // [cap] best objective known for each (order-preserving key)

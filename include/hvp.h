@@ -191,6 +191,22 @@ int hvp_mpc_solve_host(hvp_mpc* mpc, int64_t batch, const double* x0, const doub
                        const int32_t* fixed_modes, double* u, double* x, double* extra, int32_t* modes,
                        double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters);
 
+/* Multi-GPU split of LARGE trees (north_star: "allreduce-min the incumbent objective bound when a single large
+ * MIQP's tree is split across GPUs"; the reference has no counterpart -- Gurobi's threads play this role,
+ * mpcs/mpc_gear.py:185-186).  Every device of `world` calls this with the SAME batch; device `rank` searches, for
+ * every problem, the sub-trees whose depth-`prefix_depth` mode-prefix ordinal o has o % world == rank (dealt to the
+ * `groups` warps this device gives each problem by (o / world) % groups; the warps of a device share their
+ * incumbent through global memory).  incumbent [batch] (device, or NULL = +inf) seeds the bound: only leaves
+ * strictly better are accepted.  node_budget > 0 stops every warp after that many nodes (status 8) -- the cheap
+ * first wave that produces a bound to exchange; 0 searches the share to completion.  obj [batch] = best leaf of
+ * THIS device's share (+inf: none better than the incumbent; status 3).  The caller combines the devices with
+ * allreduce(min) over obj (NCCL) and takes u/x/modes from the device that attains it
+ * (hybrid_vehicle_platoon_b200/dist.py: solve_tree_split).  prefix_depth 0 = the handle's default. */
+int hvp_mpc_solve_shard_dev(hvp_mpc* mpc, int64_t batch, const double* x0, const double* mass, const double* params,
+                            int32_t rank, int32_t world, int32_t groups, int32_t prefix_depth, int32_t node_budget,
+                            const double* incumbent, double* u, double* x, double* extra, int32_t* modes, double* obj,
+                            int32_t* status, int32_t* nodes, int32_t* qp_iters, void* stream);
+
 /* eval_cost of the event-based LocalMpc (fleet_event_based.py:308-327): cost of a guess with x[:, :N]
  * and u pinned -- xg [batch][n_local][2][N+1] (column N is ignored: the last state is free),
  * ug [batch][n_local][N]; the initial condition is xg[..., 0].  cost [batch] = objVal, +inf if the guess

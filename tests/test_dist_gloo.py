@@ -58,3 +58,47 @@ def test_balanced_shards_partition_and_balance():
         assert sorted(i for s_ in sh for i in s_) == list(range(4096))
         loads = [sum(costs[i] for i in s_) for s_ in sh]
         assert max(loads) - min(loads) <= max(costs)
+
+
+def _winner_worker(rank, world, port, q):
+    """The exchange step of the multi-GPU tree split (dist.reduce_winner) on gloo with made-up per-rank results."""
+    import torch
+    import torch.distributed as dist
+    from hybrid_vehicle_platoon_b200 import dist as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inf = float("inf")
+    # problem 0: rank 1 wins; 1: tie -> lowest rank (0); 2: nobody has a leaf; 3: rank 0 wins
+    objs = [[5.0, 2.0, inf, 1.0], [3.0, 2.0, inf, inf]][rank]
+    B = 4
+    mine = dict(obj=torch.tensor(objs, dtype=torch.float64),
+                u=torch.full((B, 1, 2), float(rank + 1), dtype=torch.float64),
+                x=torch.full((B, 1, 2, 3), float(10 * (rank + 1)), dtype=torch.float64),
+                extra=torch.zeros((B, 1), dtype=torch.float64),
+                modes=torch.full((B, 1, 2), rank + 3, dtype=torch.int32),
+                nodes=torch.full((B,), 7 + rank, dtype=torch.int32), qp_iters=torch.full((B,), 20, dtype=torch.int32),
+                numeric=torch.zeros(B, dtype=torch.int32))
+    out = D.reduce_winner(mine, rank, world, D.dist_allreduce)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, {k: v.tolist() for k, v in out.items()}))
+
+
+def test_tree_split_exchange_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_winner_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    out = dict(q.get(timeout=120) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    assert out[0] == out[1]                                   # every rank ends with the same answer
+    o = out[0]
+    inf = float("inf")
+    assert o["obj"] == [3.0, 2.0, inf, 1.0]
+    assert o["winner"] == [1, 0, 2, 0]
+    assert o["status"] == [2, 2, 3, 2]
+    assert [u[0][0] for u in o["u"]] == [2.0, 1.0, 0.0, 1.0]
+    assert [m[0][0] for m in o["modes"]] == [4, 3, -1, 3]
+    assert o["nodes"] == [15] * 4
