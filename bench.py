@@ -435,13 +435,18 @@ def main():
                                 "algorithmic_bytes_per_scenario_step": r_bytes, "peak_source": peak_src}}
 
         # ---- p99 per-timestep latency: one scenario (10 MIQPs) through the host call ----
-        one = make_batch(77, 1)
+        # (>= 10^4 timesteps; every call is a DIFFERENT scenario of the bench distribution)
+        pool = make_batch(77, 512)
+        sl = lambda a, j: a[j * N_VEH:(j + 1) * N_VEH]
         lat = []
-        for i in range(1200):
+        for i in range(10200):
+            j = i % 512
             t0 = time.perf_counter()
-            hvp.local_miqp(HORIZON, one["flags"], one["mass"], one["x0"], one["xf"], one["xb"], one["xl"], ctx=ctx)
+            hvp.local_miqp(HORIZON, sl(pool["flags"], j), sl(pool["mass"], j), sl(pool["x0"], j), sl(pool["xf"], j),
+                           sl(pool["xb"], j), sl(pool["xl"], j), ctx=ctx)
             lat.append(time.perf_counter() - t0)
         lat = np.array(lat[200:]) * 1e3
+        smem_peak = hvp.api.microbench_smem(20000, ctx)
 
         cpu = None
         if not args.no_cpu:
@@ -475,9 +480,16 @@ def main():
                           "peak_source": "hvp_microbench_fp64 (measured DFMA issue peak)",
                           "flops_per_solve_model": flops_per_solve, "nodes_per_solve": nodes_mean,
                           "qp_iters_per_solve": iters_mean},
-            "latency": {"what": "one scenario-timestep = 10 local MIQPs through hvp_local_miqp_host",
+            "latency": {"what": "one scenario-timestep = 10 local MIQPs through hvp_local_miqp_host (host buffers in, "
+                                "controls out), a different scenario per call",
                         "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
-                        "samples": int(lat.size)},
+                        "max_ms": float(lat.max()), "samples": int(lat.size),
+                        "full_batch": {"what": f"{S} scenario-timesteps per launch (device-timed steps above)",
+                                       "p50_ms": float(np.percentile(ms, 50)), "max_ms": float(np.max(ms)),
+                                       "samples": int(ms.size)}},
+            "smem": {"peak_gbs": smem_peak, "peak_source": "hvp_microbench_smem (measured LDS.128 read bandwidth, whole device)",
+                     "note": "achieved shared-memory traffic of the QP kernels is read from ncu "
+                             "(l1tex__data_pipe_lsu_wavefronts_mem_shared, profiles/README.md)"},
             "rollout": rollout,
             "other_configs": other,
             "cpu_baseline": cpu,

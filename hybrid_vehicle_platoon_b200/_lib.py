@@ -91,6 +91,7 @@ def lib():
     L.hvp_mpc_eval_dev.argtypes = [_vp, C.c_int64] + [_vp] * 6
     L.hvp_mpc_eval_host.argtypes = [_vp, C.c_int64] + [_vp] * 5
     L.hvp_microbench_fp64.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
+    L.hvp_microbench_smem.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -187,3 +187,11 @@ def microbench_fp64(iters: int = 20000, ctx=None) -> float:
     t = C.c_double(0)
     check(lib().hvp_microbench_fp64(ctx.handle, int(iters), C.byref(t)))
     return t.value
+
+
+def microbench_smem(iters: int = 20000, ctx=None) -> float:
+    """Measured shared-memory read bandwidth of the device in GB/s (smem roofline of the QP kernels)."""
+    ctx = ctx or default_context()
+    t = C.c_double(0)
+    check(lib().hvp_microbench_smem(ctx.handle, int(iters), C.byref(t)))
+    return t.value

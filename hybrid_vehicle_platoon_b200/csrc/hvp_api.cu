@@ -336,3 +336,30 @@ extern "C" int hvp_microbench_fp64(hvp_ctx* c, int iters, double* tflops) {
     *tflops = flops / (best * 1e-3) / 1e12;
     return 0;
 }
+
+// measurement helper: shared-memory read bandwidth (GB/s over the whole device)
+extern "C" int hvp_microbench_smem(hvp_ctx* c, int iters, double* gbs) {
+    if (!c || !gbs) return fail(-1, "microbench: NULL argument");
+    if (iters < 1) return fail(-4, "microbench: iters < 1");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 8 * 1024));
+    int blocks = 0, threads = 0;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(launch_smem_microbench(iters, sink, &blocks, &threads, st));   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(c->ev0, st));
+        CUDA_TRY(launch_smem_microbench(iters, sink, &blocks, &threads, st));
+        CUDA_TRY(cudaEventRecord(c->ev1, st));
+        CUDA_TRY(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (ms < best) best = ms;
+    }
+    c->launches += 6;
+    CUDA_TRY(cudaFree(sink));
+    const double bytes = 4.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    *gbs = bytes / (best * 1e-3) / 1e9;
+    return 0;
+}

@@ -50,6 +50,7 @@ cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t
                               int32_t* nodes, int32_t* qp_iters, cudaStream_t stream);
 
 cudaError_t launch_fp64_microbench(int iters, double* sink, int* blocks, int* threads, cudaStream_t stream);
+cudaError_t launch_smem_microbench(int iters, double* sink, int* blocks, int* threads, cudaStream_t stream);
 
 cudaError_t launch_rollout(const RolloutParams& P, int64_t batch, const double* x, const double* u,
                            const int32_t* gear, const double* mass, const double* leader, double* x_out,

@@ -29,4 +29,32 @@ cudaError_t launch_fp64_microbench(int iters, double* sink, int* blocks, int* th
     return cudaGetLastError();
 }
 
+// shared-memory read bandwidth probe (the denominator for the smem traffic of the QP kernels):
+// every thread streams conflict-free 16-byte loads from a 32 KB tile; 4 independent accumulators
+__global__ void __launch_bounds__(256) smem_read_kernel(int iters, double* sink) {
+    __shared__ double2 tile[2048];
+    for (int i = threadIdx.x; i < 2048; i += 256) tile[i] = make_double2(i * 1e-9, 1.0);
+    __syncthreads();
+    double2 a0 = make_double2(0, 0), a1 = a0, a2 = a0, a3 = a0;
+    int j = threadIdx.x;
+#pragma unroll 2
+    for (int i = 0; i < iters; ++i) {
+        const double2 v0 = tile[j], v1 = tile[(j + 256) & 2047], v2 = tile[(j + 512) & 2047], v3 = tile[(j + 768) & 2047];
+        a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y; a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
+        j = (j + 1024) & 2047;
+    }
+    const double s = (a0.x + a0.y) + (a1.x + a1.y) + (a2.x + a2.y) + (a3.x + a3.y);
+    if (s == 123.456) sink[threadIdx.x & 1023] = s;
+}
+
+cudaError_t launch_smem_microbench(int iters, double* sink, int* blocks, int* threads, cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    *blocks = sms * 4;
+    *threads = 256;
+    smem_read_kernel<<<*blocks, *threads, 0, stream>>>(iters, sink);
+    return cudaGetLastError();
+}
+
 }  // namespace hvp

@@ -220,6 +220,8 @@ int hvp_mpc_eval_host(hvp_mpc* mpc, int64_t batch, const double* mass, const dou
  * FP64 FMA issue peak of the device: `iters` dependent-chain FMAs x 8 independent chains per
  * thread over a full grid; returns achieved TFLOP/s (2 flop per FMA) in *tflops. */
 int hvp_microbench_fp64(hvp_ctx* ctx, int iters, double* tflops);
+/* measured shared-memory read bandwidth of the whole device in GB/s (smem roofline of the QP kernels) */
+int hvp_microbench_smem(hvp_ctx* ctx, int iters, double* gbs);
 
 #ifdef __cplusplus
 }
