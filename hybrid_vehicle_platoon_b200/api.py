@@ -153,6 +153,11 @@ class CompiledMpc:
                                             p(extra), p(modes), p(obj), p(status), p(nodes), p(qp_iters),
                                             _stream_arg(stream)))
 
+    def eval_device(self, batch, mass, params, xg, ug, cost, *, stream=None):
+        """eval_cost on DEVICE buffers (hvp_mpc_eval_dev); asynchronous on `stream`."""
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        check(lib().hvp_mpc_eval_dev(self._h, int(batch), p(mass), p(params), p(xg), p(ug), p(cost), _stream_arg(stream)))
+
     def eval_cost(self, mass, params, xg, ug):
         """Cost of pinned guesses (fleet_event_based.py:308-327): xg (B,nl,2,N+1), ug (B,nl,N) -> (B,)."""
         nl, N = self.n_local, self.N

@@ -27,8 +27,15 @@
 
 #if defined(__CUDACC__)
 #define HVP_ROLL _Pragma("unroll 1")
+#define HVP_FLAT_UNROLL _Pragma("unroll")
 #else
 #define HVP_ROLL
+#define HVP_FLAT_UNROLL
+#endif
+#if defined(__CUDA_ARCH__)
+#define HVP_LDG(p) __ldg(p)
+#else
+#define HVP_LDG(p) (*(p))
 #endif
 
 namespace hvp {
@@ -131,8 +138,8 @@ struct FlatSolver {
     }
     HVP_HD double Hoff(int j) const { return hw1 * (double)(N - 1 - j) + hw2; }
     HVP_HD double Hdiag(int j) const { return hw1 * (double)(N - 1 - j) + hd; }
-    HVP_HD double sf(int j) const { return xf_[j + 1] - P->d_safe - pc; }       // rows PS_j <= sf(j)
-    HVP_HD double sb(int j) const { return xb_[j + 1] + P->d_safe - pc; }       // rows PS_j >= sb(j)
+    HVP_HD double sf(int j) const { return HVP_LDG(xf_ + j + 1) - P->d_safe - pc; }       // rows PS_j <= sf(j)
+    HVP_HD double sb(int j) const { return HVP_LDG(xb_ + j + 1) + P->d_safe - pc; }       // rows PS_j >= sb(j)
 
     // -------------------------------------------------------------------------------------
     HVP_HD void setup(double* W_, const LocalParams* P_, int flags, double mass, const double* x0,
@@ -332,11 +339,14 @@ struct FlatSolver {
         }
         ev = ib * w(LY::O_WV, k) + ((k >= 1) ? ea * w(LY::O_WV, k - 1) : 0.0);
         const double den = hvp_rcp(1.0 / (2.0 * P->qu) * s + ev);     // (1/(s*2qu) + e'H^-1e)^-1, s = +-1
+        double vr[N];                                      // v in registers: the inner loop has a compile-time trip count
+        HVP_FLAT_UNROLL
+        for (int j = 0; j < N; ++j) vr[j] = w(LY::O_WV, j);
         HVP_ROLL
         for (int i = 0; i < N; ++i) {
             const double vi = w(LY::O_WV, i) * den;
-            HVP_ROLL
-            for (int j = 0; j < N; ++j) w(LY::O_HINV, i * N + j) -= vi * w(LY::O_WV, j);
+            HVP_FLAT_UNROLL
+            for (int j = 0; j < N; ++j) w(LY::O_HINV, i * N + j) -= vi * vr[j];
         }
     }
 
@@ -364,11 +374,14 @@ struct FlatSolver {
             if (k >= 1) w(LY::O_D, k - 1) += 2.0 * qu * kc * ea;
             dual += qu * kc * kc;
         }
+        double gr[N];
+        HVP_FLAT_UNROLL
+        for (int j = 0; j < N; ++j) gr[j] = w(LY::O_D, j);
         HVP_ROLL
         for (int i = 0; i < N; ++i) {
             double s = 0.0;
-            HVP_ROLL
-            for (int j = 0; j < N; ++j) s -= w(LY::O_HINV, i * N + j) * w(LY::O_D, j);
+            HVP_FLAT_UNROLL
+            for (int j = 0; j < N; ++j) s -= w(LY::O_HINV, i * N + j) * gr[j];
             w(LY::O_X, i) = s;
             dual += 0.5 * w(LY::O_D, i) * s;      // objective at the unconstrained minimiser: c + g'x/2
         }
@@ -398,6 +411,10 @@ struct FlatSolver {
         const double qu = P->qu, ww = P->w;
         double best = tol; int bid = -1;
         double PS = 0.0, xm = v0;
+        // soft-row data comes from the caller's arrays (global memory): fetch the next stage's values one
+        // iteration ahead so that the load latency overlaps the row scan (r01i ncu: a third of the stall
+        // samples were long-scoreboard waits on exactly these loads)
+        double xf_n = has_sf ? HVP_LDG(xf_ + 2) : 0.0, xb_n = has_sb ? HVP_LDG(xb_ + 2) : 0.0;
 #define HVP_CAND(T, J, S)                                              \
     {                                                                  \
         const double s__ = (S);                                        \
@@ -406,6 +423,11 @@ struct FlatSolver {
         HVP_ROLL
         for (int j = 0; j < N; ++j) {
             const double xv = w(LY::O_X, j);
+            const double xf_c = xf_n, xb_c = xb_n;             // x_front / x_back position at stage j + 1
+            if (j >= 1 && j + 1 < N) {
+                if (has_sf) xf_n = HVP_LDG(xf_ + j + 2);
+                if (has_sb) xb_n = HVP_LDG(xb_ + j + 2);
+            }
             double lo, hi;
             bounds(j, lo, hi);
             HVP_CAND(T_UB, j, xv - hi);
@@ -421,11 +443,11 @@ struct FlatSolver {
                 HVP_CAND(T_ACC, j, dv - ((j < L || !P->hull) ? P->a_acc - j * P->tight : amax[j]));
                 HVP_CAND(T_DEC, j, ((j < L || !P->hull) ? P->a_dec + j * P->tight : amin[j]) - dv);
                 if (has_sf) {
-                    const double s = PS - sf(j);
+                    const double s = PS - (xf_c - P->d_safe - pc);             // PS - sf(j)
                     HVP_CAND(T_SF, j, ((satf >> j) & 1u) ? -s : s);
                 }
                 if (has_sb) {
-                    const double s = sb(j) - PS;
+                    const double s = (xb_c + P->d_safe - pc) - PS;             // sb(j) - PS
                     HVP_CAND(T_SB, j, ((satb >> j) & 1u) ? -s : s);
                 }
                 // position box: prefix sums increase with j once the velocity bounds hold, so the
@@ -546,8 +568,12 @@ struct FlatSolver {
         HVP_ROLL
         for (int a = 0; a < q; ++a) {
             double s = 0.0;
+            int gi = tri(a, 0);                            // row a of the packed symmetric matrix: b <= a contiguous ...
             HVP_ROLL
-            for (int b = 0; b < q; ++b) s += w(LY::O_GINV, a >= b ? tri(a, b) : tri(b, a)) * w(LY::O_D, b);
+            for (int b = 0; b <= a; ++b) s += w(LY::O_GINV, gi + b) * w(LY::O_D, b);
+            gi += 2 * a + 1;                               // ... then down column a: tri(b, a), stride b + 1
+            HVP_ROLL
+            for (int b = a + 1; b < q; ++b) { s += w(LY::O_GINV, gi) * w(LY::O_D, b); gi += b + 1; }
             w(LY::O_R, a) = s;
             nz -= s * w(LY::O_D, a);
             const double la = w(LY::O_LAM, a);
@@ -583,11 +609,14 @@ struct FlatSolver {
             }
             HVP_ROLL
             for (int a = 0; a < q; ++a) slot_axpy(a, -w(LY::O_R, a), LY::O_WV);
+            double wr[N];
+            HVP_FLAT_UNROLL
+            for (int j = 0; j < N; ++j) wr[j] = w(LY::O_WV, j);
             HVP_ROLL
             for (int i = 0; i < N; ++i) {
                 double s = 0.0;
-                HVP_ROLL
-                for (int j = 0; j < N; ++j) s += w(LY::O_HINV, i * N + j) * w(LY::O_WV, j);
+                HVP_FLAT_UNROLL
+                for (int j = 0; j < N; ++j) s += w(LY::O_HINV, i * N + j) * wr[j];
                 w(LY::O_X, i) -= t * s;
             }
             cp -= t * nz;

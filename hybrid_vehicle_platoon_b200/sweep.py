@@ -489,3 +489,147 @@ class BatchedGAdmmSweep:
         torch.cuda.synchronize()
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
                     errors=E.cpu().numpy(), solved=OK.cpu().numpy(), best_warm_start=WS.cpu().numpy())
+
+
+class BatchedEventSweep:
+    """S independent platoons under the event-based controller (fleet_event_based.py:413-646), state and guesses
+    resident on the device.  One iteration = for every distinct local formulation (agents grouped by vehicles in
+    front / behind and relative leader position) ONE eval_cost launch and ONE MIQP launch over S x agents problems,
+    then the winner selection (largest cost decrease above `threshold`, first agent on ties) and the overwrite of
+    the shared guesses as torch ops.  Scenarios whose iteration found no improver are left unchanged by the
+    remaining iterations (the same solves repeat), which is the reference's `break`."""
+
+    def __init__(self, n: int, N: int, event_iters: int = 4, masses=None, spacing_policy=ConstantSpacingPolicy(50),
+                 leader_index: int = 0, d_safe: float = Params.d_safe, threshold: float = 10.0, device: int = 0, ctx=None):
+        import torch
+        from ._lib import MPC_EVENT, NO_LEADER
+        if n < 2:
+            raise ValueError("the event-based scheme needs at least two vehicles")
+        self.torch, self.n, self.N, self.iters, self.leader_index = torch, n, N, event_iters, leader_index
+        self.threshold = float(threshold)
+        self.dev = torch.device("cuda", device)
+        self.ctx = ctx or default_context(device)
+        self.d0, self.t0 = spacing_params(spacing_policy)
+        self.d_safe = d_safe
+        self.masses = None if masses is None else np.asarray(masses, dtype=np.float64)
+        # agents with the same local structure share one compiled formulation (fleet_event_based.py:700-723)
+        self.members = [[0, 1] if i == 0 else ([n - 2, n - 1] if i == n - 1 else [i - 1, i, i + 1]) for i in range(n)]
+        if n == 2:
+            self.members = [[0, 1], [0, 1]]
+        groups: dict = {}
+        for i in range(n):
+            nf = i if i < 2 else 2
+            nb = (n - 1) - i if i > n - 3 else 2
+            rl = (-1 if i == leader_index - 1 else (0 if i == leader_index else (1 if i == leader_index + 1 else None)))
+            groups.setdefault((nf, nb, rl, len(self.members[i])), []).append(i)
+        self.groups = []
+        for (nf, nb, rl, nl), idx in groups.items():
+            cm = api.CompiledMpc(MPC_EVENT, N, n_local=nl, leader_index=NO_LEADER if rl is None else rl, n_front=nf,
+                                 n_behind=nb, d0=self.d0, t0=self.t0, ctx=self.ctx)
+            self.groups.append((cm, idx, nl, nf, nb, rl))
+        from .models import PwaGearVehicle
+        v = PwaGearVehicle(800.0)
+        lim = v.v_gear_lim
+        f64 = torch.float64
+        self.edges = torch.tensor([lim[0], lim[1], lim[2], v.alpha, lim[3], lim[4]], dtype=f64, device=self.dev)
+        g = [0, 1, 2, 3, 3, 4, 5]
+        self.cf = torch.tensor([v.c1 if r < 4 else v.c2 for r in range(7)], dtype=f64, device=self.dev)
+        self.bg = torch.tensor([float(v.b[g[r]]) for r in range(7)], dtype=f64, device=self.dev)
+        self.dd = torch.tensor([0.0 if r < 4 else v.d for r in range(7)], dtype=f64, device=self.dev)
+        self.mug = v.mu * v.grav
+
+    _const_vel_u = BatchedGAdmmSweep._const_vel_u
+
+    def run(self, x0, leader_x, ep_len: int):
+        """Returns dict of numpy arrays: X (T+1,S,2n), U (T,S,n), R (T,S), violations, errors, winners
+        (T,S,event_iters) int32 (-1: nobody improved), feasible (T,S) bool, nodes (T,S) int32 (max over agents)."""
+        torch, dev, n, N = self.torch, self.dev, self.n, self.N
+        f64, i32, np1 = torch.float64, torch.int32, N + 1
+        x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
+        S = x.shape[0]
+        lx = torch.as_tensor(np.ascontiguousarray(leader_x, dtype=np.float64), device=dev)
+        if lx.ndim == 2:
+            lx = lx.unsqueeze(0).expand(S, -1, -1)
+        if lx.shape[2] < ep_len + np1:
+            raise ValueError("leader trajectory shorter than ep_len + N + 1")
+        m = np.full((S, n), 800.0) if self.masses is None else np.broadcast_to(self.masses, (S, n))
+        mass = torch.as_tensor(np.array(m, dtype=np.float64, order="C"), device=dev)
+        edesc = api.env_desc(n, self.leader_index, self.d0, self.t0, self.d_safe, True, False, True)
+        X = torch.empty((ep_len + 1, S, 2 * n), dtype=f64, device=dev)
+        U = torch.empty((ep_len, S, n), dtype=f64, device=dev)
+        R = torch.empty((ep_len, S), dtype=f64, device=dev)
+        V = torch.empty((ep_len, S), dtype=torch.uint8, device=dev)
+        E = torch.empty((ep_len, S), dtype=i32, device=dev)
+        WIN = torch.full((ep_len, S, self.iters), -1, dtype=i32, device=dev)
+        FEAS = torch.ones((ep_len, S), dtype=torch.bool, device=dev)
+        ND = torch.zeros((ep_len, S), dtype=i32, device=dev)
+        X[0] = x
+        stream = torch.cuda.current_stream().cuda_stream
+        ts = float(Params.ts)
+        # first guesses: constant velocity, constant-velocity throttle (fleet_event_based.py:620-634)
+        xv = x.view(S, n, 2)
+        SG = torch.empty((S, n, 2, np1), dtype=f64, device=dev)
+        SG[:, :, 0, 0] = xv[:, :, 0]
+        SG[:, :, 1, :] = xv[:, :, 1:2]
+        for k in range(N):
+            SG[:, :, 0, k + 1] = SG[:, :, 0, k] + ts * SG[:, :, 1, k]
+        UG = self._const_vel_u(x, mass).unsqueeze(-1).expand(S, n, N).contiguous()
+        mem = torch.full((n, 3), -1, dtype=torch.int64, device=dev)
+        for i, ms in enumerate(self.members):
+            mem[i, :len(ms)] = torch.as_tensor(ms, device=dev)
+        sidx = torch.arange(S, device=dev)
+        zero_blk = torch.zeros((S, 1, 2 * np1), dtype=f64, device=dev)
+        for t in range(ep_len):
+            lwin = lx[:, :, t:t + np1].reshape(S, 1, 2 * np1)
+            xv = x.view(S, n, 2)
+            for it in range(self.iters):
+                cost0 = torch.empty((S, n), dtype=f64, device=dev)
+                cost1 = torch.empty((S, n), dtype=f64, device=dev)
+                XS = torch.zeros((S, n, 3, 2, np1), dtype=f64, device=dev)
+                US = torch.zeros((S, n, 3, N), dtype=f64, device=dev)
+                nd = torch.zeros((S, n), dtype=i32, device=dev)
+                for cm, idx, nl, nf, nb, rl in self.groups:
+                    k = len(idx); B = S * k
+                    mm = torch.as_tensor([self.members[i] for i in idx], device=dev)          # (k, nl)
+                    x0g = xv[:, mm].reshape(B, nl, 2).contiguous()
+                    mg = mass[:, mm].reshape(B, nl).contiguous()
+                    xg = SG[:, mm].reshape(B, nl, 2, np1).contiguous()
+                    ug = UG[:, mm].reshape(B, nl, N).contiguous()
+                    f2 = torch.stack([SG[:, i - 2].reshape(S, 2 * np1) if i > 1 else zero_blk[:, 0] for i in idx], dim=1)
+                    b2 = torch.stack([SG[:, i + 2].reshape(S, 2 * np1) if i < n - 2 else zero_blk[:, 0] for i in idx], dim=1)
+                    lead = lwin.expand(S, k, -1) if rl is not None else zero_blk.expand(S, k, -1)
+                    params = torch.cat((lead, f2, b2), dim=2).reshape(B, -1).contiguous()
+                    c0 = torch.empty(B, dtype=f64, device=dev)
+                    cm.eval_device(B, mg, params, xg, ug, c0, stream=stream)
+                    uo = torch.empty((B, nl, N), dtype=f64, device=dev); xo = torch.empty((B, nl, 2, np1), dtype=f64, device=dev)
+                    mo = torch.empty((B, nl, N), dtype=i32, device=dev); ob = torch.empty(B, dtype=f64, device=dev)
+                    st = torch.empty(B, dtype=i32, device=dev); no = torch.empty(B, dtype=i32, device=dev)
+                    cm.solve_device(B, x0g, mg, params, None, uo, xo, None, mo, ob, st, no, None, stream=stream)
+                    ii = torch.as_tensor(idx, device=dev)
+                    cost0[:, ii] = c0.view(S, k)
+                    cost1[:, ii] = torch.where(st == 2, ob, torch.full_like(ob, float("inf"))).view(S, k)
+                    XS[:, ii, :nl] = xo.view(S, k, nl, 2, np1)
+                    US[:, ii, :nl] = uo.view(S, k, nl, N)
+                    nd[:, ii] = no.view(S, k)
+                dec = cost0 - cost1                                   # inf - inf = nan compares False, as in Python
+                valid = dec > self.threshold
+                w = torch.argmax(torch.where(valid, dec, torch.full_like(dec, -float("inf"))), dim=1)   # first maximum
+                anyv = valid.any(dim=1)
+                FEAS[t] &= torch.isfinite(cost1).any(dim=1)
+                ND[t] = torch.maximum(ND[t], nd.max(dim=1).values)
+                WIN[t, :, it] = torch.where(anyv, w.to(i32), torch.full_like(w, -1, dtype=i32))
+                for l in range(3):
+                    j = mem[w, l]
+                    sel = anyv & (j >= 0)
+                    s_ = sidx[sel]
+                    SG[s_, j[sel]] = XS[s_, w[sel], l]
+                    UG[s_, j[sel]] = US[s_, w[sel], l]
+            U[t] = UG[:, :, 0]
+            api.rollout_step_device(edesc, S, x, U[t], None, mass, lx[:, :, t].contiguous(), X[t + 1], R[t], V[t], E[t],
+                                    ctx=self.ctx, stream=stream)
+            x = X[t + 1]
+            SG = torch.cat((SG[..., 1:], SG[..., -1:]), dim=-1)        # shifted previous solution (:591-603)
+            UG = torch.cat((UG[..., 1:], UG[..., -1:]), dim=-1)
+        torch.cuda.synchronize()
+        return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
+                    errors=E.cpu().numpy(), winners=WIN.cpu().numpy(), feasible=FEAS.cpu().numpy(), nodes=ND.cpu().numpy())

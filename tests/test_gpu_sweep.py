@@ -139,3 +139,22 @@ def test_batched_gadmm_sweep_matches_single_scenarios():
     for j, one in enumerate(singles):
         assert np.abs(out["X"][:, j] - one["X"]).max() < 1e-6, (j, np.abs(out["X"][:, j] - one["X"]).max())
         assert np.abs(out["U"][:, j] - one["U"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("n,li", [(4, 0), (5, 2)])
+def test_batched_event_sweep_matches_single_scenarios(n, li):
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200.sweep import BatchedEventSweep
+    from test_host_fleets import SmallSim
+    N, T, iters = 4, 6, 3
+    singles, x0s = [], []
+    for s in (5, 6, 9, 11):
+        singles.append(hvp.fleet_event_based.simulate(SmallSim(n, N, T), event_iters=iters, seed=s, leader_index=li))
+        x0s.append(singles[-1]["X"][0])
+    sw = BatchedEventSweep(n, N, event_iters=iters, leader_index=li)
+    out = sw.run(np.stack(x0s), singles[0]["leader_x"], T)
+    assert out["feasible"].all() and (out["errors"] == 0).all()
+    assert (out["winners"] >= 0).any()                     # some iteration had an improver
+    for j, one in enumerate(singles):
+        assert np.abs(out["X"][:, j] - one["X"]).max() < 1e-6, (j, np.abs(out["X"][:, j] - one["X"]).max())
+        assert np.abs(out["U"][:, j] - one["U"]).max() < 1e-6
