@@ -75,6 +75,15 @@ struct FlatLayout {
     static constexpr int SIZE = O_R + N;          // doubles per thread (87 at N = 6: 10 warps / SM)
 };
 
+// Per-problem arrays that are indexed at run time.  They live OUTSIDE the solver object, in an object of their own
+// that the caller owns: a run-time index into a member array keeps the compiler from promoting ANY member of
+// the enclosing object to registers (r01j ncu: every scalar of the solver was re-loaded from local memory at the
+// top of each block of the state machine -- long-scoreboard stalls on `L`, `act_lo`, `it`, `dual`, ...).
+template <int N>
+struct FlatCold {
+    double gt[N], xstar[N], rlo[N + 1], rhi[N + 1], amax[N], amin[N];
+};
+
 template <int N, int ST>
 struct FlatSolver {
     using LY = FlatLayout<N>;
@@ -85,8 +94,7 @@ struct FlatSolver {
     const double* xf_;                  // soft-row data is read from the caller's arrays
     const double* xb_;
     double* best_;                      // incumbent velocities go straight to the output trajectory
-    // cold per-problem arrays (touched once per node): thread-local memory
-    double gt[N], xstar[N], rlo[N + 1], rhi[N + 1], amax[N], amin[N];
+    FlatCold<N>* C;                     // cold per-problem arrays (touched once per node): thread-local memory
     double p0, v0, pc, inv_m, a_lo, a_hi, c_lo, c_hi, hw1, hw2, hd, ct;
     bool has_sf, has_sb;
     // branch and bound
@@ -143,8 +151,8 @@ struct FlatSolver {
 
     // -------------------------------------------------------------------------------------
     HVP_HD void setup(double* W_, const LocalParams* P_, int flags, double mass, const double* x0,
-                      const double* xf, const double* xb, const double* xl, double* best_out) {
-        W = W_; P = P_; xf_ = xf; xb_ = xb; best_ = best_out;
+                      const double* xf, const double* xb, const double* xl, double* best_out, FlatCold<N>* cold) {
+        W = W_; P = P_; xf_ = xf; xb_ = xb; best_ = best_out; C = cold;
         p0 = x0[0]; v0 = x0[1]; pc = p0 + v0;
         inv_m = hvp_rcp(mass);
         a_lo = 1.0 - P->c1 * inv_m; a_hi = 1.0 - P->c2 * inv_m;
@@ -158,7 +166,7 @@ struct FlatSolver {
         hw2 = 2.0 * wp * (tf ? t0 : 0.0);
         hd = 2.0 * wp * (tf ? t0 * t0 : 0.0) + 2.0 * wvv * nterm;
         HVP_ROLL
-        for (int j = 0; j < N; ++j) gt[j] = 0.0;
+        for (int j = 0; j < N; ++j) C->gt[j] = 0.0;
         ct = 0.0;
         HVP_ROLL
         for (int kind = 0; kind < 3; ++kind) {
@@ -173,7 +181,7 @@ struct FlatSolver {
                 const double Pk = (kind == 0) ? (pk - d0) : (kind == 1) ? (pk + t0 * vk + d0) : pk;
                 if (k >= 1) {
                     const double rho = pc - Pk;
-                    gt[k - 1] += 2.0 * wp * (suffix + tau * rho) - 2.0 * wvv * vk;
+                    C->gt[k - 1] += 2.0 * wp * (suffix + tau * rho) - 2.0 * wvv * vk;
                     ct += wp * rho * rho + wvv * vk * vk;
                     suffix += rho;
                 } else {
@@ -222,7 +230,7 @@ struct FlatSolver {
         for (int rg = 0; rg < NREG; ++rg)
             if (v0 >= P->edge[rg] && v0 <= P->edge[rg + 1]) c0 |= (1 << rg);
         set_cand(0, c0);
-        xstar[0] = v0; rlo[0] = v0; rhi[0] = v0;
+        C->xstar[0] = v0; C->rlo[0] = v0; C->rhi[0] = v0;
         state = S_NEXT;
     }
 
@@ -237,7 +245,7 @@ struct FlatSolver {
                 continue;
             }
             int rg = -1; double bd = HUGE_VAL;
-            const double xs = xstar[lev];
+            const double xs = C->xstar[lev];
             HVP_ROLL
             for (int c = 0; c < NREG; ++c) {
                 if (!((cset >> c) & 1)) continue;
@@ -247,25 +255,25 @@ struct FlatSolver {
             }
             set_cand(lev, cset & ~(1 << rg));
             set_mode(lev, rg);
-            const double jlo = fmax(rlo[lev], P->edge[rg]), jhi = fmin(rhi[lev], P->edge[rg + 1]);
+            const double jlo = fmax(C->rlo[lev], P->edge[rg]), jhi = fmin(C->rhi[lev], P->edge[rg + 1]);
             if (jlo > jhi + eps) continue;
             double nlo = fmax(ra(rg) * jlo + rc(rg) + rb(rg) * P->umin, jlo + P->a_dec + lev * P->tight);
             double nhi = fmin(ra(rg) * jhi + rc(rg) + rb(rg) * P->umax, jhi + P->a_acc - lev * P->tight);
             nlo = fmax(nlo, P->vmin); nhi = fmin(nhi, P->vmax);
             if (nlo > nhi + eps) continue;
             if (pc > P->pmax + eps || pc < P->pmin - eps) continue;
-            rlo[lev + 1] = nlo - eps; rhi[lev + 1] = nhi + eps;
+            C->rlo[lev + 1] = nlo - eps; C->rhi[lev + 1] = nhi + eps;
             L = lev + 1;
             if (dive && nodes >= 1 && L < N) {
                 // First descent: no incumbent exists yet, so the relaxations along the path could not
                 // prune anything -- they only guide the choice of region.  Keep following the last
                 // relaxed trajectory and solve the LEAF directly; its objective is the first incumbent.
                 ++lev;
-                xstar[lev] = w(LY::O_X, lev - 1);
+                C->xstar[lev] = w(LY::O_X, lev - 1);
                 int cn = 0;
                 HVP_ROLL
                 for (int c = 0; c < NREG; ++c)
-                    if (P->edge[c] <= rhi[lev] && P->edge[c + 1] >= rlo[lev]) cn |= (1 << c);
+                    if (P->edge[c] <= C->rhi[lev] && P->edge[c + 1] >= C->rlo[lev]) cn |= (1 << c);
                 set_cand(lev, cn);
                 continue;
             }
@@ -280,7 +288,7 @@ struct FlatSolver {
     // completion of the node's region prefix satisfies these bounds, so the relaxation may impose them.
     HVP_HD void hull() {
         const double eps = 1e-9;
-        double lo = rlo[L], hi = rhi[L];
+        double lo = C->rlo[L], hi = C->rhi[L];
         HVP_ROLL
         for (int s = L; s < N; ++s) {
             double nlo = HUGE_VAL, nhi = -HUGE_VAL, dmax = -HUGE_VAL, dmin = HUGE_VAL;
@@ -295,10 +303,10 @@ struct FlatSolver {
                 dmin = fmin(dmin, (a - 1.0) * jhi + c + b * P->umin);
             }
             const double acc = P->a_acc - s * P->tight, dec = P->a_dec + s * P->tight;
-            amax[s] = fmin(dmax + eps, acc); amin[s] = fmax(dmin - eps, dec);
+            C->amax[s] = fmin(dmax + eps, acc); C->amin[s] = fmax(dmin - eps, dec);
             nlo = fmax(fmax(nlo, lo + dec), P->vmin); nhi = fmin(fmin(nhi, hi + acc), P->vmax);
             lo = nlo - eps; hi = nhi + eps;
-            rlo[s + 1] = lo; rhi[s + 1] = hi;
+            C->rlo[s + 1] = lo; C->rhi[s + 1] = hi;
         }
     }
 
@@ -318,11 +326,11 @@ struct FlatSolver {
         }
         if (P->max_nodes > 0 && nodes >= P->max_nodes) { limit = true; state = S_DONE; return; }
         ++lev;
-        xstar[lev] = w(LY::O_X, lev - 1);                                             // relaxed v_lev
+        C->xstar[lev] = w(LY::O_X, lev - 1);                                             // relaxed v_lev
         int cn = 0;
         HVP_ROLL
         for (int c = 0; c < NREG; ++c)
-            if (P->edge[c] <= rhi[lev] && P->edge[c + 1] >= rlo[lev]) cn |= (1 << c);
+            if (P->edge[c] <= C->rhi[lev] && P->edge[c + 1] >= C->rlo[lev]) cn |= (1 << c);
         set_cand(lev, cn);
     }
 
@@ -363,7 +371,7 @@ struct FlatSolver {
         built_L = L; built_pk = modes_pk;
         // gradient g = gt + input-cost terms (into O_D), then x = -H^-1 g
         HVP_ROLL
-        for (int i = 0; i < N; ++i) w(LY::O_D, i) = gt[i];
+        for (int i = 0; i < N; ++i) w(LY::O_D, i) = C->gt[i];
         dual = ct;
         HVP_ROLL
         for (int k = 0; k < L; ++k) {
@@ -392,7 +400,7 @@ struct FlatSolver {
     // merged simple bounds of x_j = v_{j+1}: state box, region of stage j+1 if fixed, stage-0 rows
     HVP_HD void bounds(int j, double& lo, double& hi) const {
         lo = P->vmin; hi = P->vmax;
-        if (P->hull && j >= L) { lo = fmax(lo, rlo[j + 1]); hi = fmin(hi, rhi[j + 1]); }
+        if (P->hull && j >= L) { lo = fmax(lo, C->rlo[j + 1]); hi = fmin(hi, C->rhi[j + 1]); }
         if (j + 1 < L) {
             const int rg = mode(j + 1);
             lo = fmax(lo, P->edge[rg]); hi = fmin(hi, P->edge[rg + 1]);
@@ -440,8 +448,8 @@ struct FlatSolver {
                     HVP_CAND(T_ULO, j, bb * P->umin - du);
                 }
                 const double dv = xv - xm;
-                HVP_CAND(T_ACC, j, dv - ((j < L || !P->hull) ? P->a_acc - j * P->tight : amax[j]));
-                HVP_CAND(T_DEC, j, ((j < L || !P->hull) ? P->a_dec + j * P->tight : amin[j]) - dv);
+                HVP_CAND(T_ACC, j, dv - ((j < L || !P->hull) ? P->a_acc - j * P->tight : C->amax[j]));
+                HVP_CAND(T_DEC, j, ((j < L || !P->hull) ? P->a_dec + j * P->tight : C->amin[j]) - dv);
                 if (has_sf) {
                     const double s = PS - (xf_c - P->d_safe - pc);             // PS - sf(j)
                     HVP_CAND(T_SF, j, ((satf >> j) & 1u) ? -s : s);
@@ -476,7 +484,7 @@ struct FlatSolver {
             HVP_ROLL
             for (int j = 0; j < N; ++j) {
                 const double xv = w(LY::O_X, j);
-                f += xv * (0.5 * Hdiag(j) * xv + Hoff(j) * PS + gt[j]);
+                f += xv * (0.5 * Hdiag(j) * xv + Hoff(j) * PS + C->gt[j]);
                 if (j < L) {
                     const int rg = mode(j);
                     const double uu = (xv - ra(rg) * xm - rc(rg)) * hvp_rcp(rb(rg));

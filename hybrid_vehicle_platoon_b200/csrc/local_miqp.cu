@@ -90,6 +90,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
     int64_t next = (int64_t)blockIdx.x * chunk;                   // warp-uniform
     const int64_t end = next + chunk < batch ? next + chunk : batch;
     Solver sol;
+    FlatCold<N> cold;
     sol.lane_ = lane;
     bool have = false;
     int64_t i = 0;
@@ -118,7 +119,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                     i = next + __popc(need & ((1u << lane) - 1u));
                     if (i < end) {
                         sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
-                                  xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 2));
+                                  xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 2), &cold);
                         have = true;
                     }
                 }

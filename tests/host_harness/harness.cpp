@@ -62,8 +62,9 @@ static void flat_batch(int batch, const int32_t* flags, double d0, double t0, do
     for (int i = 0; i < batch; ++i) {
         hvp::FlatSolver<N, 1> sol;
         double W[hvp::FlatLayout<N>::SIZE];
+        hvp::FlatCold<N> cold;
         sol.setup(W, &P, flags[i], mass[i], x0 + 2 * (size_t)i, xf ? xf + S * i : nullptr,
-                  xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 1) + 1);
+                  xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 1) + 1, &cold);
         while (sol.state != hvp::FlatSolver<N, 1>::S_DONE) sol.trip();
         hvp::LocalResult R = sol.finish(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
         obj[i] = R.obj; status[i] = R.status; nodes[i] = R.nodes; qp_iters[i] = R.qp_iters;
