@@ -92,6 +92,8 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
     Solver sol;
     FlatCold<N> cold;
     sol.lane_ = lane;
+    sol.P = &P;     // bound here, unconditionally: the compiler then reads the parameters from the constant bank
+                    // instead of through a generic pointer (r01k ncu: LD.E of P->hull etc. on the SELECT path)
     bool have = false;
     int64_t i = 0;
     // A lane is either stepping its node QP (SELECT/STEP: the common, cheap trip) or waiting for node
