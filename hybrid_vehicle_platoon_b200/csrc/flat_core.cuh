@@ -419,23 +419,21 @@ struct FlatSolver {
         const double qu = P->qu, ww = P->w;
         double best = tol; int bid = -1;
         double PS = 0.0, xm = v0;
-        // soft-row data comes from the caller's arrays (global memory): fetch the next stage's values one
-        // iteration ahead so that the load latency overlaps the row scan (r01i ncu: a third of the stall
-        // samples were long-scoreboard waits on exactly these loads)
-        double xf_n = has_sf ? HVP_LDG(xf_ + 2) : 0.0, xb_n = has_sb ? HVP_LDG(xb_ + 2) : 0.0;
+        // The scan is UNROLLED over the stages and every stage keeps its own (best, id) pair: a rolled loop is one
+        // serial chain of ~8 N compare-selects (r01k ncu: a third of all stall samples sit on this scan, almost
+        // all fixed-latency dependency waits); unrolled, the N stage chains are independent and interleave, stage
+        // indices become immediates, and the soft-row loads are all issued up front.  The combination below keeps
+        // the first row that attains the maximum, exactly as the single chain did.
+        double bj[N]; int ij[N];
 #define HVP_CAND(T, J, S)                                              \
     {                                                                  \
         const double s__ = (S);                                        \
-        if (s__ > best) { best = s__; bid = (T) * 12 + (J); }          \
+        if (s__ > lb) { lb = s__; li = (T) * 12 + (J); }               \
     }
-        HVP_ROLL
+        HVP_FLAT_UNROLL
         for (int j = 0; j < N; ++j) {
+            double lb = tol; int li = -1;
             const double xv = w(LY::O_X, j);
-            const double xf_c = xf_n, xb_c = xb_n;             // x_front / x_back position at stage j + 1
-            if (j >= 1 && j + 1 < N) {
-                if (has_sf) xf_n = HVP_LDG(xf_ + j + 2);
-                if (has_sb) xb_n = HVP_LDG(xb_ + j + 2);
-            }
             double lo, hi;
             bounds(j, lo, hi);
             HVP_CAND(T_UB, j, xv - hi);
@@ -451,11 +449,11 @@ struct FlatSolver {
                 HVP_CAND(T_ACC, j, dv - ((j < L || !P->hull) ? P->a_acc - j * P->tight : C->amax[j]));
                 HVP_CAND(T_DEC, j, ((j < L || !P->hull) ? P->a_dec + j * P->tight : C->amin[j]) - dv);
                 if (has_sf) {
-                    const double s = PS - (xf_c - P->d_safe - pc);             // PS - sf(j)
+                    const double s = PS - sf(j);
                     HVP_CAND(T_SF, j, ((satf >> j) & 1u) ? -s : s);
                 }
                 if (has_sb) {
-                    const double s = (xb_c + P->d_safe - pc) - PS;             // sb(j) - PS
+                    const double s = sb(j) - PS;
                     HVP_CAND(T_SB, j, ((satb >> j) & 1u) ? -s : s);
                 }
                 // position box: prefix sums increase with j once the velocity bounds hold, so the
@@ -464,7 +462,11 @@ struct FlatSolver {
                 if (j == N - 1) HVP_CAND(T_PHI, j, PS - (P->pmax - pc));
             }
             PS += xv; xm = xv;
+            bj[j] = lb; ij[j] = li;
         }
+        HVP_FLAT_UNROLL
+        for (int j = 0; j < N; ++j)
+            if (bj[j] > best) { best = bj[j]; bid = ij[j]; }
 #undef HVP_CAND
         if (bid >= 0) {
             // The most violated row is already active: its residual is round-off drift (ill-conditioned,
