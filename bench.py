@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scenarios", type=int, default=32768, help="platoon scenarios per GPU per step")
+    ap.add_argument("--scenarios", type=int, default=65536, help="platoon scenarios per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: device-timed MIQP steps + rollout launches only")

@@ -51,8 +51,7 @@ extern __shared__ double hvp_flat_slab[];
 // reciprocal to ~1 ulp without the slow paths of the IEEE division sequence
 HVP_HD double hvp_rcp(double v) {
 #if defined(__CUDA_ARCH__)
-    double r = (double)__frcp_rn((float)v);
-    r = r * (2.0 - v * r);
+    double r = (double)__frcp_rn((float)v);      // 24 bits; each Newton step doubles them: two reach the double
     r = r * (2.0 - v * r);
     r = r * (2.0 - v * r);
     return r;
@@ -97,6 +96,9 @@ struct FlatSolver {
     FlatCold<N>* C;                     // cold per-problem arrays (touched once per node): thread-local memory
     double p0, v0, pc, inv_m, a_lo, a_hi, c_lo, c_hi, hw1, hw2, hd, ct;
     bool has_sf, has_sb;
+    // soft-row right-hand sides sf(j), sb(j), j = 1..N-1, read ONCE per problem.  Indexed with compile-time
+    // constants only (a run-time index would push the whole solver object back into local memory).
+    double sfv[N], sbv[N];
     // branch and bound
     int state, lev, L, nodes, iters, it;
     double inc;
@@ -200,25 +202,39 @@ struct FlatSolver {
             const double s0 = (xb[0] + ds) - p0, s1 = (xb[1] + ds) - pc;
             ct += ww * (s0 > 0 ? s0 : 0.0) + ww * (s1 > 0 ? s1 : 0.0);
         }
-        // ---- H^-1 of the pure tracking Hessian (no stage fixed) by in-place Gauss-Jordan ----
-        HVP_ROLL
-        for (int i = 0; i < N; ++i) {
-            HVP_ROLL
-            for (int j = 0; j < N; ++j) w(LY::O_HINV, i * N + j) = (i == j) ? Hdiag(i) : Hoff(i > j ? i : j);
+        HVP_FLAT_UNROLL
+        for (int j = 1; j < N; ++j) {
+            sfv[j] = has_sf ? sf(j) : 0.0;
+            sbv[j] = has_sb ? sb(j) : 0.0;
         }
-        HVP_ROLL
-        for (int k = 0; k < N; ++k) {
-            const double pinv = hvp_rcp(w(LY::O_HINV, k * N + k));
+        sfv[0] = sbv[0] = 0.0;
+        // ---- H^-1 of the pure tracking Hessian (no stage fixed): one of three matrices the host inverted ----
+        if (nterm > 0.5) {
+            const double* h0 = P->h0inv[tf ? (tb ? 2 : 1) : 0];
             HVP_ROLL
-            for (int j = 0; j < N; ++j) w(LY::O_HINV, k * N + j) *= pinv;
-            w(LY::O_HINV, k * N + k) = pinv;
+            for (int e = 0; e < N * N; ++e) w(LY::O_HINV, e) = h0[e];
+        } else {
+            // no reference term at all (a front vehicle that is also the trailer and not the leader): the Hessian
+            // is singular until a stage is fixed; keep the in-place Gauss-Jordan for this degenerate case
             HVP_ROLL
             for (int i = 0; i < N; ++i) {
-                if (i == k) continue;
-                const double f = w(LY::O_HINV, i * N + k);
                 HVP_ROLL
-                for (int j = 0; j < N; ++j)
-                    w(LY::O_HINV, i * N + j) = (j == k) ? -f * pinv : w(LY::O_HINV, i * N + j) - f * w(LY::O_HINV, k * N + j);
+                for (int j = 0; j < N; ++j) w(LY::O_HINV, i * N + j) = (i == j) ? Hdiag(i) : Hoff(i > j ? i : j);
+            }
+            HVP_ROLL
+            for (int k = 0; k < N; ++k) {
+                const double pinv = hvp_rcp(w(LY::O_HINV, k * N + k));
+                HVP_ROLL
+                for (int j = 0; j < N; ++j) w(LY::O_HINV, k * N + j) *= pinv;
+                w(LY::O_HINV, k * N + k) = pinv;
+                HVP_ROLL
+                for (int i = 0; i < N; ++i) {
+                    if (i == k) continue;
+                    const double f = w(LY::O_HINV, i * N + k);
+                    HVP_ROLL
+                    for (int j = 0; j < N; ++j)
+                        w(LY::O_HINV, i * N + j) = (j == k) ? -f * pinv : w(LY::O_HINV, i * N + j) - f * w(LY::O_HINV, k * N + j);
+                }
             }
         }
         built_L = 0; built_pk = 0;
@@ -449,11 +465,11 @@ struct FlatSolver {
                 HVP_CAND(T_ACC, j, dv - ((j < L || !P->hull) ? P->a_acc - j * P->tight : C->amax[j]));
                 HVP_CAND(T_DEC, j, ((j < L || !P->hull) ? P->a_dec + j * P->tight : C->amin[j]) - dv);
                 if (has_sf) {
-                    const double s = PS - sf(j);
+                    const double s = PS - sfv[j];
                     HVP_CAND(T_SF, j, ((satf >> j) & 1u) ? -s : s);
                 }
                 if (has_sb) {
-                    const double s = sb(j) - PS;
+                    const double s = sbv[j] - PS;
                     HVP_CAND(T_SB, j, ((satb >> j) & 1u) ? -s : s);
                 }
                 // position box: prefix sums increase with j once the velocity bounds hold, so the
@@ -483,7 +499,7 @@ struct FlatSolver {
             // ---- node solved: objective = tracking closed form + input cost + L1 penalties ----
             double f = ct;
             PS = 0.0; xm = v0;
-            HVP_ROLL
+            HVP_FLAT_UNROLL
             for (int j = 0; j < N; ++j) {
                 const double xv = w(LY::O_X, j);
                 f += xv * (0.5 * Hdiag(j) * xv + Hoff(j) * PS + C->gt[j]);
@@ -493,8 +509,8 @@ struct FlatSolver {
                     f += qu * uu * uu;
                 }
                 if (j >= 1) {
-                    if (has_sf) { const double s = PS - sf(j); if (s > 0) f += ww * s; }
-                    if (has_sb) { const double s = sb(j) - PS; if (s > 0) f += ww * s; }
+                    if (has_sf) { const double s = PS - sfv[j]; if (s > 0) f += ww * s; }
+                    if (has_sb) { const double s = sbv[j] - PS; if (s > 0) f += ww * s; }
                 }
                 PS += xv; xm = xv;
             }

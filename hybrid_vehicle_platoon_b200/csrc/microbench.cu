@@ -37,11 +37,11 @@ __global__ void __launch_bounds__(256) smem_read_kernel(int iters, double* sink)
     __syncthreads();
     double2 a0 = make_double2(0, 0), a1 = a0, a2 = a0, a3 = a0;
     int j = threadIdx.x;
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 0; i < iters; ++i) {
         const double2 v0 = tile[j], v1 = tile[(j + 256) & 2047], v2 = tile[(j + 512) & 2047], v3 = tile[(j + 768) & 2047];
         a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y; a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
-        j = (j + 1024) & 2047;
+        j = (j + 1056) & 2047;      // period 64 in i: the addresses keep changing, nothing is loop invariant
     }
     const double s = (a0.x + a0.y) + (a1.x + a1.y) + (a2.x + a2.y) + (a3.x + a3.y);
     if (s == 123.456) sink[threadIdx.x & 1023] = s;

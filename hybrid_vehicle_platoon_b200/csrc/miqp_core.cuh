@@ -55,6 +55,10 @@ struct LocalParams {
     double edge[NREG + 1];               // region r is edge[r] <= v <= edge[r+1] (models.py:414-444)
     double bgear[NREG];                  // traction gain of region r before /m (models.py:458-466)
     double c1, c2, dfr, mug;             // PWA friction (models.py:276-282), mu*g
+    // flat kernel: inverse of the pure tracking Hessian (no stage fixed) for the three cost structures a vehicle
+    // can have -- [0] one reference term without headway (leader, or back neighbour only), [1] front neighbour
+    // only, [2] front and back neighbour -- row-major N x N; filled on the host (vehicle_model.h)
+    double h0inv[3][81];
 };
 
 struct LocalResult {

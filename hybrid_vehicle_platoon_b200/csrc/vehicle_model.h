@@ -46,6 +46,29 @@ inline void fill_local_params(LocalParams& P, int N, double d0, double t0, doubl
     for (int i = 0; i <= NREG; ++i) P.edge[i] = e[i];
     const int gear_of_region[NREG] = {0, 1, 2, 3, 3, 4, 5};  // models.py:458-466
     for (int r = 0; r < NREG; ++r) P.bgear[r] = M.bgear[gear_of_region[r]];
+    // inverse tracking Hessians (flat_core.cuh setup): H[i][j] = hw1 (N-1-max(i,j)) + (i == j ? hd : hw2)
+    for (int var = 0; var < 3; ++var) {
+        const double nterm = var == 2 ? 2.0 : 1.0, tf = var >= 1 ? 1.0 : 0.0;
+        const double hw1 = 2.0 * P.qxp * nterm, hw2 = 2.0 * P.qxp * (tf * t0);
+        const double hd = 2.0 * P.qxp * (tf * t0 * t0) + 2.0 * P.qxv * nterm;
+        double A[81];
+        for (int e = 0; e < 81; ++e) P.h0inv[var][e] = 0.0;
+        if (N < 1 || N > 9) continue;
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) A[i * N + j] = hw1 * (double)(N - 1 - (i > j ? i : j)) + (i == j ? hd : hw2);
+        for (int k = 0; k < N; ++k) {                      // in-place Gauss-Jordan (SPD: no pivoting needed)
+            const double pinv = 1.0 / A[k * N + k];
+            for (int j = 0; j < N; ++j) A[k * N + j] *= pinv;
+            A[k * N + k] = pinv;
+            for (int i = 0; i < N; ++i) {
+                if (i == k) continue;
+                const double f = A[i * N + k];
+                for (int j = 0; j < N; ++j) A[i * N + j] = (j == k) ? -f * pinv : A[i * N + j] - f * A[k * N + j];
+            }
+        }
+        for (int i = 0; i < N; ++i)                        // symmetrise the round-off
+            for (int j = 0; j < N; ++j) P.h0inv[var][i * N + j] = 0.5 * (A[i * N + j] + A[j * N + i]);
+    }
 }
 
 }  // namespace hvp
