@@ -51,7 +51,9 @@ extern __shared__ double hvp_flat_slab[];
 // reciprocal to ~1 ulp without the slow paths of the IEEE division sequence
 HVP_HD double hvp_rcp(double v) {
 #if defined(__CUDA_ARCH__)
-    double r = (double)__frcp_rn((float)v);      // 24 bits; each Newton step doubles them: two reach the double
+    // MUFU.RCP64H seed (20 bits, one instruction, no slow path) + two Newton steps (40, 80 bits): ~1 ulp
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
     r = r * (2.0 - v * r);
     r = r * (2.0 - v * r);
     return r;

@@ -75,7 +75,9 @@ coop_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
 // Persistent flat-state-machine kernel: one warp per CTA, one problem per lane, each warp owns a
 // contiguous share of the batch and a lane that finishes refills from that share at once.
 template <int N>
-__global__ void __launch_bounds__(32)
+// resident CTAs per SM are set by the shared-memory slab (10 at N = 6); telling the compiler lets it use the registers
+// that occupancy leaves free instead of spilling
+__global__ void __launch_bounds__(32, (N <= 6 ? 10 : (N == 7 ? 7 : (N == 8 ? 6 : 5))))
 flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int32_t* __restrict__ flags,
                  const double* __restrict__ mass, const double* __restrict__ x0,
                  const double* __restrict__ xf, const double* __restrict__ xb,
