@@ -89,6 +89,10 @@ template <int N, int ST>
 struct FlatSolver {
     using LY = FlatLayout<N>;
     enum : int { S_NEXT = 0, S_BUILD, S_SELECT, S_STEP, S_DONE };
+    // Interval-hull tightening of the unfixed stages (hull()).  It pays in the compiled-MPC kernel (pm_kernel.cu) but
+    // not here (N = 6: same node count, more work per node), so it is compiled OUT: the kernel's code must stay
+    // inside the 32 KB instruction cache level (r01l ncu: 'no instruction' was the second largest stall reason).
+    static constexpr bool kHull = false;
 
     double* W;
     const LocalParams* P;
@@ -295,7 +299,7 @@ struct FlatSolver {
                 set_cand(lev, cn);
                 continue;
             }
-            if (P->hull) hull();
+            if (kHull) hull();
             state = S_BUILD;
             return;
         }
@@ -418,7 +422,7 @@ struct FlatSolver {
     // merged simple bounds of x_j = v_{j+1}: state box, region of stage j+1 if fixed, stage-0 rows
     HVP_HD void bounds(int j, double& lo, double& hi) const {
         lo = P->vmin; hi = P->vmax;
-        if (P->hull && j >= L) { lo = fmax(lo, C->rlo[j + 1]); hi = fmin(hi, C->rhi[j + 1]); }
+        if (kHull && j >= L) { lo = fmax(lo, C->rlo[j + 1]); hi = fmin(hi, C->rhi[j + 1]); }
         if (j + 1 < L) {
             const int rg = mode(j + 1);
             lo = fmax(lo, P->edge[rg]); hi = fmin(hi, P->edge[rg + 1]);
@@ -464,8 +468,8 @@ struct FlatSolver {
                     HVP_CAND(T_ULO, j, bb * P->umin - du);
                 }
                 const double dv = xv - xm;
-                HVP_CAND(T_ACC, j, dv - ((j < L || !P->hull) ? P->a_acc - j * P->tight : C->amax[j]));
-                HVP_CAND(T_DEC, j, ((j < L || !P->hull) ? P->a_dec + j * P->tight : C->amin[j]) - dv);
+                HVP_CAND(T_ACC, j, dv - ((j < L || !kHull) ? P->a_acc - j * P->tight : C->amax[j]));
+                HVP_CAND(T_DEC, j, ((j < L || !kHull) ? P->a_dec + j * P->tight : C->amin[j]) - dv);
                 if (has_sf) {
                     const double s = PS - sfv[j];
                     HVP_CAND(T_SF, j, ((satf >> j) & 1u) ? -s : s);

@@ -166,9 +166,8 @@ static cudaError_t launch_flat(const LocalParams& P, int64_t batch, const int32_
     static const int gdiv = env_int("HVP_FLAT_GRID_DIV", 1);
     if (g > grid_full / gdiv) g = grid_full / gdiv;
     LocalParams Q = P;
-    static const int nb = env_int("HVP_NODE_BATCH", 0), hl = env_int("HVP_FLAT_HULL", -1), dv = env_int("HVP_FLAT_DIVE", -1);
+    static const int nb = env_int("HVP_NODE_BATCH", 0), dv = env_int("HVP_FLAT_DIVE", -1);
     if (nb > 0) Q.node_batch = nb;
-    if (hl >= 0) Q.hull = hl;
     if (dv >= 0) Q.dive = dv;
     flat_miqp_kernel<N><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
                                                           status, nodes, qp_iters);
