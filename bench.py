@@ -215,6 +215,74 @@ def admm_loop_leg(ctx, S=1024, T=2, n=15, N=8, iters=20):
             "optimal_frac": float((out["status"] == 2).mean()), "rollout_exceptions": int((out["errors"] != 0).any(0).sum())}
 
 
+def mixed_sweep_leg(ctx, rank, world, dev, S=4096, T=10):
+    """BASELINE.json configs[3]: Monte-Carlo sweep of S synthetic platoon scenarios with n ~ U{5..15}, N ~ U{4..10},
+    stop-and-go leader with random change steps / speeds, 50/50 constant spacing vs time headway, whole
+    closed loops of the decentralized controller on the device.  EVERY rank calls this: the scenarios are dealt to the
+    ranks by the 7 n N cost proxy (dist.balanced_shards), no collective on the data path; time = max over ranks."""
+    import torch
+    from hybrid_vehicle_platoon_b200.dist import max_over_ranks, sum_over_ranks
+    from hybrid_vehicle_platoon_b200.misc import ConstantSpacingPolicy, ConstantTimePolicy, StopAndGoLeaderTrajectory
+    from hybrid_vehicle_platoon_b200.sweep import run_mixed_sweep
+    rng = np.random.default_rng(1234 + 3)            # the same scenario list on every rank
+    scen = []
+    for _ in range(S):
+        n, N = int(rng.integers(5, 16)), int(rng.integers(4, 11))
+        v = np.floor(rng.uniform(8, 30, n)); gaps = rng.uniform(60, 160, n)
+        p = np.floor(3000.0 - np.cumsum(gaps) + gaps[0])
+        x0 = np.empty(2 * n); x0[0::2] = p; x0[1::2] = v
+        lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=float(rng.uniform(8, 14)), vf=float(rng.uniform(22, 32)),
+                                       v_change_steps=[int(rng.integers(2, 5)), int(rng.integers(5, 9))],
+                                       trajectory_len=T + 10 + 12, ts=1).get_leader_trajectory()
+        pol = ConstantSpacingPolicy(50) if rng.random() < 0.5 else ConstantTimePolicy(10, 3)
+        scen.append(dict(n=n, N=N, x0=x0, leader_x=lx, masses=None, spacing_policy=pol))
+    run_mixed_sweep(scen[:64], 2, rank=0, world=1, device=dev.index, ctx=ctx)          # warm-up (builds nothing new)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = run_mixed_sweep(scen, T, rank=rank, world=world, device=dev.index, ctx=ctx)
+    torch.cuda.synchronize()
+    dt = max_over_ranks([time.perf_counter() - t0], device=dev)[0]
+    solves = sum(scen[i]["n"] for i in out) * T
+    opt = sum(int((r["status"] == 2).sum()) for r in out.values())
+    tot_s, tot_o, tot_n = sum_over_ranks([solves, opt, len(out)], device=dev)
+    return {"value": S * T / dt, "unit": "scenario-timesteps/s", "solves_per_s": tot_s / dt, "scenarios": int(tot_n),
+            "timesteps": T, "seconds": dt, "optimal_frac": tot_o / max(tot_s, 1), "n_range": [5, 15], "N_range": [4, 10],
+            "sharding": "dist.balanced_shards by 7 n N, no data-path collective", "n_gpus": world}
+
+
+def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=20, groups=256):
+    """ONE large centralized MIQP tree (n = 8, N = 6: 48 variables) searched by all ranks together: every rank takes
+    the sub-trees whose mode-prefix ordinal is congruent to its rank, the incumbent bound is exchanged with an NCCL
+    allreduce(min) (dist.solve_tree_split).  EVERY rank calls this; time = CUDA events, max over ranks."""
+    import torch
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200 import dist as D
+    import gen_mpc_cases as G
+    rng = np.random.default_rng(5)
+    x0, params = G.cent_cases(rng, problems, n, N, stress=False)
+    mpc = hvp.api.CompiledMpc(G.CENT, N, n_local=n, ctx=ctx)
+    tx0 = torch.as_tensor(x0, device=dev); tp = torch.as_tensor(params, device=dev)
+    tm = torch.full((problems, n), 800.0, dtype=torch.float64, device=dev)
+    ms, out = [], None
+    for rep in range(3):
+        D.dist_allreduce(torch.zeros(1, device=dev), "sum")           # line the ranks up
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = D.solve_tree_split(mpc, tx0, tm, tp, groups=groups, prefix_depth=depth, wave_budget=16)
+        b.record()
+        torch.cuda.synchronize()
+        if rep > 0:
+            ms.append(D.max_over_ranks([a.elapsed_time(b)], device=dev)[0])
+    return {"value": problems / (float(np.mean(ms)) * 1e-3), "unit": "solves/s", "ms": float(np.mean(ms)), "problems": problems,
+            "variables": n * N, "prefix_depth": depth, "warps_per_problem_per_gpu": groups,
+            "optimal_frac": float((out["status"] == 2).double().mean()), "nodes_per_solve": float(out["nodes"].double().mean()),
+            "collective": "allreduce(min) of the incumbent objective, 8 B per problem, twice per solve"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -387,6 +455,14 @@ def main():
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * e2e_steps / e2e_s
 
+    # ---- legs that every rank takes part in ----
+    shared_legs = {}
+    if not args.profile:
+        shared_legs["mixed_sweep_n5-15_N4-10 (configs[3]: 4096 scenarios sharded over the GPUs, on-device closed loops)"] = \
+            mixed_sweep_leg(ctx, rank, world, dev)
+        shared_legs["tree_split_cent_n8_N6 (one large MIQP tree searched by all GPUs, allreduce-min of the incumbent)"] = \
+            tree_split_leg(ctx, dev)
+
     out = None
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -452,6 +528,7 @@ def main():
         if not args.no_cpu:
             cpu, _, _ = cpu_reference_leg(S, budget_s=12.0)
         other = compiled_mpc_legs(hvp, torch, dev, stream, flush, with_cpu=not args.no_cpu)
+        other.update(shared_legs)
         other["closed_loop_decent_n10_N6 (configs[3] shape: 4096 scenarios, on-device episode)"] = closed_loop_leg(ctx)
         other["closed_loop_naive_admm_n15_N8 (configs[2]: 1024 scenarios x 20 ADMM rounds per timestep)"] = admm_loop_leg(ctx)
 

@@ -22,7 +22,7 @@ class BatchedDecentSweep:
     with the constant-velocity estimator), pwa_gear model, horizon N."""
 
     def __init__(self, n: int, N: int, masses=None, spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0,
-                 d_safe: float = Params.d_safe, device: int = 0, ctx=None):
+                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto"):
         import torch
         self.torch = torch
         self.n, self.N, self.leader_index = n, N, leader_index
@@ -32,6 +32,27 @@ class BatchedDecentSweep:
         self.d_safe = d_safe
         self.masses = None if masses is None else np.asarray(masses, dtype=np.float64)   # (n,) or (S,n)
         self.ldesc = api.local_desc(N, self.d0, self.t0)
+        # Which kernel solves the local MIQPs.  "local": the specialised per-vehicle kernel (csrc/local_miqp.cu) --
+        # fastest on the short-horizon, constant-spacing problems of the headline benchmark.  "compiled": the LOCAL
+        # formulation of the compiled-MPC kernel (csrc/pm_kernel.cu), whose interval-hull tightening and splitting of
+        # heavy trees over 64 warps tame the long tail of hard instances -- long horizons and the time-headway policy
+        # (N = 10, headway: worst tree 13 000 -> 6 000 nodes and searched by 64 warps; 464 -> 52 ms per 20 480 MIQPs).
+        if solver not in ("auto", "local", "compiled"):
+            raise ValueError("solver must be 'auto', 'local' or 'compiled'")
+        # "auto" follows the measured crossover (scripts/diag_mixed.py, n = 10, 5 timesteps, 53 / 4096 scenarios):
+        #   constant spacing: local wins up to N = 9 (N = 9: 22 / 123 ms vs 39 / 168 ms), compiled from N = 10 at large
+        #   batches (440 vs 207 ms); time headway: local up to N = 6, compiled from N = 8 (132 / 486 vs 40 / 179 ms).
+        self.use_compiled = solver == "compiled" or (solver == "auto" and (N >= 10 or (self.t0 != 0.0 and N >= 8)))
+        self.role_groups = []
+        if self.use_compiled:
+            from ._lib import MPC_LOCAL
+            roles: dict = {}
+            for i in range(n):
+                fl = (FRONT if i == 0 else 0) | (TRAILER if i == n - 1 else 0) | (LEADER if i == leader_index else 0)
+                roles.setdefault(fl, []).append(i)
+            for fl, idx in roles.items():
+                cm = api.CompiledMpc(MPC_LOCAL, N, flags=fl, d0=self.d0, t0=self.t0, ctx=self.ctx)
+                self.role_groups.append((cm, torch.as_tensor(idx, device=self.dev), len(idx)))
 
     def run(self, x0, leader_x, ep_len: int):
         """x0 (S,2n) initial states (e.g. PlatoonEnv.reset of each scenario), leader_x (2,>=ep_len+N+1) shared
@@ -82,12 +103,26 @@ class BatchedDecentSweep:
             xb[:, :-1] = pred[:, 1:]
             xl[:, self.leader_index] = lx[:, :, t:t + N + 1]
             # ---- solve all S*n local MIQPs ----
-            api.local_miqp_device(self.ldesc, B, d_flags, d_mass.view(B), x.view(B, 2), xf.view(B, 2, N + 1),
-                                  xb.view(B, 2, N + 1), xl.view(B, 2, N + 1), u, xs, modes, obj, status, nodes,
-                                  None, ctx=self.ctx, stream=stream)
-            U[t] = u[:, 0].view(S, n)
-            ND[t] = nodes.view(S, n)
-            ST[t] = status.view(S, n)
+            if self.use_compiled:      # one launch per role (front / interior / trailer, leader where applicable)
+                for cm, ii, k in self.role_groups:
+                    Bk = S * k
+                    params = torch.cat((xf[:, ii].reshape(S, k, -1), xb[:, ii].reshape(S, k, -1),
+                                        xl[:, ii].reshape(S, k, -1)), dim=2).reshape(Bk, -1).contiguous()
+                    uo = torch.empty((Bk, 1, N), dtype=f64, device=dev); xo = torch.empty((Bk, 1, 2, N + 1), dtype=f64, device=dev)
+                    mo = torch.empty((Bk, 1, N), dtype=torch.int32, device=dev); ob = torch.empty(Bk, dtype=f64, device=dev)
+                    st = torch.empty(Bk, dtype=torch.int32, device=dev); no = torch.empty(Bk, dtype=torch.int32, device=dev)
+                    cm.solve_device(Bk, xv[:, ii].reshape(Bk, 1, 2).contiguous(), d_mass[:, ii].reshape(Bk, 1).contiguous(),
+                                    params, None, uo, xo, None, mo, ob, st, no, None, stream=stream)
+                    U[t][:, ii] = uo.view(S, k, N)[:, :, 0]
+                    ND[t][:, ii] = no.view(S, k)
+                    ST[t][:, ii] = st.view(S, k)
+            else:
+                api.local_miqp_device(self.ldesc, B, d_flags, d_mass.view(B), x.view(B, 2), xf.view(B, 2, N + 1),
+                                      xb.view(B, 2, N + 1), xl.view(B, 2, N + 1), u, xs, modes, obj, status, nodes,
+                                      None, ctx=self.ctx, stream=stream)
+                U[t] = u[:, 0].view(S, n)
+                ND[t] = nodes.view(S, n)
+                ST[t] = status.view(S, n)
             # ---- step every platoon ----
             api.rollout_step_device(edesc, S, x, U[t], None, d_mass, lx[:, :, t].contiguous(), X[t + 1], R[t], V[t],
                                     E[t], ctx=self.ctx, stream=stream)
