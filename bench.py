@@ -89,6 +89,8 @@ class ClockSampler:
 
 
 def cpu_reference_leg(scenarios_hint, budget_s=12.0):
+    from oracle import oracle as _O
+    _O.use_all_cores()
     """The oracle port (exhaustive leaf enumeration + exact QP, oracle/hvp_oracle.c) on the host
     cores, bounded sample of the same workload."""
     from oracle import oracle as O
@@ -283,6 +285,14 @@ def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=20, groups=256):
             "collective": "allreduce(min) of the incumbent objective, 8 B per problem, twice per solve"}
 
 
+def workload_config(S):
+    """`config` of the headline workload -- identical in both arms (the reference arm times bounded samples of it)."""
+    return {"workload": f"fleet_decent_mld.py per-vehicle local MIQPs (LocalMpcMld, pwa_gear), n={N_VEH}, N={HORIZON}; "
+                        f"{S} scenarios x {N_VEH} vehicles = {S * N_VEH} MIQPs per GPU per step, reference reset "
+                        f"distribution, constant-velocity neighbour predictions, gap 0 (proven optimal)",
+            "scenarios_per_gpu": S, "n": N_VEH, "N": HORIZON}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -299,15 +309,34 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"fleet_decent_mld local MIQPs n={N_VEH} N={HORIZON} pwa_gear; bounded "
-                                   f"sample per step on host cores (reference solver Gurobi is not "
-                                   f"installable: CPU stand-in is the oracle port)"},
+            "config": dict(workload_config(args.scenarios),
+                           sample="each step is a bounded sample of the workload on the host cores (the reference's "
+                                  "solver, Gurobi behind dmpcpwa, is not installable here: the CPU stand-in is the oracle port)"),
             "cpu_baseline": base,
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, written to the process's ORIGINAL stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    # stdout must carry exactly one JSON line, but native libraries print there too (NCCL writes its version banner
+    # to fd 1 from C, whatever NCCL_DEBUG says): keep a private copy of the original stdout for the JSON line and
+    # point fd 1 at stderr for everything else.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -408,8 +437,8 @@ def main():
             api.rollout_step_device(rdesc, rb, rx, ru, rg, rm, rl, rxo, rc, rv, re_, ctx=ctx, stream=stream)
             flush.fill_(1)
         torch.cuda.synchronize()
-        print(json.dumps({"profile_run": True, "ms_per_step": float(ms.mean()), "solves_per_s": B / (ms.mean() * 1e-3),
-                          "nodes_per_solve": nodes_mean, "qp_iters_per_solve": iters_mean}))
+        emit({"profile_run": True, "ms_per_step": float(ms.mean()), "solves_per_s": B / (ms.mean() * 1e-3),
+              "nodes_per_solve": nodes_mean, "qp_iters_per_solve": iters_mean})
         return
 
     # ---- e2e: reference-facing host call with pinned host buffers ----
@@ -536,12 +565,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"fleet_decent_mld.py per-vehicle local MIQPs (LocalMpcMld, pwa_gear), "
-                                   f"n={N_VEH}, N={HORIZON}; {S} scenarios x {N_VEH} vehicles = {B} MIQPs per "
-                                   f"GPU per step, reference reset distribution, constant-velocity neighbour "
-                                   f"predictions, gap 0 (proven optimal)",
-                       "l2": "flushed (256 MiB write) between timed steps; steps timed individually with CUDA events",
-                       "scenarios_per_gpu": S, "n": N_VEH, "N": HORIZON},
+            "config": dict(workload_config(S),
+                           l2="flushed (256 MiB write) between timed steps; steps timed individually with CUDA events"),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -575,7 +600,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        emit(out)
 
 
 if __name__ == "__main__":

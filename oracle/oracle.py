@@ -247,3 +247,11 @@ def mpc_build_qp(kind, nl, N, x0, mass, params, modes, *, model=PWA_GEAR, flags=
 
 def max_threads() -> int:
     return lib().hvo_max_threads()
+
+
+def use_all_cores() -> int:
+    """Let the batch calls use every host core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().hvo_set_threads(int(n))
+    return max_threads()
