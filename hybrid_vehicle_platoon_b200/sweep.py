@@ -132,29 +132,142 @@ class BatchedDecentSweep:
                     errors=E.cpu().numpy(), nodes=ND.cpu().numpy(), status=ST.cpu().numpy())
 
 
+class MixedSizeDecentSweep:
+    """Platoons of DIFFERENT sizes n under the decentralized controller with a common horizon N and spacing policy.
+    A per-vehicle MIQP does not depend on n, so every timestep solves the vehicles of ALL platoons in one launch
+    (one per role on the compiled route); only observe and the rollout run per platoon size.  This is what keeps the
+    GPU filled in the Monte-Carlo sweep of BASELINE.json configs[3], where a (n, N, policy) cell holds ~25 scenarios."""
+
+    def __init__(self, N: int, spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0,
+                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto"):
+        import torch
+        self.torch, self.N, self.leader_index, self.d_safe = torch, N, leader_index, d_safe
+        self.dev = torch.device("cuda", device)
+        self.ctx = ctx or default_context(device)
+        self.d0, self.t0 = spacing_params(spacing_policy)
+        self.ldesc = api.local_desc(N, self.d0, self.t0)
+        probe = BatchedDecentSweep(2, N, spacing_policy=spacing_policy, device=device, ctx=self.ctx, solver=solver)
+        self.use_compiled = probe.use_compiled                      # same measured crossover
+        self.cms = {}
+
+    def _cm(self, fl):
+        from ._lib import MPC_LOCAL
+        if fl not in self.cms:
+            self.cms[fl] = api.CompiledMpc(MPC_LOCAL, self.N, flags=int(fl), d0=self.d0, t0=self.t0, ctx=self.ctx)
+        return self.cms[fl]
+
+    def run(self, parts, ep_len: int):
+        """parts: list of (n, x0 (S,2n), leader_x (S,2,>=ep_len+N+1), masses (S,n)).  Returns one result dict per
+        part with the layout of BatchedDecentSweep.run."""
+        torch, dev, N, li = self.torch, self.dev, self.N, self.leader_index
+        f64, i32, np1 = torch.float64, torch.int32, N + 1
+        ts = float(Params.ts)
+        st_parts, off = [], 0
+        for n, x0, lx, masses in parts:
+            x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
+            S = x.shape[0]
+            lxt = torch.as_tensor(np.ascontiguousarray(lx, dtype=np.float64), device=dev)
+            if lxt.shape[2] < ep_len + np1:
+                raise ValueError("leader trajectory shorter than ep_len + N + 1")
+            fl = np.zeros((S, n), np.int32)
+            fl[:, 0] |= FRONT; fl[:, -1] |= TRAILER; fl[:, li] |= LEADER
+            st_parts.append(dict(n=n, S=S, off=off, x=x, lx=lxt, flags=fl.reshape(-1),
+                                 mass=torch.as_tensor(np.ascontiguousarray(masses, dtype=np.float64), device=dev),
+                                 edesc=api.env_desc(n, li, self.d0, self.t0, self.d_safe, True, False, True),
+                                 X=torch.empty((ep_len + 1, S, 2 * n), dtype=f64, device=dev),
+                                 U=torch.empty((ep_len, S, n), dtype=f64, device=dev),
+                                 R=torch.empty((ep_len, S), dtype=f64, device=dev),
+                                 V=torch.empty((ep_len, S), dtype=torch.uint8, device=dev),
+                                 E=torch.empty((ep_len, S), dtype=i32, device=dev),
+                                 ND=torch.empty((ep_len, S, n), dtype=i32, device=dev),
+                                 ST=torch.empty((ep_len, S, n), dtype=i32, device=dev)))
+            st_parts[-1]["X"][0] = x
+            off += S * n
+        B = off
+        flags_np = np.concatenate([p["flags"] for p in st_parts]) if st_parts else np.zeros(0, np.int32)
+        d_flags = torch.as_tensor(flags_np, device=dev)
+        d_mass = torch.cat([p["mass"].reshape(-1) for p in st_parts]) if st_parts else torch.zeros(0, dtype=f64, device=dev)
+        x0b = torch.empty((B, 2), dtype=f64, device=dev)
+        xf = torch.zeros((B, 2, np1), dtype=f64, device=dev); xb = torch.zeros((B, 2, np1), dtype=f64, device=dev)
+        xl = torch.zeros((B, 2, np1), dtype=f64, device=dev)
+        u = torch.empty((B, N), dtype=f64, device=dev); xs = torch.empty((B, 2, np1), dtype=f64, device=dev)
+        modes = torch.empty((B, N), dtype=i32, device=dev); obj = torch.empty(B, dtype=f64, device=dev)
+        status = torch.empty(B, dtype=i32, device=dev); nodes = torch.empty(B, dtype=i32, device=dev)
+        roles = [(int(fl), torch.as_tensor(np.nonzero(flags_np == fl)[0], device=dev)) for fl in np.unique(flags_np)] \
+            if self.use_compiled else []
+        stream = torch.cuda.current_stream().cuda_stream
+        for t in range(ep_len):
+            # ---- observe, per platoon size (fleet_decent_mld.py:348-428) ----
+            for p in st_parts:
+                n, S, o = p["n"], p["S"], p["off"]
+                xv = p["x"].view(S, n, 2)
+                pred = torch.empty((S, n, 2, np1), dtype=f64, device=dev)
+                pred[:, :, 0, 0] = xv[:, :, 0]
+                pred[:, :, 1, :] = xv[:, :, 1:2]
+                for k in range(N):
+                    pred[:, :, 0, k + 1] = pred[:, :, 0, k] + ts * pred[:, :, 1, k]
+                sl = slice(o, o + S * n)
+                x0b[sl] = xv.reshape(S * n, 2)
+                xf[sl].view(S, n, 2, np1)[:, 1:] = pred[:, :-1]
+                xb[sl].view(S, n, 2, np1)[:, :-1] = pred[:, 1:]
+                xl[sl].view(S, n, 2, np1)[:, li] = p["lx"][:, :, t:t + np1]
+            # ---- ONE solve for the vehicles of every platoon ----
+            if self.use_compiled:
+                for fl, ii in roles:
+                    Bk = ii.numel()
+                    params = torch.cat((xf[ii].reshape(Bk, -1), xb[ii].reshape(Bk, -1), xl[ii].reshape(Bk, -1)), dim=1).contiguous()
+                    uo = torch.empty((Bk, 1, N), dtype=f64, device=dev); xo = torch.empty((Bk, 1, 2, np1), dtype=f64, device=dev)
+                    mo = torch.empty((Bk, 1, N), dtype=i32, device=dev); ob = torch.empty(Bk, dtype=f64, device=dev)
+                    st = torch.empty(Bk, dtype=i32, device=dev); no = torch.empty(Bk, dtype=i32, device=dev)
+                    self._cm(fl).solve_device(Bk, x0b[ii].reshape(Bk, 1, 2).contiguous(), d_mass[ii].reshape(Bk, 1).contiguous(),
+                                              params, None, uo, xo, None, mo, ob, st, no, None, stream=stream)
+                    u[ii] = uo.view(Bk, N); status[ii] = st; nodes[ii] = no
+            elif B:
+                api.local_miqp_device(self.ldesc, B, d_flags, d_mass, x0b, xf, xb, xl, u, xs, modes, obj, status, nodes,
+                                      None, ctx=self.ctx, stream=stream)
+            # ---- step every platoon, per size ----
+            for p in st_parts:
+                n, S, o = p["n"], p["S"], p["off"]
+                sl = slice(o, o + S * n)
+                p["U"][t] = u[sl, 0].view(S, n)
+                p["ND"][t] = nodes[sl].view(S, n)
+                p["ST"][t] = status[sl].view(S, n)
+                api.rollout_step_device(p["edesc"], S, p["x"], p["U"][t], None, p["mass"], p["lx"][:, :, t].contiguous(),
+                                        p["X"][t + 1], p["R"][t], p["V"][t], p["E"][t], ctx=self.ctx, stream=stream)
+                p["x"] = p["X"][t + 1]
+        torch.cuda.synchronize()
+        return [dict(X=p["X"].cpu().numpy(), U=p["U"].cpu().numpy(), R=p["R"].cpu().numpy(), violations=p["V"].cpu().numpy(),
+                     errors=p["E"].cpu().numpy(), nodes=p["ND"].cpu().numpy(), status=p["ST"].cpu().numpy()) for p in st_parts]
+
+
 def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, device: int = 0, ctx=None):
     """Monte-Carlo sweep over scenarios of MIXED size (BASELINE.json configs[3]): `scenarios` is a list of dicts
     {n, N, x0 (2n,), leader_x (2, >= ep_len+N+1), masses (n,) | None, spacing_policy | None}.  This rank takes
-    its load-balanced share (dist.balanced_shards), groups it by (n, N, spacing policy) and runs one
-    BatchedDecentSweep episode per group.  Returns {scenario index: dict(X (T+1,2n), U (T,n), R (T,), violations,
-    errors, nodes, status)} for the scenarios of this rank."""
+    its load-balanced share (dist.balanced_shards), groups it by (N, spacing policy) -- platoons of every size n
+    in one MixedSizeDecentSweep, so a timestep is one solve launch per group, not per (n, N) cell -- and returns
+    {scenario index: dict(X (T+1,2n), U (T,n), R (T,), violations, errors, nodes, status)} for its scenarios."""
     from .dist import balanced_shards
     mine = balanced_shards([7 * sc["n"] * sc["N"] for sc in scenarios], world)[rank]
     groups: dict = {}
     for i in mine:
         sc = scenarios[i]
         pol = sc.get("spacing_policy") or ConstantSpacingPolicy(50)
-        groups.setdefault((sc["n"], sc["N"], spacing_params(pol)), []).append(i)
+        groups.setdefault((sc["N"], spacing_params(pol)), {}).setdefault(sc["n"], []).append(i)
     out = {}
-    for (n, N, _), idx in sorted(groups.items()):
-        pol = scenarios[idx[0]].get("spacing_policy") or ConstantSpacingPolicy(50)
-        masses = np.stack([np.full(n, 800.0) if scenarios[i].get("masses") is None
-                           else np.asarray(scenarios[i]["masses"], dtype=np.float64) for i in idx])
-        sw = BatchedDecentSweep(n, N, masses=masses, spacing_policy=pol, device=device, ctx=ctx)
-        r = sw.run(np.stack([scenarios[i]["x0"] for i in idx]), np.stack([scenarios[i]["leader_x"] for i in idx]), ep_len)
-        for j, i in enumerate(idx):
-            out[i] = dict(X=r["X"][:, j], U=r["U"][:, j], R=r["R"][:, j], violations=r["violations"][:, j],
-                          errors=r["errors"][:, j], nodes=r["nodes"][:, j], status=r["status"][:, j])
+    for (N, _), by_n in sorted(groups.items()):
+        first = next(iter(by_n.values()))[0]
+        pol = scenarios[first].get("spacing_policy") or ConstantSpacingPolicy(50)
+        parts, index = [], []
+        for n, idx in sorted(by_n.items()):
+            masses = np.stack([np.full(n, 800.0) if scenarios[i].get("masses") is None
+                               else np.asarray(scenarios[i]["masses"], dtype=np.float64) for i in idx])
+            parts.append((n, np.stack([scenarios[i]["x0"] for i in idx]), np.stack([scenarios[i]["leader_x"] for i in idx]), masses))
+            index.append(idx)
+        res = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx).run(parts, ep_len)
+        for r, idx in zip(res, index):
+            for j, i in enumerate(idx):
+                out[i] = dict(X=r["X"][:, j], U=r["U"][:, j], R=r["R"][:, j], violations=r["violations"][:, j],
+                              errors=r["errors"][:, j], nodes=r["nodes"][:, j], status=r["status"][:, j])
     return out
 
 

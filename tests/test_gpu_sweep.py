@@ -184,3 +184,27 @@ def test_decent_sweep_compiled_solver_matches_local_solver(headway, N):
     close = np.abs(a["X"] - b["X"]).max(axis=(0, 2)) < 1e-6
     assert close.mean() > 0.9, close.mean()
     assert np.abs(a["U"][0] - b["U"][0]).max() < 1e-6 or (np.abs(a["U"][0] - b["U"][0]).max(axis=1) < 1e-6).mean() > 0.9
+
+
+@pytest.mark.parametrize("headway,N", [(False, 5), (True, 8)])
+def test_mixed_size_sweep_equals_per_size_sweeps(headway, N):
+    """One solve launch for the vehicles of platoons of every size == one BatchedDecentSweep per size."""
+    from hybrid_vehicle_platoon_b200.sweep import BatchedDecentSweep, MixedSizeDecentSweep
+    from hybrid_vehicle_platoon_b200.misc import ConstantSpacingPolicy, ConstantTimePolicy, StopAndGoLeaderTrajectory
+    rng = np.random.default_rng(41)
+    T = 4
+    pol = ConstantTimePolicy(10, 3) if headway else ConstantSpacingPolicy(50)
+    lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=12, vf=26, v_change_steps=[1, 3], trajectory_len=T + N + 10,
+                                   ts=1).get_leader_trajectory()
+    parts = []
+    for n, S in ((3, 5), (6, 9), (11, 4)):
+        v = np.floor(rng.uniform(8, 30, (S, n))); gaps = rng.uniform(60, 160, (S, n))
+        p = np.floor(3000.0 - np.cumsum(gaps, 1) + gaps[:, :1])
+        x0 = np.empty((S, 2 * n)); x0[:, 0::2] = p; x0[:, 1::2] = v
+        parts.append((n, x0, np.broadcast_to(lx, (S,) + lx.shape).copy(), rng.uniform(700, 1000, (S, n))))
+    res = MixedSizeDecentSweep(N, spacing_policy=pol).run(parts, T)
+    for (n, x0, lxs, masses), r in zip(parts, res):
+        one = BatchedDecentSweep(n, N, masses=masses, spacing_policy=pol).run(x0, lxs, T)
+        assert (r["status"] == 2).all() and (one["status"] == 2).all()
+        assert np.array_equal(r["X"], one["X"]) and np.array_equal(r["U"], one["U"])
+        assert np.array_equal(r["R"], one["R"]) and np.array_equal(r["nodes"], one["nodes"])
