@@ -159,85 +159,123 @@ class MixedSizeDecentSweep:
     def run(self, parts, ep_len: int):
         """parts: list of (n, x0 (S,2n), leader_x (S,2,>=ep_len+N+1), masses (S,n)).  Returns one result dict per
         part with the layout of BatchedDecentSweep.run."""
+        self.prepare(parts, ep_len)
+        for t in range(ep_len):
+            self.step(t)
+        return self.finish()
+
+    def prepare(self, parts, ep_len: int):
+        """All per-vehicle data lives in FLAT arrays over the vehicles of every platoon (platoon-major, front to back), so
+        observe is a handful of torch ops for the whole group; each part's state / result tensors are views into them.
+        prepare / step(t) / finish are separate so that several sweeps can be stepped in turn on different CUDA
+        streams (run_mixed_sweep): every call only ENQUEUES work on the current torch stream."""
         torch, dev, N, li = self.torch, self.dev, self.N, self.leader_index
         f64, i32, np1 = torch.float64, torch.int32, N + 1
         ts = float(Params.ts)
-        st_parts, off = [], 0
+        T = ep_len
+        B = sum(np.asarray(x0).shape[0] * n for n, x0, _, _ in parts)
+        Stot = sum(np.asarray(x0).shape[0] for _, x0, _, _ in parts)
+        XF = torch.empty((T + 1, B, 2), dtype=f64, device=dev)          # states of every vehicle, every timestep
+        UF = torch.empty((T, B), dtype=f64, device=dev)
+        NDF = torch.empty((T, B), dtype=i32, device=dev); STF = torch.empty((T, B), dtype=i32, device=dev)
+        flags_np = np.zeros(B, np.int32); first_np = np.zeros(B, bool); last_np = np.zeros(B, bool)
+        mass_np = np.empty(B); lead_np = []; lxs = []
+        st_parts, off, soff = [], 0, 0
         for n, x0, lx, masses in parts:
-            x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
-            S = x.shape[0]
-            lxt = torch.as_tensor(np.ascontiguousarray(lx, dtype=np.float64), device=dev)
-            if lxt.shape[2] < ep_len + np1:
+            x0 = np.ascontiguousarray(x0, dtype=np.float64)
+            S = x0.shape[0]
+            lx = np.asarray(lx, dtype=np.float64)
+            if lx.shape[2] < T + np1:
                 raise ValueError("leader trajectory shorter than ep_len + N + 1")
+            sl = slice(off, off + S * n)
             fl = np.zeros((S, n), np.int32)
             fl[:, 0] |= FRONT; fl[:, -1] |= TRAILER; fl[:, li] |= LEADER
-            st_parts.append(dict(n=n, S=S, off=off, x=x, lx=lxt, flags=fl.reshape(-1),
-                                 mass=torch.as_tensor(np.ascontiguousarray(masses, dtype=np.float64), device=dev),
+            flags_np[sl] = fl.reshape(-1)
+            fi = np.zeros((S, n), bool); fi[:, 0] = True; first_np[sl] = fi.reshape(-1)
+            la = np.zeros((S, n), bool); la[:, -1] = True; last_np[sl] = la.reshape(-1)
+            mass_np[sl] = np.ascontiguousarray(masses, dtype=np.float64).reshape(-1)
+            lead_np.append(off + np.arange(S) * n + li)
+            lxs.append(lx[:, :, :T + np1])
+            XF[0, sl] = torch.as_tensor(x0.reshape(S * n, 2), device=dev)
+            st_parts.append(dict(n=n, S=S, sl=sl, ssl=slice(soff, soff + S),
                                  edesc=api.env_desc(n, li, self.d0, self.t0, self.d_safe, True, False, True),
-                                 X=torch.empty((ep_len + 1, S, 2 * n), dtype=f64, device=dev),
-                                 U=torch.empty((ep_len, S, n), dtype=f64, device=dev),
-                                 R=torch.empty((ep_len, S), dtype=f64, device=dev),
-                                 V=torch.empty((ep_len, S), dtype=torch.uint8, device=dev),
-                                 E=torch.empty((ep_len, S), dtype=i32, device=dev),
-                                 ND=torch.empty((ep_len, S, n), dtype=i32, device=dev),
-                                 ST=torch.empty((ep_len, S, n), dtype=i32, device=dev)))
-            st_parts[-1]["X"][0] = x
-            off += S * n
-        B = off
-        flags_np = np.concatenate([p["flags"] for p in st_parts]) if st_parts else np.zeros(0, np.int32)
+                                 R=torch.empty((T, S), dtype=f64, device=dev), V=torch.empty((T, S), dtype=torch.uint8, device=dev),
+                                 E=torch.empty((T, S), dtype=i32, device=dev)))
+            off += S * n; soff += S
         d_flags = torch.as_tensor(flags_np, device=dev)
-        d_mass = torch.cat([p["mass"].reshape(-1) for p in st_parts]) if st_parts else torch.zeros(0, dtype=f64, device=dev)
-        x0b = torch.empty((B, 2), dtype=f64, device=dev)
+        d_mass = torch.as_tensor(mass_np, device=dev)
+        not_first = torch.as_tensor(~first_np, device=dev).view(B, 1, 1)
+        not_last = torch.as_tensor(~last_np, device=dev).view(B, 1, 1)
+        lead_idx = torch.as_tensor(np.concatenate(lead_np) if lead_np else np.zeros(0, np.int64), device=dev)
+        # leader trajectories of every scenario, time-major so that a window / a column is one contiguous slice
+        LX = torch.as_tensor(np.ascontiguousarray(np.concatenate(lxs, 0).transpose(2, 0, 1)) if lxs else np.zeros((T + np1, 0, 2)),
+                             device=dev)                                                     # (T+N+1, Stot, 2)
         xf = torch.zeros((B, 2, np1), dtype=f64, device=dev); xb = torch.zeros((B, 2, np1), dtype=f64, device=dev)
-        xl = torch.zeros((B, 2, np1), dtype=f64, device=dev)
+        xl = torch.zeros((B, 2, np1), dtype=f64, device=dev); pred = torch.empty((B, 2, np1), dtype=f64, device=dev)
         u = torch.empty((B, N), dtype=f64, device=dev); xs = torch.empty((B, 2, np1), dtype=f64, device=dev)
         modes = torch.empty((B, N), dtype=i32, device=dev); obj = torch.empty(B, dtype=f64, device=dev)
         status = torch.empty(B, dtype=i32, device=dev); nodes = torch.empty(B, dtype=i32, device=dev)
         roles = [(int(fl), torch.as_tensor(np.nonzero(flags_np == fl)[0], device=dev)) for fl in np.unique(flags_np)] \
             if self.use_compiled else []
+        zero = torch.zeros((), dtype=f64, device=dev)
+        self._w = dict(T=T, B=B, XF=XF, UF=UF, NDF=NDF, STF=STF, st_parts=st_parts, d_flags=d_flags, d_mass=d_mass,
+                       not_first=not_first, not_last=not_last, lead_idx=lead_idx, LX=LX, xf=xf, xb=xb, xl=xl, pred=pred, u=u,
+                       xs=xs, modes=modes, obj=obj, status=status, nodes=nodes, roles=roles, zero=zero)
+
+    def step(self, t: int):
+        """Enqueue timestep t (observe, solve, rollout) on the current torch stream."""
+        torch, dev, N = self.torch, self.dev, self.N
+        f64, i32, np1 = torch.float64, torch.int32, N + 1
+        ts = float(Params.ts)
+        w = self._w
+        B, XF, UF, d_mass, pred, xf, xb, xl, u = w["B"], w["XF"], w["UF"], w["d_mass"], w["pred"], w["xf"], w["xb"], w["xl"], w["u"]
+        status, nodes, LX = w["status"], w["nodes"], w["LX"]
         stream = torch.cuda.current_stream().cuda_stream
-        for t in range(ep_len):
-            # ---- observe, per platoon size (fleet_decent_mld.py:348-428) ----
-            for p in st_parts:
-                n, S, o = p["n"], p["S"], p["off"]
-                xv = p["x"].view(S, n, 2)
-                pred = torch.empty((S, n, 2, np1), dtype=f64, device=dev)
-                pred[:, :, 0, 0] = xv[:, :, 0]
-                pred[:, :, 1, :] = xv[:, :, 1:2]
-                for k in range(N):
-                    pred[:, :, 0, k + 1] = pred[:, :, 0, k] + ts * pred[:, :, 1, k]
-                sl = slice(o, o + S * n)
-                x0b[sl] = xv.reshape(S * n, 2)
-                xf[sl].view(S, n, 2, np1)[:, 1:] = pred[:, :-1]
-                xb[sl].view(S, n, 2, np1)[:, :-1] = pred[:, 1:]
-                xl[sl].view(S, n, 2, np1)[:, li] = p["lx"][:, :, t:t + np1]
-            # ---- ONE solve for the vehicles of every platoon ----
-            if self.use_compiled:
-                for fl, ii in roles:
-                    Bk = ii.numel()
-                    params = torch.cat((xf[ii].reshape(Bk, -1), xb[ii].reshape(Bk, -1), xl[ii].reshape(Bk, -1)), dim=1).contiguous()
-                    uo = torch.empty((Bk, 1, N), dtype=f64, device=dev); xo = torch.empty((Bk, 1, 2, np1), dtype=f64, device=dev)
-                    mo = torch.empty((Bk, 1, N), dtype=i32, device=dev); ob = torch.empty(Bk, dtype=f64, device=dev)
-                    st = torch.empty(Bk, dtype=i32, device=dev); no = torch.empty(Bk, dtype=i32, device=dev)
-                    self._cm(fl).solve_device(Bk, x0b[ii].reshape(Bk, 1, 2).contiguous(), d_mass[ii].reshape(Bk, 1).contiguous(),
-                                              params, None, uo, xo, None, mo, ob, st, no, None, stream=stream)
-                    u[ii] = uo.view(Bk, N); status[ii] = st; nodes[ii] = no
-            elif B:
-                api.local_miqp_device(self.ldesc, B, d_flags, d_mass, x0b, xf, xb, xl, u, xs, modes, obj, status, nodes,
-                                      None, ctx=self.ctx, stream=stream)
-            # ---- step every platoon, per size ----
-            for p in st_parts:
-                n, S, o = p["n"], p["S"], p["off"]
-                sl = slice(o, o + S * n)
-                p["U"][t] = u[sl, 0].view(S, n)
-                p["ND"][t] = nodes[sl].view(S, n)
-                p["ST"][t] = status[sl].view(S, n)
-                api.rollout_step_device(p["edesc"], S, p["x"], p["U"][t], None, p["mass"], p["lx"][:, :, t].contiguous(),
-                                        p["X"][t + 1], p["R"][t], p["V"][t], p["E"][t], ctx=self.ctx, stream=stream)
-                p["x"] = p["X"][t + 1]
-        torch.cuda.synchronize()
-        return [dict(X=p["X"].cpu().numpy(), U=p["U"].cpu().numpy(), R=p["R"].cpu().numpy(), violations=p["V"].cpu().numpy(),
-                     errors=p["E"].cpu().numpy(), nodes=p["ND"].cpu().numpy(), status=p["ST"].cpu().numpy()) for p in st_parts]
+        x = XF[t]
+        # ---- observe, for the vehicles of every platoon at once (fleet_decent_mld.py:348-428) ----
+        pred[:, 0, 0] = x[:, 0]
+        pred[:, 1, :] = x[:, 1:2]
+        for k in range(N):
+            pred[:, 0, k + 1] = pred[:, 0, k] + ts * pred[:, 1, k]
+        if B > 1:
+            xf[1:] = torch.where(w["not_first"][1:], pred[:-1], w["zero"])     # the vehicle in front, none for a platoon's first
+            xb[:-1] = torch.where(w["not_last"][:-1], pred[1:], w["zero"])     # the vehicle behind, none for a platoon's last
+        xl[w["lead_idx"]] = LX[t:t + np1].permute(1, 2, 0)                     # leader window leader_x[:, t:t+N+1]
+        # ---- ONE solve for the vehicles of every platoon ----
+        if self.use_compiled:
+            for fl, ii in w["roles"]:
+                Bk = ii.numel()
+                params = torch.cat((xf[ii].reshape(Bk, -1), xb[ii].reshape(Bk, -1), xl[ii].reshape(Bk, -1)), dim=1).contiguous()
+                uo = torch.empty((Bk, 1, N), dtype=f64, device=dev); xo = torch.empty((Bk, 1, 2, np1), dtype=f64, device=dev)
+                mo = torch.empty((Bk, 1, N), dtype=i32, device=dev); ob = torch.empty(Bk, dtype=f64, device=dev)
+                st = torch.empty(Bk, dtype=i32, device=dev); no = torch.empty(Bk, dtype=i32, device=dev)
+                self._cm(fl).solve_device(Bk, x[ii].reshape(Bk, 1, 2).contiguous(), d_mass[ii].reshape(Bk, 1).contiguous(),
+                                          params, None, uo, xo, None, mo, ob, st, no, None, stream=stream)
+                u[ii] = uo.view(Bk, N); status[ii] = st; nodes[ii] = no
+        elif B:
+            api.local_miqp_device(self.ldesc, B, w["d_flags"], d_mass, x, xf, xb, xl, u, w["xs"], w["modes"], w["obj"], status,
+                                  nodes, None, ctx=self.ctx, stream=stream)
+        UF[t] = u[:, 0]; w["NDF"][t] = nodes; w["STF"][t] = status
+        # ---- step every platoon: one rollout launch per platoon size, straight into the next state slice ----
+        lead_now = LX[t]
+        for p in w["st_parts"]:
+            S, sl = p["S"], p["sl"]
+            api.rollout_step_device(p["edesc"], S, XF[t, sl], UF[t, sl], None, d_mass[sl], lead_now[p["ssl"]],
+                                    XF[t + 1, sl], p["R"][t], p["V"][t], p["E"][t], ctx=self.ctx, stream=stream)
+
+    def finish(self):
+        """Wait for the device and read the results back (one dict per part)."""
+        w = self._w
+        T, XF, UF, NDF, STF, st_parts = w["T"], w["XF"], w["UF"], w["NDF"], w["STF"], w["st_parts"]
+        self.torch.cuda.synchronize()
+        Xh, Uh, Nh, Sh = XF.cpu().numpy(), UF.cpu().numpy(), NDF.cpu().numpy(), STF.cpu().numpy()
+        out = []
+        for p in st_parts:
+            n, S, sl = p["n"], p["S"], p["sl"]
+            out.append(dict(X=Xh[:, sl].reshape(T + 1, S, 2 * n), U=Uh[:, sl].reshape(T, S, n), R=p["R"].cpu().numpy(),
+                            violations=p["V"].cpu().numpy(), errors=p["E"].cpu().numpy(), nodes=Nh[:, sl].reshape(T, S, n),
+                            status=Sh[:, sl].reshape(T, S, n)))
+        return out
 
 
 def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, device: int = 0, ctx=None):
@@ -253,7 +291,8 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
         sc = scenarios[i]
         pol = sc.get("spacing_policy") or ConstantSpacingPolicy(50)
         groups.setdefault((sc["N"], spacing_params(pol)), {}).setdefault(sc["n"], []).append(i)
-    out = {}
+    import torch
+    out, work = {}, []
     for (N, _), by_n in sorted(groups.items()):
         first = next(iter(by_n.values()))[0]
         pol = scenarios[first].get("spacing_policy") or ConstantSpacingPolicy(50)
@@ -263,7 +302,20 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
                                else np.asarray(scenarios[i]["masses"], dtype=np.float64) for i in idx])
             parts.append((n, np.stack([scenarios[i]["x0"] for i in idx]), np.stack([scenarios[i]["leader_x"] for i in idx]), masses))
             index.append(idx)
-        res = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx).run(parts, ep_len)
+        sw = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx)
+        stream = torch.cuda.Stream(device=sw.dev)
+        with torch.cuda.stream(stream):
+            sw.prepare(parts, ep_len)
+        work.append((sw, stream, index))
+    # The groups are independent and a group's timestep ends in a long tail (its slowest tree): step them in turn, each
+    # on its own stream, so that the tails of different groups overlap on the device.
+    for t in range(ep_len):
+        for sw, stream, _ in work:
+            with torch.cuda.stream(stream):
+                sw.step(t)
+    for sw, stream, index in work:
+        with torch.cuda.stream(stream):
+            res = sw.finish()
         for r, idx in zip(res, index):
             for j, i in enumerate(idx):
                 out[i] = dict(X=r["X"][:, j], U=r["U"][:, j], R=r["R"][:, j], violations=r["violations"][:, j],
