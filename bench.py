@@ -536,7 +536,10 @@ def main():
                    "value": rb / (r_ms * 1e-3), "unit": "scenario-steps/s", "ms_per_launch": r_ms,
                    "batch": rb, "errors": int((re_ != 0).sum()),
                    "roofline": {"bound": "hbm", "achieved": r_ach, "peak": hbm_peak, "unit": "GB/s",
-                                "frac": r_ach / hbm_peak, "traffic": None,
+                                "frac": r_ach / hbm_peak,
+                                # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, ncu --set full
+                                # (profiles/r01g_rollout_ncu_raw.csv; the kernel has not changed since)
+                                "traffic": 552.4e6 if rb == (1 << 20) else None, "traffic_unit": "bytes per launch (ncu)",
                                 "algorithmic_bytes_per_scenario_step": r_bytes, "peak_source": peak_src}}
 
         # ---- p99 per-timestep latency: one scenario (10 MIQPs) through the host call ----
@@ -573,7 +576,10 @@ def main():
                     "call": "hvp_local_miqp_host (pinned numpy in, numpy out)"},
             "gpu_launches": int(launches_timed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
+                         "frac": achieved / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of 655 360 solves, ncu --set full
+                         # (profiles/r01m_flat_ncu_raw.csv): 523 B per solve against 568 algorithmic
+                         "traffic": 343.05e6 * (B / 655360.0), "traffic_unit": "bytes per launch (ncu, scaled by the batch)",
                          "algorithmic_bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
                          "kernel": "flat_miqp_kernel<6>",
                          "note": "on-chip FP64 branch-and-bound: HBM traffic is parameters in + solution "
