@@ -40,7 +40,7 @@ REAL_VEHICLE_REF, NO_LEADER = 8, -100
 
 def build(verbose: bool = False) -> str:
     """Compile libhvp.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", CSRC, "libhvp.so"], capture_output=True, text=True)
+    out = subprocess.run(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC, "libhvp.so"], capture_output=True, text=True)
     if verbose or out.returncode:
         print(out.stdout[-4000:])
         print(out.stderr[-4000:])
