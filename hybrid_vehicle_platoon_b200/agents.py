@@ -139,9 +139,17 @@ class MldAgent:
 
 def _solve_batch(mpcs, states):
     """All local problems of one wave in as few launches as possible."""
-    if isinstance(mpcs[0], _CompiledController):
+    comp = [i for i, m in enumerate(mpcs) if isinstance(m, _CompiledController)]
+    if len(comp) == len(mpcs):
         return solve_compiled_batch(mpcs, states)
-    return solve_local_batch(mpcs, states)
+    if not comp:
+        return solve_local_batch(mpcs, states)
+    out = [None] * len(mpcs)                      # mixed controller types: one batch per type
+    rest = [i for i in range(len(mpcs)) if i not in set(comp)]
+    for idx, fn in ((comp, solve_compiled_batch), (rest, solve_local_batch)):
+        for i, r in zip(idx, fn([mpcs[i] for i in idx], [states[i] for i in idx])):
+            out[i] = r
+    return out
 
 
 def _stack_controls(u, nu_l=1):

@@ -26,14 +26,23 @@ class _Val:
 class LocalMpcMld:
     """A local decentralized MPC for a single vehicle in the platoon (GPU solve)."""
 
+    def __new__(cls, N, pwa_system, spacing_policy=ConstantSpacingPolicy(50), quadratic_cost=True, is_front=False,
+                is_leader=False, is_trailer=False, thread_limit=None, accel_cnstr_tightening=0.0,
+                real_vehicle_as_reference=False, ctx=None):
+        # real_vehicle_as_reference (fleet_seq_mld.py:137,211-219; False in every Sim of the reference) adds a spacing
+        # term and a safe-distance row against the leader trajectory: that variant lives in the compiled LOCAL
+        # formulation (csrc/pm_build.cu), which solves the same problem as this class otherwise
+        if real_vehicle_as_reference and cls is LocalMpcMld:
+            return LocalMpcGear(N, pwa_system, spacing_policy, quadratic_cost, is_front, is_leader, is_trailer,
+                                thread_limit, accel_cnstr_tightening, True, ctx=ctx)
+        return super().__new__(cls)
+
     def __init__(self, N: int, pwa_system: dict, spacing_policy=ConstantSpacingPolicy(50),
                  quadratic_cost: bool = True, is_front: bool = False, is_leader: bool = False,
                  is_trailer: bool = False, thread_limit=None, accel_cnstr_tightening: float = 0.0,
                  real_vehicle_as_reference: bool = False, ctx=None) -> None:
         if not quadratic_cost:
             raise NotImplementedError("1-norm cost (MILP) is a SURVEY.md 8f row, not built yet")
-        if real_vehicle_as_reference:
-            raise NotImplementedError("real_vehicle_as_reference is not built on the GPU path yet")
         self.N, self.n, self.m = N, 1, 1
         self.mass = mass_of_pwa_system(pwa_system)
         self.d0, self.t0 = spacing_params(spacing_policy)

@@ -237,3 +237,42 @@ def test_tree_split_matches_oracle(hvp, monkeypatch, budget):
     r = mpc.solve(x0, 800.0, params)
     ro = O.mpc_solve(O.ADMM, 1, 6, x0, 800.0, params, rho=0.5, method=1)
     _compare(r, ro, "admm split")
+
+
+@pytest.mark.parametrize("kind", ["local", "cent"])
+def test_real_vehicle_as_reference_vs_oracle(hvp, kind):
+    """real_vehicle_as_reference (cent_mld.py:85-105,162-169; fleet_seq_mld.py:137,211-219): the leader keeps the
+    spacing policy's distance to the reference vehicle and a (soft) safe distance behind it."""
+    rng = np.random.default_rng(333)
+    B, N = 24, 4
+    if kind == "local":
+        from gen_cases import platoon_local_problems
+        cs = platoon_local_problems(rng, B, 1, N, stress=True)          # single vehicles: front + leader + trailer
+        fl = int(G.FRONT | G.LEADER | G.TRAILER | O.REAL_REF)
+        x0 = cs["x0"][:, None, :]
+        lead = G.const_vel(np.stack([cs["x0"][:, 0] + rng.uniform(20, 90, B), rng.uniform(10, 30, B)], 1), N)
+        params = np.concatenate([np.zeros((B, 2 * 2 * (N + 1))), lead.reshape(B, -1)], axis=1)
+        mpc = hvp.api.CompiledMpc(G.LOCAL, N, flags=fl)
+        r = mpc.solve(x0, 800.0, params)
+        ro = O.mpc_solve(O.LOCAL, 1, N, x0, 800.0, params, flags=fl, method=0)
+    else:
+        n = 2
+        x0, params = G.cent_cases(rng, B, n, N, stress=True)
+        params = G.const_vel(np.stack([x0[:, 0, 0] + rng.uniform(20, 90, B), rng.uniform(10, 30, B)], 1), N).reshape(B, -1)
+        mpc = hvp.api.CompiledMpc(G.CENT, N, n_local=n, flags=int(O.REAL_REF))
+        r = mpc.solve(x0, 800.0, params)
+        ro = O.mpc_solve(O.CENT, n, N, x0, 800.0, params, flags=int(O.REAL_REF), method=0)
+    _compare(r, ro, f"real_ref {kind}")
+    assert (ro["status"] == 2).sum() >= B // 2
+
+
+def test_local_mpc_mld_real_vehicle_reference_routes_to_compiled(hvp):
+    sys_ = hvp.Platoon(1, "pwa_gear", [800.0]).get_vehicle_system_dicts(1.0)[0]
+    m = hvp.LocalMpcMld(4, sys_, hvp.ConstantSpacingPolicy(50), True, True, True, True, None, 0.0, True)
+    assert isinstance(m, hvp.mpc.LocalMpcGear)
+    lead = np.stack([2000.0 + 70.0 + 20.0 * np.arange(5), np.full(5, 20.0)])
+    m.set_leader_x(lead)
+    u0, info = m.solve_mpc(np.array([[2000.0], [18.0]]))
+    assert np.isfinite(info["cost"]) and u0.shape == (1, 1)
+    plain = hvp.LocalMpcMld(4, sys_, hvp.ConstantSpacingPolicy(50), True, True, True, True)
+    assert type(plain) is hvp.LocalMpcMld
