@@ -54,15 +54,21 @@ __device__ __forceinline__ double rcp(double v) {
 // dot product with two independent accumulation chains (the solver is latency bound);
 // `sa` = stride of a in doubles
 __device__ __forceinline__ double dot2(const double* a, int sa, const double* b, int n) {
-    double s0 = 0.0, s1 = 0.0;
+    // four independent chains, 32-bit index arithmetic: the solver is latency bound (r01l ncu: this function is a
+    // quarter of all stall samples, almost all of them dependency waits)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int c = 0;
-#pragma unroll 2
-    for (; c + 1 < n; c += 2) {
-        s0 += a[(size_t)c * sa] * b[c];
-        s1 += a[(size_t)(c + 1) * sa] * b[c + 1];
+    const double* ap = a;
+#pragma unroll 1
+    for (; c + 3 < n; c += 4, ap += 4 * sa, b += 4) {
+        s0 += ap[0] * b[0];
+        s1 += ap[sa] * b[1];
+        s2 += ap[2 * sa] * b[2];
+        s3 += ap[3 * sa] * b[3];
     }
-    if (c < n) s0 += a[(size_t)c * sa] * b[c];
-    return s0 + s1;
+#pragma unroll 1
+    for (; c < n; ++c, ap += sa, ++b) s0 += ap[0] * b[0];
+    return (s0 + s1) + (s2 + s3);
 }
 // GW = lanes of the group that owns one problem (32, or 16 so that a warp carries two small problems);
 // gm = the group's lane mask.  Shuffles use width GW, so lane indices are relative to the group.
