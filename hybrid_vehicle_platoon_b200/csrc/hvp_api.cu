@@ -55,6 +55,8 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
     CUDA_TRY(cudaSetDevice(device));
     hvp_ctx* c = new hvp_ctx();
     c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0; c->hbuf = nullptr; c->hcap = 0;
+    c->counters = nullptr; c->counter_next = 0;
+    CUDA_TRY(cudaMalloc(&c->counters, HVP_COUNTER_RING * sizeof(unsigned long long)));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -68,6 +70,7 @@ extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->dbuf) cudaFree(c->dbuf);
     if (c->hbuf) cudaFreeHost(c->hbuf);
+    if (c->counters) cudaFree(c->counters);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -223,7 +226,8 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    CUDA_TRY(launch_local_miqp(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
+    unsigned long long* counter = c->counters + (c->counter_next++ % HVP_COUNTER_RING);
+    CUDA_TRY(launch_local_miqp(P, counter, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     c->launches += 1;

@@ -19,7 +19,12 @@ struct hvp_ctx {
     // pinned host mirror of dbuf for small calls: one H2D + one D2H instead of one copy per array
     char* hbuf;
     size_t hcap;
+    // work-distribution counters of the persistent local-MIQP kernel: a ring, one slot per launch, so that launches
+    // in flight on different streams never share one
+    unsigned long long* counters;
+    int counter_next;
 };
+constexpr int HVP_COUNTER_RING = 256;
 int hvp_fail(int code, const char* fmt, ...);          // records the thread's error text, returns code
 int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes);
 
@@ -44,7 +49,7 @@ struct RolloutParams {
     double default_mass;
 };
 
-cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
+cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
                               double* u, double* x, int32_t* modes, double* obj, int32_t* status,
                               int32_t* nodes, int32_t* qp_iters, cudaStream_t stream);

@@ -83,14 +83,15 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                  const double* __restrict__ xf, const double* __restrict__ xb,
                  const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
                  int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
-                 int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
+                 int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters, unsigned long long* __restrict__ counter) {
     extern __shared__ double smem[];
     using Solver = FlatSolver<N, 32>;
     const int lane = threadIdx.x;
     const size_t S = 2 * (size_t)(N + 1);
-    const int64_t chunk = (batch + gridDim.x - 1) / gridDim.x;
-    int64_t next = (int64_t)blockIdx.x * chunk;                   // warp-uniform
-    const int64_t end = next + chunk < batch ? next + chunk : batch;
+    // Problems are handed out through one global counter: a warp that needs k new problems takes the next k, so every
+    // warp stays busy until the batch is exhausted.  (Measured: launch time = 4.45 ms + batch / 43.6 M/s.  The
+    // constant is NOT load imbalance -- a static share per warp gave the same times -- but the drain of the trees that
+    // are still open when the queue runs dry: a lane needs ~0.1 ms per node and the largest trees have > 100 nodes.)
     Solver sol;
     FlatCold<N> cold;
     sol.lane_ = lane;
@@ -119,15 +120,17 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
             }
             const unsigned need = __ballot_sync(0xffffffffu, !have);
             if (need) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
                 if (!have) {
-                    i = next + __popc(need & ((1u << lane) - 1u));
-                    if (i < end) {
+                    i = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+                    if (i < batch) {
                         sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
                                   xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 2), &cold);
                         have = true;
                     }
                 }
-                next += __popc(need);
             }
             if (!__any_sync(0xffffffffu, have)) break;
             if (have) sol.trip_node();
@@ -142,7 +145,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <int N>
-static cudaError_t launch_flat(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
+static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter, int64_t batch, const int32_t* flags, const double* mass,
                                const double* x0, const double* xf, const double* xb, const double* xl, double* u,
                                double* x, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                                int32_t* qp_iters, cudaStream_t stream) {
@@ -169,8 +172,10 @@ static cudaError_t launch_flat(const LocalParams& P, int64_t batch, const int32_
     static const int nb = env_int("HVP_NODE_BATCH", 0), dv = env_int("HVP_FLAT_DIVE", -1);
     if (nb > 0) Q.node_batch = nb;
     if (dv >= 0) Q.dive = dv;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
     flat_miqp_kernel<N><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
-                                                          status, nodes, qp_iters);
+                                                          status, nodes, qp_iters, counter);
     return cudaGetLastError();
 }
 
@@ -189,7 +194,7 @@ static int kernel_choice() {
 
 static bool use_scalar_kernel() { return kernel_choice() == 1; }
 
-cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t* flags, const double* mass,
+cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
                               double* u, double* x, int32_t* modes, double* obj, int32_t* status,
                               int32_t* nodes, int32_t* qp_iters, cudaStream_t stream) {
@@ -199,7 +204,7 @@ cudaError_t launch_local_miqp(const LocalParams& P, int64_t batch, const int32_t
     const int choice = kernel_choice();
     const bool flat_ok = P.N >= 4 && P.N <= 9;
     if (flat_ok && (choice == 3 || (choice == 0 && batch >= FLAT_MIN_BATCH))) {
-#define HVP_FLAT(NN) case NN: return launch_flat<NN>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, stream);
+#define HVP_FLAT(NN) case NN: return launch_flat<NN>(P, counter, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, stream);
         switch (P.N) { HVP_FLAT(4) HVP_FLAT(5) HVP_FLAT(6) HVP_FLAT(7) HVP_FLAT(8) HVP_FLAT(9) default: break; }
 #undef HVP_FLAT
     }
