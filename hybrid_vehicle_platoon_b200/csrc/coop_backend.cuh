@@ -34,6 +34,17 @@ struct DevBK {
     __device__ __forceinline__ D todouble(I v) const { return (double)v; }
     __device__ __forceinline__ D sel(Bm c, D a, D b) const { return c ? a : b; }
     __device__ __forceinline__ I seli(Bm c, I a, I b) const { return c ? a : b; }
+    // quotients through a MUFU-seeded reciprocal (~1 ulp): the IEEE division sequence is ~25 instructions with a slow
+    // path, and this kernel is a single dependent chain per group
+    static __device__ __forceinline__ double rcp(double v) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+        r = r * (2.0 - v * r);
+        r = r * (2.0 - v * r);
+        return r;
+    }
+    __device__ __forceinline__ D div(D a, D b) const { return a * rcp(b); }
+    __device__ __forceinline__ double sdiv(double a, double b) const { return a * rcp(b); }
     __device__ __forceinline__ D dmax(D a, D b) const { return fmax(a, b); }
     __device__ __forceinline__ D dmin(D a, D b) const { return fmin(a, b); }
     __device__ __forceinline__ double bcast(D v, int src) const { return __shfl_sync(gmask, v, src, G); }
@@ -156,6 +167,8 @@ struct HostBK {
     D todouble(const I& a) const { D r; for (int i = 0; i < G; ++i) r.v[i] = (double)a.v[i]; return r; }
     D sel(const Bm& c, const D& a, const D& b) const { D r; for (int i = 0; i < G; ++i) r.v[i] = c.v[i] ? a.v[i] : b.v[i]; return r; }
     I seli(const Bm& c, const I& a, const I& b) const { I r; for (int i = 0; i < G; ++i) r.v[i] = c.v[i] ? a.v[i] : b.v[i]; return r; }
+    D div(const D& a, const D& b) const { D r; for (int i = 0; i < G; ++i) r.v[i] = a.v[i] / b.v[i]; return r; }
+    double sdiv(double a, double b) const { return a / b; }
     D dmax(const D& a, const D& b) const { D r; for (int i = 0; i < G; ++i) r.v[i] = fmax(a.v[i], b.v[i]); return r; }
     D dmin(const D& a, const D& b) const { D r; for (int i = 0; i < G; ++i) r.v[i] = fmin(a.v[i], b.v[i]); return r; }
     double bcast(const D& v, int src) const { return v.v[src]; }

@@ -278,7 +278,7 @@ struct CoopSolver {
         for (int k = 0; k < G; ++k) {
             if (k < L) {
                 const int rg = mode(k);
-                const double ib = 1.0 / rb(rg), ea = -ra(rg) * ib;
+                const double ib = bk.sdiv(1.0, rb(rg)), ea = -ra(rg) * ib;
                 const double kc = (k == 0) ? -(ra(rg) * v0 + rc(rg)) * ib : -rc(rg) * ib;
                 hinv[k] += bk.sel(ln == k, bk.splat(2.0 * qu * ib * ib), bk.splat(0.0));
                 g += bk.sel(ln == k, bk.splat(2.0 * qu * kc * ib), bk.splat(0.0));
@@ -297,7 +297,7 @@ struct CoopSolver {
             if (k < N) {
                 const double piv = bk.bcast(hinv[k], k);
                 bad = bad || !(piv > 0.0);
-                const double pinv = 1.0 / piv;
+                const double pinv = bk.sdiv(1.0, piv);
                 const D f = hinv[k];
                 const Bm isk = ln == k;
 #pragma unroll
@@ -377,7 +377,7 @@ struct CoopSolver {
             const D hoff_l = hw1 * ((double)(N - 1) - lnd) + hw2;
             const D hdiag_l = hw1 * ((double)(N - 1) - lnd) + hd;
             D term = x * (0.5 * hdiag_l * x + hoff_l * PS + gt);
-            const D uu = du / bl;
+            const D uu = bk.div(du, bl);
             term += bk.sel(ln < L, qu * uu * uu, bk.splat(0.0));
             if (has_sf) { const D s = PS - sf; term += bk.sel((ln >= 1) & (s > 0.0), ww * s, bk.splat(0.0)); }
             if (has_sb) { const D s = sb - PS; term += bk.sel((ln >= 1) & (s > 0.0), ww * s, bk.splat(0.0)); }
@@ -439,15 +439,15 @@ struct CoopSolver {
         const bool dependent = (q == N) || !(nz > 1e-11 * nHn);
         const double INF = HUGE_VAL;
         if (zero_step && dependent) { node_done(2, 0.0); return; }
-        const double t2 = dependent ? INF : (zero_step ? 0.0 : cp / nz);
+        const double t2 = dependent ? INF : (zero_step ? 0.0 : bk.sdiv(cp, nz));
         double t1, t3; int k1, k3;
         {
             const Bm act_ok = ln < q;
             const Bm pos = act_ok & (r > 1e-14);
-            const D c1v = bk.sel(pos, lam / bk.sel(pos, r, bk.splat(1.0)), bk.splat(INF));
+            const D c1v = bk.sel(pos, bk.div(lam, bk.sel(pos, r, bk.splat(1.0))), bk.splat(INF));
             bk.gmin_arg(c1v, ln, t1, k1);
             const Bm softneg = act_ok & (r < -1e-14) & (s_id >= T_SF * 12);
-            const D c3v = bk.sel(softneg, (ww - lam) / bk.sel(softneg, -r, bk.splat(1.0)), bk.splat(INF));
+            const D c3v = bk.sel(softneg, bk.div(ww - lam, bk.sel(softneg, -r, bk.splat(1.0))), bk.splat(INF));
             bk.gmin_arg(c3v, ln, t3, k3);
         }
         const double t3p = p_soft ? (ww - lam_p) : INF;
@@ -468,7 +468,7 @@ struct CoopSolver {
         lam_p += t;
         if (t == t2) {
             // p becomes slot q: bordering update of Ginv with Schur complement nz
-            const double is = 1.0 / nz;
+            const double is = bk.sdiv(1.0, nz);
             const Bm isq = ln == q;
 #pragma unroll
             for (int b = 0; b < G; ++b) {
@@ -513,7 +513,7 @@ struct CoopSolver {
             double gkk = 1.0;
 #pragma unroll
             for (int b = 0; b < G; ++b) gkk = (b == drop) ? rowk[b] : gkk;
-            const double ikk = 1.0 / gkk;
+            const double ikk = bk.sdiv(1.0, gkk);
             const Bm mv = ln >= drop;
 #pragma unroll
             for (int b = 0; b < G; ++b) ginv[b] -= ck * (rowk[b] * ikk);
