@@ -31,6 +31,7 @@ int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes);
 namespace hvp {
 
 constexpr int LOCAL_BLOCK = 32;     // threads (= MIQPs) per CTA of the local-MIQP kernel (one warp)
+constexpr int COOP_SPREAD_MAX = 1184;  // batches up to 8 warps per SM: one problem per warp (latency), else packed
 constexpr int COOP_BLOCK = 128;     // threads per CTA of the cooperative MIQP kernel (16 groups of 8)
 constexpr int FLAT_MIN_BATCH = 16384; // batches at least this large use the persistent flat kernel
 constexpr int ROLLOUT_BLOCK = 256;  // threads per CTA of the rollout kernel

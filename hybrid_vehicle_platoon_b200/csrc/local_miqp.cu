@@ -55,8 +55,13 @@ coop_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                  const double* __restrict__ xf, const double* __restrict__ xb,
                  const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
                  int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
-                 int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;   // problem of this group
+                 int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters, int spread) {
+    // packed: 32 / G problems per warp (throughput).  spread: ONE problem per warp, lanes G.. idle -- the groups of
+    // a warp run different trees and serialise each other (r01m ncu: 15 of 32 lanes active), which is what a small
+    // latency-critical batch (one scenario-timestep = n MIQPs) must not pay for
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (spread && (threadIdx.x & 31) >= G) return;
+    const int64_t i = spread ? (t >> 5) : t / G;                              // problem of this group
     if (i >= batch) return;                                                   // whole group leaves
     const int N = P.N;
     const size_t S = 2 * (size_t)(N + 1);
@@ -210,15 +215,25 @@ cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter,
     }
     if (!use_scalar_kernel()) {
         if (P.N <= 8) {
+            if (batch <= COOP_SPREAD_MAX) {
+                coop_miqp_kernel<8><<<(unsigned)batch, 32, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes,
+                                                                      obj, status, nodes, qp_iters, 1);
+                return cudaGetLastError();
+            }
             const int per_block = COOP_BLOCK / 8;
             const unsigned g = (unsigned)((batch + per_block - 1) / per_block);
             coop_miqp_kernel<8><<<g, COOP_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
-                                                             status, nodes, qp_iters);
+                                                             status, nodes, qp_iters, 0);
         } else {
+            if (batch <= COOP_SPREAD_MAX) {
+                coop_miqp_kernel<16><<<(unsigned)batch, 32, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes,
+                                                                       obj, status, nodes, qp_iters, 1);
+                return cudaGetLastError();
+            }
             const int per_block = COOP_BLOCK / 16;
             const unsigned g = (unsigned)((batch + per_block - 1) / per_block);
             coop_miqp_kernel<16><<<g, COOP_BLOCK, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
-                                                              status, nodes, qp_iters);
+                                                              status, nodes, qp_iters, 0);
         }
         return cudaGetLastError();
     }
