@@ -55,7 +55,7 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
     CUDA_TRY(cudaSetDevice(device));
     hvp_ctx* c = new hvp_ctx();
     c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0; c->hbuf = nullptr; c->hcap = 0;
-    c->counters = nullptr; c->counter_next = 0;
+    c->counters = nullptr; c->counter_next = 0; c->side_ok = false;
     CUDA_TRY(cudaMalloc(&c->counters, HVP_COUNTER_RING * sizeof(unsigned long long)));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
@@ -71,6 +71,7 @@ extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
     if (c->dbuf) cudaFree(c->dbuf);
     if (c->hbuf) cudaFreeHost(c->hbuf);
     if (c->counters) cudaFree(c->counters);
+    if (c->side_ok) { for (int i = 0; i < 3; ++i) cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->side_ev); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -290,6 +291,55 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
         memcpy(u, h + off(du), B * N * 8); memcpy(x, h + off(dx), B * S * 8); memcpy(modes, h + off(dmo), B * N * 4);
         memcpy(obj, h + off(dob), B * 8); memcpy(status, h + off(dst), B * 4); memcpy(nodes, h + off(dno), B * 4);
         if (qp_iters) memcpy(qp_iters, h + off(dit), B * 4);
+        return 0;
+    }
+    // Large batches go through in CHUNKS on three side streams: the H2D copy of one chunk, the kernel of another and
+    // the D2H copy of a third overlap (PCIe is full duplex), and so do the kernels themselves at their ends -- the
+    // persistent kernel of a chunk drains its last, longest trees while the next chunk's CTAs take the freed slots.
+    // (Host buffers should be pinned for the copies to be asynchronous; pageable memory still works, serialised.)
+    const size_t CH = 131072;
+    if (B >= 2 * CH) {
+        if (!c->side_ok) {
+            for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->side_ev, cudaEventDisableTiming));
+            c->side_ok = true;
+        }
+        CUDA_TRY(cudaEventRecord(c->side_ev, st));              // the side streams start after earlier work on `st`
+        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamWaitEvent(c->side[i], c->side_ev, 0));
+        CUDA_TRY(cudaEventRecord(c->ev0, st));
+        int k = 0;
+        for (size_t o = 0; o < B; o += CH, ++k) {
+            const size_t nb = (B - o < CH + CH / 2) ? B - o : CH;   // the last chunk takes a short remainder with it
+            cudaStream_t ss = c->side[k % 3];
+            CUDA_TRY(cudaMemcpyAsync(dfl + o, flags + o, nb * 4, cudaMemcpyHostToDevice, ss));
+            CUDA_TRY(cudaMemcpyAsync(dma + o, mass + o, nb * 8, cudaMemcpyHostToDevice, ss));
+            CUDA_TRY(cudaMemcpyAsync(dx0 + 2 * o, x0 + 2 * o, nb * 16, cudaMemcpyHostToDevice, ss));
+            if (xf) CUDA_TRY(cudaMemcpyAsync(dxf + S * o, xf + S * o, nb * S * 8, cudaMemcpyHostToDevice, ss));
+            if (xb) CUDA_TRY(cudaMemcpyAsync(dxb + S * o, xb + S * o, nb * S * 8, cudaMemcpyHostToDevice, ss));
+            if (xl) CUDA_TRY(cudaMemcpyAsync(dxl + S * o, xl + S * o, nb * S * 8, cudaMemcpyHostToDevice, ss));
+            LocalParams P;
+            fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes);
+            unsigned long long* counter = c->counters + (c->counter_next++ % HVP_COUNTER_RING);
+            CUDA_TRY(launch_local_miqp(P, counter, (int64_t)nb, dfl + o, dma + o, dx0 + 2 * o, dxf ? dxf + S * o : nullptr,
+                                       dxb ? dxb + S * o : nullptr, dxl ? dxl + S * o : nullptr, du + N * o, dx + S * o,
+                                       dmo + N * o, dob + o, dst + o, dno + o, dit ? dit + o : nullptr, ss));
+            c->launches += 1;
+            CUDA_TRY(cudaMemcpyAsync(u + N * o, du + N * o, nb * N * 8, cudaMemcpyDeviceToHost, ss));
+            CUDA_TRY(cudaMemcpyAsync(x + S * o, dx + S * o, nb * S * 8, cudaMemcpyDeviceToHost, ss));
+            CUDA_TRY(cudaMemcpyAsync(modes + N * o, dmo + N * o, nb * N * 4, cudaMemcpyDeviceToHost, ss));
+            CUDA_TRY(cudaMemcpyAsync(obj + o, dob + o, nb * 8, cudaMemcpyDeviceToHost, ss));
+            CUDA_TRY(cudaMemcpyAsync(status + o, dst + o, nb * 4, cudaMemcpyDeviceToHost, ss));
+            CUDA_TRY(cudaMemcpyAsync(nodes + o, dno + o, nb * 4, cudaMemcpyDeviceToHost, ss));
+            if (qp_iters) CUDA_TRY(cudaMemcpyAsync(qp_iters + o, dit + o, nb * 4, cudaMemcpyDeviceToHost, ss));
+            if (nb != CH) break;
+        }
+        for (int i = 0; i < 3; ++i) {                            // `st` continues after all three side streams
+            CUDA_TRY(cudaEventRecord(c->side_ev, c->side[i]));
+            CUDA_TRY(cudaStreamWaitEvent(st, c->side_ev, 0));
+        }
+        CUDA_TRY(cudaEventRecord(c->ev1, st));
+        c->timed = true;
+        CUDA_TRY(cudaStreamSynchronize(st));
         return 0;
     }
     CUDA_TRY(cudaMemcpyAsync(dfl, flags, B * 4, cudaMemcpyHostToDevice, st));

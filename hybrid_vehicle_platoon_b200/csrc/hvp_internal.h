@@ -23,6 +23,10 @@ struct hvp_ctx {
     // in flight on different streams never share one
     unsigned long long* counters;
     int counter_next;
+    // side streams of the chunked *_host path (copies of one chunk overlap the kernel of another)
+    cudaStream_t side[3];
+    cudaEvent_t side_ev;
+    bool side_ok;
 };
 constexpr int HVP_COUNTER_RING = 256;
 int hvp_fail(int code, const char* fmt, ...);          // records the thread's error text, returns code

@@ -96,3 +96,28 @@ def test_bench_size_properties(hvp_ctx, oracle):
                            c["xl"][idx])
     sub = {k: v[idx] for k, v in r.items() if isinstance(v, np.ndarray)}
     _check(sub, ro)
+
+
+def test_chunked_host_path_equals_device_path():
+    """Large host batches go through in chunks on side streams (hvp_local_miqp_host): same results as one device
+    launch on the same inputs, remainder chunk included."""
+    import torch
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200 import api
+    from gen_cases import platoon_local_problems
+    N, n, S = 6, 10, 40000 + 7                       # 400 070 problems: 131 072 + 131 072 + 137 926 (remainder merged)
+    cs = platoon_local_problems(np.random.default_rng(5), S, n, N)
+    r = hvp.local_miqp(N, cs["flags"], cs["mass"], cs["x0"], cs["xf"], cs["xb"], cs["xl"])
+    dev = torch.device("cuda", 0)
+    B = S * n
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cs.items()}
+    u = torch.empty((B, N), dtype=torch.float64, device=dev); x = torch.empty((B, 2, N + 1), dtype=torch.float64, device=dev)
+    mo = torch.empty((B, N), dtype=torch.int32, device=dev); ob = torch.empty(B, dtype=torch.float64, device=dev)
+    st = torch.empty(B, dtype=torch.int32, device=dev); no = torch.empty(B, dtype=torch.int32, device=dev)
+    api.local_miqp_device(api.local_desc(N), B, d["flags"], d["mass"], d["x0"], d["xf"], d["xb"], d["xl"], u, x, mo, ob, st, no,
+                          None, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (r["status"] == 2).all()
+    assert np.array_equal(r["obj"], ob.cpu().numpy()) and np.array_equal(r["u"], u.cpu().numpy())
+    assert np.array_equal(r["modes"], mo.cpu().numpy()) and np.array_equal(r["nodes"], no.cpu().numpy())
+    assert np.array_equal(r["x"], x.cpu().numpy())
