@@ -1,6 +1,7 @@
 // hvp_api.cu -- the C ABI of libhvp.so (include/hvp.h): contexts, error reporting, host-buffer
 // wrappers.  No torch types, no CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -297,7 +298,7 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
     // the D2H copy of a third overlap (PCIe is full duplex), and so do the kernels themselves at their ends -- the
     // persistent kernel of a chunk drains its last, longest trees while the next chunk's CTAs take the freed slots.
     // (Host buffers should be pinned for the copies to be asynchronous; pageable memory still works, serialised.)
-    const size_t CH = 131072;
+    static const size_t CH = getenv("HVP_HOST_CHUNK") ? (size_t)atoll(getenv("HVP_HOST_CHUNK")) : 131072;
     if (B >= 2 * CH) {
         if (!c->side_ok) {
             for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
