@@ -256,6 +256,42 @@ struct FlatSolver {
         state = S_NEXT;
     }
 
+    // ---- sub-tree adoption (tail of a launch: idle lanes of the warp take open branches of a busy lane) -------
+    // Shallowest level of the depth-first stack that still has untried regions, and how many are open in total.
+    // Valid in state S_NEXT (levels above `lev` are exhausted there).
+    HVP_HD bool open_level(int& l, int& cb, int& total) const {
+        l = -1; cb = 0; total = 0;
+        HVP_ROLL
+        for (int lv = 0; lv <= lev; ++lv) {
+            const int c = cand(lv);
+            if (c && l < 0) { l = lv; cb = c; }
+            total += __builtin_popcount((unsigned)c);
+        }
+        return l >= 0;
+    }
+    // After setup() of the SAME problem: follow the donor's region prefix (levels 0..l-1, interval propagation as in
+    // do_next, nothing is solved) and search only region `c` at level l, starting from the donor's incumbent.
+    HVP_HD void adopt_prefix(uint64_t donor_modes, int l, int c, double donor_inc) {
+        const double eps = 1e-9;
+        HVP_ROLL
+        for (int lv = 0; lv < l; ++lv) {
+            const int rg = mode_of(donor_modes, lv);
+            set_mode(lv, rg);
+            set_cand(lv, 0);
+            const double jlo = fmax(C->rlo[lv], P->edge[rg]), jhi = fmin(C->rhi[lv], P->edge[rg + 1]);
+            double nlo = fmax(ra(rg) * jlo + rc(rg) + rb(rg) * P->umin, jlo + P->a_dec + lv * P->tight);
+            double nhi = fmin(ra(rg) * jhi + rc(rg) + rb(rg) * P->umax, jhi + P->a_acc - lv * P->tight);
+            nlo = fmax(nlo, P->vmin); nhi = fmin(nhi, P->vmax);
+            C->rlo[lv + 1] = nlo - eps; C->rhi[lv + 1] = nhi + eps;
+            C->xstar[lv + 1] = v0;
+        }
+        set_cand(l, 1 << c);
+        lev = l;
+        inc = donor_inc;
+        dive = false;
+        state = S_NEXT;
+    }
+
     // ---- NEXT: next node of the depth-first search (or finished) --------------------------
     HVP_HD void do_next() {
         const double eps = 1e-9;

@@ -56,7 +56,8 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
     CUDA_TRY(cudaSetDevice(device));
     hvp_ctx* c = new hvp_ctx();
     c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0; c->hbuf = nullptr; c->hcap = 0;
-    c->counters = nullptr; c->counter_next = 0; c->side_ok = false;
+    c->counters = nullptr; c->counter_next = 0; c->side_ok = false; c->steal_scratch = nullptr; c->steal_slot_doubles = HVP_STEAL_SLOT_DOUBLES;
+    CUDA_TRY(cudaMalloc(&c->steal_scratch, HVP_STEAL_RING * HVP_STEAL_SLOT_DOUBLES * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->counters, HVP_COUNTER_RING * sizeof(unsigned long long)));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
@@ -72,6 +73,7 @@ extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
     if (c->dbuf) cudaFree(c->dbuf);
     if (c->hbuf) cudaFreeHost(c->hbuf);
     if (c->counters) cudaFree(c->counters);
+    if (c->steal_scratch) cudaFree(c->steal_scratch);
     if (c->side_ok) { for (int i = 0; i < 3; ++i) cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->side_ev); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -228,8 +230,10 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    unsigned long long* counter = c->counters + (c->counter_next++ % HVP_COUNTER_RING);
-    CUDA_TRY(launch_local_miqp(P, counter, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
+    const int slot = c->counter_next++;
+    unsigned long long* counter = c->counters + (slot % HVP_COUNTER_RING);
+    double* steal = c->steal_scratch + (size_t)(slot % HVP_STEAL_RING) * c->steal_slot_doubles;
+    CUDA_TRY(launch_local_miqp(P, counter, steal, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     c->launches += 1;
@@ -320,8 +324,10 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
             if (xl) CUDA_TRY(cudaMemcpyAsync(dxl + S * o, xl + S * o, nb * S * 8, cudaMemcpyHostToDevice, ss));
             LocalParams P;
             fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes);
-            unsigned long long* counter = c->counters + (c->counter_next++ % HVP_COUNTER_RING);
-            CUDA_TRY(launch_local_miqp(P, counter, (int64_t)nb, dfl + o, dma + o, dx0 + 2 * o, dxf ? dxf + S * o : nullptr,
+            const int slot = c->counter_next++;
+            unsigned long long* counter = c->counters + (slot % HVP_COUNTER_RING);
+            double* steal = c->steal_scratch + (size_t)(slot % HVP_STEAL_RING) * c->steal_slot_doubles;
+            CUDA_TRY(launch_local_miqp(P, counter, steal, (int64_t)nb, dfl + o, dma + o, dx0 + 2 * o, dxf ? dxf + S * o : nullptr,
                                        dxb ? dxb + S * o : nullptr, dxl ? dxl + S * o : nullptr, du + N * o, dx + S * o,
                                        dmo + N * o, dob + o, dst + o, dno + o, dit ? dit + o : nullptr, ss));
             c->launches += 1;

@@ -23,12 +23,18 @@ struct hvp_ctx {
     // in flight on different streams never share one
     unsigned long long* counters;
     int counter_next;
+    // scratch rows of the sub-tree adoption in the flat kernel's tail (one row per lane of the persistent grid), a ring
+    // like the counters so that launches in flight on different streams do not share rows
+    double* steal_scratch;
+    size_t steal_slot_doubles;
     // side streams of the chunked *_host path (copies of one chunk overlap the kernel of another)
     cudaStream_t side[3];
     cudaEvent_t side_ev;
     bool side_ok;
 };
 constexpr int HVP_COUNTER_RING = 256;
+constexpr int HVP_STEAL_RING = 16;
+constexpr size_t HVP_STEAL_SLOT_DOUBLES = (size_t)160 * 20 * 32 * 9;   // SMs x CTAs/SM x lanes x N (upper bounds)
 int hvp_fail(int code, const char* fmt, ...);          // records the thread's error text, returns code
 int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes);
 
@@ -54,7 +60,7 @@ struct RolloutParams {
     double default_mass;
 };
 
-cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter, int64_t batch, const int32_t* flags, const double* mass,
+cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter, double* steal_scratch, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
                               double* u, double* x, int32_t* modes, double* obj, int32_t* status,
                               int32_t* nodes, int32_t* qp_iters, cudaStream_t stream);

@@ -88,7 +88,8 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                  const double* __restrict__ xf, const double* __restrict__ xb,
                  const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
                  int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
-                 int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters, unsigned long long* __restrict__ counter) {
+                 int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters, unsigned long long* __restrict__ counter,
+                 double* __restrict__ scratch) {
     extern __shared__ double smem[];
     using Solver = FlatSolver<N, 32>;
     const int lane = threadIdx.x;
@@ -104,6 +105,16 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                     // instead of through a generic pointer (r01k ncu: LD.E of P->hull etc. on the SELECT path)
     bool have = false;
     int64_t i = 0;
+    // Tail of the launch: when the queue has run dry, the lanes that are idle ADOPT open branches of the lanes of their
+    // warp that are still searching (the launch time is 4.45 ms + batch / 43.6 M/s, and the 4.45 ms are exactly these
+    // last, largest trees).  The donor hands out untried regions of the shallowest open level of its
+    // depth-first stack; an adopter sets the same problem up, follows the donor's region prefix without solving it and
+    // searches that one branch from the donor's incumbent, keeping its best leaf in a scratch row; when it is done the
+    // owner takes the better of the two.  Everything stays inside the warp: shuffles, no atomics, no global queue.
+    const bool steal = scratch != nullptr && P.max_nodes == 0;
+    bool thief = false, drained = false;
+    int owner = lane, pending = 0;
+    double* const my_scratch = scratch ? scratch + ((size_t)blockIdx.x * 32 + lane) * N : nullptr;
     // A lane is either stepping its node QP (SELECT/STEP: the common, cheap trip) or waiting for node
     // work (store a finished problem, load the next one, NEXT + BUILD of a new node).  Node work is
     // several times the cost of a step and only ~1 lane in 6 needs it on a given trip, so the warp
@@ -115,7 +126,33 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
         const bool slow = !have || sol.state == Solver::S_DONE || sol.wants_node();
         const unsigned ms = __ballot_sync(0xffffffffu, slow);
         if (ms == 0xffffffffu || __popc(ms) >= node_batch) {
-            if (have && sol.state == Solver::S_DONE) {
+            if (drained) {
+                // adopters that finished their branch report to the owner of the problem
+                unsigned rep = __ballot_sync(0xffffffffu, have && thief && sol.state == Solver::S_DONE);
+                while (rep) {
+                    const int r = __ffs(rep) - 1;
+                    rep &= rep - 1;
+                    const int o = __shfl_sync(0xffffffffu, owner, r);
+                    const double v = __shfl_sync(0xffffffffu, sol.inc, r);
+                    const unsigned long long bm = __shfl_sync(0xffffffffu, (unsigned long long)sol.best_modes, r);
+                    const int nn = __shfl_sync(0xffffffffu, sol.nodes, r), ii = __shfl_sync(0xffffffffu, sol.iters, r);
+                    const int tr = __shfl_sync(0xffffffffu, (int)sol.trouble, r);
+                    __syncwarp();
+                    if (lane == o) {
+                        --pending;
+                        sol.nodes += nn; sol.iters += ii;
+                        if (tr) sol.trouble = true;
+                        if (v < sol.inc) {
+                            sol.inc = v; sol.best_modes = bm;
+                            const double* src = scratch + ((size_t)blockIdx.x * 32 + r) * N;
+                            for (int j = 0; j < N; ++j) sol.best_[j] = src[j];
+                        }
+                    }
+                    if (lane == r) { have = false; thief = false; owner = lane; }
+                }
+                __syncwarp();
+            }
+            if (have && !thief && sol.state == Solver::S_DONE && pending == 0) {
                 const LocalResult R = sol.finish(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
                 obj[i] = R.obj;
                 status[i] = R.status;
@@ -123,19 +160,64 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                 if (qp_iters) qp_iters[i] = R.qp_iters;
                 have = false;
             }
+            // new work for idle lanes: a fresh problem from the queue, or (tail) a branch of a busy lane
+            bool start = false, adopting = false;
+            int a_l = 0, a_c = 0, a_owner = lane;
+            unsigned long long a_modes = 0;
+            double a_inc = 0.0;
             const unsigned need = __ballot_sync(0xffffffffu, !have);
-            if (need) {
+            if (need && !drained) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(need));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (!have) {
-                    i = (int64_t)base + __popc(need & ((1u << lane) - 1u));
-                    if (i < batch) {
-                        sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
-                                  xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr, x + S * i + (N + 2), &cold);
-                        have = true;
-                    }
+                    const int64_t cand_i = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+                    if (cand_i < batch) { i = cand_i; start = true; }
                 }
+                if ((int64_t)base + __popc(need) > batch) drained = true;          // warp-uniform
+            }
+            if (steal && drained) {
+                // adopters pick up the owner's current incumbent
+                const double oi = __shfl_sync(0xffffffffu, sol.inc, thief ? owner : lane);
+                if (have && thief && oi < sol.inc) sol.inc = oi;
+                unsigned idle = __ballot_sync(0xffffffffu, !have && !start);
+                int l = -1, cb = 0, total = 0;
+                const bool can = have && !thief && sol.state == Solver::S_NEXT && sol.open_level(l, cb, total) && total >= 2;
+                unsigned don = __ballot_sync(0xffffffffu, can);
+                for (int round = 0; round < 4 && don && idle; ++round) {
+                    const int d = __ffs(don) - 1;
+                    don &= don - 1;
+                    const int dl = __shfl_sync(0xffffffffu, l, d), dcb = __shfl_sync(0xffffffffu, cb, d);
+                    const int dtot = __shfl_sync(0xffffffffu, total, d);
+                    const long long di = __shfl_sync(0xffffffffu, (long long)i, d);
+                    const unsigned long long dm = __shfl_sync(0xffffffffu, (unsigned long long)sol.modes_pk, d);
+                    const double dinc = __shfl_sync(0xffffffffu, sol.inc, d);
+                    int m = __popc((unsigned)dcb) - (dtot == __popc((unsigned)dcb) ? 1 : 0);   // the donor keeps work
+                    if (m > __popc(idle)) m = __popc(idle);
+                    if (m <= 0) continue;
+                    const bool me_idle = (idle >> lane) & 1u;
+                    const int rk = __popc(idle & ((1u << lane) - 1u));
+                    if (me_idle && rk < m) {
+                        int bits = dcb;
+                        for (int t = 0; t < rk; ++t) bits &= bits - 1;
+                        a_c = __ffs(bits) - 1; a_l = dl; a_modes = dm; a_inc = dinc; a_owner = d;
+                        i = di; start = true; adopting = true;
+                    }
+                    if (lane == d) {
+                        int bits = dcb, rm = 0;
+                        for (int t = 0; t < m; ++t) { rm |= bits & -bits; bits &= bits - 1; }
+                        sol.set_cand(dl, dcb & ~rm);
+                        pending += m;
+                    }
+                    idle = __ballot_sync(0xffffffffu, !have && !start);
+                }
+            }
+            if (start) {
+                sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
+                          xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr,
+                          adopting ? my_scratch : x + S * i + (N + 2), &cold);
+                if (adopting) sol.adopt_prefix(a_modes, a_l, a_c, a_inc);
+                have = true; thief = adopting; owner = a_owner;
             }
             if (!__any_sync(0xffffffffu, have)) break;
             if (have) sol.trip_node();
@@ -150,7 +232,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <int N>
-static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter, int64_t batch, const int32_t* flags, const double* mass,
+static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter, double* steal_scratch, int64_t batch, const int32_t* flags, const double* mass,
                                const double* x0, const double* xf, const double* xb, const double* xl, double* u,
                                double* x, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                                int32_t* qp_iters, cudaStream_t stream) {
@@ -177,10 +259,12 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
     static const int nb = env_int("HVP_NODE_BATCH", 0), dv = env_int("HVP_FLAT_DIVE", -1);
     if (nb > 0) Q.node_batch = nb;
     if (dv >= 0) Q.dive = dv;
+    static const int steal_on = env_int("HVP_FLAT_STEAL", 1);
+    if ((size_t)g * 32 * N > HVP_STEAL_SLOT_DOUBLES) steal_scratch = nullptr;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     flat_miqp_kernel<N><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
-                                                          status, nodes, qp_iters, counter);
+                                                          status, nodes, qp_iters, counter, steal_on ? steal_scratch : nullptr);
     return cudaGetLastError();
 }
 
@@ -199,7 +283,7 @@ static int kernel_choice() {
 
 static bool use_scalar_kernel() { return kernel_choice() == 1; }
 
-cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter, int64_t batch, const int32_t* flags, const double* mass,
+cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter, double* steal_scratch, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
                               double* u, double* x, int32_t* modes, double* obj, int32_t* status,
                               int32_t* nodes, int32_t* qp_iters, cudaStream_t stream) {
@@ -209,7 +293,7 @@ cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter,
     const int choice = kernel_choice();
     const bool flat_ok = P.N >= 4 && P.N <= 9;
     if (flat_ok && (choice == 3 || (choice == 0 && batch >= FLAT_MIN_BATCH))) {
-#define HVP_FLAT(NN) case NN: return launch_flat<NN>(P, counter, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, stream);
+#define HVP_FLAT(NN) case NN: return launch_flat<NN>(P, counter, steal_scratch, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, stream);
         switch (P.N) { HVP_FLAT(4) HVP_FLAT(5) HVP_FLAT(6) HVP_FLAT(7) HVP_FLAT(8) HVP_FLAT(9) default: break; }
 #undef HVP_FLAT
     }
