@@ -126,9 +126,9 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
         const bool slow = !have || sol.state == Solver::S_DONE || sol.wants_node();
         const unsigned ms = __ballot_sync(0xffffffffu, slow);
         if (ms == 0xffffffffu || __popc(ms) >= node_batch) {
-            if (drained) {
+            if (__builtin_expect(drained, 0)) {
                 // adopters that finished their branch report to the owner of the problem
-                unsigned rep = __ballot_sync(0xffffffffu, have && thief && sol.state == Solver::S_DONE);
+                unsigned rep = __ballot_sync(0xffffffffu, have && thief && sol.state == Solver::S_DONE && pending == 0);
                 while (rep) {
                     const int r = __ffs(rep) - 1;
                     rep &= rep - 1;
@@ -176,13 +176,13 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                 }
                 if ((int64_t)base + __popc(need) > batch) drained = true;          // warp-uniform
             }
-            if (steal && drained) {
+            if (__builtin_expect(steal && drained, 0)) {
                 // adopters pick up the owner's current incumbent
                 const double oi = __shfl_sync(0xffffffffu, sol.inc, thief ? owner : lane);
                 if (have && thief && oi < sol.inc) sol.inc = oi;
                 unsigned idle = __ballot_sync(0xffffffffu, !have && !start);
                 int l = -1, cb = 0, total = 0;
-                const bool can = have && !thief && sol.state == Solver::S_NEXT && sol.open_level(l, cb, total) && total >= 2;
+                const bool can = have && sol.state == Solver::S_NEXT && sol.open_level(l, cb, total) && total >= 2;   // adopters donate too
                 unsigned don = __ballot_sync(0xffffffffu, can);
                 for (int round = 0; round < 4 && don && idle; ++round) {
                     const int d = __ffs(don) - 1;
