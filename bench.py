@@ -475,7 +475,9 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(ho["status"], d_status.cpu().numpy())
-    assert np.allclose(ho["obj"], d_obj.cpu().numpy(), rtol=0, atol=0)
+    # the host path (chunks) and the device path (one launch) agree to round-off: which lane solves a leaf in the tail
+    # of a launch depends on the launch shape (sub-tree adoption)
+    assert np.allclose(ho["obj"], d_obj.cpu().numpy(), rtol=1e-9, atol=0)
     clocks = sampler.stop()
 
     # ---- max over ranks ----
