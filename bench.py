@@ -580,8 +580,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch of 655 360 solves, ncu --set full
-                         # (profiles/r01m_flat_ncu_raw.csv): 523 B per solve against 568 algorithmic
-                         "traffic": 343.05e6 * (B / 655360.0), "traffic_unit": "bytes per launch (ncu, scaled by the batch)",
+                         # (profiles/r01o_flat_ncu_raw.csv): 517 B per solve against 568 algorithmic
+                         "traffic": 338.67e6 * (B / 655360.0), "traffic_unit": "bytes per launch (ncu, scaled by the batch)",
                          "algorithmic_bytes_per_solve": bytes_per_solve, "peak_source": peak_src,
                          "kernel": "flat_miqp_kernel<6>",
                          "note": "on-chip FP64 branch-and-bound: HBM traffic is parameters in + solution "
