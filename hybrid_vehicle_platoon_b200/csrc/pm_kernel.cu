@@ -425,7 +425,7 @@ struct Warp {
         const double den = rcp(s * (0.5 / S.qu) + ev);
         LANES(j, nv) {
             const double vj = wv[j] * den;
-            _Pragma("unroll 1")
+            _Pragma("unroll 4")
             for (int c = 0; c < nv; ++c) Hinv[j * ld + c] -= vj * wv[c];
         }
         __syncwarp(gm);
@@ -708,7 +708,7 @@ struct Warp {
             const double is = rcp(nz);
             LANES(a, q) {
                 const double ra = rv[a] * is;
-                _Pragma("unroll 1")
+                _Pragma("unroll 4")
                 for (int b = 0; b < q; ++b) Ginv[a * ld + b] += ra * rv[b];
                 Ginv[a * ld + q] = -ra;
                 Ginv[q * ld + a] = -ra;
@@ -749,7 +749,7 @@ struct Warp {
             __syncwarp(gm);
             LANES(a, q) {
                 const double da = dv[a] * idd;
-                _Pragma("unroll 1")
+                _Pragma("unroll 4")
                 for (int b = 0; b < q; ++b) Ginv[a * ld + b] -= da * dv[b];
             }
             __syncwarp(gm);
