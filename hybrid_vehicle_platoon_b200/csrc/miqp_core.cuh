@@ -47,6 +47,7 @@ struct LocalParams {
     int hull;                            // flat kernel: interval-hull tightening of the unfixed stages
     int dive;                            // flat kernel: first descent solves only the leaf
     int node_batch;                      // flat kernel: lanes that must wait for node set-up before a warp runs it
+                                         // (27 of 32: measured optimum 26-28 after the r01 profile pass; 32 before it)
     double d0, t0, tight;
     double qxp, qxv, qu, w;              // Params.Q_x, Q_u, w (common_controller_params.py:14-23)
     double a_acc, a_dec, d_safe;
