@@ -302,7 +302,7 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
     // the D2H copy of a third overlap (PCIe is full duplex), and so do the kernels themselves at their ends -- the
     // persistent kernel of a chunk drains its last, longest trees while the next chunk's CTAs take the freed slots.
     // (Host buffers should be pinned for the copies to be asynchronous; pageable memory still works, serialised.)
-    static const size_t CH = getenv("HVP_HOST_CHUNK") ? (size_t)atoll(getenv("HVP_HOST_CHUNK")) : 65536;
+    static const size_t CH = getenv("HVP_HOST_CHUNK") ? (size_t)atoll(getenv("HVP_HOST_CHUNK")) : 98304;
     if (B >= 2 * CH) {
         if (!c->side_ok) {
             for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));

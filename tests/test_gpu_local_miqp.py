@@ -105,7 +105,7 @@ def test_chunked_host_path_equals_device_path():
     import hybrid_vehicle_platoon_b200 as hvp
     from hybrid_vehicle_platoon_b200 import api
     from gen_cases import platoon_local_problems
-    N, n, S = 6, 10, 40000 + 7                       # 400 070 problems: five chunks of 65 536 and a merged remainder
+    N, n, S = 6, 10, 40000 + 7                       # 400 070 problems: three chunks of 98 304 and a merged remainder
     cs = platoon_local_problems(np.random.default_rng(5), S, n, N)
     r = hvp.local_miqp(N, cs["flags"], cs["mass"], cs["x0"], cs["xf"], cs["xb"], cs["xl"])
     dev = torch.device("cuda", 0)
