@@ -79,3 +79,66 @@ extern "C" int hvh_flat_miqp_batch(int batch, int N, const int32_t* flags, doubl
     switch (N) { HVH_CASE(2) HVH_CASE(3) HVH_CASE(4) HVH_CASE(5) HVH_CASE(6) HVH_CASE(7) HVH_CASE(8) HVH_CASE(9) default: return -1; }
 #undef HVH_CASE
 }
+
+// Host check of the sub-tree adoption of the flat kernel's tail (flat_core.cuh: open_level / adopt_prefix): the owner
+// runs `after_nodes` nodes, then hands EVERY open region of its shallowest open level but (if nothing else is open)
+// one to fresh solvers, each of which sets the same problem up, follows the owner's prefix and searches its branch from
+// the owner's incumbent; the owner finishes the rest.  Returns the best objective over owner and adopters and the
+// number of adopters; the caller compares it with the plain solve.
+template <int N>
+static double flat_adopt_one(int flags, double d0, double t0, double tight, double mass, const double* x0, const double* xf,
+                             const double* xb, const double* xl, int after_nodes, int* n_adopters, int* total_nodes) {
+    hvp::LocalParams P;
+    hvp::fill_local_params(P, N, d0, t0, tight, 0);
+    using Sol = hvp::FlatSolver<N, 1>;
+    Sol own;
+    double W[hvp::FlatLayout<N>::SIZE], best[N];
+    hvp::FlatCold<N> cold;
+    own.setup(W, &P, flags, mass, x0, xf, xb, xl, best, &cold);
+    *n_adopters = 0;
+    double result = HUGE_VAL;
+    int nodes = 0;
+    bool donated = false;
+    while (own.state != Sol::S_DONE) {
+        if (!donated && own.state == Sol::S_NEXT && own.nodes >= after_nodes) {
+            int l, cb, total;
+            if (own.open_level(l, cb, total) && total >= 2) {
+                int give = cb, keep = 0;
+                if (total == __builtin_popcount((unsigned)cb)) { keep = cb & -cb; give = cb & ~keep; }
+                for (int c = 0; c < 7; ++c) {
+                    if (!((give >> c) & 1)) continue;
+                    Sol th;
+                    double W2[hvp::FlatLayout<N>::SIZE], best2[N];
+                    hvp::FlatCold<N> cold2;
+                    th.setup(W2, &P, flags, mass, x0, xf, xb, xl, best2, &cold2);
+                    th.adopt_prefix(own.modes_pk, l, c, own.inc);
+                    while (th.state != Sol::S_DONE) th.trip();
+                    if (th.inc < result) result = th.inc;
+                    nodes += th.nodes;
+                    ++*n_adopters;
+                }
+                own.set_cand(l, cb & ~give);
+                donated = true;
+            }
+        }
+        own.trip();
+    }
+    if (own.inc < result) result = own.inc;
+    *total_nodes = nodes + own.nodes;
+    return result;
+}
+
+extern "C" int hvh_flat_adopt_batch(int batch, int N, const int32_t* flags, double d0, double t0, double tight,
+                                    const double* mass, const double* x0, const double* xf, const double* xb,
+                                    const double* xl, int after_nodes, double* obj, int32_t* adopters, int32_t* nodes) {
+    const size_t S = 2 * (size_t)(N + 1);
+    for (int i = 0; i < batch; ++i) {
+        int na = 0, nn = 0;
+        double r;
+#define HVH_CASE(NN) case NN: r = flat_adopt_one<NN>(flags[i], d0, t0, tight, mass[i], x0 + 2 * (size_t)i, xf + S * i, xb + S * i, xl + S * i, after_nodes, &na, &nn); break;
+        switch (N) { HVH_CASE(3) HVH_CASE(4) HVH_CASE(5) HVH_CASE(6) HVH_CASE(7) HVH_CASE(8) default: return -1; }
+#undef HVH_CASE
+        obj[i] = r; adopters[i] = na; nodes[i] = nn;
+    }
+    return 0;
+}

@@ -37,3 +37,17 @@ def local_miqp(N, flags, mass, x0, xf, xb, xl, d0=50.0, t0=0.0, tight=0.0, max_n
     fn(B, N, c(flags, np.int32), d0, t0, tight, max_nodes, c(mass), c(x0), c(xf),
                            c(xb), c(xl), u, x, modes, obj, st, nodes, it)
     return dict(u=u, x=x, modes=modes, obj=obj, status=st, nodes=nodes, qp_iters=it)
+
+
+def flat_adopt(N, flags, mass, x0, xf, xb, xl, after_nodes=1, d0=50.0, t0=0.0, tight=0.0):
+    """Host emulation of the flat kernel's sub-tree adoption (harness.cpp: hvh_flat_adopt_batch)."""
+    L = C.CDLL(build())
+    fn = L.hvh_flat_adopt_batch
+    fn.argtypes = [C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _ip, _ip]
+    fn.restype = C.c_int
+    B = x0.shape[0]
+    c = lambda a, t=np.float64: np.ascontiguousarray(a, dtype=t)
+    obj = np.zeros(B); ad = np.zeros(B, np.int32); nodes = np.zeros(B, np.int32)
+    rc = fn(B, N, c(flags, np.int32), d0, t0, tight, c(mass), c(x0), c(xf), c(xb), c(xl), int(after_nodes), obj, ad, nodes)
+    assert rc == 0
+    return dict(obj=obj, adopters=ad, nodes=nodes)

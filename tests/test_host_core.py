@@ -39,3 +39,19 @@ def test_core_infeasible(oracle):
     z = np.zeros((1, 2, N + 1))
     r = harness.local_miqp(N, np.array([7]), np.array([800.0]), np.array([[3000.0, 1.0]]), z, z, xl)
     assert r["status"][0] == 3 and np.isinf(r["obj"][0])
+
+
+@pytest.mark.parametrize("N,after,t0", [(6, 1, 0.0), (6, 4, 0.0), (5, 2, 3.0), (8, 3, 0.0)])
+def test_flat_subtree_adoption_partitions_the_tree(N, after, t0):
+    """Tail of a flat-kernel launch (flat_core.cuh open_level / adopt_prefix), emulated on the host: an owner that
+    hands open branches to fresh solvers, plus those solvers, find exactly the optimum of the plain search."""
+    import harness as H
+    rng = np.random.default_rng(500 + N + after)
+    cs = platoon_local_problems(rng, 40, 10, N, stress=True)
+    d0 = 10.0 if t0 else 50.0
+    plain = H.local_miqp(N, cs["flags"], cs["mass"], cs["x0"], cs["xf"], cs["xb"], cs["xl"], d0=d0, t0=t0, flat=True)
+    r = H.flat_adopt(N, cs["flags"], cs["mass"], cs["x0"], cs["xf"], cs["xb"], cs["xl"], after_nodes=after, d0=d0, t0=t0)
+    ok = plain["status"] == 2
+    assert ok.sum() > 300 and (r["adopters"] > 0).mean() > 0.3          # the split really happened
+    assert np.isinf(r["obj"][~ok]).all()
+    assert np.allclose(r["obj"][ok], plain["obj"][ok], rtol=1e-9, atol=0)
