@@ -56,9 +56,8 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
     CUDA_TRY(cudaSetDevice(device));
     hvp_ctx* c = new hvp_ctx();
     c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0; c->hbuf = nullptr; c->hcap = 0;
-    c->counters = nullptr; c->counter_next = 0; c->side_ok = false; c->steal_scratch = nullptr; c->steal_slot_doubles = HVP_STEAL_SLOT_DOUBLES;
-    CUDA_TRY(cudaMalloc(&c->steal_scratch, HVP_STEAL_RING * HVP_STEAL_SLOT_DOUBLES * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c->counters, HVP_COUNTER_RING * sizeof(unsigned long long)));
+    c->counters = nullptr; c->counter_next = 0; c->side_ok = false; c->n_slots = 0;
+    CUDA_TRY(cudaMalloc(&c->counters, (HVP_STREAM_SLOTS + HVP_COUNTER_RING) * sizeof(unsigned long long)));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -73,7 +72,7 @@ extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
     if (c->dbuf) cudaFree(c->dbuf);
     if (c->hbuf) cudaFreeHost(c->hbuf);
     if (c->counters) cudaFree(c->counters);
-    if (c->steal_scratch) cudaFree(c->steal_scratch);
+    for (int i = 0; i < c->n_slots; ++i) if (c->slot_scratch[i]) cudaFree(c->slot_scratch[i]);
     if (c->side_ok) { for (int i = 0; i < 3; ++i) cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->side_ev); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -207,6 +206,23 @@ extern "C" int hvp_rollout_step_host(hvp_ctx* c, const hvp_env_desc* desc, int64
 // ------------------------------------------------------------------------------------------
 // local MIQP
 // ------------------------------------------------------------------------------------------
+// counter and adoption scratch of a launch on `st` (see hvp_ctx): per stream, allocated on first use
+static int launch_slot(hvp_ctx* c, cudaStream_t st, unsigned long long** counter, double** scratch) {
+    for (int i = 0; i < c->n_slots; ++i)
+        if (c->slot_stream[i] == st) { *counter = c->counters + i; *scratch = c->slot_scratch[i]; return 0; }
+    if (c->n_slots < HVP_STREAM_SLOTS) {
+        double* p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, HVP_STEAL_SLOT_DOUBLES * sizeof(double)));
+        const int i = c->n_slots++;
+        c->slot_stream[i] = st; c->slot_scratch[i] = p;
+        *counter = c->counters + i; *scratch = p;
+        return 0;
+    }
+    *counter = c->counters + HVP_STREAM_SLOTS + (c->counter_next++ % HVP_COUNTER_RING);
+    *scratch = nullptr;
+    return 0;
+}
+
 static int check_local_desc(const hvp_local_desc* d) {
     if (!d) return fail(-1, "local_miqp: desc is NULL");
     if (d->N < 2 || d->N > 12) return fail(-4, "local_miqp: N=%d out of range [2,12]", d->N);
@@ -230,9 +246,10 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    const int slot = c->counter_next++;
-    unsigned long long* counter = c->counters + (slot % HVP_COUNTER_RING);
-    double* steal = c->steal_scratch + (size_t)(slot % HVP_STEAL_RING) * c->steal_slot_doubles;
+    unsigned long long* counter = nullptr;
+    double* steal = nullptr;
+    rc = launch_slot(c, st, &counter, &steal);
+    if (rc) return rc;
     CUDA_TRY(launch_local_miqp(P, counter, steal, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
@@ -324,9 +341,10 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
             if (xl) CUDA_TRY(cudaMemcpyAsync(dxl + S * o, xl + S * o, nb * S * 8, cudaMemcpyHostToDevice, ss));
             LocalParams P;
             fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes);
-            const int slot = c->counter_next++;
-            unsigned long long* counter = c->counters + (slot % HVP_COUNTER_RING);
-            double* steal = c->steal_scratch + (size_t)(slot % HVP_STEAL_RING) * c->steal_slot_doubles;
+            unsigned long long* counter = nullptr;
+            double* steal = nullptr;
+            rc = launch_slot(c, ss, &counter, &steal);
+            if (rc) return rc;
             CUDA_TRY(launch_local_miqp(P, counter, steal, (int64_t)nb, dfl + o, dma + o, dx0 + 2 * o, dxf ? dxf + S * o : nullptr,
                                        dxb ? dxb + S * o : nullptr, dxl ? dxl + S * o : nullptr, du + N * o, dx + S * o,
                                        dmo + N * o, dob + o, dst + o, dno + o, dit ? dit + o : nullptr, ss));

@@ -19,22 +19,23 @@ struct hvp_ctx {
     // pinned host mirror of dbuf for small calls: one H2D + one D2H instead of one copy per array
     char* hbuf;
     size_t hcap;
-    // work-distribution counters of the persistent local-MIQP kernel: a ring, one slot per launch, so that launches
-    // in flight on different streams never share one
-    unsigned long long* counters;
+    // Per-STREAM launch state of the persistent local-MIQP kernel: its work-distribution counter and the scratch rows of
+    // the sub-tree adoption (one row per lane of the persistent grid).  Launches on one stream are serialised, so one
+    // slot per stream can never be shared by two launches in flight; a stream beyond the table runs without adoption
+    // and with a counter of its own from a ring that is only reused after HVP_COUNTER_RING further launches.
+    unsigned long long* counters;                 // [HVP_STREAM_SLOTS + HVP_COUNTER_RING]
     int counter_next;
-    // scratch rows of the sub-tree adoption in the flat kernel's tail (one row per lane of the persistent grid), a ring
-    // like the counters so that launches in flight on different streams do not share rows
-    double* steal_scratch;
-    size_t steal_slot_doubles;
+    cudaStream_t slot_stream[64];
+    double* slot_scratch[64];
+    int n_slots;
     // side streams of the chunked *_host path (copies of one chunk overlap the kernel of another)
     cudaStream_t side[3];
     cudaEvent_t side_ev;
     bool side_ok;
 };
 constexpr int HVP_COUNTER_RING = 256;
-constexpr int HVP_STEAL_RING = 16;
-constexpr size_t HVP_STEAL_SLOT_DOUBLES = (size_t)160 * 20 * 32 * 9;   // SMs x CTAs/SM x lanes x N (upper bounds)
+constexpr int HVP_STREAM_SLOTS = 64;
+constexpr size_t HVP_STEAL_SLOT_DOUBLES = (size_t)3 << 17;   // 3 MiB of doubles: >= grid x 32 lanes x N for every N (<= 2.6 MB)
 int hvp_fail(int code, const char* fmt, ...);          // records the thread's error text, returns code
 int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes);
 
