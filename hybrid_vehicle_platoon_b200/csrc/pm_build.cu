@@ -423,20 +423,101 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
         for (int t = 0; t < npv; ++t) B0[(size_t)g * npv + t] = e.p[t];
         w0[g] = B.wmax[cst[g]];
     }
+    // gradient map of the FULL variable vector: g = G . pvec, G = RW2.Cres + Lz'.La
+    std::vector<double> G((size_t)nv * npv, 0.0);
+    for (int j = 0; j < nv; ++j)
+        for (int t = 0; t < npv; ++t) {
+            double s = 0.0;
+            for (int r = 0; r < S.nres; ++r) s += RW2[(size_t)j * S.nres + r] * Cres[(size_t)r * npv + t];
+            for (int l = 0; l < S.nlin; ++l) s += Lz[(size_t)l * nv + j] * La[(size_t)l * npv + t];
+            G[(size_t)j * npv + t] = s;
+        }
+    // ---- elimination of the free copies that appear in no row (pm_types.h) ----
+    std::vector<int> emap(B.ne > 0 ? B.ne : 1, 0);
+    std::vector<double> Rz, GE, HE;
+    int nk = nv;
+    {
+        static const int elim_on = getenv("HVP_MPC_ELIM") ? atoi(getenv("HVP_MPC_ELIM")) : 1;
+        std::vector<int> K, E;
+        for (int j = 0; j < nv; ++j) {
+            bool in_row = j < B.nl * B.N;
+            for (int g = 0; g < S.ng && !in_row; ++g) in_row = AT[(size_t)j * S.ng + g] != 0.0;
+            (in_row || !elim_on ? K : E).push_back(j);
+        }
+        const int nel = (int)E.size();
+        nk = (int)K.size();
+        int kept = 0, gone = 0;
+        for (int e = 0; e < B.ne; ++e) {
+            const int j = B.nl * B.N + e;
+            bool is_e = false;
+            for (int q : E) is_e = is_e || q == j;
+            emap[e] = is_e ? -1 - gone++ : kept++;
+        }
+        if (nel > 0) {
+            std::vector<double> C((size_t)nel * nel), Cinv, Bm((size_t)nk * nel);
+            for (int a = 0; a < nel; ++a)
+                for (int b = 0; b < nel; ++b) C[(size_t)a * nel + b] = H0[(size_t)E[a] * nv + E[b]];
+            if (!spd_inverse(nel, C, Cinv)) { delete Bp; delete m; return fail(-5, "mpc_create: eliminated block is not positive definite"); }
+            for (int a = 0; a < nk; ++a)
+                for (int b = 0; b < nel; ++b) Bm[(size_t)a * nel + b] = H0[(size_t)K[a] * nv + E[b]];
+            std::vector<double> BC((size_t)nk * nel, 0.0);                 // B C^-1
+            for (int a = 0; a < nk; ++a)
+                for (int b = 0; b < nel; ++b) {
+                    double s2 = 0.0;
+                    for (int c2 = 0; c2 < nel; ++c2) s2 += Bm[(size_t)a * nel + c2] * Cinv[(size_t)c2 * nel + b];
+                    BC[(size_t)a * nel + b] = s2;
+                }
+            std::vector<double> H0r((size_t)nk * nk), Gr((size_t)nk * npv), ATr((size_t)nk * S.ng);
+            for (int a = 0; a < nk; ++a) {
+                for (int b = 0; b < nk; ++b) {
+                    double s2 = H0[(size_t)K[a] * nv + K[b]];
+                    for (int c2 = 0; c2 < nel; ++c2) s2 -= BC[(size_t)a * nel + c2] * Bm[(size_t)b * nel + c2];
+                    H0r[(size_t)a * nk + b] = s2;
+                }
+                for (int t = 0; t < npv; ++t) {
+                    double s2 = G[(size_t)K[a] * npv + t];
+                    for (int c2 = 0; c2 < nel; ++c2) s2 -= BC[(size_t)a * nel + c2] * G[(size_t)E[c2] * npv + t];
+                    Gr[(size_t)a * npv + t] = s2;
+                }
+                for (int g = 0; g < S.ng; ++g) ATr[(size_t)a * S.ng + g] = AT[(size_t)K[a] * S.ng + g];
+            }
+            for (int a = 0; a < nk; ++a)                                   // symmetrise the round-off
+                for (int b = 0; b < a; ++b) {
+                    const double s2 = 0.5 * (H0r[(size_t)a * nk + b] + H0r[(size_t)b * nk + a]);
+                    H0r[(size_t)a * nk + b] = H0r[(size_t)b * nk + a] = s2;
+                }
+            GE.assign((size_t)nel * npv, 0.0); HE.assign((size_t)nel * npv, 0.0); Rz.assign((size_t)nel * nk, 0.0);
+            for (int a = 0; a < nel; ++a) {
+                for (int t = 0; t < npv; ++t) {
+                    GE[(size_t)a * npv + t] = G[(size_t)E[a] * npv + t];
+                    double s2 = 0.0;
+                    for (int c2 = 0; c2 < nel; ++c2) s2 -= Cinv[(size_t)a * nel + c2] * G[(size_t)E[c2] * npv + t];
+                    HE[(size_t)a * npv + t] = s2;
+                }
+                for (int b = 0; b < nk; ++b) Rz[(size_t)a * nk + b] = -BC[(size_t)b * nel + a];   // -(C^-1 B')[a][b], C^-1 symmetric
+            }
+            // the kernel works on the kept variables; the residual maps of the fallback path (no precompute) do not
+            // carry the elimination, so they are cut down only to keep the indexing consistent
+            std::vector<double> RW2r((size_t)nk * S.nres), Lzr((size_t)S.nlin * nk);
+            for (int a = 0; a < nk; ++a)
+                for (int r = 0; r < S.nres; ++r) RW2r[(size_t)a * S.nres + r] = RW2[(size_t)K[a] * S.nres + r];
+            for (int l = 0; l < S.nlin; ++l)
+                for (int a = 0; a < nk; ++a) Lzr[(size_t)l * nk + a] = Lz[(size_t)l * nv + K[a]];
+            H0.swap(H0r); G.swap(Gr); AT.swap(ATr); RW2.swap(RW2r); Lz.swap(Lzr);
+            if (!spd_inverse(nk, H0, H0inv)) { delete Bp; delete m; return fail(-5, "mpc_create: reduced Hessian is not positive definite"); }
+            S.nv = nk;
+        }
+        S.nel = nel;
+    }
     // stacked matrix of the tensor-core precompute (pm_types.h)
     {
-        const int nres = S.nres, nlin = S.nlin;
+        const int nres = S.nres, nlin = S.nlin, nel = S.nel;
         S.kw = (npv + 3) / 4 * 4;
-        S.mw = (nv + S.ng + S.n0 + nres + 2 * nlin + 7) / 8 * 8;
+        S.mw = (nk + S.ng + S.n0 + nres + 2 * nlin + 2 * nel + 7) / 8 * 8;
         std::vector<double> Wm((size_t)S.mw * S.kw, 0.0);
-        for (int j = 0; j < nv; ++j)
-            for (int t = 0; t < npv; ++t) {
-                double s = 0.0;
-                for (int r = 0; r < nres; ++r) s += RW2[(size_t)j * nres + r] * Cres[(size_t)r * npv + t];
-                for (int l = 0; l < nlin; ++l) s += Lz[(size_t)l * nv + j] * La[(size_t)l * npv + t];
-                Wm[(size_t)j * S.kw + t] = s;
-            }
-        int row = nv;
+        for (int j = 0; j < nk; ++j)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)j * S.kw + t] = G[(size_t)j * npv + t];
+        int row = nk;
         for (int g = 0; g < S.ng; ++g, ++row)
             for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = BR[(size_t)g * npv + t];
         for (int g = 0; g < S.n0; ++g, ++row)
@@ -449,6 +530,11 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
             for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = La[(size_t)l * npv + t];
         for (int l = 0; l < nlin; ++l, ++row)
             for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = Lp[(size_t)l * npv + t];
+        S.o_yel = row;
+        for (int e = 0; e < nel; ++e, ++row)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = GE[(size_t)e * npv + t];
+        for (int e = 0; e < nel; ++e, ++row)
+            for (int t = 0; t < npv; ++t) Wm[(size_t)row * S.kw + t] = HE[(size_t)e * npv + t];
         rc = upload(m, Wm, &S.W);
         if (rc) { delete Bp; hvp_mpc_destroy(m); return rc; }
     }
@@ -461,6 +547,12 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     if (!rc) rc = upload(m, La, &S.La); if (!rc) rc = upload(m, Lz, &S.Lz); if (!rc) rc = upload(m, Lp, &S.Lp);
     if (!rc) rc = upload(m, AT, &S.AT); if (!rc) rc = upload(m, BR, &S.BR); if (!rc) rc = upload(m, wmax, &S.wmax);
     if (!rc) rc = upload(m, B0, &S.B0); if (!rc) rc = upload(m, w0, &S.w0);
+    if (!rc) rc = upload(m, Rz, &S.Rz);
+    if (!rc) {
+        void* pe = nullptr;
+        if (cudaMalloc(&pe, emap.size() * sizeof(int)) != cudaSuccess) rc = fail(-100, "mpc_create: cudaMalloc failed");
+        else { m->dev.push_back(pe); cudaMemcpy(pe, emap.data(), emap.size() * sizeof(int), cudaMemcpyHostToDevice); S.emap = (const int*)pe; }
+    }
     if (!rc) { const double* cn = nullptr; rc = upload(m, std::vector<double>(2, 0.0), &cn); m->counter = (unsigned long long*)cn; }
     if (rc) { hvp_mpc_destroy(m); return rc; }
     // tree splitting of heavy problems (PmSplit): prefix depth of the split; the scratch is sized per batch
@@ -679,6 +771,7 @@ extern "C" int hvp_mpc_eval_dev(hvp_mpc* m, int64_t batch, const double* mass, c
     if (batch < 0) return fail(-4, "mpc_eval: negative batch");
     if (batch == 0) return 0;
     if (!mass || !params || !xg || !ug || !cost) return fail(-1, "mpc_eval: NULL array argument");
+    if (m->S.nel > 0) return fail(-4, "mpc_eval: not available for formulations with eliminated free copies");
     hvp_ctx* c = m->ctx;
     const PmDev& S = m->S;
     CUDA_TRY(cudaSetDevice(c->device));

@@ -126,6 +126,7 @@ struct Warp {
     // tree splitting (PmSplit)
     int sub_M, sub_D, sub_code, sub_ord, budget, stop_nodes;
     double own;                        // objective of this warp's own best leaf
+    const double* yel;                 // gE, hE of the eliminated copies of this problem (PmDev::nel)
     unsigned long long* shared;        // incumbent shared by the warps working on one problem
     const PmSplit* sp;
     int64_t prob;
@@ -186,6 +187,8 @@ struct Warp {
                 LANES(r, S.nres) c += S.wres[r] * yr[r] * yr[r];
                 LANES(l, S.nlin) c += yr[S.nres + l] * yr[S.nres + S.nlin + l];
             }
+            yel = Y + S.o_yel;
+            LANES(e, S.nel) c += 0.5 * yel[e] * yel[S.nel + e];     // - gE' C^-1 gE / 2 of the eliminated copies
         } else {
             // residual constants, param-linear factors, generic right-hand sides, constant rows
             LANES(r, S.nres) {
@@ -879,7 +882,18 @@ struct Warp {
                 for (int k = 0; k <= N; ++k) { xo[k] = 0.0; xo[np1 + k] = 0.0; }
             }
         }
-        if (e_out) LANES(e, S.ne) e_out[e] = ok ? best[nl * N + e] : 0.0;
+        if (e_out) LANES(e, S.ne) {
+            double val = 0.0;
+            if (ok) {
+                const int ix = S.nel ? S.emap[e] : e;
+                if (ix >= 0) val = best[nl * N + ix];
+                else {                                              // eliminated copy: zE* = hE + Rz zK
+                    const int ee = -1 - ix;
+                    val = yel[S.nel + ee] + dot2(S.Rz + (size_t)ee * S.nv, 1, best, S.nv);
+                }
+            }
+            e_out[e] = val;
+        }
         if (lane == 0) {
             *obj = ok ? own : HUGE_VAL;
             *status = limit ? HVP_ST_NODE_LIMIT

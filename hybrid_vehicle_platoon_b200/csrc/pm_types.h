@@ -55,6 +55,15 @@ struct PmDev {                   // kernel argument
     //                   c0 = sum_r w_r c_r^2 + sum_l a_l p_l
     const double* W;
     int mw, kw;
+    // Free copies that appear in NO row (the velocity copies of the naive-ADMM formulation) are eliminated when the
+    // formulation is compiled: with z = (zK, zE) and H0 = [[A, B], [B', C]], minimising over zE gives the reduced
+    // Hessian A - B C^-1 B', gradient gK - B C^-1 gE and constant c - gE' C^-1 gE / 2, and zE* = -C^-1 (B' zK + gE).
+    // nv counts the KEPT variables; ne stays the number of extras REPORTED.  The precompute appends gE and
+    // hE = -C^-1 gE to Y (rows o_yel .. o_yel + 2 nel); emap[e] >= 0: kept extra (index among the kept extras),
+    // < 0: eliminated extra -1 - emap[e]; Rz = -C^-1 B' ([nel][nv]).
+    int nel, o_yel;
+    const int* emap;             // [ne]
+    const double* Rz;            // [nel][nv]
     // shared-memory carve-up (offsets in doubles / ints), filled by pm_layout()
     int o_hinv, o_ginv, o_nact, o_vec, o_cres, o_bgen, o_pvec, o_misc, smem_doubles;
     int o_int, smem_bytes;
