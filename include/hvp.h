@@ -176,7 +176,8 @@ typedef struct {
 typedef struct hvp_mpc hvp_mpc;
 int hvp_mpc_create(hvp_ctx* ctx, const hvp_mpc_desc* desc, hvp_mpc** out);
 int hvp_mpc_destroy(hvp_mpc* mpc);
-/* info[8] = { n_var, n_extra, n_param, n_modes, n_local, N, n_rows (coupling), smem bytes per warp } */
+/* info[8] = { n_var (variables of a node QP after the compile-time elimination of free copies that appear in no
+ * row), n_extra (free copies REPORTED in `extra`), n_param, n_modes, n_local, N, n_rows (coupling), smem bytes per warp } */
 int hvp_mpc_info(const hvp_mpc* mpc, int32_t* info);
 /* PWA mode table of the model: lo/hi velocity interval and the gear (1..6) of each of n_modes modes */
 int hvp_mpc_mode_table(const hvp_mpc* mpc, double* lo, double* hi, int32_t* gear);
