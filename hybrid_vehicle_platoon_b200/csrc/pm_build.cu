@@ -563,6 +563,7 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
         int D = 3 * S.nl > 5 ? 3 * S.nl : 5;
         if (D > S.depth - 1) D = S.depth - 1;
         if (env && atoi(env) == 0) D = 0;
+        else if (env && atoi(env) > 1) D = atoi(env) < S.depth - 1 ? atoi(env) : S.depth - 1;   // explicit prefix depth
         m->split_D = D;
     }
     *out = m;
@@ -607,7 +608,7 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
     }
     if (m->split_D >= 1 && !fixed_modes && m->S.max_nodes == 0) {
         // cap heavy problems x M warps each; sized from the batch (grow-only)
-        static const int envM = getenv("HVP_MPC_SPLIT_M") ? atoi(getenv("HVP_MPC_SPLIT_M")) : 64;
+        static const int envM = getenv("HVP_MPC_SPLIT_M") ? atoi(getenv("HVP_MPC_SPLIT_M")) : 128;
         static const int envB = getenv("HVP_MPC_BUDGET") ? atoi(getenv("HVP_MPC_BUDGET")) : 128;
         size_t cap = (size_t)batch / 8;
         if (cap < 256) cap = 256;
