@@ -35,8 +35,8 @@ class BatchedDecentSweep:
         # Which kernel solves the local MIQPs.  "local": the specialised per-vehicle kernel (csrc/local_miqp.cu) --
         # fastest on the short-horizon, constant-spacing problems of the headline benchmark.  "compiled": the LOCAL
         # formulation of the compiled-MPC kernel (csrc/pm_kernel.cu), whose interval-hull tightening and splitting of
-        # heavy trees over 64 warps tame the long tail of hard instances -- long horizons and the time-headway policy
-        # (N = 10, headway: worst tree 13 000 -> 6 000 nodes and searched by 64 warps; 464 -> 52 ms per 20 480 MIQPs).
+        # heavy trees over many warps tame the long tail of hard instances -- long horizons and the time-headway policy
+        # (N = 10, headway: worst tree 13 000 -> 6 000 nodes and searched by 64-128 warps; 464 -> 52 ms per 20 480 MIQPs).
         if solver not in ("auto", "local", "compiled"):
             raise ValueError("solver must be 'auto', 'local' or 'compiled'")
         # "auto" follows the measured crossover (scripts/diag_mixed.py, n = 10, 5 timesteps, 53 / 4096 scenarios):
