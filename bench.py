@@ -217,6 +217,29 @@ def admm_loop_leg(ctx, S=1024, T=2, n=15, N=8, iters=20):
             "optimal_frac": float((out["status"] == 2).mean()), "rollout_exceptions": int((out["errors"] != 0).any(0).sum())}
 
 
+def gadmm_loop_leg(ctx, S=256, T=2, n=15, N=8, iters=100):
+    """BASELINE.json configs[2], the convex half: switching ("g") ADMM at n = 15, N = 8 for S scenarios on the device
+    (sweep.BatchedGAdmmSweep): per round the S*n fixed-mode QPs are one launch per role through the FP64 tensor-core
+    precompute, z / y updates and the re-identification of the mode sequences are torch ops; up to two warm starts per
+    timestep, 100 rounds each (fleet_g_admm.py:255-301, :405)."""
+    from hybrid_vehicle_platoon_b200.sweep import BatchedGAdmmSweep
+    from hybrid_vehicle_platoon_b200.misc import ConstantVelocityLeaderTrajectory
+    rng = np.random.default_rng(1234 + 2)
+    v = np.floor(rng.uniform(12, 28, (S, n))); gaps = rng.uniform(60, 120, (S, n))
+    p = np.floor(3000.0 - np.cumsum(gaps, 1) + gaps[:, :1])
+    x0 = np.empty((S, 2 * n)); x0[:, 0::2] = p; x0[:, 1::2] = v
+    lx = ConstantVelocityLeaderTrajectory(p=3000, v=20, trajectory_len=T + N + 10, ts=1).get_leader_trajectory()
+    sw = BatchedGAdmmSweep(n, N, admm_iters=iters, rho=0.5, ctx=ctx)
+    sw.run(x0[:16], lx, 1)
+    t0 = time.perf_counter()
+    out = sw.run(x0, lx, T)
+    dt = time.perf_counter() - t0
+    rounds = S * iters * (1 + 2 * (T - 1))            # one warm start at t = 0, two afterwards
+    return {"value": rounds / dt, "unit": "scenario-ADMM-rounds/s", "qp_solves_per_s": rounds * n / dt, "scenarios": S,
+            "timesteps": T, "admm_iters": iters, "seconds": dt, "solved_frac": float(out["solved"].mean()),
+            "rollout_exceptions": int((out["errors"] != 0).any(0).sum())}
+
+
 def mixed_sweep_leg(ctx, rank, world, dev, S=4096, T=10):
     """BASELINE.json configs[3]: Monte-Carlo sweep of S synthetic platoon scenarios with n ~ U{5..15}, N ~ U{4..10},
     stop-and-go leader with random change steps / speeds, 50/50 constant spacing vs time headway, whole
@@ -565,6 +588,7 @@ def main():
         other.update(shared_legs)
         other["closed_loop_decent_n10_N6 (configs[3] shape: 4096 scenarios, on-device episode)"] = closed_loop_leg(ctx)
         other["closed_loop_naive_admm_n15_N8 (configs[2]: 1024 scenarios x 20 ADMM rounds per timestep)"] = admm_loop_leg(ctx)
+        other["closed_loop_g_admm_n15_N8 (configs[2]: 256 scenarios x 100 ADMM rounds x <= 2 warm starts per timestep)"] = gadmm_loop_leg(ctx)
 
         out = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,

@@ -578,7 +578,7 @@ class BatchedGAdmmSweep:
 
     def _const_vel_u(self, x, mass):  # PwaGearVehicle.get_u_for_constant_vel (models.py:537-556), vectorised
         S, n = mass.shape
-        v = x.view(S, n, 2)[:, :, 1]
+        v = x.view(S, n, 2)[:, :, 1].contiguous()
         r = self.torch.bucketize(v, self.edges + 1e-4, right=False)
         return (1.0 / (self.bg[r] / mass)) * (-(-(self.cf[r]) / mass) * v - (-self.mug - self.dd[r] / mass))
 
