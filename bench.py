@@ -217,7 +217,7 @@ def admm_loop_leg(ctx, S=1024, T=2, n=15, N=8, iters=20):
             "optimal_frac": float((out["status"] == 2).mean()), "rollout_exceptions": int((out["errors"] != 0).any(0).sum())}
 
 
-def gadmm_loop_leg(ctx, S=256, T=2, n=15, N=8, iters=100):
+def gadmm_loop_leg(ctx, S=1024, T=2, n=15, N=8, iters=100):
     """BASELINE.json configs[2], the convex half: switching ("g") ADMM at n = 15, N = 8 for S scenarios on the device
     (sweep.BatchedGAdmmSweep): per round the S*n fixed-mode QPs are one launch per role through the FP64 tensor-core
     precompute, z / y updates and the re-identification of the mode sequences are torch ops; up to two warm starts per
@@ -588,7 +588,7 @@ def main():
         other.update(shared_legs)
         other["closed_loop_decent_n10_N6 (configs[3] shape: 4096 scenarios, on-device episode)"] = closed_loop_leg(ctx)
         other["closed_loop_naive_admm_n15_N8 (configs[2]: 1024 scenarios x 20 ADMM rounds per timestep)"] = admm_loop_leg(ctx)
-        other["closed_loop_g_admm_n15_N8 (configs[2]: 256 scenarios x 100 ADMM rounds x <= 2 warm starts per timestep)"] = gadmm_loop_leg(ctx)
+        other["closed_loop_g_admm_n15_N8 (configs[2]: 1024 scenarios x 100 ADMM rounds x <= 2 warm starts per timestep)"] = gadmm_loop_leg(ctx)
 
         out = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
