@@ -1,0 +1,135 @@
+"""Closed-loop parity against the REFERENCE's own coordinator code.
+
+tests/golden/fleet_golden.npz holds X / U / R of 47 closed loops produced by the reference's unmodified
+fleet_{cent,decent,seq}_mld.py, fleet_event_based.py, fleet_naive_admm.py (their coordinators and
+simulate()), env.py, models.py and misc/* with only the MPC class names re-bound to the repo's controllers
+(tests/golden/make_fleet_golden.py).  Here the same runs are replayed with the REPO's coordinators, env and
+Sim objects:
+  * on the CPU oracle backend (not gpu): isolates the coordinator / env / agent-loop restatement -- the MPC
+    backend is the same as in the golden runs, so trajectories must agree to round-off;
+  * on libhvp.so (gpu): the full product path, tolerance 1e-6 on X and U (BASELINE.json asks 1e-4);
+  * through the on-device Batched*Sweep classes (gpu): several golden runs per sweep, same tolerance.
+Citations: fleet_decent_mld.py:314-455, fleet_seq_mld.py:332-431, fleet_event_based.py:460-646,
+fleet_naive_admm.py:379-587, fleet_cent_mld.py:80-101."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import hybrid_vehicle_platoon_b200 as hvp
+from oracle_backend import oracle_backend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "fleet_golden.npz"))
+META = {m["name"]: m for m in json.loads(str(G["meta"]))}
+
+# the CPU suite replays one run per category (the whole set takes minutes on the oracle); the GPU suite all
+CPU_SUBSET = ["decent_default_s1", "seq_default_s2", "decent_task2_s0", "seq_task2_s1", "seq_task2_lead3_s0",
+              "decent_task2_lead2_s1", "decent_default_two_point", "decent_default_sat", "decent_friction_gear",
+              "seq_friction_gear", "decent_task2_C2_n10_N6", "seq_task2_C2_n10_N6", "cent_default_C1_s0",
+              "cent_task2_C1_s1", "cent_task2_lead1", "cent_friction_gear", "event_default_s1", "event_task2_s1",
+              "event_task2_lead2_s0", "event_friction_gear", "admm_default_s1", "admm_task2_s0", "admm_task2_lead1_s0",
+              "admm_friction_gear", "admm_task2_C3_n15_N8"]
+
+
+def make_sim(spec):
+    """The repo's Sim objects, built the way tests/golden/make_fleet_golden.py builds the reference's."""
+    if spec["task"] == 2:
+        sim = hvp.Sim_n_task_2(spec["n"], seed=spec.get("mass_seed", 0), leader_index=spec.get("leader_index"),
+                               N=spec["N"])
+    else:
+        sim = hvp.Sim()
+        sim.n, sim.N = spec["n"], spec["N"]
+        sim.id = f"default_n_{sim.n}_N_{sim.N}"
+    sim.ep_len = spec["ep_len"]
+    if "model" in spec:
+        sim.vehicle_model_type = spec["model"]
+    return sim
+
+
+def replay(name):
+    m = META[name]
+    sim = make_sim(m["spec"])
+    li = m["spec"].get("leader_index") or 0
+    mod = {"cent": hvp.fleet_cent_mld, "decent": hvp.fleet_decent_mld, "seq": hvp.fleet_seq_mld,
+           "event": hvp.fleet_event_based, "admm": hvp.fleet_naive_admm}[m["ctrl"]]
+    return mod.simulate(sim, seed=m["seed"], leader_index=li, **m["kw"])
+
+
+def agree(name, out, tol):
+    gX, gU, gR = G[f"{name}/X"], G[f"{name}/U"], G[f"{name}/R"]
+    assert out["X"].shape == gX.shape and out["U"].shape == gU.shape
+    dX, dU = np.abs(out["X"] - gX).max(), np.abs(out["U"] - gU).max()
+    assert dX < tol and dU < tol, (name, dX, dU)
+    np.testing.assert_allclose(np.asarray(out["R"], dtype=np.float64).reshape(-1), gR.reshape(-1), rtol=1e-7, atol=tol)
+    np.testing.assert_array_equal(np.asarray(out["violations"], dtype=np.float64), G[f"{name}/violations"])
+    np.testing.assert_array_equal(out["leader_x"], G[f"{name}/leader_x"])
+
+
+def test_golden_inventory():
+    assert len(META) == 47
+    assert {m["ctrl"] for m in META.values()} == {"cent", "decent", "seq", "event", "admm"}
+    assert set(CPU_SUBSET) <= set(META)
+
+
+@pytest.mark.parametrize("name", CPU_SUBSET)
+def test_repo_coordinators_match_reference_coordinators_on_oracle(name):
+    with oracle_backend():
+        out = replay(name)
+    agree(name, out, 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(META))
+def test_gpu_closed_loop_matches_reference_coordinators(hvp_ctx, name):
+    agree(name, replay(name), 1e-6)
+
+
+# ---- the on-device sweeps against the same golden runs --------------------------------------------
+def _group(ctrl, pred=lambda m: True):
+    """Golden runs of one controller grouped by everything a Batched*Sweep shares across its scenarios."""
+    groups = {}
+    for name, m in sorted(META.items()):
+        sp = m["spec"]
+        if m["ctrl"] != ctrl or sp.get("model", "pwa_gear") != "pwa_gear" or not pred(m):
+            continue
+        key = (sp["task"], sp["n"], sp["N"], sp["ep_len"], sp.get("leader_index") or 0, json.dumps(m["kw"], sort_keys=True))
+        groups.setdefault(key, []).append(name)
+    return groups
+
+
+def _sweep_inputs(names):
+    sims = [make_sim(META[nm]["spec"]) for nm in names]
+    x0 = np.stack([G[f"{nm}/X"][0] for nm in names])
+    masses = np.array([[800.0] * s.n if s.masses is None else s.masses for s in sims])
+    return sims[0], x0, masses, G[f"{names[0]}/leader_x"]
+
+
+def _sweep_agree(names, r, tol=1e-6):
+    for j, nm in enumerate(names):
+        gX, gU = G[f"{nm}/X"], G[f"{nm}/U"]
+        dX, dU = np.abs(r["X"][:, j] - gX).max(), np.abs(r["U"][:, j] - gU).max()
+        assert dX < tol and dU < tol, (nm, dX, dU)
+        np.testing.assert_allclose(r["R"][:, j], G[f"{nm}/R"].reshape(-1), rtol=1e-7, atol=tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ctrl", ["decent", "seq", "event", "admm"])
+def test_batched_sweeps_match_reference_coordinators(hvp_ctx, ctrl):
+    from hybrid_vehicle_platoon_b200 import sweep as S
+    groups = _group(ctrl, lambda m: "velocity_estimator" not in m["kw"])
+    assert groups
+    for (task, n, N, ep_len, li, kw), names in groups.items():
+        kw = json.loads(kw)
+        sim, x0, masses, leader_x = _sweep_inputs(names)
+        common = dict(masses=masses, spacing_policy=sim.spacing_policy, leader_index=li, ctx=hvp_ctx)
+        if ctrl == "decent":
+            sw = S.BatchedDecentSweep(n, N, **common)
+        elif ctrl == "seq":
+            sw = S.BatchedSeqSweep(n, N, **common)
+        elif ctrl == "event":
+            sw = S.BatchedEventSweep(n, N, event_iters=kw["event_iters"], **common)
+        else:
+            sw = S.BatchedAdmmSweep(n, N, admm_iters=kw["admm_iters"], **common)
+        _sweep_agree(names, sw.run(x0, leader_x, ep_len))
