@@ -255,3 +255,69 @@ def use_all_cores() -> int:
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     lib().hvo_set_threads(int(n))
     return max_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline port (oracle/hvp_cpu_bnb.cpp): the product's branch-and-bound compiled for the host cores.
+# Used ONLY by bench.py's cpu_baseline / --impl reference legs and by the test that checks it against the
+# enumeration oracle above.
+_BNB = {}
+
+
+def _cpu_tag() -> str:
+    """Identifies the host CPU, so that a -march=native build made on another machine is never loaded."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        keep = [ln for ln in txt.splitlines() if ln.startswith(("model name", "flags"))][:2]
+        return hashlib.sha1("\n".join(keep).encode()).hexdigest()[:12]
+    except OSError:
+        return "unknown"
+
+
+def build_cpu_bnb(native: bool = False, force: bool = False) -> str:
+    """Generic build: libhvp_cpu_bnb.so (-O3).  Native build: libhvp_cpu_bnb_native_<cpu tag>.so (-O3 -march=native),
+    compiled on the machine that runs it (a native build does not travel between hosts)."""
+    src = os.path.join(_HERE, "hvp_cpu_bnb.cpp")
+    hdr = os.path.join(_HERE, "..", "hybrid_vehicle_platoon_b200", "csrc", "flat_core.cuh")
+    out = os.path.join(_HERE, f"libhvp_cpu_bnb_native_{_cpu_tag()}.so" if native else "libhvp_cpu_bnb.so")
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O3", "-fopenmp", "-fPIC", "-shared", "-std=c++17"] + (["-march=native"] if native else []) + ["-o", out, src]
+        subprocess.check_call(cmd)
+    return out
+
+
+def _bnb_lib(native: bool):
+    if native not in _BNB:
+        L = C.CDLL(build_cpu_bnb(native))
+        L.hvc_local_miqp_bnb.argtypes = [C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp,
+                                         _dp, _dp, _dp, _ip, _dp, _ip, _ip, _ip]
+        L.hvc_local_miqp_bnb.restype = C.c_int
+        L.hvc_max_threads.restype = C.c_int
+        _BNB[native] = L
+    return _BNB[native]
+
+
+def local_miqp_bnb(N, flags, mass, x0, xf, xb, xl, d0=50.0, t0=0.0, tight=0.0, native=False, threads=None):
+    """The CPU branch-and-bound port on a batch of local MIQPs (same contract as local_miqp; `nodes` instead of
+    `leaves`).  threads=None: every core this process may run on."""
+    L = _bnb_lib(native)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    B = x0.shape[0]
+    c = lambda a, t=np.float64: np.ascontiguousarray(a, dtype=t)
+    flags = c(np.broadcast_to(flags, (B,)), np.int32)
+    mass = c(np.broadcast_to(mass, (B,)))
+    ref = lambda a: np.zeros((B, 2, N + 1)) if a is None else c(a).reshape(B, 2, N + 1)
+    if threads is None:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    L.hvc_set_threads(int(threads))
+    u = np.zeros((B, N)); x = np.zeros((B, 2, N + 1)); modes = np.zeros((B, N), np.int32)
+    obj = np.zeros(B); st = np.zeros(B, np.int32); nodes = np.zeros(B, np.int32); it = np.zeros(B, np.int32)
+    rc = L.hvc_local_miqp_bnb(B, int(N), flags, float(d0), float(t0), float(tight), mass, x0, ref(xf), ref(xb), ref(xl),
+                              u, x, modes, obj, st, nodes, it)
+    if rc != 0:
+        raise ValueError(f"hvc_local_miqp_bnb: unsupported horizon N={N}")
+    return dict(u=u, x=x, modes=modes, obj=obj, status=st, nodes=nodes, qp_iters=it, threads=L.hvc_max_threads())

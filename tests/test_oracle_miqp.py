@@ -68,3 +68,20 @@ def test_infeasible_and_boundary(oracle):
     assert r["status"][0] == 2 and r["modes"][0, 0] in (2, 3)
     assert lo["modes"][0, 0] == 2 and hi["modes"][0, 0] == 3
     assert abs(r["obj"][0] - min(lo["obj"][0], hi["obj"][0])) < 1e-4
+
+
+def test_cpu_bnb_port_matches_enumeration(oracle):
+    """bench.py's CPU arm (oracle/hvp_cpu_bnb.cpp: the product's branch-and-bound compiled for the host) returns the
+    optimum of the independent exhaustive enumeration on the bench distribution and on the stress distribution."""
+    from gen_cases import platoon_local_problems
+    rng = np.random.default_rng(11)
+    for N, stress, d0, t0 in ((6, False, 50.0, 0.0), (6, True, 10.0, 3.0), (4, True, 50.0, 0.0), (8, True, 10.0, 3.0)):
+        c = platoon_local_problems(rng, 40, 10, N, 2, stress, True)
+        a = (N, c["flags"], c["mass"], c["x0"], c["xf"], c["xb"], c["xl"])
+        r = oracle.local_miqp_bnb(*a, d0=d0, t0=t0, threads=2)
+        ro = oracle.local_miqp(*a, d0=d0, t0=t0)
+        assert (r["status"] == ro["status"]).all()
+        ok = ro["status"] == 2
+        rel = np.abs(r["obj"][ok] - ro["obj"][ok]) / np.maximum(1.0, np.abs(ro["obj"][ok]))
+        assert rel.max() < 1e-7, rel.max()
+        assert r["nodes"][ok].mean() < ro["leaves"][ok].mean()
