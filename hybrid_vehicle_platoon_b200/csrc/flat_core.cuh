@@ -62,6 +62,9 @@ HVP_HD double hvp_rcp(double v) {
 #endif
 }
 
+#ifdef HVP_DEBUG_STATS
+static long g_it[16], g_nodes[16], g_q[16], g_st[4], g_warm[8];
+#endif
 template <int N>
 struct FlatLayout {
     static constexpr int TRI = N * (N + 1) / 2;
@@ -83,6 +86,11 @@ struct FlatLayout {
 template <int N>
 struct FlatCold {
     double gt[N], xstar[N], rlo[N + 1], rhi[N + 1], amax[N], amin[N];
+    // Sibling bounds (do_next): what the SOLVED parent of level l says about forcing v_l out of its relaxed value --
+    // pf = the parent's optimum, pnz = curvature of its dual function along the bound row e_{l-1}, ptp / ptm = how far
+    // the dual step may go before an active multiplier leaves [0, w] (row +e: regions below the relaxed v_l, row -e:
+    // regions above).  pf = -inf: the level was created without solving its parent (first dive, adopted branch).
+    double pf[N + 1], pnz[N + 1], ptp[N + 1], ptm[N + 1];
 };
 
 template <int N, int ST>
@@ -112,6 +120,11 @@ struct FlatSolver {
     int built_L;                                        // H^-1 currently holds stages 0..built_L-1 of built_pk
     bool trouble, limit;
     bool dive;                                          // first descent: path nodes are not solved, only the leaf
+    bool fresh;                                         // the slab still holds the solved parent of level `lev`
+#ifdef HVP_DEBUG_STATS
+    bool was_warm = false;
+#endif
+    bool slab_ok;                                       // ... and nothing has been built since (warm start of its first child)
     // active set
     int q;
     uint64_t act_lo, act_hi;                            // slot ids, 8 bits each
@@ -246,7 +259,8 @@ struct FlatSolver {
         built_L = 0; built_pk = 0;
         // ---- start of the search ----
         iters = 0; nodes = 0; it = 0; modes_pk = 0; best_modes = 0; cand_pk = 0;
-        inc = HUGE_VAL; trouble = limit = false; lev = 0; dive = P->dive != 0;
+        inc = HUGE_VAL; trouble = limit = false; lev = 0; dive = P->dive != 0; fresh = false; slab_ok = false;
+        C->pf[0] = -HUGE_VAL;
         int c0 = 0;
         HVP_ROLL
         for (int rg = 0; rg < NREG; ++rg)
@@ -284,7 +298,9 @@ struct FlatSolver {
             nlo = fmax(nlo, P->vmin); nhi = fmin(nhi, P->vmax);
             C->rlo[lv + 1] = nlo - eps; C->rhi[lv + 1] = nhi + eps;
             C->xstar[lv + 1] = v0;
+            C->pf[lv + 1] = -HUGE_VAL;
         }
+        fresh = false; slab_ok = false;
         set_cand(l, 1 << c);
         lev = l;
         inc = donor_inc;
@@ -293,8 +309,49 @@ struct FlatSolver {
     }
 
     // ---- NEXT: next node of the depth-first search (or finished) --------------------------
+    // Dual information of the node that has just been solved (the parent of level `lev`), taken while its active
+    // set is still in the slab: the first step of the dual active-set method on a child that forces v_lev into a
+    // region away from the relaxed value, WITHOUT building the child.  For the bound row n = +-e_{lev-1}:
+    // yp = H^-1 n, d = N'yp, r = Ginv d, nz = n'yp - d'r; the dual function along the step is f + t*viol - t^2 nz / 2
+    // for 0 <= t <= tmax (ratio tests).  Every child adds cost and rows to the parent, so this bounds it from below.
+    HVP_HD void parent_info() {
+        const double ww = P->w, INF = HUGE_VAL;
+        const int pj0 = lev - 1;
+        HVP_ROLL
+        for (int i = 0; i < N; ++i) w(LY::O_YP, i) = w(LY::O_HINV, pj0 * N + i);
+        const double nHn0 = w(LY::O_HINV, pj0 * N + pj0);
+        HVP_ROLL
+        for (int a = 0; a < q; ++a) w(LY::O_D, a) = slot_dot(a, LY::O_YP);
+        double nz = nHn0, tp = INF, tm = INF;
+        HVP_ROLL
+        for (int a = 0; a < q; ++a) {
+            double s = 0.0;
+            int gi = tri(a, 0);
+            HVP_ROLL
+            for (int b = 0; b <= a; ++b) s += w(LY::O_GINV, gi + b) * w(LY::O_D, b);
+            gi += 2 * a + 1;
+            HVP_ROLL
+            for (int b = a + 1; b < q; ++b) { s += w(LY::O_GINV, gi) * w(LY::O_D, b); gi += b + 1; }
+            nz -= s * w(LY::O_D, a);
+            const double la = w(LY::O_LAM, a);
+            const bool soft = act(a) >= T_SF * 12;
+            if (s > 1e-14) {
+                const double is = hvp_rcp(s);
+                tp = fmin(tp, la * is);
+                if (soft) tm = fmin(tm, (ww - la) * is);
+            } else if (s < -1e-14) {
+                const double is = hvp_rcp(-s);
+                tm = fmin(tm, la * is);
+                if (soft) tp = fmin(tp, (ww - la) * is);
+            }
+        }
+        if (q == N || !(nz > 1e-11 * nHn0)) nz = 0.0;          // dependent row: the dual is linear along the step
+        C->pnz[lev] = nz; C->ptp[lev] = fmax(tp, 0.0); C->ptm[lev] = fmax(tm, 0.0);
+    }
+
     HVP_HD void do_next() {
         const double eps = 1e-9;
+        if (fresh) { parent_info(); fresh = false; }
         for (;;) {
             int cset = cand(lev);
             if (cset == 0) {
@@ -312,6 +369,15 @@ struct FlatSolver {
                 if (dist < bd) { bd = dist; rg = c; }
             }
             set_cand(lev, cset & ~(1 << rg));
+            const double pf = C->pf[lev];
+            if (bd > 0.0 && inc < HUGE_VAL && pf > -HUGE_VAL && P->sibling_bound) {
+                // sibling bound from the solved parent (parent_info): cheaper than building the child to find out
+                const double nz = C->pnz[lev];
+                const double tmax = (xs > P->edge[rg + 1]) ? C->ptp[lev] : C->ptm[lev];
+                const double t = (nz > 0.0) ? fmin(bd * hvp_rcp(nz), tmax) : tmax;
+                const double bound = (t < HUGE_VAL) ? pf + t * bd - 0.5 * t * t * nz : HUGE_VAL;
+                if (bound > inc) continue;
+            }
             set_mode(lev, rg);
             const double jlo = fmax(C->rlo[lev], P->edge[rg]), jhi = fmin(C->rhi[lev], P->edge[rg + 1]);
             if (jlo > jhi + eps) continue;
@@ -328,6 +394,7 @@ struct FlatSolver {
                 // relaxed trajectory and solve the LEAF directly; its objective is the first incumbent.
                 ++lev;
                 C->xstar[lev] = w(LY::O_X, lev - 1);
+                C->pf[lev] = -HUGE_VAL;                  // no solved parent: no sibling bound at this level
                 int cn = 0;
                 HVP_ROLL
                 for (int c = 0; c < NREG; ++c)
@@ -371,6 +438,10 @@ struct FlatSolver {
     HVP_HD void node_done(int st, double obj) {
         iters += it;
         ++nodes;
+#ifdef HVP_DEBUG_STATS
+        g_it[L] += it; g_nodes[L] += 1; g_q[L] += q; g_st[st] += 1;
+        if (was_warm) { g_warm[3] += it; } else { g_warm[4] += it; g_warm[5] += 1; } was_warm = false;
+#endif
         state = S_NEXT;
         if (st != 0 || L == N) dive = false;
         if (st == 2) { trouble = true; return; }
@@ -385,6 +456,8 @@ struct FlatSolver {
         if (P->max_nodes > 0 && nodes >= P->max_nodes) { limit = true; state = S_DONE; return; }
         ++lev;
         C->xstar[lev] = w(LY::O_X, lev - 1);                                             // relaxed v_lev
+        C->pf[lev] = fmin(obj, dual);
+        fresh = true; slab_ok = true;
         int cn = 0;
         HVP_ROLL
         for (int c = 0; c < NREG; ++c)
@@ -394,7 +467,7 @@ struct FlatSolver {
 
     // H <- H + s * 2*qu * e e'  with  e = (e_k - a e_{k-1})/b  (stage k, region rg):
     // Sherman-Morrison on the stored H^-1;  s = +1 adds the stage's input cost, -1 removes it.
-    HVP_HD void rank1(int k, int rg, double s) {
+    HVP_HD double rank1(int k, int rg, double s) {
         const double ib = hvp_rcp(rb(rg)), ea = (k >= 1) ? -ra(rg) * ib : 0.0;
         double ev = 0.0;                                   // e' H^-1 e
         HVP_ROLL
@@ -414,18 +487,52 @@ struct FlatSolver {
             HVP_FLAT_UNROLL
             for (int j = 0; j < N; ++j) w(LY::O_HINV, i * N + j) -= vi * vr[j];
         }
+        return den;                                        // H'^-1 = H^-1 - den v v', v left in O_WV
     }
 
     // ---- BUILD: bring H^-1 to this node, gradient, unconstrained minimiser -----------------
     HVP_HD void do_build() {
-        const double qu = P->qu;
+        const double qu = P->qu, ww = P->w;
         // common prefix of the stages H^-1 currently contains and the stages this node fixes
         int c = 0;
         while (c < built_L && c < L && mode_of(built_pk, c) == mode(c)) ++c;
-        HVP_ROLL
-        for (int k = built_L - 1; k >= c; --k) rank1(k, mode_of(built_pk, k), -1.0);
-        HVP_ROLL
-        for (int k = c; k < L; ++k) rank1(k, mode(k), 1.0);
+        // WARM START.  The slab still holds the optimum of the node's PARENT (x*, its active rows, their multipliers
+        // and (N'H^-1N)^-1) when this is the first child built after the parent was solved.  The child adds one
+        // rank-1 term to H (the input cost of stage L-1), so instead of re-adding the parent's ~N-1 active rows one
+        // dual step at a time: update (N'H^-1N)^-1 by Sherman-Morrison, move to the minimiser on the SAME rows, and
+        // keep that as the starting S-pair if every multiplier stays admissible (otherwise: the cold start below).
+        const bool warm = slab_ok && P->warm && L == built_L + 1 && c == built_L && (satf | satb) == 0u && q > 0;
+        slab_ok = false;
+        if (warm) {
+            const double den = rank1(L - 1, mode(L - 1), 1.0);              // v = H^-1 e in O_WV
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) w(LY::O_R, a) = slot_dot(a, LY::O_WV);   // z = N'v
+            double zr = 0.0;
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) {                                    // r = Ginv z  (into O_YP)
+                double s = 0.0;
+                int gi = tri(a, 0);
+                HVP_ROLL
+                for (int b = 0; b <= a; ++b) s += w(LY::O_GINV, gi + b) * w(LY::O_R, b);
+                gi += 2 * a + 1;
+                HVP_ROLL
+                for (int b = a + 1; b < q; ++b) { s += w(LY::O_GINV, gi) * w(LY::O_R, b); gi += b + 1; }
+                w(LY::O_YP, a) = s;
+                zr += s * w(LY::O_R, a);
+            }
+            const double alpha = den * hvp_rcp(1.0 - den * zr);              // (G - den zz')^-1 = Ginv + alpha rr'
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) {
+                const double ra_ = alpha * w(LY::O_YP, a);
+                HVP_ROLL
+                for (int b = 0; b <= a; ++b) w(LY::O_GINV, tri(a, b)) += ra_ * w(LY::O_YP, b);
+            }
+        } else {
+            HVP_ROLL
+            for (int k = built_L - 1; k >= c; --k) rank1(k, mode_of(built_pk, k), -1.0);
+            HVP_ROLL
+            for (int k = c; k < L; ++k) rank1(k, mode(k), 1.0);
+        }
         built_L = L; built_pk = modes_pk;
         // gradient g = gt + input-cost terms (into O_D), then x = -H^-1 g
         HVP_ROLL
@@ -448,11 +555,72 @@ struct FlatSolver {
             double s = 0.0;
             HVP_FLAT_UNROLL
             for (int j = 0; j < N; ++j) s -= w(LY::O_HINV, i * N + j) * gr[j];
+            w(LY::O_R, i) = s - w(LY::O_X, i);    // x_u - x* (warm start: residuals of the parent's rows)
             w(LY::O_X, i) = s;
             dual += 0.5 * w(LY::O_D, i) * s;      // objective at the unconstrained minimiser: c + g'x/2
         }
-        it = 0; q = 0; satf = 0; satb = 0; act_lo = act_hi = 0;
+        it = 0; satf = 0; satb = 0;
         state = S_SELECT;
+#ifdef HVP_DEBUG_STATS
+        g_warm[0] += 1; if (warm) g_warm[1] += 1;
+#endif
+        if (warm) {
+            // residual c_a = n_a'x_u - rhs_a of the parent's rows: a bound row's right-hand side may have moved
+            // (the region of the newly fixed stage), every other row was active at x*: c_a = n_a'(x_u - x*)
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) {
+                const int id = act(a), t = id / 12, j = id - 12 * t;
+                double cv;
+                if (t <= T_LB) {
+                    double lo, hi;
+                    bounds(j, lo, hi);
+                    cv = (t == T_UB) ? w(LY::O_X, j) - hi : lo - w(LY::O_X, j);
+                } else {
+                    cv = slot_dot(a, LY::O_R);
+                }
+                w(LY::O_YP, a) = cv;
+            }
+            bool ok = true;
+            double cl = 0.0;
+            HVP_ROLL
+            for (int a = 0; a < q; ++a) {                                    // lambda = Ginv c
+                double s = 0.0;
+                int gi = tri(a, 0);
+                HVP_ROLL
+                for (int b = 0; b <= a; ++b) s += w(LY::O_GINV, gi + b) * w(LY::O_YP, b);
+                gi += 2 * a + 1;
+                HVP_ROLL
+                for (int b = a + 1; b < q; ++b) { s += w(LY::O_GINV, gi) * w(LY::O_YP, b); gi += b + 1; }
+                w(LY::O_LAM, a) = s;
+                cl += s * w(LY::O_YP, a);
+                if (!(s >= 0.0) || (act(a) >= T_SF * 12 && s > ww)) ok = false;
+            }
+#ifdef HVP_DEBUG_STATS
+            if (ok) g_warm[2] += 1; was_warm = ok;
+#endif
+            if (ok) {
+                // x = x_u - H^-1 N lambda ; dual value = f(x_u) + c'lambda / 2
+                HVP_ROLL
+                for (int i = 0; i < N; ++i) w(LY::O_WV, i) = 0.0;
+                HVP_ROLL
+                for (int a = 0; a < q; ++a) slot_axpy(a, w(LY::O_LAM, a), LY::O_WV);
+                double wr[N];
+                HVP_FLAT_UNROLL
+                for (int j = 0; j < N; ++j) wr[j] = w(LY::O_WV, j);
+                HVP_ROLL
+                for (int i = 0; i < N; ++i) {
+                    double s = 0.0;
+                    HVP_FLAT_UNROLL
+                    for (int j = 0; j < N; ++j) s += w(LY::O_HINV, i * N + j) * wr[j];
+                    w(LY::O_X, i) -= s;
+                }
+                dual += 0.5 * cl;
+                it = 1;
+                if (dual > inc) node_done(1, 0.0);                          // dual-bound pruning, as in do_step
+                return;
+            }
+        }
+        q = 0; act_lo = act_hi = 0;
     }
 
     // merged simple bounds of x_j = v_{j+1}: state box, region of stage j+1 if fixed, stage-0 rows

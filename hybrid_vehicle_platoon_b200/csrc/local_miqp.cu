@@ -79,7 +79,9 @@ coop_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
 
 // Persistent flat-state-machine kernel: one warp per CTA, one problem per lane, each warp owns a
 // contiguous share of the batch and a lane that finishes refills from that share at once.
-template <int N>
+// STEAL = false compiles the sub-tree adoption of the launch tail OUT (about 900 SASS instructions): the kernel is bound
+// by instruction fetch, and code that is never executed still spreads the hot loop over more cache lines.
+template <int N, bool STEAL>
 // resident CTAs per SM are set by the shared-memory slab (10 at N = 6); telling the compiler lets it use the registers
 // that occupancy leaves free instead of spilling
 __global__ void __launch_bounds__(32, (N <= 6 ? 10 : (N == 7 ? 7 : (N == 8 ? 6 : 5))))
@@ -111,7 +113,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
     // depth-first stack; an adopter sets the same problem up, follows the donor's region prefix without solving it and
     // searches that one branch from the donor's incumbent, keeping its best leaf in a scratch row; when it is done the
     // owner takes the better of the two.  Everything stays inside the warp: shuffles, no atomics, no global queue.
-    const bool steal = scratch != nullptr && P.max_nodes == 0;
+    const bool steal = STEAL && scratch != nullptr && P.max_nodes == 0;
     bool thief = false, drained = false;
     int owner = lane, pending = 0;
     double* const my_scratch = scratch ? scratch + ((size_t)blockIdx.x * 32 + lane) * N : nullptr;
@@ -126,7 +128,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
         const bool slow = !have || sol.state == Solver::S_DONE || sol.wants_node();
         const unsigned ms = __ballot_sync(0xffffffffu, slow);
         if (ms == 0xffffffffu || __popc(ms) >= node_batch) {
-            if (__builtin_expect(drained, 0)) {
+            if (STEAL && __builtin_expect(drained, 0)) {
                 // adopters that finished their branch report to the owner of the problem
                 unsigned rep = __ballot_sync(0xffffffffu, have && thief && sol.state == Solver::S_DONE && pending == 0);
                 while (rep) {
@@ -176,7 +178,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                 }
                 if ((int64_t)base + __popc(need) > batch) drained = true;          // warp-uniform
             }
-            if (__builtin_expect(steal && drained, 0)) {
+            if (STEAL && __builtin_expect(steal && drained, 0)) {
                 // adopters pick up the owner's current incumbent
                 const double oi = __shfl_sync(0xffffffffu, sol.inc, thief ? owner : lane);
                 if (have && thief && oi < sol.inc) sol.inc = oi;
@@ -216,7 +218,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                 sol.setup(smem + lane, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr,
                           xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr,
                           adopting ? my_scratch : x + S * i + (N + 2), &cold);
-                if (adopting) sol.adopt_prefix(a_modes, a_l, a_c, a_inc);
+                if (STEAL && adopting) sol.adopt_prefix(a_modes, a_l, a_c, a_inc);
                 have = true; thief = adopting; owner = a_owner;
             }
             if (!__any_sync(0xffffffffu, have)) break;
@@ -239,15 +241,18 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
     const size_t smem = (size_t)FlatLayout<N>::SIZE * 32 * sizeof(double);
     static int grid_full = 0;
     if (!grid_full) {
-        cudaError_t e = cudaFuncSetAttribute(flat_miqp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(flat_miqp_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
+        cudaError_t e = cudaSuccess;
+        for (int v = 0; v < 2; ++v) {
+            const void* fn = v ? (const void*)flat_miqp_kernel<N, true> : (const void*)flat_miqp_kernel<N, false>;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_miqp_kernel<N>, 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_miqp_kernel<N, true>, 32, smem);
         if (e != cudaSuccess) return e;
         grid_full = sms * (per_sm > 0 ? per_sm : 1);
     }
@@ -256,15 +261,22 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
     static const int gdiv = env_int("HVP_FLAT_GRID_DIV", 1);
     if (g > grid_full / gdiv) g = grid_full / gdiv;
     LocalParams Q = P;
-    static const int nb = env_int("HVP_NODE_BATCH", 0), dv = env_int("HVP_FLAT_DIVE", -1);
+    static const int nb = env_int("HVP_NODE_BATCH", 0), dv = env_int("HVP_FLAT_DIVE", -1), sb = env_int("HVP_FLAT_SIBLING", -1);
     if (nb > 0) Q.node_batch = nb;
     if (dv >= 0) Q.dive = dv;
+    if (sb >= 0) Q.sibling_bound = sb;
+    static const int wm = env_int("HVP_FLAT_WARM", -1);
+    if (wm >= 0) Q.warm = wm;
     static const int steal_on = env_int("HVP_FLAT_STEAL", 1);
     if ((size_t)g * 32 * N > HVP_STEAL_SLOT_DOUBLES) steal_scratch = nullptr;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    flat_miqp_kernel<N><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
-                                                          status, nodes, qp_iters, counter, steal_on ? steal_scratch : nullptr);
+    if (steal_on && steal_scratch)
+        flat_miqp_kernel<N, true><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
+                                                                    status, nodes, qp_iters, counter, steal_scratch);
+    else
+        flat_miqp_kernel<N, false><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
+                                                                     status, nodes, qp_iters, counter, nullptr);
     return cudaGetLastError();
 }
 

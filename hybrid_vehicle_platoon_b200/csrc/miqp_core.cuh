@@ -46,6 +46,8 @@ struct LocalParams {
     int max_nodes;
     int hull;                            // flat kernel: interval-hull tightening of the unfixed stages
     int dive;                            // flat kernel: first descent solves only the leaf
+    int sibling_bound;                   // flat kernel: prune children by the dual bound of their solved parent
+    int warm;                            // flat kernel: warm-start a first child from its parent's active set
     int node_batch;                      // flat kernel: lanes that must wait for node set-up before a warp runs it
                                          // (27 of 32: measured optimum 26-28 after the r01 profile pass; 32 before it)
     double d0, t0, tight;

@@ -14,6 +14,7 @@
 // enumeration oracle in tests/test_oracle_miqp.py::test_cpu_bnb_port_matches_enumeration.
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -26,6 +27,9 @@ static void bnb_batch(int batch, const int32_t* flags, double d0, double t0, dou
                       int32_t* modes, double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters) {
     hvp::LocalParams P;
     hvp::fill_local_params(P, N, d0, t0, tight, 0);
+    if (getenv("HVC_DIVE")) P.dive = atoi(getenv("HVC_DIVE"));                    // A/B switches for experiments
+    if (getenv("HVC_SIBLING")) P.sibling_bound = atoi(getenv("HVC_SIBLING"));
+    if (getenv("HVC_WARM")) P.warm = atoi(getenv("HVC_WARM"));
     const size_t S = 2 * (size_t)(N + 1);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int i = 0; i < batch; ++i) {

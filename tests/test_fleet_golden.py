@@ -80,10 +80,18 @@ def test_repo_coordinators_match_reference_coordinators_on_oracle(name):
     agree(name, out, 1e-9)
 
 
+def _tol(ctrl):
+    """BASELINE.json asks 1e-4 on closed-loop trajectories.  The single-pass controllers are held to 1e-6; the
+    iterative ones (naive ADMM: up to 20 rounds of n MIQPs per timestep, event-based: up to 4) to the stated 1e-4 --
+    GPU and oracle agree to ~1e-9 per solve, and a consensus iteration over non-convex local problems amplifies
+    that over tens of rounds x tens of timesteps (largest observed: 9.5e-5 on admm_default_s3 after 300 rounds)."""
+    return 1e-4 if ctrl in ("admm", "event") else 1e-6
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(META))
 def test_gpu_closed_loop_matches_reference_coordinators(hvp_ctx, name):
-    agree(name, replay(name), 1e-6)
+    agree(name, replay(name), _tol(META[name]["ctrl"]))
 
 
 # ---- the on-device sweeps against the same golden runs --------------------------------------------
@@ -132,4 +140,4 @@ def test_batched_sweeps_match_reference_coordinators(hvp_ctx, ctrl):
             sw = S.BatchedEventSweep(n, N, event_iters=kw["event_iters"], **common)
         else:
             sw = S.BatchedAdmmSweep(n, N, admm_iters=kw["admm_iters"], **common)
-        _sweep_agree(names, sw.run(x0, leader_x, ep_len))
+        _sweep_agree(names, sw.run(x0, leader_x, ep_len), _tol(ctrl))
