@@ -261,12 +261,9 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
     static const int gdiv = env_int("HVP_FLAT_GRID_DIV", 1);
     if (g > grid_full / gdiv) g = grid_full / gdiv;
     LocalParams Q = P;
-    static const int nb = env_int("HVP_NODE_BATCH", 0), dv = env_int("HVP_FLAT_DIVE", -1), sb = env_int("HVP_FLAT_SIBLING", -1);
+    static const int nb = env_int("HVP_NODE_BATCH", 0), dv = env_int("HVP_FLAT_DIVE", -1);
     if (nb > 0) Q.node_batch = nb;
     if (dv >= 0) Q.dive = dv;
-    if (sb >= 0) Q.sibling_bound = sb;
-    static const int wm = env_int("HVP_FLAT_WARM", -1);
-    if (wm >= 0) Q.warm = wm;
     static const int steal_on = env_int("HVP_FLAT_STEAL", 1);
     if ((size_t)g * 32 * N > HVP_STEAL_SLOT_DOUBLES) steal_scratch = nullptr;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);

@@ -29,7 +29,7 @@ struct VehicleModel {
 // Controller parameters (Params, misc/common_controller_params.py:14-23) + PWA-gear region data.
 inline void fill_local_params(LocalParams& P, int N, double d0, double t0, double tight, int max_nodes) {
     VehicleModel M;
-    P.N = N; P.max_nodes = max_nodes; P.hull = 0; P.dive = 0; P.node_batch = 20; P.sibling_bound = 1; P.warm = 1; P.d0 = d0; P.t0 = t0; P.tight = tight;
+    P.N = N; P.max_nodes = max_nodes; P.hull = 0; P.dive = 1; P.node_batch = 27; P.sibling_bound = 1; P.warm = 1; P.d0 = d0; P.t0 = t0; P.tight = tight;
     P.qxp = 1.0; P.qxv = 0.1; P.qu = 1.0; P.w = 1e4;
     P.a_acc = 2.5; P.a_dec = -2.0; P.d_safe = 25.0;
     P.vmin = M.v_min; P.vmax = M.v_max; P.pmin = M.p_min; P.pmax = M.p_max;

@@ -2,9 +2,11 @@
 // bench.py's cpu_baseline / `--impl reference` legs ONLY (test infrastructure; the product never loads it).
 //
 // What it is: the product's own branch-and-bound (depth-first over the PWA region sequence, relaxed
-// unfixed stages, bounded-multiplier dual active-set QP, dual-bound pruning, first dive; the algorithm of
-// hybrid_vehicle_platoon_b200/csrc/flat_core.cuh, which is written to compile for the host as well)
-// compiled with -O3 -march=native and run under OpenMP over every host core, one problem per task.
+// unfixed stages, bounded-multiplier dual active-set QP, dual-bound pruning; the algorithm of
+// hybrid_vehicle_platoon_b200/csrc/flat_core.cuh, which is written to compile for the host as well) WITH the
+// two refinements that pay on a CPU (sibling bounds from the parent's dual, warm-started first children:
+// FlatSolver<N, 1, ALG2 = true>; a third less work per solve, measured slower on the GPU and therefore not
+// in the CUDA kernels), compiled with -O3 -march=native and run under OpenMP over every host core.
 // Problem definition: fleet_decent_mld.py:61-208 on dmpcpwa MpcMld.
 //
 // Why it exists: the independent checker (hvp_oracle.c) enumerates every reachable mode sequence
@@ -27,18 +29,19 @@ static void bnb_batch(int batch, const int32_t* flags, double d0, double t0, dou
                       int32_t* modes, double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters) {
     hvp::LocalParams P;
     hvp::fill_local_params(P, N, d0, t0, tight, 0);
+    P.dive = 0; P.sibling_bound = 1; P.warm = 1;        // the variant that is fastest on a CPU (flat_core.cuh: ALG2)
     if (getenv("HVC_DIVE")) P.dive = atoi(getenv("HVC_DIVE"));                    // A/B switches for experiments
     if (getenv("HVC_SIBLING")) P.sibling_bound = atoi(getenv("HVC_SIBLING"));
     if (getenv("HVC_WARM")) P.warm = atoi(getenv("HVC_WARM"));
     const size_t S = 2 * (size_t)(N + 1);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int i = 0; i < batch; ++i) {
-        hvp::FlatSolver<N, 1> sol;
+        hvp::FlatSolver<N, 1, true> sol;
         double W[hvp::FlatLayout<N>::SIZE];
         hvp::FlatCold<N> cold;
         sol.setup(W, &P, flags[i], mass[i], x0 + 2 * (size_t)i, xf ? xf + S * i : nullptr, xb ? xb + S * i : nullptr,
                   xl ? xl + S * i : nullptr, x + S * i + (N + 1) + 1, &cold);
-        while (sol.state != hvp::FlatSolver<N, 1>::S_DONE) sol.trip();
+        while (sol.state != hvp::FlatSolver<N, 1, true>::S_DONE) sol.trip();
         hvp::LocalResult R = sol.finish(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
         obj[i] = R.obj; status[i] = R.status; nodes[i] = R.nodes; qp_iters[i] = R.qp_iters;
     }
