@@ -35,6 +35,7 @@ struct hvp_ctx {
 };
 constexpr int HVP_COUNTER_RING = 256;
 constexpr int HVP_STREAM_SLOTS = 64;
+constexpr int HVP_MAX_DEVICES = 64;   // per-device caches of function attributes / occupancy
 constexpr size_t HVP_STEAL_SLOT_DOUBLES = (size_t)3 << 17;   // 3 MiB of doubles: >= grid x 32 lanes x N for every N (<= 2.6 MB)
 int hvp_fail(int code, const char* fmt, ...);          // records the thread's error text, returns code
 int hvp_ensure_dbuf(hvp_ctx* c, size_t bytes);

@@ -239,7 +239,12 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
                                double* x, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                                int32_t* qp_iters, cudaStream_t stream) {
     const size_t smem = (size_t)FlatLayout<N>::SIZE * 32 * sizeof(double);
-    static int grid_full = 0;
+    // attributes and occupancy are per DEVICE (several devices per process: Context(device)): cached per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int grid_cache[HVP_MAX_DEVICES] = {0};
+    int uncached = 0;
+    int& grid_full = (dev >= 0 && dev < HVP_MAX_DEVICES) ? grid_cache[dev] : uncached;
     if (!grid_full) {
         cudaError_t e = cudaSuccess;
         for (int v = 0; v < 2; ++v) {
@@ -249,8 +254,7 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
             e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
         }
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_miqp_kernel<N, true>, 32, smem);
         if (e != cudaSuccess) return e;
@@ -334,7 +338,11 @@ cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter,
 #define HVP_LAUNCH(NM)                                                                                   \
     {                                                                                                    \
         const size_t smem = (size_t)(LOCAL_BLOCK / 32) * LocalLayout<NM>::SIZE * 32 * sizeof(double);    \
-        static bool configured = false;                                                                  \
+        static bool configured_dev[HVP_MAX_DEVICES] = {false};                                           \
+        int dev__ = 0;                                                                                   \
+        cudaGetDevice(&dev__);                                                                           \
+        bool uncached__ = false;                                                                         \
+        bool& configured = (dev__ >= 0 && dev__ < HVP_MAX_DEVICES) ? configured_dev[dev__] : uncached__; \
         if (!configured) {                                                                               \
             cudaError_t e = cudaFuncSetAttribute(local_miqp_kernel<NM>,                                  \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/hvp.h"
@@ -29,6 +30,11 @@ using namespace hvp;
     } while (0)
 
 struct hvp_mpc {
+    // Calls on one handle are serialised: the scratch buffers (ybuf, split / shard scratch, work counter) belong to the
+    // handle, and a call both (re)allocates them and enqueues a launch SEQUENCE that must not interleave with another
+    // thread's (dist.ThreadRanks plays several ranks on one handle).  Concurrent calls must also use the same stream:
+    // the device-side scratch is shared.
+    std::mutex mu;
     hvp_ctx* ctx;
     hvp_mpc_desc desc;
     PmDev S;
@@ -45,6 +51,13 @@ struct hvp_mpc {
     PmScratch shard;             // scratch of hvp_mpc_solve_shard_dev: batch x groups work items
     void* shard_mem = nullptr;
     size_t shard_items = 0;
+};
+
+// hvp_mpc_solve_host / hvp_mpc_eval_host call the *_dev entry points on the same handle: the lock is taken once per thread
+static thread_local int hvp_mpc_locked_by_this_thread = 0;
+struct HvpReentry {
+    HvpReentry() { ++hvp_mpc_locked_by_this_thread; }
+    ~HvpReentry() { --hvp_mpc_locked_by_this_thread; }
 };
 
 namespace {
@@ -592,6 +605,10 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
                                  const double* params, const int32_t* fixed_modes, double* u, double* x,
                                  double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                                  int32_t* qp_iters, void* stream) {
+    if (!m) return fail(-1, "hvp_mpc_solve_dev: NULL handle");
+    std::unique_lock<std::mutex> lk__(m->mu, std::defer_lock);
+    if (!hvp_mpc_locked_by_this_thread) lk__.lock();
+    HvpReentry re__;
     if (!m) return fail(-1, "mpc_solve: handle is NULL");
     if (batch < 0) return fail(-4, "mpc_solve: negative batch");
     if (batch == 0) return 0;
@@ -651,6 +668,10 @@ extern "C" int hvp_mpc_solve_shard_dev(hvp_mpc* m, int64_t batch, const double* 
                                        int32_t prefix_depth, int32_t node_budget, const double* incumbent, double* u,
                                        double* x, double* extra, int32_t* modes, double* obj, int32_t* status,
                                        int32_t* nodes, int32_t* qp_iters, void* stream) {
+    if (!m) return fail(-1, "hvp_mpc_solve_shard_dev: NULL handle");
+    std::unique_lock<std::mutex> lk__(m->mu, std::defer_lock);
+    if (!hvp_mpc_locked_by_this_thread) lk__.lock();
+    HvpReentry re__;
     if (!m) return fail(-1, "mpc_solve_shard: handle is NULL");
     if (batch < 0) return fail(-4, "mpc_solve_shard: negative batch");
     if (world < 1 || rank < 0 || rank >= world) return fail(-4, "mpc_solve_shard: rank %d outside world %d", rank, world);
@@ -712,6 +733,10 @@ extern "C" int hvp_mpc_solve_host(hvp_mpc* m, int64_t batch, const double* x0, c
                                   const double* params, const int32_t* fixed_modes, double* u, double* x,
                                   double* extra, int32_t* modes, double* obj, int32_t* status, int32_t* nodes,
                                   int32_t* qp_iters) {
+    if (!m) return fail(-1, "hvp_mpc_solve_host: NULL handle");
+    std::unique_lock<std::mutex> lk__(m->mu, std::defer_lock);
+    if (!hvp_mpc_locked_by_this_thread) lk__.lock();
+    HvpReentry re__;
     if (!m) return fail(-1, "mpc_solve: handle is NULL");
     if (batch < 0) return fail(-4, "mpc_solve: negative batch");
     if (batch == 0) return 0;
@@ -768,6 +793,10 @@ __global__ void pm_gather_x0(int64_t total, int np1, const double* __restrict__ 
 
 extern "C" int hvp_mpc_eval_dev(hvp_mpc* m, int64_t batch, const double* mass, const double* params,
                                 const double* xg, const double* ug, double* cost, void* stream) {
+    if (!m) return fail(-1, "hvp_mpc_eval_dev: NULL handle");
+    std::unique_lock<std::mutex> lk__(m->mu, std::defer_lock);
+    if (!hvp_mpc_locked_by_this_thread) lk__.lock();
+    HvpReentry re__;
     if (!m) return fail(-1, "mpc_eval: handle is NULL");
     if (batch < 0) return fail(-4, "mpc_eval: negative batch");
     if (batch == 0) return 0;
@@ -794,6 +823,10 @@ extern "C" int hvp_mpc_eval_dev(hvp_mpc* m, int64_t batch, const double* mass, c
 
 extern "C" int hvp_mpc_eval_host(hvp_mpc* m, int64_t batch, const double* mass, const double* params,
                                  const double* xg, const double* ug, double* cost) {
+    if (!m) return fail(-1, "hvp_mpc_eval_host: NULL handle");
+    std::unique_lock<std::mutex> lk__(m->mu, std::defer_lock);
+    if (!hvp_mpc_locked_by_this_thread) lk__.lock();
+    HvpReentry re__;
     if (!m) return fail(-1, "mpc_eval: handle is NULL");
     if (batch < 0) return fail(-4, "mpc_eval: negative batch");
     if (batch == 0) return 0;

@@ -1116,14 +1116,15 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     while (gpb > 1 && (size_t)gpb * S.smem_bytes > 200 * 1024) gpb >>= 1;
     const size_t smem = (size_t)gpb * S.smem_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = smem;
-    }
+    // function attributes are per DEVICE (one process may drive several: Context(device)): cached per device
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    static size_t attr_set[HVP_MAX_DEVICES] = {0};
+    if (dev < 0 || dev >= HVP_MAX_DEVICES || smem > attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < HVP_MAX_DEVICES) attr_set[dev] = smem;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int threads = gpb * GW;
     int per_sm = (int)((220 * 1024) / smem);
@@ -1250,14 +1251,17 @@ cudaError_t launch_pm_eval(const PmDev& S, int64_t batch, const double* x0, cons
     int wpb = 4;
     while (wpb > 1 && (size_t)wpb * S.smem_bytes > 200 * 1024) wpb >>= 1;
     const size_t smem = (size_t)wpb * S.smem_bytes;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static size_t attr_set[HVP_MAX_DEVICES] = {0};
+    if (dev < 0 || dev >= HVP_MAX_DEVICES || smem > attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(pm_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = smem;
+        if (dev >= 0 && dev < HVP_MAX_DEVICES) attr_set[dev] = smem;
     }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t blocks = (batch + wpb - 1) / wpb;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     pm_eval_kernel<<<(unsigned)blocks, wpb * 32, smem, stream>>>(S, batch, x0, mass, params, xg, ug, cost);
     return cudaGetLastError();
 }

@@ -57,12 +57,12 @@ def replay(name):
     return mod.simulate(sim, seed=m["seed"], leader_index=li, **m["kw"])
 
 
-def agree(name, out, tol, tol_u=None):
+def agree(name, out, tol, tol_u=None, rtol_r=1e-7):
     gX, gU, gR = G[f"{name}/X"], G[f"{name}/U"], G[f"{name}/R"]
     assert out["X"].shape == gX.shape and out["U"].shape == gU.shape
     dX, dU = np.abs(out["X"] - gX).max(), np.abs(out["U"] - gU).max()
     assert dX < tol and dU < (tol_u or tol), (name, dX, dU)
-    np.testing.assert_allclose(np.asarray(out["R"], dtype=np.float64).reshape(-1), gR.reshape(-1), rtol=1e-7, atol=tol)
+    np.testing.assert_allclose(np.asarray(out["R"], dtype=np.float64).reshape(-1), gR.reshape(-1), rtol=rtol_r, atol=tol)
     np.testing.assert_array_equal(np.asarray(out["violations"], dtype=np.float64), G[f"{name}/violations"])
     np.testing.assert_array_equal(out["leader_x"], G[f"{name}/leader_x"])
 
@@ -107,7 +107,8 @@ KNOWN_TIES = {
 def test_gpu_closed_loop_matches_reference_coordinators(hvp_ctx, name):
     tx, tu = _tol(META[name]["ctrl"])
     if name in KNOWN_TIES:
-        tx, tu = 1e-2, 1e-2
+        agree(name, replay(name), 1e-2, 1e-2, rtol_r=1e-3)     # stage costs of ~8e3 follow the parted trajectories
+        return
     agree(name, replay(name), tx, tu)
 
 
