@@ -22,7 +22,7 @@ from .misc import (  # noqa: F401,E402
 from .models import Platoon, PwaFrictionVehicle, PwaGearVehicle, Vehicle  # noqa: F401,E402
 from .mpc import (  # noqa: F401,E402
     EventLocalMpc, GAdmmLocalMpc, LocalMpcADMM, LocalMpcGear, LocalMpcMld, MpcGearCent, MpcMldCent,
-    eval_compiled_batch, solve_compiled_batch, solve_local_batch,
+    eval_compiled_batch, set_solver_options, solve_compiled_batch, solve_local_batch,
 )
 from . import (  # noqa: F401,E402
     fleet_cent_mld, fleet_decent_mld, fleet_event_based, fleet_g_admm, fleet_naive_admm, fleet_seq_mld,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libhvp.so")
 
-OPTIMAL, INFEASIBLE, NODE_LIMIT, NUMERIC = 2, 3, 8, 12
+OPTIMAL, INFEASIBLE, NODE_LIMIT, TIME_LIMIT, NUMERIC = 2, 3, 8, 9, 12
 FRONT, LEADER, TRAILER = 1, 2, 4
 ENV_QUADRATIC, ENV_REAL_VEHICLE_REF, ENV_MASS_PER_SCENARIO = 1, 2, 4
 
@@ -23,14 +23,15 @@ class EnvDesc(C.Structure):
 
 class LocalDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("max_nodes", C.c_int32), ("d0", C.c_double), ("t0", C.c_double),
-                ("tight", C.c_double)]
+                ("tight", C.c_double), ("mip_gap", C.c_double), ("time_limit_ms", C.c_double)]
 
 
 class MpcDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("model", C.c_int32), ("n_local", C.c_int32), ("N", C.c_int32),
                 ("flags", C.c_int32), ("leader_index", C.c_int32), ("n_front", C.c_int32),
-                ("n_behind", C.c_int32), ("max_nodes", C.c_int32), ("reserved", C.c_int32),
-                ("d0", C.c_double), ("t0", C.c_double), ("tight", C.c_double), ("rho", C.c_double)]
+                ("n_behind", C.c_int32), ("max_nodes", C.c_int32), ("one_norm", C.c_int32),
+                ("d0", C.c_double), ("t0", C.c_double), ("tight", C.c_double), ("rho", C.c_double),
+                ("mip_gap", C.c_double), ("time_limit_ms", C.c_double)]
 
 
 MPC_CENT, MPC_LOCAL, MPC_EVENT, MPC_ADMM, MPC_GADMM = 1, 2, 3, 4, 5

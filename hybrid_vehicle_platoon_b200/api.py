@@ -61,12 +61,14 @@ def rollout_step_device(desc: EnvDesc, batch, x, u, gear, mass, leader, x_out, c
                                      _stream_arg(stream)))
 
 
-def local_desc(N, d0=50.0, t0=0.0, tight=0.0, max_nodes=0) -> LocalDesc:
-    return LocalDesc(int(N), int(max_nodes), float(d0), float(t0), float(tight))
+def local_desc(N, d0=50.0, t0=0.0, tight=0.0, max_nodes=0, mip_gap=0.0, time_limit_ms=0.0) -> LocalDesc:
+    """mip_gap: relative gap at which nodes are pruned (Gurobi MIPGap; 0 = proven optimal); time_limit_ms: per-problem
+    device-clock budget, status 9 with the incumbent when it runs out (0 = none)."""
+    return LocalDesc(int(N), int(max_nodes), float(d0), float(t0), float(tight), float(mip_gap), float(time_limit_ms))
 
 
 def local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0, tight=0.0,
-               max_nodes=0, ctx=None):
+               max_nodes=0, mip_gap=0.0, time_limit_ms=0.0, ctx=None):
     """Batched LocalMpcMld solves (fleet_decent_mld.py:21-223) on host (numpy) buffers.
     x0 (B,2); xf/xb/xl (B,2,N+1) or None; flags (B,) of FRONT|LEADER|TRAILER; mass (B,)."""
     ctx = ctx or default_context()
@@ -78,7 +80,7 @@ def local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0
     for a in (xf, xb, xl):
         if a is not None and a.size != B * 2 * (N + 1):
             raise ValueError(f"reference arrays must have shape ({B}, 2, {N + 1})")
-    d = local_desc(N, d0, t0, tight, max_nodes)
+    d = local_desc(N, d0, t0, tight, max_nodes, mip_gap, time_limit_ms)
     u = np.empty((B, N)); x = np.empty((B, 2, N + 1)); modes = np.empty((B, N), np.int32)
     obj = np.empty(B); status = np.empty(B, np.int32); nodes = np.empty(B, np.int32)
     iters = np.empty(B, np.int32)
@@ -104,11 +106,12 @@ class CompiledMpc:
     reference builds one Gurobi model per controller -- and solved for batches of (x0, mass, params)."""
 
     def __init__(self, kind, N, *, n_local=1, model=_lib.MODEL_PWA_GEAR, flags=0, leader_index=0, n_front=0,
-                 n_behind=0, d0=50.0, t0=0.0, tight=0.0, rho=0.5, max_nodes=0, ctx=None):
+                 n_behind=0, d0=50.0, t0=0.0, tight=0.0, rho=0.5, max_nodes=0, one_norm=False, mip_gap=0.0,
+                 time_limit_ms=0.0, ctx=None):
         self.ctx = ctx or default_context()
         self.desc = MpcDesc(int(kind), int(model), int(n_local), int(N), int(flags), int(leader_index),
-                            int(n_front), int(n_behind), int(max_nodes), 0, float(d0), float(t0), float(tight),
-                            float(rho))
+                            int(n_front), int(n_behind), int(max_nodes), int(bool(one_norm)), float(d0), float(t0),
+                            float(tight), float(rho), float(mip_gap), float(time_limit_ms))
         h = C.c_void_p()
         check(lib().hvp_mpc_create(self.ctx.handle, C.byref(self.desc), C.byref(h)))
         self._h = h

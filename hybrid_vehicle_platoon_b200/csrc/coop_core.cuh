@@ -143,7 +143,8 @@ struct CoopSolver {
     double dual;                 // value of the node's dual function: lower bound on the node optimum
     bool dive;                   // first descent: path nodes are not solved, only the leaf
     uint64_t best_modes, cand_lo, cand_hi;
-    bool trouble, limit;
+    bool trouble, limit, timeout;
+    long long t_start;
     // constraint being added
     int pid, pkind, pj;
     double psgn, pcoef, prhs, nHn, lam_p;
@@ -162,7 +163,7 @@ struct CoopSolver {
 
     HVP_CD void begin() {
         iters = 0; modes_pk = 0; nodes = 0; it = 0;
-        inc = HUGE_VAL; best_modes = 0; cand_lo = cand_hi = 0; trouble = limit = false; dive = P->dive != 0;
+        inc = HUGE_VAL; best_modes = 0; cand_lo = cand_hi = 0; trouble = limit = timeout = false; dive = P->dive != 0; t_start = P->time_limit_ns > 0 ? hvp_now_ns() : 0;
         best = bk.splat(0.0); xstar = bk.splat(v0); rlo = bk.splat(0.0); rhi = bk.splat(0.0);
         lev = 0;
         int c0 = 0;
@@ -242,9 +243,10 @@ struct CoopSolver {
         if (st != 0 || L == N) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
-        if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
+        if (inc < HUGE_VAL && !(obj < hvp_cut(inc, P->mip_gap))) return;              // bound
         if (L == N) { inc = obj; best = x; best_modes = modes_pk; return; }          // leaf
         if (P->max_nodes > 0 && nodes >= P->max_nodes) { limit = true; state = S_DONE; return; }
+        if (P->time_limit_ns > 0 && hvp_now_ns() - t_start > P->time_limit_ns) { timeout = true; state = S_DONE; return; }
         const double eps = 1e-9;
         const I ln = bk.lane();
         ++lev;
@@ -548,7 +550,7 @@ struct CoopSolver {
         const int np1 = N + 1;
         if (inc < HUGE_VAL) {
             R.obj = inc;
-            R.status = limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_OPTIMAL);
+            R.status = timeout ? HVP_ST_TIME_LIMIT : limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_OPTIMAL);
             const I rg = bk.bits3(best_modes, ln);
             const D vprev = bk.up1(best, v0);
             const D uu = (best - ra_l(rg) * vprev - rc_l(rg)) / rb_l(rg);
@@ -561,7 +563,7 @@ struct CoopSolver {
             bk.st(x_out, ln + np1, bk.splat(v0), ln == 0);
         } else {
             R.obj = HUGE_VAL;
-            R.status = limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_INFEASIBLE);
+            R.status = timeout ? HVP_ST_TIME_LIMIT : limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_INFEASIBLE);
             bk.st(u_out, ln, bk.splat(0.0), valid);
             bk.sti(mode_out, ln, bk.splati(-1), valid);
             bk.st(x_out, ln + 1, bk.splat(0.0), valid);

@@ -86,6 +86,7 @@ struct FlatLayout {
 template <int N>
 struct FlatCold {
     double gt[N], xstar[N], rlo[N + 1], rhi[N + 1], amax[N], amin[N];
+    long long t_start;                  // device clock when the problem was picked up (time_limit_ns)
     // Sibling bounds (do_next): what the SOLVED parent of level l says about forcing v_l out of its relaxed value --
     // pf = the parent's optimum, pnz = curvature of its dual function along the bound row e_{l-1}, ptp / ptm = how far
     // the dual step may go before an active multiplier leaves [0, w] (row +e: regions below the relaxed v_l, row -e:
@@ -123,7 +124,7 @@ struct FlatSolver {
     double inc;
     uint64_t modes_pk, best_modes, cand_pk, built_pk;   // 3 bits / stage; 7 candidate bits / level
     int built_L;                                        // H^-1 currently holds stages 0..built_L-1 of built_pk
-    bool trouble, limit;
+    bool trouble, limit, timeout;
     bool dive;                                          // first descent: path nodes are not solved, only the leaf
     bool fresh;                                         // the slab still holds the solved parent of level `lev`
 #ifdef HVP_DEBUG_STATS
@@ -264,7 +265,8 @@ struct FlatSolver {
         built_L = 0; built_pk = 0;
         // ---- start of the search ----
         iters = 0; nodes = 0; it = 0; modes_pk = 0; best_modes = 0; cand_pk = 0;
-        inc = HUGE_VAL; trouble = limit = false; lev = 0; dive = P->dive != 0; fresh = false; slab_ok = false;
+        inc = HUGE_VAL; trouble = limit = timeout = false; lev = 0; dive = P->dive != 0; fresh = false; slab_ok = false;
+        if (P->time_limit_ns > 0) C->t_start = hvp_now_ns();
         if (ALG2) C->pf[0] = -HUGE_VAL;
         int c0 = 0;
         HVP_ROLL
@@ -451,7 +453,7 @@ struct FlatSolver {
         if (st != 0 || L == N) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
-        if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
+        if (inc < HUGE_VAL && !(obj < hvp_cut(inc, P->mip_gap))) return;              // bound
         if (L == N) {                                                                // leaf
             inc = obj; best_modes = modes_pk;
             HVP_ROLL
@@ -459,6 +461,7 @@ struct FlatSolver {
             return;
         }
         if (P->max_nodes > 0 && nodes >= P->max_nodes) { limit = true; state = S_DONE; return; }
+        if (P->time_limit_ns > 0 && hvp_now_ns() - C->t_start > P->time_limit_ns) { timeout = true; state = S_DONE; return; }
         ++lev;
         C->xstar[lev] = w(LY::O_X, lev - 1);                                             // relaxed v_lev
         if (ALG2) { C->pf[lev] = fmin(obj, dual); fresh = true; slab_ok = true; }
@@ -944,7 +947,7 @@ struct FlatSolver {
         const int np1 = N + 1;
         if (inc < HUGE_VAL) {
             R.obj = inc;
-            R.status = limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_OPTIMAL);
+            R.status = timeout ? HVP_ST_TIME_LIMIT : limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_OPTIMAL);
             double p = p0, v = v0;
             x_out[0] = p; x_out[np1] = v;
             HVP_ROLL
@@ -958,7 +961,7 @@ struct FlatSolver {
             }
         } else {
             R.obj = HUGE_VAL;
-            R.status = limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_INFEASIBLE);
+            R.status = timeout ? HVP_ST_TIME_LIMIT : limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_INFEASIBLE);
             HVP_ROLL
             for (int k = 0; k < N; ++k) { u_out[k] = 0.0; mode_out[k] = -1; }
             HVP_ROLL

@@ -227,6 +227,8 @@ static int check_local_desc(const hvp_local_desc* d) {
     if (!d) return fail(-1, "local_miqp: desc is NULL");
     if (d->N < 2 || d->N > 12) return fail(-4, "local_miqp: N=%d out of range [2,12]", d->N);
     if (d->max_nodes < 0) return fail(-4, "local_miqp: negative max_nodes");
+    if (!(d->mip_gap >= 0.0) || !(d->mip_gap < 1.0)) return fail(-4, "local_miqp: mip_gap must be in [0, 1)");
+    if (!(d->time_limit_ms >= 0.0)) return fail(-4, "local_miqp: negative time_limit_ms");
     return 0;
 }
 
@@ -242,7 +244,7 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
     if (!flags || !mass || !x0 || !u || !x || !modes || !obj || !status || !nodes)
         return fail(-1, "local_miqp: NULL array argument");
     LocalParams P;
-    fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes);
+    fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes, desc->mip_gap, desc->time_limit_ms);
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_TRY(cudaEventRecord(c->ev0, st));
@@ -340,7 +342,7 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
             if (xb) CUDA_TRY(cudaMemcpyAsync(dxb + S * o, xb + S * o, nb * S * 8, cudaMemcpyHostToDevice, ss));
             if (xl) CUDA_TRY(cudaMemcpyAsync(dxl + S * o, xl + S * o, nb * S * 8, cudaMemcpyHostToDevice, ss));
             LocalParams P;
-            fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes);
+            fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes, desc->mip_gap, desc->time_limit_ms);
             unsigned long long* counter = nullptr;
             double* steal = nullptr;
             rc = launch_slot(c, ss, &counter, &steal);

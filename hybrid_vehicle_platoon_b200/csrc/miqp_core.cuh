@@ -38,6 +38,22 @@
 
 namespace hvp {
 
+// device clock in ns (%globaltimer); the host builds of the solvers (tests, CPU port) have no time limit
+HVP_HD long long hvp_now_ns() {
+#if defined(__CUDA_ARCH__)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return (long long)t;
+#else
+    return 0;
+#endif
+}
+// an objective must be below this to replace / beat the incumbent
+HVP_HD double hvp_cut(double inc, double gap) {
+    const double a = fabs(inc);
+    return inc - fmax(1e-9 * fmax(1.0, a), gap * a);
+}
+
 constexpr int NREG = 7;
 
 // Constants shared by every problem of a batch (filled on the host, see vehicle_model.h).
@@ -50,6 +66,8 @@ struct LocalParams {
     int warm;                            // flat kernel: warm-start a first child from its parent's active set
     int node_batch;                      // flat kernel: lanes that must wait for node set-up before a warp runs it
                                          // (27 of 32: measured optimum 26-28 after the r01 profile pass; 32 before it)
+    double mip_gap;                      // relative pruning gap (0: proven optimal)
+    long long time_limit_ns;             // per-problem budget on the device clock (0: none)
     double d0, t0, tight;
     double qxp, qxv, qu, w;              // Params.Q_x, Q_u, w (common_controller_params.py:14-23)
     double a_acc, a_dec, d_safe;
@@ -74,6 +92,7 @@ struct LocalResult {
 #define HVP_ST_OPTIMAL 2
 #define HVP_ST_INFEASIBLE 3
 #define HVP_ST_NODE_LIMIT 8
+#define HVP_ST_TIME_LIMIT 9
 #define HVP_ST_NUMERIC 12
 
 // constraint types of the velocity-space node QP (all written as  n'x <= rhs)

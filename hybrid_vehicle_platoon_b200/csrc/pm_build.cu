@@ -382,6 +382,8 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     if (d->kind != HVP_MPC_CENT && d->kind != HVP_MPC_EVENT && d->n_local != 1)
         return fail(-4, "mpc_create: kind %d has exactly one local vehicle", d->kind);
     if (d->max_nodes < 0) return fail(-4, "mpc_create: negative max_nodes");
+    if (!(d->mip_gap >= 0.0) || !(d->mip_gap < 1.0)) return fail(-4, "mpc_create: mip_gap must be in [0, 1)");
+    if (!(d->time_limit_ms >= 0.0)) return fail(-4, "mpc_create: negative time_limit_ms");
     Builder* Bp = nullptr;
     int rc = build_formulation(*d, Bp);
     if (rc) { delete Bp; return rc; }
@@ -392,6 +394,7 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     memset(&S, 0, sizeof S);
     S.nl = B.nl; S.N = B.N; S.ne = B.ne; S.nv = B.nv; S.npar = B.npar; S.npv = B.npv;
     S.depth = B.nl * B.N; S.max_nodes = d->max_nodes;
+    S.mip_gap = d->mip_gap; S.time_limit_ns = (long long)(d->time_limit_ms * 1e6);
     fill_model(S.M, d->model);
     VehicleModel V;
     S.qu = QU; S.w = WSL; S.vmin = V.v_min; S.vmax = V.v_max; S.pmin = V.p_min; S.pmax = V.p_max;

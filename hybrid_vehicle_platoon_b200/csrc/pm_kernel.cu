@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include "hvp_internal.h"
+#include "miqp_core.cuh"   // status codes, hvp_now_ns, hvp_cut
 #include "pm_types.h"
 
 namespace hvp {
@@ -122,7 +123,8 @@ struct Warp {
     // warp-uniform scalars (replicated in registers)
     int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
     double inc, c0, cp, nHn, lam_p, dual;
-    bool p_soft, trouble, limit, dive;
+    bool p_soft, trouble, limit, dive, timeout;
+    long long t_start;
     // tree splitting (PmSplit)
     int sub_M, sub_D, sub_code, sub_ord, budget, stop_nodes;
     double own;                        // objective of this warp's own best leaf
@@ -242,7 +244,8 @@ struct Warp {
         }
         built_L = -1;                      // H^-1 not loaded yet
         iters = nodes = it = q = 0;
-        inc = HUGE_VAL; own = HUGE_VAL; trouble = limit = false; dive = true; sub_ord = 0;
+        inc = HUGE_VAL; own = HUGE_VAL; trouble = limit = timeout = false; dive = true; sub_ord = 0;
+        t_start = S.time_limit_ns > 0 ? hvp_now_ns() : 0;
         lev = 0; L = 0; fixed = (fm != nullptr);
         if (infeas) { state = PS_DONE; __syncwarp(gm); return; }
         if (fixed) {
@@ -385,7 +388,7 @@ struct Warp {
         if (st != 0 || L == S.depth) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
-        if (inc < HUGE_VAL && !(obj < inc - 1e-9 * fmax(1.0, fabs(inc)))) return;      // bound
+        if (inc < HUGE_VAL && !(obj < hvp_cut(inc, S.mip_gap))) return;              // bound
         if (L == S.depth) {                                                           // leaf
             inc = obj; own = obj;
             LANES(j, S.nv) best[j] = x[j];
@@ -395,6 +398,12 @@ struct Warp {
             return;
         }
         if (S.max_nodes > 0 && nodes >= S.max_nodes) { limit = true; state = PS_DONE; return; }
+        if (S.time_limit_ns > 0) {          // warp-uniform decision: lane 0 reads the clock
+            long long now = 0;
+            if (lane == 0) now = hvp_now_ns();
+            now = __shfl_sync(gm, now, 0, GW);
+            if (now - t_start > S.time_limit_ns) { timeout = true; state = PS_DONE; return; }
+        }
         if (stop_nodes > 0 && nodes >= stop_nodes) { limit = true; state = PS_DONE; return; }
         if (budget > 0 && nodes >= budget) {
             // heavy tree: hand it to the sub-tree pass if the list has room, else finish it here
@@ -896,7 +905,7 @@ struct Warp {
         }
         if (lane == 0) {
             *obj = ok ? own : HUGE_VAL;
-            *status = limit ? HVP_ST_NODE_LIMIT
+            *status = timeout ? HVP_ST_TIME_LIMIT : limit ? HVP_ST_NODE_LIMIT
                             : (trouble ? HVP_ST_NUMERIC : (ok ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE));
             *nodes_out = nodes;
             if (iters_out) *iters_out = iters;
@@ -973,7 +982,7 @@ pm_merge_kernel(const __grid_constant__ PmDev S, const __grid_constant__ PmSplit
     const size_t nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
     double bestv = obj[i];                       // incumbent of the budgeted pass (+inf if it had none)
     int bw = -1, nsum = 0, isum = 0;
-    bool numeric = false, limited = false;
+    bool numeric = false, limited = false, timed = false;
     for (int c = 0; c < sp.M; ++c) {
         const size_t w = (size_t)f * sp.M + c;
         if (sobj[w] < bestv) { bestv = sobj[w]; bw = (int)w; }
@@ -981,6 +990,7 @@ pm_merge_kernel(const __grid_constant__ PmDev S, const __grid_constant__ PmSplit
         if (sit) isum += sit[w];
         if (sst[w] == HVP_ST_NUMERIC) numeric = true;
         if (sst[w] == HVP_ST_NODE_LIMIT) limited = true;
+        if (sst[w] == HVP_ST_TIME_LIMIT) timed = true;
     }
     if (bw >= 0) {
         for (size_t e = lane; e < nu; e += 32) { u[nu * i + e] = su_[nu * bw + e]; modes[nu * i + e] = sm_[nu * bw + e]; }
@@ -993,7 +1003,7 @@ pm_merge_kernel(const __grid_constant__ PmDev S, const __grid_constant__ PmSplit
     }
     if (lane == 0) {
         obj[i] = bestv;
-        status[i] = limited ? HVP_ST_NODE_LIMIT
+        status[i] = timed ? HVP_ST_TIME_LIMIT : limited ? HVP_ST_NODE_LIMIT
                             : (numeric ? HVP_ST_NUMERIC : (bestv < HUGE_VAL ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE));
         nodes[i] += nsum;
         if (qp_iters) qp_iters[i] += isum;

@@ -32,6 +32,8 @@ struct PmDev {                   // kernel argument
     int nres, nlin, ng, n0;      // residuals, param-linear cost terms, generic rows, constant rows
     int depth;                   // nl * N branching decisions (stage-major: d = k nl + i)
     int max_nodes;
+    double mip_gap;              // relative pruning gap (0: proven optimal)
+    long long time_limit_ns;     // per-problem budget on the device clock (0: none)
     PmModel M;
     double qu, w, vmin, vmax, pmin, pmax, umin, umax, a_acc, a_dec, tight;
     // device arrays (shared by all problems; read-only, L1/L2 resident)

@@ -43,6 +43,50 @@ __device__ __forceinline__ double div_by(double a, double b, double y) {
     return fma(r, y, q);
 }
 
+// Ten explicit-Euler sub-steps with the gear held (models.py:236-257, Q5).  FAST = u finite and c_fric a power of two:
+// `v + 0*u` is v bit for bit (v > 0 inside a gear's range) and c_fric*(v*v)/m == (v*v)/(m/c_fric), so the loop needs
+// 12 FP64 instructions per sub-step instead of 16; the flat-part test compares the HIGH WORDS of the doubles on the
+// integer pipe (conservative: anything near the edges takes the exact path below).  r02h ncu: in the bench
+// distribution 65 % of the warp-iterations have a lane or two on the sloped part of a traction curve (the PWA gear
+// regions reach 0.06-0.16 m/s beyond the flat part), so that path is a real share of the kernel.
+template <bool FAST>
+__device__ __forceinline__ int32_t substeps(const RolloutParams& P, double& p, double& v, double ui, double zu, double m,
+                                            double ym, double mf, double ymf, double Bu_flat, int j, int i, int v1h,
+                                            int v2h) {
+    const double DT = 1.0 / 10;
+    const double mug = P.mug;
+    asm volatile("" : "+d"(mf), "+d"(ymf));           // loop invariants stay in registers (not re-derived per sub-step)
+#pragma unroll 1
+    for (int s = 0; s < 10; ++s) {
+        double Bu = Bu_flat;                                                 // B(x) u, models.py:109-112
+        const int vh = __double2hiint(v);
+        if (!(vh > v1h && vh < v2h)) {                // conservative: strictly inside by the high words
+            // rare path.  It works on an opaque copy of v, so that its FP64 comparisons cannot be hoisted into the
+            // hot loop (the compiler did exactly that: the integer test bought nothing)
+            double vs = v;
+            asm volatile("" : "+d"(vs));
+            const double v1 = P.tr_v[j][1], v2 = P.tr_v[j][2];
+            if (!(vs >= v1 && vs <= v2)) {
+                const double v0 = P.tr_v[j][0], v3 = P.tr_v[j][3];
+                if (!(vs > v0 && vs < v3))
+                    return ((vs < P.tr_v[0][0] || vs > P.tr_v[5][3]) ? 1 : 3) | (i << 8) | (s << 16);
+                const double t0 = P.tr_t[j][0], t1 = P.tr_t[j][1], t2 = P.tr_t[j][2];
+                double Bv;
+                if (vs < v1) Bv = div_by(div_by(vs - v0, v1 - v0, P.inv_rise[j]) * (t1 - t0) + t0, m, ym);
+                else Bv = div_by(t1 - div_by(vs - v2, v3 - v2, P.inv_fall[j]) * (t1 - t2), m, ym);
+                Bu = Bv * ui;
+            }
+        }
+        const double vv = FAST ? v * v : (P.fric_pow2 ? v * v : P.c_fric * (v * v));
+        const double Av = -div_by(vv, mf, ymf) - mug;                        // models.py:99-107
+        const double va = FAST ? v : v + zu;
+        const double pn = p + DT * va;
+        const double vn = v + DT * (Av + Bu);
+        p = pn; v = vn;
+    }
+    return 0;
+}
+
 __global__ void __launch_bounds__(ROLLOUT_BLOCK, 8)
 rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const double* __restrict__ x,
                const double* __restrict__ u, const int32_t* __restrict__ gear,
@@ -110,7 +154,6 @@ rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const dou
         s_gap[tid] = gapflag;
 
         // ---- ten explicit Euler sub-steps with the gear held (models.py:236-257, Q5) ----
-        const double DT = 1.0 / 10;
         const double vlo = P.tr_v[0][0], vhi = P.tr_v[5][3];
         if (g < 1 || g > 6) {
             // Vehicle.step's own velocity check fires first (models.py:119-122)
@@ -124,33 +167,11 @@ rollout_kernel(const __grid_constant__ RolloutParams P, int64_t batch, const dou
             // by 2^k commutes with rounding), which saves the multiplication by c_fric
             const double mf = P.fric_pow2 ? m * P.inv_c_fric : m, ymf = P.fric_pow2 ? ym * P.c_fric : ym;
             const double zu = 0.0 * ui;                      // the reference adds 0*u to v (models.py:124)
-            const double Bu_flat = Bv_flat * ui;             // loop invariant on the flat part of the curve
-#pragma unroll 1
-            for (int s = 0; s < 10; ++s) {
-                // traction (models.py:43-51).  On the flat part of the curve -- where the PWA-derived
-                // gears always are -- T = t1, T/m is the same correctly rounded value every sub-step and
-                // v is inside the gear's range, so two comparisons guard everything; the sloped parts
-                // and the reference's exceptions (models.py:119-122, :39-42) take the rare branch, which
-                // fetches its constants on demand to keep the hot loop's register footprint small.
-                double Bu = Bu_flat;                                                 // B(x) u, models.py:109-112
-                if (!(v >= v1 && v <= v2)) {
-                    const double v0 = P.tr_v[j][0], v3 = P.tr_v[j][3];
-                    if (!(v > v0 && v < v3)) {
-                        myerr = ((v < vlo || v > vhi) ? 1 : 3) | (i << 8) | (s << 16);
-                        break;
-                    }
-                    const double t0 = P.tr_t[j][0], t1 = P.tr_t[j][1], t2 = P.tr_t[j][2];
-                    double Bv;
-                    if (v < v1) Bv = div_by(div_by(v - v0, v1 - v0, P.inv_rise[j]) * (t1 - t0) + t0, m, ym);
-                    else Bv = div_by(t1 - div_by(v - v2, v3 - v2, P.inv_fall[j]) * (t1 - t2), m, ym);
-                    Bu = Bv * ui;
-                }
-                const double vv = P.fric_pow2 ? v * v : P.c_fric * (v * v);
-                const double Av = -div_by(vv, mf, ymf) - P.mug;                      // models.py:99-107
-                const double pn = p + DT * (v + zu);         // v + 0*u == v bit for bit unless u is inf/nan
-                const double vn = v + DT * (Av + Bu);
-                p = pn; v = vn;
-            }
+            double Bu_flat = Bv_flat * ui;                   // loop invariant on the flat part of the curve
+            asm volatile("" : "+d"(Bu_flat));                // ... kept as a value, not re-multiplied per sub-step
+            const int v1h = __double2hiint(v1), v2h = __double2hiint(v2);
+            if (zu == 0.0 && P.fric_pow2) myerr = substeps<true>(P, p, v, ui, zu, m, ym, mf, ymf, Bu_flat, j, i, v1h, v2h);
+            else myerr = substeps<false>(P, p, v, ui, zu, m, ym, mf, ymf, Bu_flat, j, i, v1h, v2h);
         }
         s_err[tid] = myerr;
     }

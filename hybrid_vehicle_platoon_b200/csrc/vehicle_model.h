@@ -1,6 +1,6 @@
 // vehicle_model.h -- host-side constants of the vehicle / PWA model and controller parameters.
 // Values restate models.py:13-28,57-92,276-282,397-492 and misc/common_controller_params.py:14-23
-// of the reference; tests/test_model_tables.py checks them against tables captured from the
+// of the reference; tests/test_host_logic.py::test_model_tables_match_reference checks them against tables captured from the
 // reference itself (tests/golden/rollout_golden.npz).
 #pragma once
 #include <math.h>
@@ -27,9 +27,10 @@ struct VehicleModel {
 };
 
 // Controller parameters (Params, misc/common_controller_params.py:14-23) + PWA-gear region data.
-inline void fill_local_params(LocalParams& P, int N, double d0, double t0, double tight, int max_nodes) {
+inline void fill_local_params(LocalParams& P, int N, double d0, double t0, double tight, int max_nodes,
+                              double mip_gap = 0.0, double time_limit_ms = 0.0) {
     VehicleModel M;
-    P.N = N; P.max_nodes = max_nodes; P.hull = 0; P.dive = 1; P.node_batch = 27; P.sibling_bound = 1; P.warm = 1; P.d0 = d0; P.t0 = t0; P.tight = tight;
+    P.N = N; P.max_nodes = max_nodes; P.mip_gap = mip_gap; P.time_limit_ns = (long long)(time_limit_ms * 1e6); P.hull = 0; P.dive = 1; P.node_batch = 27; P.sibling_bound = 1; P.warm = 1; P.d0 = d0; P.t0 = t0; P.tight = tight;
     P.qxp = 1.0; P.qxv = 0.1; P.qu = 1.0; P.w = 1e4;
     P.a_acc = 2.5; P.a_dec = -2.0; P.d_safe = 25.0;
     P.vmin = M.v_min; P.vmax = M.v_max; P.pmin = M.p_min; P.pmax = M.p_max;

@@ -23,6 +23,26 @@ class _Val:
         self.shape = shape
 
 
+class SolverOptions:
+    """Solver parameters every controller snapshots when it is constructed -- the analogue of the Gurobi parameters the
+    reference sets on its model (mpcs/mpc_gear.py:182-186) or leaves at their defaults.
+    mip_gap: relative gap at which a node is pruned (Gurobi MIPGap, 1e-4 there); 0 = proven optimal (default here).
+    time_limit: seconds per problem (Gurobi TimeLimit); when it runs out the solve ends with status 9 (TIME_LIMIT),
+    which solve_mpc treats like every status other than 2: raise, or zeros + inf cost.  0 = none."""
+    mip_gap = 0.0
+    time_limit = 0.0
+
+
+OPTIONS = SolverOptions()
+
+
+def set_solver_options(mip_gap=None, time_limit=None):
+    if mip_gap is not None:
+        OPTIONS.mip_gap = float(mip_gap)
+    if time_limit is not None:
+        OPTIONS.time_limit = float(time_limit)
+
+
 class LocalMpcMld:
     """A local decentralized MPC for a single vehicle in the platoon (GPU solve)."""
 
@@ -53,6 +73,7 @@ class LocalMpcMld:
         self.x, self.u = _Val((2, N + 1)), _Val((1, N))
         self.num_bin_vars = 7 * N                     # delta (s, N) of the MLD model
         self._ctx = ctx
+        self.mip_gap, self.time_limit_ms = OPTIONS.mip_gap, OPTIONS.time_limit * 1e3
 
     # parameter setters (fleet_decent_mld.py:210-223)
     def set_leader_x(self, leader_x):
@@ -73,12 +94,14 @@ def solve_local_batch(mpcs, states, raises: bool = True, ctx=None):
     kernel launch.  Returns [(u0, info), ...] exactly as each mpc.solve_mpc(state) would."""
     m0 = mpcs[0]
     N = m0.N
-    if any((m.N, m.d0, m.t0, m.tight) != (N, m0.d0, m0.t0, m0.tight) for m in mpcs):
-        raise ValueError("solve_local_batch needs controllers with identical N / spacing / tightening")
+    if any((m.N, m.d0, m.t0, m.tight, m.mip_gap, m.time_limit_ms) !=
+           (N, m0.d0, m0.t0, m0.tight, m0.mip_gap, m0.time_limit_ms) for m in mpcs):
+        raise ValueError("solve_local_batch needs controllers with identical N / spacing / tightening / solver options")
     x0 = np.stack([np.asarray(s, dtype=np.float64).reshape(2) for s in states])
     r = api.local_miqp(N, np.array([m.flags for m in mpcs], np.int32), np.array([m.mass for m in mpcs]), x0,
                        np.stack([m._xf for m in mpcs]), np.stack([m._xb for m in mpcs]),
-                       np.stack([m._xl for m in mpcs]), d0=m0.d0, t0=m0.t0, tight=m0.tight, ctx=ctx)
+                       np.stack([m._xl for m in mpcs]), d0=m0.d0, t0=m0.t0, tight=m0.tight, mip_gap=m0.mip_gap,
+                       time_limit_ms=m0.time_limit_ms, ctx=ctx)
     run_time = r["run_time"]
     out = []
     for i, m in enumerate(mpcs):
@@ -110,9 +133,10 @@ def _handle(key, ctx):
     with the same structure (e.g. all interior vehicles of a platoon) share it and batch together."""
     k = (key, id(ctx))
     if k not in _handles:
-        kind, model, nl, N, flags, li, nf, nb, d0, t0, tight, rho = key
+        kind, model, nl, N, flags, li, nf, nb, d0, t0, tight, rho, one_norm, gap, tl = key
         _handles[k] = api.CompiledMpc(kind, N, n_local=nl, model=model, flags=flags, leader_index=li, n_front=nf,
-                                      n_behind=nb, d0=d0, t0=t0, tight=tight, rho=rho, ctx=ctx)
+                                      n_behind=nb, d0=d0, t0=t0, tight=tight, rho=rho, one_norm=one_norm,
+                                      mip_gap=gap, time_limit_ms=tl, ctx=ctx)
     return _handles[k]
 
 
@@ -135,7 +159,7 @@ class _CompiledController:
         self.discrete_gears = self.model == MODEL_FRICTION_GEAR
         d0, t0 = spacing_params(spacing_policy)
         self._key = (kind, self.model, self.nl, self.N, int(flags), int(leader_index), int(n_front), int(n_behind),
-                     d0, t0, float(tight), float(rho))
+                     d0, t0, float(tight), float(rho), not quadratic_cost, OPTIONS.mip_gap, OPTIONS.time_limit * 1e3)
         self._ctx = ctx
         self._cm = _handle(self._key, ctx)
         self._blk = 2 * (self.N + 1)

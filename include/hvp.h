@@ -32,12 +32,13 @@
 extern "C" {
 #endif
 
-#define HVP_VERSION 100
+#define HVP_VERSION 101
 
 /* status[] codes (Gurobi numbering, mpcs/mpc_gear.py:119) */
 #define HVP_OPTIMAL 2
 #define HVP_INFEASIBLE 3
 #define HVP_NODE_LIMIT 8
+#define HVP_TIME_LIMIT 9 /* time_limit_ms ran out: the best solution found so far is returned (Gurobi TIME_LIMIT) */
 #define HVP_NUMERIC 12
 
 /* per-vehicle role flags of a local problem (fleet_decent_mld.py:33-45: is_front/is_leader/is_trailer) */
@@ -108,6 +109,12 @@ typedef struct {
     int32_t max_nodes;  /* per problem; 0 = unlimited */
     double d0, t0;      /* spacing policy */
     double tight;       /* accel_cnstr_tightening (fleet_decent_mld.py:43) */
+    /* Solver options (Gurobi parameters of mpcs/mpc_gear.py:182-186, Q12).  mip_gap: relative gap at
+     * which a node is pruned (Gurobi MIPGap, default there 1e-4); 0 = proven optimal.  time_limit_ms: budget per
+     * problem, measured on the device from the moment the problem is picked up; when it runs out the incumbent is
+     * returned with status HVP_TIME_LIMIT (9); 0 = none. */
+    double mip_gap;
+    double time_limit_ms;
 } hvp_local_desc;
 
 /* flags [batch] (HVP_FRONT|HVP_LEADER|HVP_TRAILER), mass [batch], x0 [batch][2],
@@ -168,10 +175,12 @@ typedef struct {
     int32_t n_front;      /* EVENT: num_vehicles_in_front (0..2); GADMM: copies in front of own state */
     int32_t n_behind;     /* EVENT: num_vehicles_behind (0..2);   GADMM: copies behind own state */
     int32_t max_nodes;    /* per problem; 0 = unlimited */
-    int32_t reserved;
+    int32_t one_norm;     /* 0: 2-norm cost (MIQP); 1: 1-norm cost sum |Q e| (MILP; quadratic_cost=False, cent_mld.py:58-61) */
     double d0, t0;        /* spacing policy */
     double tight;         /* accel_cnstr_tightening */
     double rho;           /* ADMM / GADMM penalty */
+    double mip_gap;       /* as in hvp_local_desc; 0 = proven optimal */
+    double time_limit_ms; /* as in hvp_local_desc; 0 = none */
 } hvp_mpc_desc;
 typedef struct hvp_mpc hvp_mpc;
 int hvp_mpc_create(hvp_ctx* ctx, const hvp_mpc_desc* desc, hvp_mpc** out);

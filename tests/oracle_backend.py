@@ -16,7 +16,7 @@ def _rollout_step(x, u, gear=None, mass=None, leader=None, *, d0=50.0, t0=0.0, l
 
 
 def _local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0, tight=0.0, max_nodes=0,
-                ctx=None):
+                mip_gap=0.0, time_limit_ms=0.0, ctx=None):
     r = O.local_miqp(N, flags, mass, x0, xf, xb, xl, d0=d0, t0=t0, tight=tight)
     return dict(u=r["u"], x=r["x"], modes=r["modes"], obj=r["obj"], status=r["status"],
                 nodes=r["leaves"].astype(np.int32), qp_iters=np.zeros(len(r["obj"]), np.int32), run_time=0.0)
@@ -62,7 +62,8 @@ class _OracleCompiledMpc:
     """api.CompiledMpc with the same attributes, solved by oracle/hvp_oracle_mpc.c."""
 
     def __init__(self, kind, N, *, n_local=1, model=0, flags=0, leader_index=0, n_front=0, n_behind=0, d0=50.0,
-                 t0=0.0, tight=0.0, rho=0.5, max_nodes=0, ctx=None):
+                 t0=0.0, tight=0.0, rho=0.5, max_nodes=0, one_norm=False, mip_gap=0.0, time_limit_ms=0.0, ctx=None):
+        assert not one_norm, "the C oracle restates the 2-norm formulations; the 1-norm oracle is tests/mld_bigm.py (milp)"
         self.kind, self.N, self.n_local, self.model = kind, N, n_local, model
         self.kw = dict(model=model, flags=flags, leader_index=leader_index, n_front=n_front, n_behind=n_behind,
                        d0=d0, t0=t0, tight=tight, rho=rho)

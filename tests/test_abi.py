@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol():
     assert len(names) >= 12
     for nme in names:
         assert hasattr(L, nme), nme
-    assert L.hvp_version() == 100
+    assert L.hvp_version() == 101
 
 
 def test_no_cpu_fallback():

@@ -125,3 +125,29 @@ def test_chunked_host_path_equals_device_path():
     du = np.abs(r["u"] - u.cpu().numpy()).max(axis=1)
     assert (du < 1e-6).mean() > 0.999, (du < 1e-6).mean()
     assert (np.abs(r["x"] - x.cpu().numpy()).max(axis=(1, 2)) < 1e-6).mean() > 0.999
+
+
+# ---- solver options at the boundary (mip_gap, time_limit, status 9) -----------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel_batch", [96, 12000])       # cooperative kernel / flat kernel
+def test_mip_gap_and_time_limit_options(hvp_ctx, kernel_batch):
+    """mip_gap > 0 prunes nodes whose bound is within the gap of the incumbent: fewer nodes, objective within the gap of
+    the proven optimum; a time limit far below one tree's duration returns status 9 (or 2 / 3 for the problems that
+    finished in time) and whatever it returns as a solution is feasible for the optimum's bound (obj >= optimum)."""
+    rng = np.random.default_rng(5)
+    S = kernel_batch // 10
+    c = platoon_local_problems(rng, S, 10, 6, stress=True)
+    args = (6, c["flags"], c["mass"], c["x0"], c["xf"], c["xb"], c["xl"])
+    exact = hvp.local_miqp(*args, ctx=hvp_ctx)
+    loose = hvp.local_miqp(*args, mip_gap=0.05, ctx=hvp_ctx)
+    ok = exact["status"] == 2
+    assert (loose["status"] == exact["status"]).all()
+    assert (loose["obj"][ok] >= exact["obj"][ok] - 1e-9 * np.abs(exact["obj"][ok])).all()
+    assert (loose["obj"][ok] <= exact["obj"][ok] + 0.05 * np.abs(exact["obj"][ok]) + 1e-9).all()
+    assert loose["nodes"].sum() < exact["nodes"].sum()
+    timed = hvp.local_miqp(*args, time_limit_ms=1e-3, ctx=hvp_ctx)        # 1 microsecond per problem
+    assert set(np.unique(timed["status"])) <= {2, 3, 9} and (timed["status"] == 9).any()
+    has = np.isfinite(timed["obj"]) & ok
+    assert (timed["obj"][has] >= exact["obj"][has] - 1e-9 * np.abs(exact["obj"][has])).all()
+    with pytest.raises(RuntimeError):
+        hvp.local_miqp(*args, mip_gap=-0.1, ctx=hvp_ctx)

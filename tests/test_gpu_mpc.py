@@ -276,3 +276,25 @@ def test_local_mpc_mld_real_vehicle_reference_routes_to_compiled(hvp):
     assert np.isfinite(info["cost"]) and u0.shape == (1, 1)
     plain = hvp.LocalMpcMld(4, sys_, hvp.ConstantSpacingPolicy(50), True, True, True, True)
     assert type(plain) is hvp.LocalMpcMld
+
+
+@pytest.mark.gpu
+def test_compiled_mip_gap_and_time_limit(hvp):
+    """Solver options of hvp_mpc_desc: a 5 % gap gives objectives within 5 % of the proven optimum with
+    fewer nodes; a 1-microsecond time limit ends trees with status 9 and never reports an objective below the optimum."""
+    rng = np.random.default_rng(3)
+    n, N = 3, 5
+    x0, params = G.cent_cases(rng, 64, n, N, stress=True)
+    exact = hvp.api.CompiledMpc(G.CENT, N, n_local=n).solve(x0, 800.0, params)
+    loose = hvp.api.CompiledMpc(G.CENT, N, n_local=n, mip_gap=0.05).solve(x0, 800.0, params)
+    ok = exact["status"] == 2
+    assert (loose["status"] == exact["status"]).all()
+    a = np.abs(exact["obj"][ok])
+    assert (loose["obj"][ok] >= exact["obj"][ok] - 1e-8 * a).all() and (loose["obj"][ok] <= exact["obj"][ok] + 0.05 * a + 1e-8).all()
+    assert loose["nodes"].sum() < exact["nodes"].sum()
+    timed = hvp.api.CompiledMpc(G.CENT, N, n_local=n, time_limit_ms=1e-3).solve(x0, 800.0, params)
+    assert set(np.unique(timed["status"])) <= {2, 3, 9} and (timed["status"] == 9).any()
+    has = np.isfinite(timed["obj"]) & ok
+    assert (timed["obj"][has] >= exact["obj"][has] - 1e-8 * np.abs(exact["obj"][has])).all()
+    with pytest.raises(RuntimeError):
+        hvp.api.CompiledMpc(G.CENT, N, n_local=n, mip_gap=1.5)
