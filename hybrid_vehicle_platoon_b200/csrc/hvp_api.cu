@@ -152,10 +152,9 @@ extern "C" int hvp_rollout_step_dev(hvp_ctx* c, const hvp_env_desc* desc, int64_
     if (((uintptr_t)x & 15) || ((uintptr_t)x_out & 15)) return fail(-5, "rollout: x / x_out must be 16-byte aligned");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(hvp_mark(c, c->ev0, st, false));
     CUDA_TRY(launch_rollout(P, batch, x, u, gear, mass, leader, x_out, cost, viol, err, st));
-    CUDA_TRY(cudaEventRecord(c->ev1, st));
-    c->timed = true;
+    CUDA_TRY(hvp_mark(c, c->ev1, st, true));
     c->launches += 1;
     return 0;
 }
@@ -210,7 +209,9 @@ extern "C" int hvp_rollout_step_host(hvp_ctx* c, const hvp_env_desc* desc, int64
 static int launch_slot(hvp_ctx* c, cudaStream_t st, unsigned long long** counter, double** scratch) {
     for (int i = 0; i < c->n_slots; ++i)
         if (c->slot_stream[i] == st) { *counter = c->counters + i; *scratch = c->slot_scratch[i]; return 0; }
-    if (c->n_slots < HVP_STREAM_SLOTS) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+    if (c->n_slots < HVP_STREAM_SLOTS && !capturing) {      // no allocation while the stream is being captured
         double* p = nullptr;
         CUDA_TRY(cudaMalloc(&p, HVP_STEAL_SLOT_DOUBLES * sizeof(double)));
         const int i = c->n_slots++;
@@ -247,14 +248,13 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
     fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes, desc->mip_gap, desc->time_limit_ms);
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(hvp_mark(c, c->ev0, st, false));
     unsigned long long* counter = nullptr;
     double* steal = nullptr;
     rc = launch_slot(c, st, &counter, &steal);
     if (rc) return rc;
     CUDA_TRY(launch_local_miqp(P, counter, steal, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
-    CUDA_TRY(cudaEventRecord(c->ev1, st));
-    c->timed = true;
+    CUDA_TRY(hvp_mark(c, c->ev1, st, true));
     c->launches += 1;
     return 0;
 }
@@ -364,8 +364,7 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
             CUDA_TRY(cudaEventRecord(c->side_ev, c->side[i]));
             CUDA_TRY(cudaStreamWaitEvent(st, c->side_ev, 0));
         }
-        CUDA_TRY(cudaEventRecord(c->ev1, st));
-        c->timed = true;
+        CUDA_TRY(hvp_mark(c, c->ev1, st, true));
         CUDA_TRY(cudaStreamSynchronize(st));
         return 0;
     }

@@ -33,6 +33,21 @@ struct hvp_ctx {
     cudaEvent_t side_ev;
     bool side_ok;
 };
+
+// Timing events of the *_dev entry points.  While the caller's stream is being CAPTURED into a CUDA graph (sweep.py
+// replays whole timesteps / ADMM rounds as graphs) a recorded event would belong to the capture and could not be read
+// afterwards, so nothing is recorded and the context reports "not timed".
+inline cudaError_t hvp_mark(hvp_ctx* c, cudaEvent_t ev, cudaStream_t st, bool last) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+        c->timed = false;
+        return cudaSuccess;
+    }
+    const cudaError_t e = cudaEventRecord(ev, st);
+    if (last && e == cudaSuccess) c->timed = true;
+    return e;
+}
+
 constexpr int HVP_COUNTER_RING = 256;
 constexpr int HVP_STREAM_SLOTS = 64;
 constexpr int HVP_MAX_DEVICES = 64;   // per-device caches of function attributes / occupancy

@@ -656,12 +656,11 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
         m->scratch.sp.cap = (int)cap;
         m->scratch.sp.budget = envB;
     }
-    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(hvp_mark(c, c->ev0, st, false));
     CUDA_TRY(launch_pm_precompute(m->S, batch, x0, params, m->ybuf, st));
     CUDA_TRY(launch_pm_miqp(m->S, batch, x0, mass, params, fixed_modes, m->ybuf, u, x, extra, modes, obj, status,
                             nodes, qp_iters, m->counter, (m->split_D >= 1 && m->scratch_mem) ? &m->scratch : nullptr, st));
-    CUDA_TRY(cudaEventRecord(c->ev1, st));
-    c->timed = true;
+    CUDA_TRY(hvp_mark(c, c->ev1, st, true));
     c->launches += 2;
     return 0;
 }
@@ -720,12 +719,11 @@ extern "C" int hvp_mpc_solve_shard_dev(hvp_mpc* m, int64_t batch, const double* 
     PmScratch sc = m->shard;
     sc.sp.M = groups; sc.sp.D = D; sc.sp.cap = (int)batch; sc.sp.budget = node_budget;
     sc.sp.rank = rank; sc.sp.world = world;
-    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(hvp_mark(c, c->ev0, st, false));
     CUDA_TRY(launch_pm_precompute(S, batch, x0, params, m->ybuf, st));
     CUDA_TRY(launch_pm_shard(S, batch, x0, mass, params, m->ybuf, incumbent, u, x, extra, modes, obj, status, nodes,
                              qp_iters, m->counter, &sc, st));
-    CUDA_TRY(cudaEventRecord(c->ev1, st));
-    c->timed = true;
+    CUDA_TRY(hvp_mark(c, c->ev1, st, true));
     c->launches += 4;
     return 0;
 }

@@ -17,6 +17,91 @@ from ._lib import FRONT, LEADER, TRAILER, default_context
 from .misc import ConstantSpacingPolicy, Params, spacing_params
 
 
+def _graphs_enabled():
+    import os
+    return os.environ.get("HVP_SWEEP_GRAPH", "1") != "0"
+
+
+class _StepGraph:
+    """One timestep (or one consensus phase) of a sweep as a CUDA graph.
+
+    `body` is a closure that enqueues a FIXED sequence of launches -- the library's kernels through the C ABI and the
+    torch glue between them -- on torch's current stream, reading and writing only tensors that live as long as the
+    sweep; everything that changes from step to step (the timestep index, the leader window, where the logs go) is
+    addressed through DEVICE-side indices that the body itself advances.  The first `warm` calls run eagerly (they size
+    the library's scratch buffers and torch's allocator, neither of which may happen during capture); the next call
+    captures the body once and every later call is a single graph launch, so the per-kernel launch and Python costs
+    that bounded the closed loops (4.3x between kernel-only and closed-loop g-ADMM) are paid once.
+    HVP_SWEEP_GRAPH=0 keeps every call eager (A/B and debugging)."""
+
+    _side = {}          # one capture stream per device, shared by every sweep (the library keeps per-stream launch state)
+
+    def __init__(self, torch, body, warm: int = 1, enabled: bool = True):
+        self.torch, self.body, self.warm = torch, body, warm
+        self.calls, self.graph = 0, None
+        self.enabled = enabled and _graphs_enabled()
+        if self.enabled:
+            d = torch.cuda.current_device()
+            if d not in _StepGraph._side:
+                _StepGraph._side[d] = torch.cuda.Stream(device=d)
+            self.stream = _StepGraph._side[d]
+
+    def __call__(self):
+        torch = self.torch
+        if not self.enabled:
+            self.body()
+            return
+        cur = torch.cuda.current_stream()
+        if self.calls < self.warm:
+            # eager, but already on the stream the capture will use: the library allocates its per-stream launch state
+            # (work counter, adoption scratch) on first use, which must not happen during capture
+            self.calls += 1
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                self.body()
+            cur.wait_stream(self.stream)
+            return
+        if self.graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                self.body()
+            self.graph = g
+        self.calls += 1
+        self.graph.replay()
+
+
+class _Fork:
+    """Runs independent pieces of a timestep on side streams (fork from / join to torch's current stream; both are
+    captured when the surrounding body is being recorded into a CUDA graph).  The launches of the different ROLES of
+    a round (front / interior / trailer) are independent -- different compiled formulations, disjoint output slices --
+    and the small ones (1 vehicle per scenario) are pure latency next to the interior one."""
+    _pool = {}
+
+    def __init__(self, torch, k, enabled: bool = True):
+        import os
+        self.enabled = enabled and os.environ.get("HVP_SWEEP_FORK", "1") != "0"
+        d = torch.cuda.current_device()
+        pool = _Fork._pool.setdefault(d, [])
+        while self.enabled and len(pool) < k:
+            pool.append(torch.cuda.Stream(device=d))
+        self.torch, self.streams = torch, pool[:k]
+
+    def run(self, pieces):
+        torch = self.torch
+        if not self.enabled:
+            for piece in pieces:
+                piece()
+            return
+        cur = torch.cuda.current_stream()
+        for st, piece in zip(self.streams, pieces):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                piece()
+        for st in self.streams[:len(pieces)]:
+            cur.wait_stream(st)
+
+
 class BatchedDecentSweep:
     """S independent platoons of n vehicles under the decentralized MLD-MPC (TrackingDecentMldCoordinator
     with the constant-velocity estimator), pwa_gear model, horizon N."""
@@ -90,18 +175,29 @@ class BatchedDecentSweep:
         ND = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
         ST = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
         X[0] = x
-        stream = torch.cuda.current_stream().cuda_stream
         ts = float(Params.ts)
-        for t in range(ep_len):
+        # everything a timestep touches is static; the timestep itself is a DEVICE index the body advances
+        x_cur = x.clone()
+        x_next = torch.empty_like(x_cur)
+        u0 = torch.empty((S, n), dtype=f64, device=dev)
+        r_t = torch.empty(S, dtype=f64, device=dev); v_t = torch.empty(S, dtype=torch.uint8, device=dev)
+        e_t = torch.empty(S, dtype=torch.int32, device=dev)
+        nd_t = torch.empty((S, n), dtype=torch.int32, device=dev); st_t = torch.empty((S, n), dtype=torch.int32, device=dev)
+        t_idx = torch.zeros(1, dtype=torch.int64, device=dev)
+        win = torch.arange(N + 1, dtype=torch.int64, device=dev)
+        lxc = lx.contiguous()
+
+        def body():
+            stream = torch.cuda.current_stream().cuda_stream
             # ---- observe: p_{k+1} = p_k + ts v_k (sequential sums, as the reference), v constant ----
-            xv = x.view(S, n, 2)
+            xv = x_cur.view(S, n, 2)
             pred[:, :, 0, 0] = xv[:, :, 0]
             pred[:, :, 1, :] = xv[:, :, 1:2]
             for k in range(N):
                 pred[:, :, 0, k + 1] = pred[:, :, 0, k] + ts * pred[:, :, 1, k]
             xf[:, 1:] = pred[:, :-1]
             xb[:, :-1] = pred[:, 1:]
-            xl[:, self.leader_index] = lx[:, :, t:t + N + 1]
+            xl[:, self.leader_index] = lxc.index_select(2, t_idx + win)           # leader_x[:, t:t+N+1] (:329-331)
             # ---- solve all S*n local MIQPs ----
             if self.use_compiled:      # one launch per role (front / interior / trailer, leader where applicable)
                 for cm, ii, k in self.role_groups:
@@ -113,20 +209,31 @@ class BatchedDecentSweep:
                     st = torch.empty(Bk, dtype=torch.int32, device=dev); no = torch.empty(Bk, dtype=torch.int32, device=dev)
                     cm.solve_device(Bk, xv[:, ii].reshape(Bk, 1, 2).contiguous(), d_mass[:, ii].reshape(Bk, 1).contiguous(),
                                     params, None, uo, xo, None, mo, ob, st, no, None, stream=stream)
-                    U[t][:, ii] = uo.view(S, k, N)[:, :, 0]
-                    ND[t][:, ii] = no.view(S, k)
-                    ST[t][:, ii] = st.view(S, k)
+                    u0[:, ii] = uo.view(S, k, N)[:, :, 0]
+                    nd_t[:, ii] = no.view(S, k)
+                    st_t[:, ii] = st.view(S, k)
             else:
-                api.local_miqp_device(self.ldesc, B, d_flags, d_mass.view(B), x.view(B, 2), xf.view(B, 2, N + 1),
+                api.local_miqp_device(self.ldesc, B, d_flags, d_mass.view(B), x_cur.view(B, 2), xf.view(B, 2, N + 1),
                                       xb.view(B, 2, N + 1), xl.view(B, 2, N + 1), u, xs, modes, obj, status, nodes,
                                       None, ctx=self.ctx, stream=stream)
-                U[t] = u[:, 0].view(S, n)
-                ND[t] = nodes.view(S, n)
-                ST[t] = status.view(S, n)
+                u0.copy_(u[:, 0].view(S, n))
+                nd_t.copy_(nodes.view(S, n))
+                st_t.copy_(status.view(S, n))
             # ---- step every platoon ----
-            api.rollout_step_device(edesc, S, x, U[t], None, d_mass, lx[:, :, t].contiguous(), X[t + 1], R[t], V[t],
-                                    E[t], ctx=self.ctx, stream=stream)
-            x = X[t + 1]
+            lead_now = lxc.index_select(2, t_idx).squeeze(2).contiguous()
+            api.rollout_step_device(edesc, S, x_cur, u0, None, d_mass, lead_now, x_next, r_t, v_t, e_t, ctx=self.ctx,
+                                    stream=stream)
+            # ---- logs at the device-side timestep, then advance ----
+            X.index_copy_(0, t_idx + 1, x_next.unsqueeze(0))
+            U.index_copy_(0, t_idx, u0.unsqueeze(0)); R.index_copy_(0, t_idx, r_t.unsqueeze(0))
+            V.index_copy_(0, t_idx, v_t.unsqueeze(0)); E.index_copy_(0, t_idx, e_t.unsqueeze(0))
+            ND.index_copy_(0, t_idx, nd_t.unsqueeze(0)); ST.index_copy_(0, t_idx, st_t.unsqueeze(0))
+            x_cur.copy_(x_next)
+            t_idx.add_(1)
+
+        step = _StepGraph(torch, body)
+        for t in range(ep_len):
+            step()
         torch.cuda.synchronize()
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
                     errors=E.cpu().numpy(), nodes=ND.cpu().numpy(), status=ST.cpu().numpy())
@@ -331,9 +438,10 @@ class BatchedAdmmSweep:
 
     def __init__(self, n: int, N: int, admm_iters: int = 20, rho: float = 0.5, masses=None,
                  spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0, d_safe: float = Params.d_safe,
-                 device: int = 0, ctx=None):
+                 device: int = 0, ctx=None, graph: bool = False, fork: bool = True):
         import torch
         from ._lib import MPC_ADMM
+        self.graph, self.fork = graph, fork
         if n < 2:
             raise ValueError("the ADMM scheme needs at least two vehicles")
         self.torch, self.n, self.N, self.iters, self.rho, self.leader_index = torch, n, N, admm_iters, rho, leader_index
@@ -387,45 +495,66 @@ class BatchedAdmmSweep:
         E = torch.empty((ep_len, S), dtype=torch.int32, device=dev)
         ST = torch.empty((ep_len, S, n), dtype=torch.int32, device=dev)
         X[0] = x
-        stream = torch.cuda.current_stream().cuda_stream
         u0 = torch.empty((S, n), dtype=f64, device=dev)
         stat = torch.empty((S, n), dtype=torch.int32, device=dev)
+        x_cur = x.clone()                                         # state the rounds of this timestep start from (static)
+        lwin = torch.empty((S, 1, 2 * np1), dtype=f64, device=dev)
+
+        def role_piece(fl, g):
+            def piece():
+                stream = torch.cuda.current_stream().cuda_stream
+                idx, k, B = g["idx"], g["k"], g["B"]
+                params = torch.cat((lwin.expand(S, k, -1), y_front[:, idx].reshape(S, k, -1), zf[:, idx].reshape(S, k, -1),
+                                    y_back[:, idx].reshape(S, k, -1), zb[:, idx].reshape(S, k, -1)), dim=2).reshape(B, -1).contiguous()
+                x0g = x_cur.view(S, n, 2)[:, idx].reshape(B, 1, 2).contiguous()
+                mg = d_mass[:, idx].reshape(B, 1).contiguous()
+                g["cm"].solve_device(B, x0g, mg, params, None, g["u"], g["x"], g["e"], g["mo"], g["ob"], g["st"],
+                                     g["no"], None, stream=stream)
+                xs[:, idx] = g["x"].view(S, k, 2, np1)
+                u0[:, idx] = g["u"].view(S, k, N)[:, :, 0]
+                stat[:, idx] = g["st"].view(S, k)
+                e = g["e"].view(S, k, -1)
+                o = 0
+                if not fl & FRONT:
+                    cf[:, idx] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1); o += 2 * np1
+                if not fl & TRAILER:
+                    cb[:, idx] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1)
+            return piece
+
+        pieces = [role_piece(fl, g) for fl, g in groups.items()]
+        # Measured (r02, 1024 scenarios, n = 15, N = 8, 20 rounds x 3 timesteps): eager 1584 ms, round as a graph 1187 ms,
+        # roles on forked streams 976 ms, both 1425 ms -- the MIQP rounds are kernel-bound (2.8 ms per interior launch), what
+        # pays is running the two one-vehicle roles beside the interior one; inside a graph the branches did not overlap.
+        fork = _Fork(torch, len(pieces), enabled=self.fork)
+
+        def one_round():
+            # ---- x-update: all vehicles of a role in one launch, the roles side by side on forked streams ----
+            fork.run(pieces)
+            # ---- z-update: average of a vehicle's own prediction and its neighbours' copies of it (:421-447) ----
+            z[:, 0] = (xs[:, 0] + cf[:, 1]) / 2.0
+            z[:, n - 1] = (xs[:, n - 1] + cb[:, n - 2]) / 2.0
+            if n > 2:
+                z[:, 1:n - 1] = (xs[:, 1:n - 1] + cf[:, 2:] + cb[:, :n - 2]) / 3.0
+            # ---- y-update and the z each copy is pulled towards in the next round (:426-468) ----
+            y_front[:, 1:] += rho * (cf[:, 1:] - z[:, :-1])
+            y_back[:, :-1] += rho * (cb[:, :-1] - z[:, 1:])
+            zf[:, 1:] = z[:, :-1]
+            zb[:, :-1] = z[:, 1:]
+
+        # one consensus round = one CUDA graph (3 compiled-MPC solves + the z / y updates): the round, not the timestep,
+        # is the unit -- it repeats admm_iters times per timestep with nothing changing but the tensors it updates
+        rnd = _StepGraph(torch, one_round, enabled=self.graph)
+        stream = torch.cuda.current_stream().cuda_stream
         for t in range(ep_len):
             # coupling guesses from the previous step's predictions, shifted (fleet_naive_admm.py:392-402)
             if have_pred:
                 sh = torch.cat((xs[..., 1:], xs[..., -1:]), dim=-1)
                 zf[:, 1:] = sh[:, :-1]
                 zb[:, :-1] = sh[:, 1:]
-            lwin = lx[:, :, t:t + np1].reshape(S, 1, 2 * np1)
+            lwin.copy_(lx[:, :, t:t + np1].reshape(S, 1, 2 * np1))
+            x_cur.copy_(x)
             for _ in range(self.iters):
-                # ---- x-update: all vehicles of a role in one launch ----
-                for fl, g in groups.items():
-                    idx, k, B = g["idx"], g["k"], g["B"]
-                    params = torch.cat((lwin.expand(S, k, -1), y_front[:, idx].reshape(S, k, -1), zf[:, idx].reshape(S, k, -1),
-                                        y_back[:, idx].reshape(S, k, -1), zb[:, idx].reshape(S, k, -1)), dim=2).reshape(B, -1).contiguous()
-                    x0g = x.view(S, n, 2)[:, idx].reshape(B, 1, 2).contiguous()
-                    mg = d_mass[:, idx].reshape(B, 1).contiguous()
-                    g["cm"].solve_device(B, x0g, mg, params, None, g["u"], g["x"], g["e"], g["mo"], g["ob"], g["st"],
-                                         g["no"], None, stream=stream)
-                    xs[:, idx] = g["x"].view(S, k, 2, np1)
-                    u0[:, idx] = g["u"].view(S, k, N)[:, :, 0]
-                    stat[:, idx] = g["st"].view(S, k)
-                    e = g["e"].view(S, k, -1)
-                    o = 0
-                    if not fl & FRONT:
-                        cf[:, idx] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1); o += 2 * np1
-                    if not fl & TRAILER:
-                        cb[:, idx] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1)
-                # ---- z-update: average of a vehicle's own prediction and its neighbours' copies of it (:421-447) ----
-                z[:, 0] = (xs[:, 0] + cf[:, 1]) / 2.0
-                z[:, n - 1] = (xs[:, n - 1] + cb[:, n - 2]) / 2.0
-                if n > 2:
-                    z[:, 1:n - 1] = (xs[:, 1:n - 1] + cf[:, 2:] + cb[:, :n - 2]) / 3.0
-                # ---- y-update and the z each copy is pulled towards in the next round (:426-468) ----
-                y_front[:, 1:] += rho * (cf[:, 1:] - z[:, :-1])
-                y_back[:, :-1] += rho * (cb[:, :-1] - z[:, 1:])
-                zf[:, 1:] = z[:, :-1]
-                zb[:, :-1] = z[:, 1:]
+                rnd()
             have_pred = True
             U[t] = u0
             ST[t] = stat
@@ -528,9 +657,11 @@ class BatchedGAdmmSweep:
     (leader / interior / last); sequences are re-identified from a PWA roll-out of the current inputs as torch ops."""
 
     def __init__(self, n: int, N: int, admm_iters: int = 100, rho: float = 0.5, masses=None,
-                 spacing_policy=ConstantSpacingPolicy(50), d_safe: float = Params.d_safe, device: int = 0, ctx=None):
+                 spacing_policy=ConstantSpacingPolicy(50), d_safe: float = Params.d_safe, device: int = 0, ctx=None,
+                 graph: bool = True, fork: bool = False):
         import torch
         from ._lib import MPC_GADMM
+        self.graph, self.fork = graph, fork
         from .models import PwaGearVehicle
         if n < 2:
             raise ValueError("the g-ADMM scheme needs at least two vehicles")
@@ -558,12 +689,14 @@ class BatchedGAdmmSweep:
     def _region(self, vel):           # first region whose closed interval (+1e-9) contains v (fleet_g_admm._region_of)
         return self.torch.bucketize(vel, self.edges + 1e-9, right=False)
 
-    def _rollout(self, x, u, mass):
-        """PWA roll-out of all vehicles under inputs u (S,n,N): trajectories (S,n,2,N+1), region sequences (S,n,N)."""
+    def _rollout(self, x, u, mass, tr=None, seq=None):
+        """PWA roll-out of all vehicles under inputs u (S,n,N): trajectories (S,n,2,N+1), region sequences (S,n,N)
+        (written into `tr` / `seq` when given: the consensus rounds keep them in static tensors)."""
         torch, N = self.torch, self.N
         S, n = u.shape[0], u.shape[1]
-        tr = torch.empty((S, n, 2, N + 1), dtype=torch.float64, device=self.dev)
-        seq = torch.empty((S, n, N), dtype=torch.int64, device=self.dev)
+        if tr is None:
+            tr = torch.empty((S, n, 2, N + 1), dtype=torch.float64, device=self.dev)
+            seq = torch.empty((S, n, N), dtype=torch.int64, device=self.dev)
         p, v = x.view(S, n, 2)[:, :, 0].clone(), x.view(S, n, 2)[:, :, 1].clone()
         tr[:, :, 0, 0], tr[:, :, 1, 0] = p, v
         for k in range(N):
@@ -582,26 +715,35 @@ class BatchedGAdmmSweep:
         r = self.torch.bucketize(v, self.edges + 1e-4, right=False)
         return (1.0 / (self.bg[r] / mass)) * (-(-(self.cf[r]) / mass) * v - (-self.mug - self.dd[r] / mass))
 
-    def _admm(self, x, u, mass, lwin):
-        """One g_admm_control call for all scenarios.  Returns (u (S,n,N), cost (S,), ok (S,) bool)."""
+    def _make_admm(self, S, x, mass, lwin):
+        """g_admm_control for all S scenarios (fleet_g_admm.py:255-301 + the restated round logic): returns
+        admm(u_start) -> (u (S,n,N), cost (S,), ok (S,) bool).  x (S,2n), mass (S,n) and lwin (S,2,N+1) are STATIC
+        tensors the caller refreshes per timestep; every consensus variable lives in a static tensor too, so ONE
+        ROUND -- the fixed-sequence QPs of all agents (one launch of the compiled-MPC kernel per role, FP64 tensor-core
+        precompute), the z / y updates and the re-identification of the PWA sequences -- is one CUDA graph that is
+        replayed admm_iters times per warm start."""
         torch, n, N, rho, dev = self.torch, self.n, self.N, self.rho, self.dev
         f64, np1 = torch.float64, N + 1
-        S = u.shape[0]
         zer = lambda *s: torch.zeros(s, dtype=f64, device=dev)
         # augmented blocks per vehicle: [front copy (i > 0), own, back copy (i < n-1)], y and z alike
         yF, yO, yB = zer(S, n, 2, np1), zer(S, n, 2, np1), zer(S, n, 2, np1)
-        tr, seq = self._rollout(x, u, mass)
-        zbar = tr.clone()
+        u = zer(S, n, N)
+        tr = zer(S, n, 2, np1); seq = torch.zeros((S, n, N), dtype=torch.int64, device=dev)
+        zbar = zer(S, n, 2, np1)
         ok = torch.ones(S, dtype=torch.bool, device=dev)
         cost = zer(S)
         own, cF, cB = zer(S, n, 2, np1), zer(S, n, 2, np1), zer(S, n, 2, np1)
-        stream = torch.cuda.current_stream().cuda_stream
+        cnt = torch.ones(n, dtype=f64, device=dev); cnt[:-1] += 1; cnt[1:] += 1
         groups = [(self.cm_lead, [0]), (self.cm_last, [n - 1])] + ([(self.cm_mid, list(range(1, n - 1)))] if n > 2 else [])
-        for _ in range(self.iters):
-            cost.zero_()
-            for cm, idx in groups:
+        groups = [(cm, idx, torch.as_tensor(idx, device=dev)) for cm, idx in groups]
+
+        okp = [torch.ones(S, dtype=torch.bool, device=dev) for _ in groups]
+        costp = [zer(S) for _ in groups]
+
+        def role_piece(j, cm, idx, ii):
+            def piece():
+                stream = torch.cuda.current_stream().cuda_stream
                 k = len(idx); B = S * k
-                ii = torch.as_tensor(idx, device=dev)
                 blocks_y, blocks_z = [], []
                 if idx[0] > 0:
                     blocks_y.append(yF[:, ii]); blocks_z.append(zbar[:, ii - 1])
@@ -619,8 +761,8 @@ class BatchedGAdmmSweep:
                 st = torch.empty(B, dtype=torch.int32, device=dev); no = torch.empty(B, dtype=torch.int32, device=dev)
                 cm.solve_device(B, x0g, mg, params, fm, uo, xo, eo, mo, ob, st, no, None, stream=stream)
                 good = (st == 2).view(S, k)
-                ok &= good.all(dim=1)
-                cost += torch.where(good, ob.view(S, k), torch.zeros_like(ob.view(S, k))).sum(dim=1)
+                okp[j].copy_(good.all(dim=1))
+                costp[j].copy_(torch.where(good, ob.view(S, k), torch.zeros_like(ob.view(S, k))).sum(dim=1))
                 u[:, ii] = torch.where(good.unsqueeze(-1), uo.view(S, k, N), u[:, ii])
                 own[:, ii] = xo.view(S, k, 2, np1)
                 e = eo.view(S, k, -1)
@@ -629,19 +771,46 @@ class BatchedGAdmmSweep:
                     cF[:, ii] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1); o += 2 * np1
                 if idx[-1] < n - 1:
                     cB[:, ii] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1)
+            return piece
+
+        pieces = [role_piece(j, cm, idx, ii) for j, (cm, idx, ii) in enumerate(groups)]
+        # Measured (r02, 1024 scenarios, n = 15, N = 8, 100 rounds): eager 689 ms, round as a graph 629 ms, forked roles 1086 ms,
+        # both 696 ms -- the QP rounds are a few hundred tiny launches, which the graph removes and forking only adds to.
+        fork = _Fork(torch, len(pieces), enabled=self.fork)
+
+        def one_round():
+            # the roles (leader / last / interior) side by side on forked streams, then the shared sums in group order
+            fork.run(pieces)
+            cost.zero_()
+            for j in range(len(groups)):
+                ok.logical_and_(okp[j])
+                cost.add_(costp[j])
             # z-update: average of every copy of vehicle j's trajectory (own, the copy held by j+1, the one held by j-1)
-            cnt = torch.ones(n, dtype=f64, device=dev); cnt[:-1] += 1; cnt[1:] += 1
             acc = own.clone()
             acc[:, :-1] += cF[:, 1:]
             acc[:, 1:] += cB[:, :-1]
-            zbar = acc / cnt.view(1, n, 1, 1)
+            torch.div(acc, cnt.view(1, n, 1, 1), out=zbar)
             # y-update on every block with the new z
-            yO += rho * (own - zbar)
+            yO.add_(rho * (own - zbar))
             yF[:, 1:] += rho * (cF[:, 1:] - zbar[:, :-1])
             yB[:, :-1] += rho * (cB[:, :-1] - zbar[:, 1:])
-            tr, seq = self._rollout(x, u, mass)
-        infeas = ((tr[:, :, 1, 1:] > 45.84 + 1e-6) | (tr[:, :, 1, 1:] < 3.94 - 1e-6)).any(dim=2).any(dim=1)
-        return u, cost, ok & ~infeas
+            self._rollout(x, u, mass, tr, seq)
+
+        rnd = _StepGraph(torch, one_round, enabled=self.graph)
+
+        def admm(u_start):
+            for t_ in (yF, yO, yB, own, cF, cB):
+                t_.zero_()
+            u.copy_(u_start)
+            self._rollout(x, u, mass, tr, seq)
+            zbar.copy_(tr)
+            ok.fill_(True)
+            for _ in range(self.iters):
+                rnd()
+            infeas = ((tr[:, :, 1, 1:] > 45.84 + 1e-6) | (tr[:, :, 1, 1:] < 3.94 - 1e-6)).any(dim=2).any(dim=1)
+            return u.clone(), cost.clone(), ok & ~infeas
+
+        return admm
 
     def run(self, x0, leader_x, ep_len: int):
         torch, dev, n, N = self.torch, self.dev, self.n, self.N
@@ -664,8 +833,12 @@ class BatchedGAdmmSweep:
         X[0] = x
         stream = torch.cuda.current_stream().cuda_stream
         prev = None
+        x_cur = x.clone()
+        lwin = torch.empty((S, 2, np1), dtype=f64, device=dev)
+        admm = self._make_admm(S, x_cur, mass, lwin)
         for t in range(ep_len):
-            lwin = lx[:, :, t:t + np1].contiguous()
+            lwin.copy_(lx[:, :, t:t + np1])
+            x_cur.copy_(x)
             starts = [self._const_vel_u(x, mass).unsqueeze(-1).expand(S, n, N).clone()]
             if prev is not None:        # shifted previous solution (fleet_g_admm.py:266-272)
                 starts.append(torch.cat((prev[..., 1:], prev[..., -1:]), dim=-1))
@@ -673,7 +846,7 @@ class BatchedGAdmmSweep:
             best_u = torch.zeros((S, n, N), dtype=f64, device=dev)
             which = torch.zeros(S, dtype=torch.int32, device=dev)
             for w, u in enumerate(starts):
-                uu, cost, ok = self._admm(x, u.clone(), mass, lwin)
+                uu, cost, ok = admm(u)
                 cost = torch.where(ok, cost, torch.full_like(cost, float("inf")))
                 better = cost < best_cost
                 best_cost = torch.where(better, cost, best_cost)
