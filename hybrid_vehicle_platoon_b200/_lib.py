@@ -34,6 +34,17 @@ class MpcDesc(C.Structure):
                 ("mip_gap", C.c_double), ("time_limit_ms", C.c_double)]
 
 
+class GAdmmRole(C.Structure):      # hvp_gadmm_role: the buffers of one role's hvp_mpc_solve_dev call
+    _fields_ = [(k, C.c_void_p) for k in ("params", "x0", "mass", "fixed_modes", "u", "x", "extra", "obj", "status")]
+
+
+class GAdmmRound(C.Structure):     # hvp_gadmm_round
+    _fields_ = [("n", C.c_int32), ("N", C.c_int32), ("S", C.c_int32), ("init", C.c_int32), ("rho", C.c_double),
+                ("mug", C.c_double), ("edge", C.c_double * 6), ("cf", C.c_double * 7), ("bg", C.c_double * 7),
+                ("dd", C.c_double * 7), ("role", GAdmmRole * 3)] + \
+               [(k, C.c_void_p) for k in ("x", "mass", "lwin", "y", "u", "tr", "cost", "ok")]
+
+
 MPC_CENT, MPC_LOCAL, MPC_EVENT, MPC_ADMM, MPC_GADMM = 1, 2, 3, 4, 5
 MODEL_PWA_GEAR, MODEL_FRICTION_GEAR = 0, 1
 REAL_VEHICLE_REF, NO_LEADER = 8, -100
@@ -91,6 +102,7 @@ def lib():
     L.hvp_mpc_solve_shard_dev.argtypes = [_vp, C.c_int64, _vp, _vp, _vp] + [C.c_int32] * 5 + [_vp] * 10
     L.hvp_mpc_eval_dev.argtypes = [_vp, C.c_int64] + [_vp] * 6
     L.hvp_mpc_eval_host.argtypes = [_vp, C.c_int64] + [_vp] * 5
+    L.hvp_gadmm_round_dev.argtypes = [_vp, C.POINTER(GAdmmRound), _vp]
     L.hvp_microbench_fp64.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     L.hvp_microbench_smem.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     _lib = L

@@ -203,3 +203,11 @@ def microbench_smem(iters: int = 20000, ctx=None) -> float:
     t = C.c_double(0)
     check(lib().hvp_microbench_smem(ctx.handle, int(iters), C.byref(t)))
     return t.value
+
+
+def gadmm_round_device(g, *, init: bool, ctx=None, stream=None):
+    """Fused coordinator glue of one g-ADMM consensus round (hvp_gadmm_round_dev, include/hvp.h); `g` is a
+    _lib.GAdmmRound whose pointers refer to torch CUDA tensors the caller keeps alive."""
+    ctx = ctx or default_context()
+    g.init = 1 if init else 0
+    check(lib().hvp_gadmm_round_dev(ctx.handle, C.byref(g), _stream_arg(stream)))

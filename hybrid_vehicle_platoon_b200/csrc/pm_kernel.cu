@@ -1055,7 +1055,12 @@ pm_precompute_kernel(const __grid_constant__ PmDev S, int64_t batch, const doubl
         if (k < npv - 1) return params[(size_t)b * S.npar + (k - nx)];
         return 1.0;
     };
-    for (int n0 = 0; n0 < mw; n0 += 32) {
+    // the 32-column tiles of the output are dealt over gridDim.y: a small batch (the one-vehicle roles of a consensus
+    // round: 1024 problems = 16 CTAs) would otherwise walk all of them serially on a handful of SMs (r02i launch list:
+    // 113 us per launch, as long as the QPs it prepares)
+    const int tiles = (mw + 31) / 32, per_y = (tiles + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int n_begin = (int)blockIdx.y * per_y * 32, n_end = min(mw, n_begin + per_y * 32);
+    for (int n0 = n_begin; n0 < n_end; n0 += 32) {
         double acc[2][4][2];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
@@ -1092,7 +1097,11 @@ cudaError_t launch_pm_precompute(const PmDev& S, int64_t batch, const double* x0
     if (batch <= 0) return cudaSuccess;
     const int64_t warps = (batch + 15) / 16;
     const int64_t blocks = (warps + 3) / 4;
-    pm_precompute_kernel<<<(unsigned)blocks, 128, 0, stream>>>(S, batch, x0, params, Y);
+    const int tiles = (S.mw + 31) / 32;
+    int64_t gy = (8 * 148 + blocks - 1) / blocks;            // aim at ~8 CTAs per SM in total
+    if (gy > tiles) gy = tiles;
+    if (gy < 1) gy = 1;
+    pm_precompute_kernel<<<dim3((unsigned)blocks, (unsigned)gy), 128, 0, stream>>>(S, batch, x0, params, Y);
     return cudaGetLastError();
 }
 

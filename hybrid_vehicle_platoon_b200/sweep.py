@@ -658,10 +658,14 @@ class BatchedGAdmmSweep:
 
     def __init__(self, n: int, N: int, admm_iters: int = 100, rho: float = 0.5, masses=None,
                  spacing_policy=ConstantSpacingPolicy(50), d_safe: float = Params.d_safe, device: int = 0, ctx=None,
-                 graph: bool = True, fork: bool = False):
+                 graph: bool = True, fork: bool = False, fused=None):
+        import os
         import torch
         from ._lib import MPC_GADMM
         self.graph, self.fork = graph, fork
+        # fused: the glue of a round as one CUDA kernel (csrc/coord.cu); False keeps it as torch ops (the reference the
+        # fused kernel is tested against)
+        self.fused = (os.environ.get("HVP_GADMM_FUSED", "1") != "0") if fused is None else bool(fused)
         from .models import PwaGearVehicle
         if n < 2:
             raise ValueError("the g-ADMM scheme needs at least two vehicles")
@@ -715,6 +719,60 @@ class BatchedGAdmmSweep:
         r = self.torch.bucketize(v, self.edges + 1e-4, right=False)
         return (1.0 / (self.bg[r] / mass)) * (-(-(self.cf[r]) / mass) * v - (-self.mug - self.dd[r] / mass))
 
+    def _make_admm_fused(self, S, x, mass, lwin):
+        """_make_admm with the glue of a round in ONE kernel (csrc/coord.cu, hvp_gadmm_round_dev): a round is the three
+        role solves (precompute + QP kernel each) and that kernel -- 7 launches instead of ~290 -- replayed as a graph."""
+        import ctypes as C
+        from . import _lib
+        torch, n, N, dev = self.torch, self.n, self.N, self.dev
+        f64, i32, np1 = torch.float64, torch.int32, N + 1
+        zer = lambda *s: torch.zeros(s, dtype=f64, device=dev)
+        y = zer(S, n, 3, 2, np1); u = zer(S, n, N); tr = zer(S, n, 2, np1); cost = zer(S)
+        ok = torch.ones(S, dtype=torch.uint8, device=dev)
+        g = _lib.GAdmmRound()
+        g.n, g.N, g.S, g.rho, g.mug = n, N, S, self.rho, self.mug
+        for k, v in enumerate(self.edges.cpu().tolist()):
+            g.edge[k] = v
+        for name, t in (("cf", self.cf), ("bg", self.bg), ("dd", self.dd)):
+            for k, v in enumerate(t.cpu().tolist()):
+                getattr(g, name)[k] = v
+        roles = []
+        for r, (cm, cnt) in enumerate(((self.cm_lead, 1), (self.cm_last, 1), (self.cm_mid, n - 2))):
+            if cnt <= 0:
+                continue
+            B, na = S * cnt, (3 if r == 2 else 2)
+            assert cm.n_param == (1 + 2 * na) * 2 * np1 and cm.n_extra == (na - 1) * 2 * np1
+            buf = dict(params=zer(B, cm.n_param), x0=zer(B, 1, 2), mass=zer(B, 1), fm=torch.zeros((B, 1, N), dtype=i32, device=dev),
+                       u=zer(B, 1, N), x=zer(B, 1, 2, np1), e=zer(B, cm.n_extra), mo=torch.zeros((B, 1, N), dtype=i32, device=dev),
+                       ob=zer(B), st=torch.zeros(B, dtype=i32, device=dev), no=torch.zeros(B, dtype=i32, device=dev))
+            R = g.role[r]
+            R.params, R.x0, R.mass, R.fixed_modes = (buf[k].data_ptr() for k in ("params", "x0", "mass", "fm"))
+            R.u, R.x, R.extra, R.obj, R.status = (buf[k].data_ptr() for k in ("u", "x", "e", "ob", "st"))
+            roles.append((cm, B, buf))
+        g.x, g.mass, g.lwin = x.data_ptr(), mass.data_ptr(), lwin.data_ptr()
+        g.y, g.u, g.tr, g.cost, g.ok = y.data_ptr(), u.data_ptr(), tr.data_ptr(), cost.data_ptr(), ok.data_ptr()
+        keep = (y, u, tr, cost, ok, roles, x, mass, lwin)          # the struct holds raw pointers
+
+        def one_round():
+            stream = torch.cuda.current_stream().cuda_stream
+            for cm, B, b in roles:
+                cm.solve_device(B, b["x0"], b["mass"], b["params"], b["fm"], b["u"], b["x"], b["e"], b["mo"], b["ob"],
+                                b["st"], b["no"], None, stream=stream)
+            api.gadmm_round_device(g, init=False, ctx=self.ctx, stream=stream)
+
+        rnd = _StepGraph(torch, one_round, enabled=self.graph)
+
+        def admm(u_start):
+            _ = keep
+            u.copy_(u_start)
+            api.gadmm_round_device(g, init=True, ctx=self.ctx, stream=torch.cuda.current_stream().cuda_stream)
+            for _r in range(self.iters):
+                rnd()
+            infeas = ((tr[:, :, 1, 1:] > 45.84 + 1e-6) | (tr[:, :, 1, 1:] < 3.94 - 1e-6)).any(dim=2).any(dim=1)
+            return u.clone(), cost.clone(), ok.bool() & ~infeas
+
+        return admm
+
     def _make_admm(self, S, x, mass, lwin):
         """g_admm_control for all S scenarios (fleet_g_admm.py:255-301 + the restated round logic): returns
         admm(u_start) -> (u (S,n,N), cost (S,), ok (S,) bool).  x (S,2n), mass (S,n) and lwin (S,2,N+1) are STATIC
@@ -722,6 +780,8 @@ class BatchedGAdmmSweep:
         ROUND -- the fixed-sequence QPs of all agents (one launch of the compiled-MPC kernel per role, FP64 tensor-core
         precompute), the z / y updates and the re-identification of the PWA sequences -- is one CUDA graph that is
         replayed admm_iters times per warm start."""
+        if self.fused:
+            return self._make_admm_fused(S, x, mass, lwin)
         torch, n, N, rho, dev = self.torch, self.n, self.N, self.rho, self.dev
         f64, np1 = torch.float64, N + 1
         zer = lambda *s: torch.zeros(s, dtype=f64, device=dev)
@@ -812,7 +872,7 @@ class BatchedGAdmmSweep:
 
         return admm
 
-    def run(self, x0, leader_x, ep_len: int):
+    def run(self, x0, leader_x, ep_len: int, strict: bool = False):
         torch, dev, n, N = self.torch, self.dev, self.n, self.N
         f64, np1 = torch.float64, N + 1
         x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
@@ -860,8 +920,21 @@ class BatchedGAdmmSweep:
                                     ctx=self.ctx, stream=stream)
             x = X[t + 1]
         torch.cuda.synchronize()
+        solved = OK.cpu().numpy()
+        # The reference RAISES when no warm start of a timestep yields a solution (fleet_g_admm.py:295-297); a batch
+        # cannot stop for one scenario, so the outcome is reported instead of hidden: status 2 / 3 per (timestep,
+        # scenario) with the Gurobi codes of include/hvp.h, and the first failing timestep of every scenario (-1: none).
+        # From that timestep on the scenario's inputs are the zeros the failed step applied -- NOT what the reference
+        # would have produced (it has no trajectory there); strict=True turns any failure into the reference's error.
+        bad = ~solved
+        aborted_at = np.where(bad.any(axis=0), bad.argmax(axis=0), -1).astype(np.int32)
+        if strict and bad.any():
+            who = np.nonzero(aborted_at >= 0)[0]
+            raise RuntimeError(f"No solution found for any of the warm starts: scenarios {who[:8].tolist()}"
+                               f"{' ...' if len(who) > 8 else ''} (first at timestep {int(aborted_at[who].min())})")
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
-                    errors=E.cpu().numpy(), solved=OK.cpu().numpy(), best_warm_start=WS.cpu().numpy())
+                    errors=E.cpu().numpy(), solved=solved, status=np.where(solved, 2, 3).astype(np.int32),
+                    aborted_at=aborted_at, best_warm_start=WS.cpu().numpy())
 
 
 class BatchedEventSweep:

@@ -233,6 +233,36 @@ int hvp_microbench_fp64(hvp_ctx* ctx, int iters, double* tflops);
 /* measured shared-memory read bandwidth of the whole device in GB/s (smem roofline of the QP kernels) */
 int hvp_microbench_smem(hvp_ctx* ctx, int iters, double* gbs);
 
+/* ---- fused coordinator glue of the switching ("g") ADMM controller ---------------------------------
+ * Replaces, per consensus round and for all scenarios at once, what fleet_g_admm.py:255-301 and the round logic of
+ * dmpcpwa's GAdmmCoordinator do between two batches of local QPs: z-update (mean of the copies of each vehicle's
+ * trajectory), y-update, adoption of the solved QPs' inputs, PWA roll-out of the inputs and re-identification of the
+ * region sequences (the next round's fixed_modes), and the packing of the next round's parameter vectors.
+ * Roles: [0] vehicle 0 (GADMM, leader, n_behind = 1), [1] vehicle n-1 (n_front = 1, n_behind = 0), [2] vehicles
+ * 1..n-2 (n_front = n_behind = 1; unused when n == 2).  A role's buffers are the arguments of ITS hvp_mpc_solve_dev
+ * call, problems ordered [scenario][vehicle of the role]: params / x0 / mass / fixed_modes are WRITTEN here (the next
+ * solve's inputs), u / x / extra / obj / status are READ (the last solve's outputs; not with init = 1).
+ * init = 1 starts a warm start: y = 0, z = the roll-out of `u`, ok = 1.  All pointers are device pointers. */
+typedef struct {
+    double* params; double* x0; double* mass; int32_t* fixed_modes;
+    const double* u; const double* x; const double* extra; const double* obj; const int32_t* status;
+} hvp_gadmm_role;
+typedef struct {
+    int32_t n, N, S, init;
+    double rho;
+    double mug, edge[6], cf[7], bg[7], dd[7]; /* pwa_gear regions: v+ = (1 - cf/m) v + (bg/m) u - mug - dd/m, edges between them */
+    hvp_gadmm_role role[3];
+    const double* x;    /* [S][n][2]      */
+    const double* mass; /* [S][n]         */
+    const double* lwin; /* [S][2][N+1]    leader trajectory window of this timestep */
+    double* y;          /* [S][n][3][2][N+1]  multipliers: front copy, own, back copy */
+    double* u;          /* [S][n][N]      inputs: start / previous round in, updated out */
+    double* tr;         /* [S][n][2][N+1] PWA roll-out of u (out) */
+    double* cost;       /* [S]            sum of the solved QPs' objectives (out) */
+    uint8_t* ok;        /* [S]            1 while every QP of every round was solved */
+} hvp_gadmm_round;
+int hvp_gadmm_round_dev(hvp_ctx* ctx, const hvp_gadmm_round* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

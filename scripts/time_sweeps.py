@@ -57,3 +57,19 @@ if "event" in which:
     S, T, n, N = 1024, 6, 6, 5
     lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=10, vf=30, v_change_steps=[3, 5], trajectory_len=T + N + 10, ts=1).get_leader_trajectory()
     ab("event", lambda: SW.BatchedEventSweep(n, N, event_iters=4, ctx=ctx), states(rng, S, n, 10, 30, 60, 140), lx, T, S * T * n * 4, 64)
+if "gfused" in which:      # fused glue kernel vs torch glue (both graphed)
+    S, T, n, N, it = 1024, 2, 15, 8, 100
+    lx = ConstantVelocityLeaderTrajectory(p=3000, v=20, trajectory_len=T + N + 10, ts=1).get_leader_trajectory()
+    x0 = states(rng, S, n, 12, 28, 60, 120)
+    os.environ["HVP_SWEEP_GRAPH"] = "1"
+    res = {}
+    for fused in (False, True):
+        sw = SW.BatchedGAdmmSweep(n, N, admm_iters=it, rho=0.5, ctx=ctx, fused=fused)
+        sw.run(x0[:16], lx, 1)
+        t0 = time.perf_counter(); out = sw.run(x0, lx, T); dt = time.perf_counter() - t0
+        res[fused] = out
+        print(f"gadmm fused={fused}: {dt*1e3:.1f} ms  {S*it*(1+2*(T-1))*n/dt/1e6:.3f} M QPs/s solved {out['solved'].mean():.4f}", flush=True)
+    for k in res[False]:
+        a, b = res[False][k], res[True][k]
+        if not np.array_equal(a, b):
+            print(f"   {k}: differs, max |d| {np.nanmax(np.abs(a.astype(np.float64) - b.astype(np.float64))):.3e}")

@@ -208,3 +208,30 @@ def test_mixed_size_sweep_equals_per_size_sweeps(headway, N):
         assert (r["status"] == 2).all() and (one["status"] == 2).all()
         assert np.array_equal(r["X"], one["X"]) and np.array_equal(r["U"], one["U"])
         assert np.array_equal(r["R"], one["R"]) and np.array_equal(r["nodes"], one["nodes"])
+
+
+def test_gadmm_fused_glue_kernel_equals_torch_glue():
+    """csrc/coord.cu (hvp_gadmm_round_dev: z / y updates, adoption of the QP inputs, PWA re-roll, sequence
+    re-identification and parameter packing of a consensus round in one kernel) against the same round as torch ops:
+    identical arithmetic order, so every result must be bit-equal; and unsolved scenarios are reported, not hidden."""
+    from hybrid_vehicle_platoon_b200.sweep import BatchedGAdmmSweep
+    from hybrid_vehicle_platoon_b200.misc import ConstantVelocityLeaderTrajectory
+    rng = np.random.default_rng(12)
+    for n, N, S, T, iters in ((5, 6, 48, 3, 12), (2, 4, 16, 2, 6)):
+        v = np.floor(rng.uniform(12, 28, (S, n))); gaps = rng.uniform(60, 120, (S, n))
+        p = np.floor(3000.0 - np.cumsum(gaps, 1) + gaps[:, :1])
+        x0 = np.empty((S, 2 * n)); x0[:, 0::2] = p; x0[:, 1::2] = v
+        lx = ConstantVelocityLeaderTrajectory(p=3000, v=20, trajectory_len=T + N + 4, ts=1).get_leader_trajectory()
+        a = BatchedGAdmmSweep(n, N, admm_iters=iters, fused=False).run(x0, lx, T)
+        b = BatchedGAdmmSweep(n, N, admm_iters=iters, fused=True).run(x0, lx, T)
+        for k in ("X", "U", "R", "solved", "status", "aborted_at", "best_warm_start"):
+            assert np.array_equal(a[k], b[k], equal_nan=(a[k].dtype.kind == "f")), (n, N, k)
+        assert ((b["status"] == 2) == b["solved"]).all()
+        assert ((b["aborted_at"] >= 0) == (~b["solved"]).any(axis=0)).all()
+    # strict=True: the reference's RuntimeError (fleet_g_admm.py:295-297) if any scenario has no solution
+    hard = x0.copy(); hard[:, 1::2] = 4.0          # at the lower edge of the velocity box: no feasible warm start
+    sw = BatchedGAdmmSweep(n, N, admm_iters=4)
+    out = sw.run(hard, lx, 1)
+    if not out["solved"].all():
+        with pytest.raises(RuntimeError):
+            sw.run(hard, lx, 1, strict=True)
