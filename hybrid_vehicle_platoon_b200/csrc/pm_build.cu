@@ -89,6 +89,7 @@ struct Builder {
     std::vector<Aff> res; std::vector<double> wres;
     std::vector<Aff> la, lb;                       // cost += la(pvec) * lb(z, pvec)
     std::vector<Aff> rows; std::vector<double> wmax;   // e <= 0
+    bool one_norm = false;                             // cost terms are w |e| instead of w e^2 (cent_mld.py:58-61)
     Builder(int nl_, int N_, int ne_, int npar_)
         : nl(nl_), N(N_), ne(ne_), nv(nl_ * N_ + ne_), npar(npar_), npv(2 * nl_ + npar_ + 1) {}
     Aff zero() const { return Aff(nv, npv); }
@@ -111,7 +112,13 @@ struct Builder {
     // entry (row, k) of the b-th (2, N+1) parameter block
     Aff PB(int b, int row, int k) const { return PAR(b * 2 * (N + 1) + row * (N + 1) + k); }
     Aff K(double c) const { Aff a = zero(); a.p[npv - 1] = c; return a; }
-    void residual(const Aff& e, double w) { res.push_back(e); wres.push_back(w); }
+    // a cost term on the expression e: w e^2 (2-norm), or w |e| = w max(0, e) + w max(0, -e) as a pair of L1-penalised
+    // rows (1-norm: min_1_norm of dmpcpwa's MpcMld, ||Q e||_1 with the diagonal Q)
+    void residual(const Aff& e, double w) {
+        if (!one_norm) { res.push_back(e); wres.push_back(w); return; }
+        rows.push_back(e); wmax.push_back(w);
+        rows.push_back((-1.0) * e); wmax.push_back(w);
+    }
     void product(const Aff& a, const Aff& b) { la.push_back(a); lb.push_back(b); }
     void row(const Aff& e, double w) { rows.push_back(e); wmax.push_back(w); }
 };
@@ -130,6 +137,8 @@ int build_formulation(const hvp_mpc_desc& d, Builder*& out) {
     const bool real_ref = d.flags & HVP_REAL_VEHICLE_REF;
     const double d0 = d.d0, t0 = d.t0;
     Builder* Bp = nullptr;
+    if (d.one_norm && d.kind != HVP_MPC_CENT && d.kind != HVP_MPC_LOCAL)
+        return fail(-4, "mpc_create: the 1-norm cost is built for the centralized and the local formulation (kind %d asked)", d.kind);
     switch (d.kind) {
         case HVP_MPC_CENT: {          // mpcs/cent_mld.py:48-177
             const int n = d.n_local, L = d.leader_index;
@@ -137,6 +146,7 @@ int build_formulation(const hvp_mpc_desc& d, Builder*& out) {
             if (real_ref && L != 0) return fail(-4, "mpc_create: real_vehicle_as_reference needs leader_index 0 (cent_mld.py:63-66)");
             Bp = new Builder(n, N, 0, 2 * np1);
             Builder& B = *Bp;
+            B.one_norm = d.one_norm != 0;
             for (int k = 0; k <= N; ++k) {
                 if (!real_ref) {      // :83-92
                     B.residual(B.P(L, k) - B.PB(0, 0, k), QXP);
@@ -155,6 +165,7 @@ int build_formulation(const hvp_mpc_desc& d, Builder*& out) {
         case HVP_MPC_LOCAL: {         // fleet_decent_mld.py:61-208, fleet_seq_mld.py:63-219
             Bp = new Builder(1, N, 0, 3 * 2 * np1);
             Builder& B = *Bp;
+            B.one_norm = d.one_norm != 0;
             for (int k = 0; k <= N; ++k) {
                 if (!front && !leader) track(B, B.P(0, k), B.V(0, k), B.PB(0, 0, k), B.PB(0, 1, k), d0, t0);
                 if (!trailer && !leader) track(B, B.PB(1, 0, k), B.PB(1, 1, k), B.P(0, k), B.V(0, k), d0, t0);
@@ -417,6 +428,13 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
             for (int j = 0; j < nv; ++j) H0[(size_t)i * nv + j] += 2.0 * w * e.z[i] * e.z[j];
         }
     }
+    S.one_norm = B.one_norm ? 1 : 0;
+    // rho: small enough that a round reaches the solution set in one or two steps (step ~ cost slope / rho), large
+    // enough that saturating a w = 1e4 slack row does not send the iterate through 1e8 (round-off 1e-8: measured, 2.5 %
+    // of the C1-shaped problems did not settle at rho = 1e-4, 0.1 % at 1e-3 .. 1e-2 before the objective criterion)
+    S.rho_px = getenv("HVP_RHO_PX") ? atof(getenv("HVP_RHO_PX")) : 1e-3;
+    if (B.one_norm)                    // no quadratic cost term: the proximal term of the node LPs (pm_types.h)
+        for (int j = 0; j < nv; ++j) H0[(size_t)j * nv + j] = S.rho_px;
     if (!spd_inverse(nv, H0, H0inv)) {
         delete Bp; delete m;
         return fail(-5, "mpc_create: the tracking Hessian of this formulation is not positive definite");

@@ -38,7 +38,8 @@ namespace hvp {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-enum : int { PT_UB = 0, PT_LB, PT_UHI, PT_ULO, PT_ACC, PT_DEC, PT_PHI, PT_PLO, PT_GEN };
+// PT_USP / PT_USN: the pair of soft rows  b u <= 0 / -b u <= 0  (weight qu / b) of a fixed stage under the 1-norm cost
+enum : int { PT_UB = 0, PT_LB, PT_UHI, PT_ULO, PT_ACC, PT_DEC, PT_PHI, PT_PLO, PT_USP, PT_USN, PT_GEN };
 enum : int { PS_NEXT = 0, PS_BUILD, PS_SELECT, PS_STEP, PS_DONE };
 #define PM_ID(t, idx) ((t) * 4096 + (idx))
 #define LANES(j, n) _Pragma("unroll 1") for (int j = lane; j < (n); j += GW)
@@ -116,10 +117,12 @@ struct Warp {
     unsigned gm;                       // lane mask of this group
     // shared-memory views
     double *Hinv, *Ginv, *Nact;
-    double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best;
+    double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best, *zc;
     double *cres, *bgen, *pvec;
     double *inv_m, *pc, *v0, *xstar, *rlo, *rhi, *am, *bm, *cm, *amax, *amin;
-    int *act, *cand, *modes, *bmodes, *built, *orient, *aflag, *agen;
+    int *act, *cand, *modes, *bmodes, *built, *orient, *aflag, *agen, *uor;
+    double f_prev;
+    int ppa, retry;                    // proximal-point rounds / restarts done on the current node (1-norm cost)
     // warp-uniform scalars (replicated in registers)
     int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
     double inc, c0, cp, nHn, lam_p, dual;
@@ -138,7 +141,7 @@ struct Warp {
         Hinv = base + S.o_hinv; Ginv = base + S.o_ginv; Nact = base + S.o_nact;
         double* v = base + S.o_vec;
         x = v; g0 = v + nv; gn = v + 2 * nv; yp = v + 3 * nv; wv = v + 4 * nv; zd = v + 5 * nv;
-        dv = v + 6 * nv; rv = v + 7 * nv; lam = v + 8 * nv; np_ = v + 9 * nv; best = v + 10 * nv;
+        dv = v + 6 * nv; rv = v + 7 * nv; lam = v + 8 * nv; np_ = v + 9 * nv; best = v + 10 * nv; zc = v + 11 * nv;
         cres = base + S.o_cres; bgen = base + S.o_bgen; pvec = base + S.o_pvec;
         double* m = base + S.o_misc;
         const int nl = S.nl, N = S.N, D = S.depth;
@@ -147,7 +150,8 @@ struct Warp {
         amax = cm + D; amin = amax + D;
         int* ib = reinterpret_cast<int*>(base + S.smem_doubles);
         act = ib; cand = ib + nv; modes = cand + D + 1; bmodes = modes + D; built = bmodes + D;
-        orient = built + D; aflag = orient + S.ng; agen = aflag + nv;
+        orient = built + D; aflag = orient + S.ng; agen = aflag + nv; uor = agen + S.ng;
+        ppa = 0; retry = 0;
         (void)ld;
         sub_M = sub_D = sub_code = sub_ord = budget = stop_nodes = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
     }
@@ -242,6 +246,10 @@ struct Warp {
                 g0[j] = s;
             }
         }
+        if (S.one_norm) {                  // proximal centre: constant velocity
+            LANES(j, nv) zc[j] = (j < nl * N) ? x0[2 * (j / N) + 1] : 0.0;
+        }
+        ppa = 0; retry = 0;
         built_L = -1;                      // H^-1 not loaded yet
         iters = nodes = it = q = 0;
         inc = HUGE_VAL; own = HUGE_VAL; trouble = limit = timeout = false; dive = true; sub_ord = 0;
@@ -383,6 +391,23 @@ struct Warp {
     // st: 0 solved, 1 infeasible, 2 numerical trouble
     __device__ void node_done(int st, double obj) {
         iters += it;
+        if (S.one_norm) {
+            // An LP node is degenerate far more often than a QP node (a full active set is the rule, ties between a
+            // partial and a full step are common): a round that ends in numerical trouble is repeated from a slightly
+            // different proximal centre, which changes the path of the active-set method but not the LP it converges to.
+            if (st == 2 && retry < 4) {
+                ++retry;
+                LANES(j, S.nv) {
+                    const unsigned h = (unsigned)(j * 2654435761u) ^ (unsigned)(retry * 40503u) ^ (unsigned)(nodes * 9973u);
+                    zc[j] += 1e-3 * ((double)((h >> 8) & 0xffff) / 65536.0 - 0.5) * (double)retry;
+                }
+                ppa = 0;
+                state = PS_BUILD;
+                __syncwarp(gm);
+                return;
+            }
+            retry = 0;
+        }
         ++nodes;
         state = fixed ? PS_DONE : PS_NEXT;
         if (st != 0 || L == S.depth) dive = false;
@@ -420,6 +445,21 @@ struct Warp {
         ++lev;
         if (lane == 0) open_level(lev);
         __syncwarp(gm);
+    }
+
+    // L1 weight of a row id (+inf: hard row).  Soft rows: generic rows with a finite wmax, and the |u| pair of a fixed stage.
+    __device__ __forceinline__ double soft_w(int id) const {
+        const int pt = id / 4096, ix = id % 4096;
+        if (pt == PT_GEN) return S.wmax[ix];
+        if (pt == PT_USP || pt == PT_USN) return S.qu * rcp(bm[(ix % S.N) * S.nl + ix / S.N]);
+        return HUGE_VAL;
+    }
+    // a saturated soft row changes orientation (its penalty gradient stays in x, which is only ever updated incrementally)
+    __device__ __forceinline__ void flip(int id) {
+        const int pt = id / 4096, ix = id % 4096;
+        if (pt == PT_GEN) orient[ix] = -orient[ix];
+        else if (pt == PT_USP) uor[ix] = -uor[ix];
+        else if (pt == PT_USN) uor[S.nv + ix] = -uor[S.nv + ix];
     }
 
     // H <- H + s * 2 qu e e',  e = (e_jk - a e_jm)/b  (decision d in mode rg): Sherman-Morrison on H^-1
@@ -463,10 +503,12 @@ struct Warp {
             c = 0; built_L = 0;
             __syncwarp(gm);
         }
-        _Pragma("unroll 1")
-        for (int d = built_L - 1; d >= c; --d) rank1(d, built[d], -1.0);
-        _Pragma("unroll 1")
-        for (int d = c; d < L; ++d) rank1(d, modes[d], 1.0);
+        if (!S.one_norm) {                 // 1-norm: no quadratic input cost, H^-1 = I / rho_px for every node
+            _Pragma("unroll 1")
+            for (int d = built_L - 1; d >= c; --d) rank1(d, built[d], -1.0);
+            _Pragma("unroll 1")
+            for (int d = c; d < L; ++d) rank1(d, modes[d], 1.0);
+        }
         LANES(d, L) {
             built[d] = modes[d];
             const int i = d % nl, r = modes[d];
@@ -477,7 +519,8 @@ struct Warp {
         const double qu = S.qu;
         LANES(j, nv) {
             double g = g0[j];
-            if (j < nl * N) {
+            if (S.one_norm) g -= S.rho_px * zc[j];          // gradient of rho/2 |z - zc|^2 at 0
+            else if (j < nl * N) {
                 const int i = j / N, kk = j % N;
                 const int d0 = kk * nl + i, d1 = d0 + nl;
                 if (d0 < L) {
@@ -507,7 +550,7 @@ struct Warp {
         // value of the node's dual function at the unconstrained minimiser; it only grows from here
         dual = c0 + wsum<GW>(gm, dpart);
         LANES(r, S.ng) { orient[r] = 1; agen[r] = 0; }
-        LANES(j, nv) aflag[j] = 0;
+        LANES(j, nv) { aflag[j] = 0; uor[j] = 1; uor[nv + j] = 1; }
         it = 0; q = 0;
         state = PS_SELECT;
         __syncwarp(gm);
@@ -537,6 +580,11 @@ struct Warp {
             }
             if (d0 >= L) {       // stage kk not fixed: reachable interval of v_{kk+1}
                 lo = fmax(lo, rlo[i * (N + 1) + kk + 1]); hi = fmin(hi, rhi[i * (N + 1) + kk + 1]);
+            }
+            if (S.one_norm && soft && d0 < L) {      // qu |u| of a fixed stage: the pair of soft rows on b u
+                const double du = xv - am[d0] * (kk == 0 ? v0[i] : x[j - 1]) - cm[d0];
+                PM_CAND(PT_USP, j, uor[j] > 0 ? du : -du);
+                PM_CAND(PT_USN, j, uor[nv + j] > 0 ? -du : du);
             }
             if (kk == 0) {
                 lo = fmax(lo, v0[i] + S.a_dec); hi = fmin(hi, v0[i] + S.a_acc);
@@ -585,15 +633,17 @@ struct Warp {
     __device__ double objective() {
         const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
         double f = 0.0;
-        LANES(j, nv) {
-            const double s = dot2(S.H0 + (size_t)j * nv, 1, x, nv);
-            f += x[j] * (g0[j] + 0.5 * s);
+        if (!S.one_norm) {
+            LANES(j, nv) {
+                const double s = dot2(S.H0 + (size_t)j * nv, 1, x, nv);
+                f += x[j] * (g0[j] + 0.5 * s);
+            }
         }
         LANES(d, L) {
             const int i = d % nl, k = d / nl, jk = i * N + k;
             const double xp = (k >= 1) ? x[jk - 1] : v0[i];
             const double uu = (x[jk] - am[d] * xp - cm[d]) * rcp(bm[d]);
-            f += S.qu * uu * uu;
+            f += S.one_norm ? S.qu * fabs(uu) : S.qu * uu * uu;     // the proximal term is not part of the LP objective
         }
         LANES(r, ng) {
             const double wm = S.wmax[r];
@@ -611,13 +661,37 @@ struct Warp {
         double best_v; int bid;
         scan(best_v, bid, 1e-9, true);
         if (bid == 0x7fffffff) {
+            if (S.one_norm) {
+                // Proximal-point round done.  The node LP is solved once the centre stops moving -- or, when the
+                // optimum is a face and round-off keeps the point wandering on it, once the LP objective stops
+                // decreasing: f(zc) - f(x) >= rho/2 |x - zc|^2, so a stalled objective means a stalled point, and a
+                // proximal step from a non-optimal centre always decreases f.
+                double dl = 0.0; int dj = 0;
+                LANES(j, nv) { const double a = fabs(x[j] - zc[j]); if (a > dl) dl = a; }
+                wargmax<GW>(gm, dl, dj);
+                const double f = objective();
+                const bool stalled = ppa >= 1 && f_prev - f <= 1e-12 * fmax(1.0, fabs(f));
+                if (dl > 1e-6 && !stalled && ppa < 200) {
+                    LANES(j, nv) zc[j] = x[j];
+                    ++ppa;
+                    f_prev = f;
+                    iters += it;
+                    state = PS_BUILD;
+                    __syncwarp(gm);
+                    return;
+                }
+                if (dl > 1e-6 && !stalled) { node_done(2, 0.0); return; }
+                ppa = 0;
+                node_done(0, f);
+                return;
+            }
+            ppa = 0;
             node_done(0, objective());
             return;
         }
         pid = bid;
         const int pt = pid / 4096, idx = pid % 4096;
-        p_soft = false;
-        if (pt == PT_GEN) p_soft = isfinite(S.wmax[idx]);
+        p_soft = isfinite(soft_w(pid));
         // dense normal of p
         LANES(j, nv) {
             double v = 0.0;
@@ -628,6 +702,11 @@ struct Warp {
                     const int i = idx / N, kk = idx % N, d0 = kk * nl + i;
                     v = (j == idx) ? 1.0 : ((j == idx - 1) ? -am[d0] : 0.0);
                     if (pt == PT_ULO) v = -v;
+                } break;
+                case PT_USP: case PT_USN: {
+                    const int i = idx / N, kk = idx % N, d0 = kk * nl + i;
+                    v = (j == idx) ? 1.0 : ((j == idx - 1 && kk > 0) ? -am[d0] : 0.0);
+                    v *= (pt == PT_USP) ? (double)uor[idx] : -(double)uor[nv + idx];
                 } break;
                 case PT_ACC: v = (j == idx) ? 1.0 : ((j == idx - 1) ? -1.0 : 0.0); break;
                 case PT_DEC: v = (j == idx) ? -1.0 : ((j == idx - 1) ? 1.0 : 0.0); break;
@@ -656,7 +735,7 @@ struct Warp {
     __device__ void do_step() {
         const int nv = S.nv, ld = S.ld;
         const double tol = 1e-9, INF = HUGE_VAL;
-        if (++it > 40 * nv + 200) { node_done(2, 0.0); return; }
+        if (++it > (S.one_norm ? 200 * nv + 2000 : 40 * nv + 200)) { node_done(2, 0.0); return; }
         // p can reach its boundary exactly at the end of a PARTIAL step (t1 = t2 tie): it then joins the
         // active set with the multiplier it has accumulated (a full step of length zero) -- returning to
         // SELECT here would drop lam_p * n_p from the stationarity condition
@@ -679,13 +758,10 @@ struct Warp {
                 const double t = la * rcp(s);
                 if (t < t1) { t1 = t; k1 = a; }
             } else if (s < -1e-14) {
-                const int id = act[a];
-                if (id >= PM_ID(PT_GEN, 0)) {
-                    const double wm = S.wmax[id - PM_ID(PT_GEN, 0)];
-                    if (isfinite(wm)) {
-                        const double t = (wm - la) * rcp(-s);
-                        if (t < t3) { t3 = t; k3 = a; }
-                    }
+                const double wm = soft_w(act[a]);
+                if (isfinite(wm)) {
+                    const double t = (wm - la) * rcp(-s);
+                    if (t < t3) { t3 = t; k3 = a; }
                 }
             }
         }
@@ -695,12 +771,13 @@ struct Warp {
         const bool dependent = (q == nv) || !(nz > 1e-11 * nHn);
         if (zero_step && dependent) { node_done(2, 0.0); return; }
         const double t2 = dependent ? INF : (zero_step ? 0.0 : cp * rcp(nz));
-        const double t3p = p_soft ? (S.wmax[pid - PM_ID(PT_GEN, 0)] - lam_p) : INF;
+        const double t3p = p_soft ? (soft_w(pid) - lam_p) : INF;
         const double t = fmin(fmin(t1, t2), fmin(t3, t3p));
         if (!(t < INF)) { node_done(1, 0.0); return; }          // infeasible node
         // d(dual)/dt = violation of p along the step: the dual value is a lower bound on the node optimum
         dual += t * cp - (dependent ? 0.0 : 0.5 * t * t * nz);
-        if (dual > inc) { node_done(1, 0.0); return; }          // the node cannot beat the incumbent
+        // (not under the 1-norm cost: the dual of a proximal sub-problem does not bound the node LP)
+        if (!S.one_norm && dual > inc) { node_done(1, 0.0); return; }          // the node cannot beat the incumbent
         __syncwarp(gm);
         if (!dependent) {
             // w = n_p - N r ;  x -= t H^-1 w ;  the violation of p shrinks by t nz
@@ -739,7 +816,7 @@ struct Warp {
             return;
         }
         if (t == t3p) {                                          // soft p saturates: flip, not added
-            if (lane == 0) orient[pid - PM_ID(PT_GEN, 0)] = -orient[pid - PM_ID(PT_GEN, 0)];
+            if (lane == 0) flip(pid);
             state = PS_SELECT;
             __syncwarp(gm);
             return;
@@ -748,7 +825,7 @@ struct Warp {
         if (t == t1) drop = k1;
         else {                                                   // active soft row saturates: flip + drop
             drop = k3;
-            if (lane == 0) { const int r = act[drop] - PM_ID(PT_GEN, 0); orient[r] = -orient[r]; }
+            if (lane == 0) flip(act[drop]);
         }
         if (lane == 0) {
             const int id_ = act[drop], pt_ = id_ / 4096, ix_ = id_ % 4096;
@@ -1113,13 +1190,13 @@ void pm_layout(PmDev& S) {
     S.o_hinv = o; o += nv * S.ld;
     S.o_ginv = o; o += nv * S.ld;
     S.o_nact = o; o += nv * S.ld;
-    S.o_vec = o; o += 11 * nv;
+    S.o_vec = o; o += 12 * nv;
     S.o_cres = o; o += S.nres + S.nlin;
     S.o_bgen = o; o += S.ng;
     S.o_pvec = o; o += S.npv;
     S.o_misc = o; o += 3 * S.nl + (D + 1) + 2 * S.nl * (S.N + 1) + 5 * D;
     S.smem_doubles = o;
-    const int ints = nv + (D + 1) + 3 * D + S.ng + nv + S.ng;
+    const int ints = nv + (D + 1) + 3 * D + S.ng + nv + S.ng + 2 * nv;
     S.o_int = o;
     S.smem_bytes = (o * 8 + ints * 4 + 15) / 16 * 16;
 }

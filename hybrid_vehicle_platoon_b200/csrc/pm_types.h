@@ -32,6 +32,12 @@ struct PmDev {                   // kernel argument
     int nres, nlin, ng, n0;      // residuals, param-linear cost terms, generic rows, constant rows
     int depth;                   // nl * N branching decisions (stage-major: d = k nl + i)
     int max_nodes;
+    // 1-norm cost (quadratic_cost = False, cent_mld.py:58-61): every cost term w |e| is a PAIR of L1-penalised rows
+    // (e <= 0 and -e <= 0, weight w), the input cost qu |u| of a fixed stage a pair of on-the-fly rows, and a node LP is
+    // solved by the proximal-point method on the same bounded-multiplier dual active-set code: H = rho_px I around a
+    // centre z_k that moves to the solution until it stops moving (finite for an LP; one or two rounds in practice).
+    int one_norm;
+    double rho_px;
     double mip_gap;              // relative pruning gap (0: proven optimal)
     long long time_limit_ns;     // per-problem budget on the device clock (0: none)
     PmModel M;

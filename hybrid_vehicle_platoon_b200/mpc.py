@@ -52,17 +52,17 @@ class LocalMpcMld:
         # real_vehicle_as_reference (fleet_seq_mld.py:137,211-219; False in every Sim of the reference) adds a spacing
         # term and a safe-distance row against the leader trajectory: that variant lives in the compiled LOCAL
         # formulation (csrc/pm_build.cu), which solves the same problem as this class otherwise
-        if real_vehicle_as_reference and cls is LocalMpcMld:
+        # quadratic_cost=False (the 1-norm / MILP variant, fleet_decent_mld.py:75-78) lives there too: LP node problems
+        # through the proximal-point wrapper of the compiled-MPC kernel (csrc/pm_types.h)
+        if (real_vehicle_as_reference or not quadratic_cost) and cls is LocalMpcMld:
             return LocalMpcGear(N, pwa_system, spacing_policy, quadratic_cost, is_front, is_leader, is_trailer,
-                                thread_limit, accel_cnstr_tightening, True, ctx=ctx)
+                                thread_limit, accel_cnstr_tightening, real_vehicle_as_reference, ctx=ctx)
         return super().__new__(cls)
 
     def __init__(self, N: int, pwa_system: dict, spacing_policy=ConstantSpacingPolicy(50),
                  quadratic_cost: bool = True, is_front: bool = False, is_leader: bool = False,
                  is_trailer: bool = False, thread_limit=None, accel_cnstr_tightening: float = 0.0,
                  real_vehicle_as_reference: bool = False, ctx=None) -> None:
-        if not quadratic_cost:
-            raise NotImplementedError("1-norm cost (MILP) is a SURVEY.md 8f row, not built yet")
         self.N, self.n, self.m = N, 1, 1
         self.mass = mass_of_pwa_system(pwa_system)
         self.d0, self.t0 = spacing_params(spacing_policy)
@@ -146,8 +146,9 @@ class _CompiledController:
 
     def _setup(self, kind, N, systems, spacing_policy, quadratic_cost, *, flags=0, leader_index=0, n_front=0,
                n_behind=0, tight=0.0, rho=0.5, ctx=None):
-        if not quadratic_cost:
-            raise NotImplementedError("1-norm cost (MILP) is a SURVEY.md 8f row, not built yet")
+        if not quadratic_cost and kind not in (MPC_CENT, MPC_LOCAL):
+            raise NotImplementedError("the 1-norm cost (MILP) is built for the centralized and the per-vehicle local "
+                                      "controllers (SURVEY.md 8f rank 3); event-based / ADMM variants are not")
         mm = [model_of_pwa_system(sy) for sy in systems]
         if len({m for m, _ in mm}) != 1:
             raise ValueError("all vehicles of one controller must use the same model type")

@@ -1,0 +1,127 @@
+"""1-norm cost variant (quadratic_cost=False: MILP; mpcs/cent_mld.py:58-61, fleet_decent_mld.py:
+75-78, env.py:122-124) of the centralized and the per-vehicle local controllers against an INDEPENDENT exact solver:
+the explicit big-M MLD model of tests/mld_bigm.py handed to scipy.optimize.milp (HiGHS branch and bound).  Nothing is
+shared between the two sides: the product solves LP node problems in velocity space (proximal-point rounds on the
+bounded-multiplier dual active-set code, csrc/pm_kernel.cu), HiGHS works on (x, u, z, delta) with big-M rows.
+Bar (BASELINE.json): objective 1e-6 relative; modes identical and inputs 1e-5 where the optimum is unique -- an LP
+optimum is a face more often than a QP's is a point, so inputs are compared through the objective they attain."""
+import numpy as np
+import pytest
+
+import mld_bigm as MB
+from gen_cases import platoon_local_problems
+import gen_mpc_cases as G
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def _sysd(m):
+    from hybrid_vehicle_platoon_b200.models import Platoon
+    return Platoon(1, "pwa_gear", masses=[m]).get_vehicle_system_dicts(1.0)[0]
+
+
+@pytest.mark.parametrize("N,stress,t0", [(3, False, 0.0), (4, True, 0.0), (4, True, 3.0), (6, False, 0.0)])
+def test_local_one_norm_vs_milp(hvp_ctx, N, stress, t0):
+    import hybrid_vehicle_platoon_b200 as hvp
+    rng = np.random.default_rng(40 + N)
+    d0 = 10.0 if t0 else 50.0
+    c = platoon_local_problems(rng, 2, 4, N, 0, stress, True)
+    B = len(c["flags"])
+    for fl in sorted(set(int(f) for f in c["flags"])):
+        sel = np.nonzero(c["flags"] == fl)[0]
+        mpc = hvp.api.CompiledMpc(G.LOCAL, N, flags=fl, d0=d0, t0=t0, one_norm=True, ctx=hvp_ctx)
+        params = np.concatenate([c["xf"][sel].reshape(len(sel), -1), c["xb"][sel].reshape(len(sel), -1),
+                                 c["xl"][sel].reshape(len(sel), -1)], axis=1)
+        r = mpc.solve(c["x0"][sel].reshape(-1, 1, 2), c["mass"][sel].reshape(-1, 1), params)
+        for j, b in enumerate(sel):
+            M, x, u, dl = MB.build_local(_sysd(float(c["mass"][b])), N, c["x0"][b], c["xf"][b], c["xb"][b], c["xl"][b],
+                                         is_front=bool(fl & 1), is_leader=bool(fl & 2), is_trailer=bool(fl & 4),
+                                         d0=d0, t0=t0, quadratic=False)
+            ok, xs, obj = MB.solve_milp(M)
+            if not ok:
+                assert r["status"][j] == 3, (b, r["status"][j])
+                continue
+            assert r["status"][j] == 2, (b, fl, r["status"][j])
+            assert abs(r["obj"][j] - obj) <= TOL * max(1.0, abs(obj)), (b, fl, r["obj"][j], obj)
+            # the GPU's inputs are feasible for the independent model with its modes fixed, at the same objective
+            fixed = {}
+            for k in range(N):
+                for rg in range(dl.shape[0]):
+                    fixed[int(dl[rg, k])] = 1.0 if r["modes"][j].reshape(-1)[k] == rg else 0.0
+                fixed_u = float(r["u"][j].reshape(-1)[k])
+                M.lb[int(u[0, k])] = fixed_u - 1e-7; M.ub[int(u[0, k])] = fixed_u + 1e-7
+            ok2, _, obj2 = MB.solve_qp_fixed(M, fixed, tol=1e-7)
+            assert ok2 and abs(obj2 - obj) <= 1e-5 * max(1.0, abs(obj)), (b, fl, obj2, obj)
+
+
+@pytest.mark.parametrize("n,N,stress", [(2, 3, True), (3, 3, False), (3, 5, False)])
+def test_centralized_one_norm_vs_milp(hvp_ctx, n, N, stress):
+    """BASELINE configs[0] shape (n = 3, N = 5) with quadratic_cost=False."""
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200.models import Platoon
+    rng = np.random.default_rng(70 + n * 10 + N)
+    Bn = 3 if n * N > 9 else 5
+    x0, params = G.cent_cases(rng, Bn, n, N, stress)
+    mpc = hvp.api.CompiledMpc(G.CENT, N, n_local=n, one_norm=True, ctx=hvp_ctx)
+    r = mpc.solve(x0, 800.0, params)
+    systems = Platoon(n, "pwa_gear", masses=[800.0] * n).get_vehicle_system_dicts(1.0)
+    for b in range(Bn):
+        M, xs, us, ds = MB.build_cent(systems, N, x0[b], params[b].reshape(2, N + 1), quadratic=False)
+        ok, sol, obj = MB.solve_milp(M, time_limit=120.0)
+        if not ok:
+            assert r["status"][b] == 3
+            continue
+        assert r["status"][b] == 2, (b, r["status"][b])
+        assert abs(r["obj"][b] - obj) <= TOL * max(1.0, abs(obj)), (b, r["obj"][b], obj, r["nodes"][b])
+
+
+def test_controller_classes_accept_one_norm(hvp_ctx):
+    """MpcMldCent / LocalMpcMld with quadratic_cost=False solve (the drop-in signature of the reference); the
+    event-based and ADMM controllers say that the variant is not built."""
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200.models import Platoon
+    from hybrid_vehicle_platoon_b200.misc import ConstantSpacingPolicy
+    n, N = 3, 4
+    systems = Platoon(n, "pwa_gear", masses=[800.0] * n).get_vehicle_system_dicts(1.0)
+    cent = hvp.MpcMldCent(n, N, systems, ConstantSpacingPolicy(50), quadratic_cost=False, ctx=hvp_ctx)
+    lt = np.vstack([3000 + 20.0 * np.arange(N + 1), np.full(N + 1, 20.0)])
+    cent.set_leader_traj(lt)
+    state = np.array([[2990.0], [19.0], [2930.0], [21.0], [2870.0], [20.0]])
+    u0, info = cent.solve_mpc(state)
+    assert u0.shape == (n, 1) and np.isfinite(info["cost"])
+    loc = hvp.LocalMpcMld(N, systems[1], ConstantSpacingPolicy(50), quadratic_cost=False, ctx=hvp_ctx)
+    loc.set_x_front(np.vstack([2990 + 19.0 * np.arange(N + 1), np.full(N + 1, 19.0)]))
+    loc.set_x_back(np.vstack([2870 + 20.0 * np.arange(N + 1), np.full(N + 1, 20.0)]))
+    u1, info1 = loc.solve_mpc(np.array([[2930.0], [21.0]]))
+    assert u1.shape == (1, 1) and np.isfinite(info1["cost"])
+    with pytest.raises(NotImplementedError):
+        hvp.LocalMpcADMM(N, systems[1], 0.5, quadratic_cost=False, ctx=hvp_ctx)
+
+
+def test_centralized_one_norm_closed_loop(hvp_ctx):
+    """fleet_cent_mld.simulate with Sim.quadratic_cost = False (bash_scripts/performance.cmd:8 sweeps it): the MILP
+    controller drives the 1-norm env (env.py:122-124) for a few steps; every step's optimal cost is re-derived by
+    HiGHS from the logged state, and the logged stage costs are the 1-norm ones."""
+    import hybrid_vehicle_platoon_b200 as hvp
+    from hybrid_vehicle_platoon_b200.models import Platoon
+    from test_host_fleets import SmallSim
+    n, N, T = 2, 3, 4
+    sim = SmallSim(n, N, T)
+    sim.quadratic_cost = False
+    out = hvp.fleet_cent_mld.simulate(sim, seed=3)
+    assert out["X"].shape == (T + 1, 2 * n) and np.isfinite(out["X"]).all()
+    systems = Platoon(n, "pwa_gear", masses=[800.0] * n).get_vehicle_system_dicts(1.0)
+    mpc = hvp.api.CompiledMpc(G.CENT, N, n_local=n, one_norm=True, ctx=hvp_ctx)
+    lx = out["leader_x"]
+    for t in range(T):
+        x0 = out["X"][t].reshape(n, 2)
+        lt = lx[:, t:t + N + 1]
+        r = mpc.solve(x0[None], 800.0, lt.reshape(1, -1))
+        M, xs, us, ds = MB.build_cent(systems, N, x0, lt, quadratic=False)
+        ok, sol, obj = MB.solve_milp(M)
+        assert ok and r["status"][0] == 2 and abs(r["obj"][0] - obj) <= TOL * max(1.0, abs(obj)), (t, r["obj"][0], obj)
+        # stage cost of the env at this step: 1-norm tracking of the leader + spacing + effort (env.py:126-180)
+        e = abs(x0[0, 0] - lx[0, t]) + 0.1 * abs(x0[0, 1] - lx[1, t]) + abs(x0[1, 0] - x0[0, 0] + 50.0) \
+            + 0.1 * abs(x0[1, 1] - x0[0, 1]) + np.abs(out["U"][t]).sum()
+        assert abs(float(np.asarray(out["R"][t]).reshape(-1)[0]) - e) <= 1e-9 * max(1.0, e), (t, out["R"][t], e)
