@@ -8,9 +8,9 @@
 //       The node QPs have 4..12 variables -- far too small for a CTA -- so a warp carries 4 (or 2)
 //       independent branch-and-bound trees and the batch (scenario x vehicle x ADMM round)
 //       fills the grid.
-//   local_miqp_kernel<NMAX> (HVP_LOCAL_KERNEL=scalar): the first design, one thread per MIQP
-//       with its state in shared memory (miqp_core.cuh); kept for A/B measurements -- ncu showed
-//       5.8 of 32 lanes active per instruction because every lane runs its own tree.
+//   flat_miqp_kernel<N>  (batches >= 8192): one problem per lane, persistent warps (flat_core.cuh).
+//   (The first design -- one thread per MIQP with nested loops, 5.8 of 32 lanes active -- left the library in
+//   round 2; it survives as a second implementation for the host tests, tests/host_harness/scalar_solver.h.)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -22,31 +22,6 @@
 #include "miqp_core.cuh"
 
 namespace hvp {
-
-template <int NMAX>
-__global__ void __launch_bounds__(LOCAL_BLOCK, 6)
-local_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int32_t* __restrict__ flags,
-                  const double* __restrict__ mass, const double* __restrict__ x0,
-                  const double* __restrict__ xf, const double* __restrict__ xb,
-                  const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
-                  int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
-                  int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters) {
-    extern __shared__ double smem[];
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= batch) return;
-    const int N = P.N;
-    const size_t S = 2 * (size_t)(N + 1);
-    // per-warp slab of LocalLayout::SIZE x 32 doubles; element e of lane l is slab[e*32 + l]
-    double* W = smem + (size_t)(threadIdx.x >> 5) * (LocalLayout<NMAX>::SIZE * 32) + (threadIdx.x & 31);
-    LocalSolver<NMAX, 32> sol;
-    sol.setup(W, &P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr, xb ? xb + S * i : nullptr,
-              xl ? xl + S * i : nullptr);
-    LocalResult R = sol.solve(u + (size_t)N * i, x + S * i, modes + (size_t)N * i);
-    obj[i] = R.obj;
-    status[i] = R.status;
-    nodes[i] = R.nodes;
-    if (qp_iters) qp_iters[i] = R.qp_iters;
-}
 
 template <int G>
 __global__ void __launch_bounds__(COOP_BLOCK)
@@ -281,20 +256,17 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
     return cudaGetLastError();
 }
 
-// 0 auto, 1 scalar (first design), 2 coop, 3 flat
+// 0 auto, 2 coop, 3 flat
 static int kernel_choice() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("HVP_LOCAL_KERNEL");
         v = 0;
-        if (e && strcmp(e, "scalar") == 0) v = 1;
         if (e && strcmp(e, "coop") == 0) v = 2;
         if (e && strcmp(e, "flat") == 0) v = 3;
     }
     return v;
 }
-
-static bool use_scalar_kernel() { return kernel_choice() == 1; }
 
 cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter, double* steal_scratch, int64_t batch, const int32_t* flags, const double* mass,
                               const double* x0, const double* xf, const double* xb, const double* xl,
@@ -310,7 +282,7 @@ cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter,
         switch (P.N) { HVP_FLAT(4) HVP_FLAT(5) HVP_FLAT(6) HVP_FLAT(7) HVP_FLAT(8) HVP_FLAT(9) default: break; }
 #undef HVP_FLAT
     }
-    if (!use_scalar_kernel()) {
+    {
         if (P.N <= 8) {
             if (batch <= COOP_SPREAD_MAX) {
                 coop_miqp_kernel<8><<<(unsigned)batch, 32, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes,
@@ -334,32 +306,7 @@ cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter,
         }
         return cudaGetLastError();
     }
-    const unsigned grid = (unsigned)((batch + LOCAL_BLOCK - 1) / LOCAL_BLOCK);
-#define HVP_LAUNCH(NM)                                                                                   \
-    {                                                                                                    \
-        const size_t smem = (size_t)(LOCAL_BLOCK / 32) * LocalLayout<NM>::SIZE * 32 * sizeof(double);    \
-        static bool configured_dev[HVP_MAX_DEVICES] = {false};                                           \
-        int dev__ = 0;                                                                                   \
-        cudaGetDevice(&dev__);                                                                           \
-        bool uncached__ = false;                                                                         \
-        bool& configured = (dev__ >= 0 && dev__ < HVP_MAX_DEVICES) ? configured_dev[dev__] : uncached__; \
-        if (!configured) {                                                                               \
-            cudaError_t e = cudaFuncSetAttribute(local_miqp_kernel<NM>,                                  \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                              \
-            e = cudaFuncSetAttribute(local_miqp_kernel<NM>, cudaFuncAttributePreferredSharedMemoryCarveout, \
-                                     cudaSharedmemCarveoutMaxShared);                                    \
-            if (e != cudaSuccess) return e;                                                              \
-            configured = true;                                                                           \
-        }                                                                                                \
-        local_miqp_kernel<NM><<<grid, LOCAL_BLOCK, smem, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, \
-                                                                   x, modes, obj, status, nodes, qp_iters); \
-    }
-    if (P.N <= 6) HVP_LAUNCH(6)
-    else if (P.N <= 8) HVP_LAUNCH(8)
-    else HVP_LAUNCH(12)
-#undef HVP_LAUNCH
-    return cudaGetLastError();
+    return cudaErrorInvalidConfiguration;
 }
 
 }  // namespace hvp

@@ -5,6 +5,7 @@
 #include "../../hybrid_vehicle_platoon_b200/csrc/vehicle_model.h"
 #include "../../hybrid_vehicle_platoon_b200/csrc/coop_core.cuh"
 #include "../../hybrid_vehicle_platoon_b200/csrc/flat_core.cuh"
+#include "scalar_solver.h"
 
 extern "C" void hvh_local_miqp_batch(int batch, int N, const int32_t* flags, double d0, double t0,
                                      double tight, int max_nodes, const double* mass, const double* x0,
