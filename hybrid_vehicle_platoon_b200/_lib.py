@@ -23,7 +23,8 @@ class EnvDesc(C.Structure):
 
 class LocalDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("max_nodes", C.c_int32), ("d0", C.c_double), ("t0", C.c_double),
-                ("tight", C.c_double), ("mip_gap", C.c_double), ("time_limit_ms", C.c_double)]
+                ("tight", C.c_double), ("mip_gap", C.c_double), ("time_limit_ms", C.c_double),
+                ("modes_hint", C.c_void_p)]
 
 
 class MpcDesc(C.Structure):

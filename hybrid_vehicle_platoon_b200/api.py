@@ -64,7 +64,7 @@ def rollout_step_device(desc: EnvDesc, batch, x, u, gear, mass, leader, x_out, c
 def local_desc(N, d0=50.0, t0=0.0, tight=0.0, max_nodes=0, mip_gap=0.0, time_limit_ms=0.0) -> LocalDesc:
     """mip_gap: relative gap at which nodes are pruned (Gurobi MIPGap; 0 = proven optimal); time_limit_ms: per-problem
     device-clock budget, status 9 with the incumbent when it runs out (0 = none)."""
-    return LocalDesc(int(N), int(max_nodes), float(d0), float(t0), float(tight), float(mip_gap), float(time_limit_ms))
+    return LocalDesc(int(N), int(max_nodes), float(d0), float(t0), float(tight), float(mip_gap), float(time_limit_ms), None)
 
 
 def local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0, tight=0.0,
@@ -92,10 +92,14 @@ def local_miqp(N, flags, mass, x0, xf=None, xb=None, xl=None, *, d0=50.0, t0=0.0
 
 
 def local_miqp_device(desc: LocalDesc, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status,
-                      nodes, qp_iters=None, *, ctx=None, stream=None):
-    """Same on DEVICE buffers (torch CUDA tensors); asynchronous on `stream`."""
+                      nodes, qp_iters=None, *, ctx=None, stream=None, modes_hint=None):
+    """Same on DEVICE buffers (torch CUDA tensors); asynchronous on `stream`.  modes_hint: optional (batch, N) int32
+    CUDA tensor of region sequences to try first (include/hvp.h)."""
     ctx = ctx or default_context()
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    if modes_hint is not None:
+        desc = LocalDesc(desc.N, desc.max_nodes, desc.d0, desc.t0, desc.tight, desc.mip_gap, desc.time_limit_ms,
+                         modes_hint.data_ptr())
     check(lib().hvp_local_miqp_dev(ctx.handle, C.byref(desc), int(batch), p(flags), p(mass), p(x0), p(xf),
                                    p(xb), p(xl), p(u), p(x), p(modes), p(obj), p(status), p(nodes),
                                    p(qp_iters), _stream_arg(stream)))

@@ -126,6 +126,8 @@ struct FlatSolver {
     int built_L;                                        // H^-1 currently holds stages 0..built_L-1 of built_pk
     bool trouble, limit, timeout;
     bool dive;                                          // first descent: path nodes are not solved, only the leaf
+    bool hinted;                                        // the node being solved is the caller's hinted leaf
+    int hint_c0;
     bool fresh;                                         // the slab still holds the solved parent of level `lev`
 #ifdef HVP_DEBUG_STATS
     bool was_warm = false;
@@ -266,6 +268,7 @@ struct FlatSolver {
         // ---- start of the search ----
         iters = 0; nodes = 0; it = 0; modes_pk = 0; best_modes = 0; cand_pk = 0;
         inc = HUGE_VAL; trouble = limit = timeout = false; lev = 0; dive = P->dive != 0; fresh = false; slab_ok = false;
+        hinted = false;
         if (P->time_limit_ns > 0) C->t_start = hvp_now_ns();
         if (ALG2) C->pf[0] = -HUGE_VAL;
         int c0 = 0;
@@ -274,6 +277,53 @@ struct FlatSolver {
             if (v0 >= P->edge[rg] && v0 <= P->edge[rg + 1]) c0 |= (1 << rg);
         set_cand(0, c0);
         C->xstar[0] = v0; C->rlo[0] = v0; C->rhi[0] = v0;
+        state = S_NEXT;
+    }
+
+    // ---- incumbent hint (include/hvp.h: modes_hint) ----------------------------------------------------------------
+    // In a closed loop the previous timestep's optimal region sequence, shifted by one stage, is almost always a
+    // feasible leaf of this timestep's tree and very often the optimal one.  Solving that ONE leaf first gives the
+    // search an incumbent before any relaxation is solved: the first dive (two QPs whose only purpose is an incumbent)
+    // is skipped and the root relaxations are pruned by their dual bounds.  The hint is advice, never trusted: a
+    // sequence that is out of range, starts in a region that does not contain v0 or turns out infeasible is dropped and
+    // the search runs as if no hint had been given; either way the search that follows proves the optimum.
+    HVP_HD void apply_hint(const int32_t* h) {
+        // descend along the hinted sequence exactly as the first dive would: regions fixed, intervals propagated,
+        // siblings left on the depth-first stack, NOTHING solved on the way -- only the leaf
+        const double eps = 1e-9;
+        const int c0 = cand(0);
+        bool ok = true;
+        HVP_ROLL
+        for (int lv = 0; lv < N && ok; ++lv) {
+            const int rg = h[lv];
+            int cn = c0;
+            if (lv > 0) {
+                cn = 0;
+                HVP_ROLL
+                for (int c = 0; c < NREG; ++c)
+                    if (P->edge[c] <= C->rhi[lv] && P->edge[c + 1] >= C->rlo[lv]) cn |= (1 << c);
+            }
+            if (rg < 0 || rg >= NREG || !((cn >> rg) & 1)) { ok = false; break; }
+            set_mode(lv, rg);
+            set_cand(lv, cn & ~(1 << rg));
+            const double jlo = fmax(C->rlo[lv], P->edge[rg]), jhi = fmin(C->rhi[lv], P->edge[rg + 1]);
+            double nlo = fmax(ra(rg) * jlo + rc(rg) + rb(rg) * P->umin, jlo + P->a_dec + lv * P->tight);
+            double nhi = fmin(ra(rg) * jhi + rc(rg) + rb(rg) * P->umax, jhi + P->a_acc - lv * P->tight);
+            nlo = fmax(nlo, P->vmin); nhi = fmin(nhi, P->vmax);
+            if (jlo > jhi + eps || nlo > nhi + eps) { ok = false; break; }
+            if (lv + 1 < N) { C->rlo[lv + 1] = nlo - eps; C->rhi[lv + 1] = nhi + eps; C->xstar[lv + 1] = v0; }
+        }
+        if (!ok || pc > P->pmax + eps || pc < P->pmin - eps) { unhint(c0); return; }
+        hint_c0 = c0;
+        lev = N - 1;
+        L = N;
+        hinted = true;
+        state = S_BUILD;
+    }
+    HVP_HD void unhint(int c0) {           // back to the untouched start of the search
+        modes_pk = 0; cand_pk = 0;
+        set_cand(0, c0);
+        lev = 0;
         state = S_NEXT;
     }
 
@@ -450,6 +500,12 @@ struct FlatSolver {
         if (was_warm) { g_warm[3] += it; } else { g_warm[4] += it; g_warm[5] += 1; } was_warm = false;
 #endif
         state = S_NEXT;
+        if (hinted) {
+            hinted = false;
+            if (st != 0) { --nodes; unhint(hint_c0); return; }   // infeasible hinted leaf: as if there had been no hint
+            HVP_ROLL
+            for (int lv = 1; lv < N; ++lv) C->xstar[lv] = w(LY::O_X, lv - 1);   // sibling order: distance to the leaf
+        }
         if (st != 0 || L == N) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;

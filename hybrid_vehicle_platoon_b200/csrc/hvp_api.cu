@@ -246,6 +246,7 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
         return fail(-1, "local_miqp: NULL array argument");
     LocalParams P;
     fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes, desc->mip_gap, desc->time_limit_ms);
+    P.hint = desc->modes_hint;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_TRY(hvp_mark(c, c->ev0, st, false));

@@ -194,6 +194,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                           xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr,
                           adopting ? my_scratch : x + S * i + (N + 2), &cold);
                 if (STEAL && adopting) sol.adopt_prefix(a_modes, a_l, a_c, a_inc);
+                else if (P.hint) sol.apply_hint(P.hint + (size_t)N * i);
                 have = true; thief = adopting; owner = a_owner;
             }
             if (!__any_sync(0xffffffffu, have)) break;

@@ -66,6 +66,7 @@ struct LocalParams {
     int warm;                            // flat kernel: warm-start a first child from its parent's active set
     int node_batch;                      // flat kernel: lanes that must wait for node set-up before a warp runs it
                                          // (27 of 32: measured optimum 26-28 after the r01 profile pass; 32 before it)
+    const int32_t* hint;                 // [batch][N] device pointer or NULL: region sequence to try FIRST (hvp.h modes_hint)
     double mip_gap;                      // relative pruning gap (0: proven optimal)
     long long time_limit_ns;             // per-problem budget on the device clock (0: none)
     double d0, t0, tight;

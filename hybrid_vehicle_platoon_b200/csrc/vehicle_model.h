@@ -30,7 +30,7 @@ struct VehicleModel {
 inline void fill_local_params(LocalParams& P, int N, double d0, double t0, double tight, int max_nodes,
                               double mip_gap = 0.0, double time_limit_ms = 0.0) {
     VehicleModel M;
-    P.N = N; P.max_nodes = max_nodes; P.mip_gap = mip_gap; P.time_limit_ns = (long long)(time_limit_ms * 1e6); P.hull = 0; P.dive = 1; P.node_batch = 27; P.sibling_bound = 1; P.warm = 1; P.d0 = d0; P.t0 = t0; P.tight = tight;
+    P.N = N; P.hint = nullptr; P.max_nodes = max_nodes; P.mip_gap = mip_gap; P.time_limit_ns = (long long)(time_limit_ms * 1e6); P.hull = 0; P.dive = 1; P.node_batch = 27; P.sibling_bound = 1; P.warm = 1; P.d0 = d0; P.t0 = t0; P.tight = tight;
     P.qxp = 1.0; P.qxv = 0.1; P.qu = 1.0; P.w = 1e4;
     P.a_acc = 2.5; P.a_dec = -2.0; P.d_safe = 25.0;
     P.vmin = M.v_min; P.vmax = M.v_max; P.pmin = M.p_min; P.pmax = M.p_max;

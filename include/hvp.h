@@ -115,6 +115,12 @@ typedef struct {
      * returned with status HVP_TIME_LIMIT (9); 0 = none. */
     double mip_gap;
     double time_limit_ms;
+    /* Optional incumbent hint for hvp_local_miqp_dev: DEVICE pointer to [batch][N] int32 region sequences (the codes
+     * modes[] returns) to be tried first -- in a closed loop the previous step's optimal sequence shifted by one
+     * stage (fleet_decent_mld.py:314-316 calls solve_mpc once per timestep with a warm model; Gurobi does the same
+     * with its MIP start).  Advice only: the result is the proven optimum with or without it.  NULL = none; ignored
+     * by the *_host entry point and by batches small enough for the cooperative kernel. */
+    const int32_t* modes_hint;
 } hvp_local_desc;
 
 /* flags [batch] (HVP_FRONT|HVP_LEADER|HVP_TRAILER), mass [batch], x0 [batch][2],

@@ -73,3 +73,15 @@ if "gfused" in which:      # fused glue kernel vs torch glue (both graphed)
         a, b = res[False][k], res[True][k]
         if not np.array_equal(a, b):
             print(f"   {k}: differs, max |d| {np.nanmax(np.abs(a.astype(np.float64) - b.astype(np.float64))):.3e}")
+if "hint" in which:        # MIP start from the previous timestep (modes_hint) on / off
+    S, T, n, N = 4096, 20, 10, 6
+    lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=10, vf=30, v_change_steps=[5, 12], trajectory_len=T + N + 10, ts=1).get_leader_trajectory()
+    x0 = states(rng, S, n, 5, 35, 60, 160)
+    res = {}
+    for h in (False, True):
+        sw = SW.BatchedDecentSweep(n, N, ctx=ctx, use_hint=h)
+        sw.run(x0[:256], lx, 3)
+        t0 = time.perf_counter(); out = sw.run(x0, lx, T); dt = time.perf_counter() - t0
+        res[h] = out
+        print(f"decent hint={h}: {dt*1e3:.1f} ms  {S*T*n/dt/1e6:.3f} M solves/s  nodes {out['nodes'].mean():.2f}  optimal {np.mean(out['status']==2):.4f}", flush=True)
+    print("   max |dX|", np.abs(res[False]["X"] - res[True]["X"]).max(), " max |dU|", np.abs(res[False]["U"] - res[True]["U"]).max())

@@ -151,3 +151,41 @@ def test_mip_gap_and_time_limit_options(hvp_ctx, kernel_batch):
     assert (timed["obj"][has] >= exact["obj"][has] - 1e-9 * np.abs(exact["obj"][has])).all()
     with pytest.raises(RuntimeError):
         hvp.local_miqp(*args, mip_gap=-0.1, ctx=hvp_ctx)
+
+
+@pytest.mark.gpu
+def test_modes_hint_never_changes_the_optimum(hvp_ctx):
+    """hvp_local_desc.modes_hint (MIP start): the optimal sequence itself, the shifted sequence, random sequences and
+    garbage as hints all return the proven optimum of the un-hinted solve; a good hint cuts the node count."""
+    import torch
+    from hybrid_vehicle_platoon_b200 import api
+    rng = np.random.default_rng(21)
+    N, n, S = 6, 10, 1024                                   # 10 240 problems: the flat kernel
+    c = platoon_local_problems(rng, S, n, N, stress=True)
+    B = S * n
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = {k: t(v) for k, v in c.items()}
+    f64, i32 = torch.float64, torch.int32
+
+    def solve(hint):
+        u = torch.empty((B, N), dtype=f64, device=dev); x = torch.empty((B, 2, N + 1), dtype=f64, device=dev)
+        mo = torch.empty((B, N), dtype=i32, device=dev); ob = torch.empty(B, dtype=f64, device=dev)
+        st = torch.empty(B, dtype=i32, device=dev); no = torch.empty(B, dtype=i32, device=dev)
+        api.local_miqp_device(api.local_desc(N), B, d["flags"], d["mass"], d["x0"], d["xf"], d["xb"], d["xl"], u, x, mo, ob, st,
+                              no, None, ctx=hvp_ctx, stream=torch.cuda.current_stream().cuda_stream, modes_hint=hint)
+        torch.cuda.synchronize()
+        return dict(u=u.cpu().numpy(), modes=mo.cpu().numpy(), obj=ob.cpu().numpy(), status=st.cpu().numpy(), nodes=no.cpu().numpy())
+
+    base = solve(None)
+    ok = base["status"] == 2
+    shifted = np.concatenate([base["modes"][:, 1:], base["modes"][:, -1:]], axis=1)
+    hints = {"optimal": base["modes"], "shifted": shifted, "random": rng.integers(0, 7, (B, N)).astype(np.int32),
+             "garbage": rng.integers(-5, 12, (B, N)).astype(np.int32)}
+    for name, h in hints.items():
+        r = solve(t(h.astype(np.int32)))
+        assert (r["status"] == base["status"]).all(), name
+        rel = np.abs(r["obj"][ok] - base["obj"][ok]) / np.maximum(1.0, np.abs(base["obj"][ok]))
+        assert rel.max() < 1e-9, (name, rel.max(), int(rel.argmax()))
+        if name == "optimal":
+            assert r["nodes"][ok].mean() < base["nodes"][ok].mean(), (r["nodes"][ok].mean(), base["nodes"][ok].mean())
