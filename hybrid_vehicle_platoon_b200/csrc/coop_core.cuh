@@ -145,6 +145,15 @@ struct CoopSolver {
     uint64_t best_modes, cand_lo, cand_hi;
     bool trouble, limit, timeout;
     long long t_start;
+    // ---- one tree searched by several workers (latency path: a scenario-timestep is ten MIQPs, the GPU has room for a
+    // hundred warps).  Every worker runs the SAME root relaxation and first dive -- deterministic, so all of them hold
+    // the same depth-first stack and the same first incumbent -- and from there the sub-trees that hang off the dive
+    // path are dealt round robin: the k-th sibling popped ON the path belongs to worker k mod sub_M, whoever owns it
+    // searches it completely.  path_lev = deepest level still on the path (a pop at a deeper level is inside an owned
+    // sub-tree).  The workers share their incumbent through `shared` (atomicMin on an order-preserving key).
+    int sub_M = 1, sub_w = 0, sub_cnt = 0, path_lev = 1 << 20;
+    double own = HUGE_VAL;                  // objective of THIS worker's best leaf (inc may be another worker's)
+    unsigned long long* shared = nullptr;
     // constraint being added
     int pid, pkind, pj;
     double psgn, pcoef, prhs, nHn, lam_p;
@@ -171,6 +180,8 @@ struct CoopSolver {
             if (v0 >= P->edge[rg] && v0 <= P->edge[rg + 1]) c0 |= (1 << rg);
         cand_set(cand_lo, cand_hi, 0, c0);
         state = S_NEXT;
+        sub_cnt = 0; own = HUGE_VAL;
+        path_lev = dive ? (1 << 20) : 0;             // no dive: the path is the root, its candidates are dealt at once
     }
 
     // ---- NEXT: pick the next node of the depth-first search (or finish) -------------------
@@ -194,6 +205,10 @@ struct CoopSolver {
             }
             cset &= ~(1 << rg);
             cand_set(cand_lo, cand_hi, lev, cset);
+            if (sub_M > 1 && !dive) {
+                if (lev < path_lev) path_lev = lev;
+                if (lev == path_lev && (sub_cnt++ % sub_M) != sub_w) continue;      // another worker's sub-tree
+            }
             set_mode(lev, rg);
             const double cur_lo = lev == 0 ? v0 : bk.bcast(rlo, lev - 1);
             const double cur_hi = lev == 0 ? v0 : bk.bcast(rhi, lev - 1);
@@ -235,16 +250,34 @@ struct CoopSolver {
         }
     }
 
+    // incumbent exchange between the workers of one tree (device only; a single worker / the host build: no-ops)
+    HVP_CD void share_in() {
+#if defined(__CUDA_ARCH__)
+        if (shared) {
+            const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(shared);
+            const double g = hvp_key2d(k);
+            if (g < inc) inc = g;
+        }
+#endif
+    }
+    HVP_CD void share_out() {
+#if defined(__CUDA_ARCH__)
+        if (shared) atomicMin(shared, hvp_d2key(own));
+#endif
+    }
+
     // outcome of a node: st 0 solved (obj valid), 1 infeasible, 2 numeric trouble
     HVP_CD void node_done(int st, double obj) {
         iters += it;
         ++nodes;
         state = S_NEXT;
+        if (dive && (st != 0 || L == N)) { dive = false; path_lev = lev; }           // the dive ends here: the path is known
         if (st != 0 || L == N) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
+        share_in();
         if (inc < HUGE_VAL && !(obj < hvp_cut(inc, P->mip_gap))) return;              // bound
-        if (L == N) { inc = obj; best = x; best_modes = modes_pk; return; }          // leaf
+        if (L == N) { inc = obj; own = obj; best = x; best_modes = modes_pk; share_out(); return; }   // leaf
         if (P->max_nodes > 0 && nodes >= P->max_nodes) { limit = true; state = S_DONE; return; }
         if (P->time_limit_ns > 0 && hvp_now_ns() - t_start > P->time_limit_ns) { timeout = true; state = S_DONE; return; }
         const double eps = 1e-9;
@@ -548,8 +581,8 @@ struct CoopSolver {
         const I ln = bk.lane();
         const Bm valid = ln < N;
         const int np1 = N + 1;
-        if (inc < HUGE_VAL) {
-            R.obj = inc;
+        if ((sub_M > 1 ? own : inc) < HUGE_VAL) {
+            R.obj = sub_M > 1 ? own : inc;
             R.status = timeout ? HVP_ST_TIME_LIMIT : limit ? HVP_ST_NODE_LIMIT : (trouble ? HVP_ST_NUMERIC : HVP_ST_OPTIMAL);
             const I rg = bk.bits3(best_modes, ln);
             const D vprev = bk.up1(best, v0);

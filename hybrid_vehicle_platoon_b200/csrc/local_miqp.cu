@@ -52,6 +52,73 @@ coop_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
     }
 }
 
+// Latency path: ONE tree searched by M workers (one warp each, G lanes cooperating), see CoopSolver::sub_M.  Worker
+// results go to scratch rows; the worker that finishes last (atomic count) keeps the best and writes the outputs.
+// Scratch (per launch, armed by one 0xFF memset): done[batch] u32 counting up from 0xFFFFFFFF, keys[batch] u64 (0xFF..
+// decodes to NaN = "no incumbent"), then batch x M result rows.
+constexpr int COOP_SPLIT_MAX = 64;      // problems per launch that get several workers each
+constexpr int COOP_SPLIT_ROW = 48;      // doubles per result row: u[N] x[2(N+1)] modes[N as double] obj status nodes iters
+
+template <int G>
+__global__ void __launch_bounds__(32)
+coop_split_kernel(const __grid_constant__ LocalParams P, int64_t batch, int M, const int32_t* __restrict__ flags,
+                  const double* __restrict__ mass, const double* __restrict__ x0,
+                  const double* __restrict__ xf, const double* __restrict__ xb,
+                  const double* __restrict__ xl, double* __restrict__ u, double* __restrict__ x,
+                  int32_t* __restrict__ modes, double* __restrict__ obj, int32_t* __restrict__ status,
+                  int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters, unsigned* __restrict__ done,
+                  unsigned long long* __restrict__ keys, double* __restrict__ rows) {
+    if (threadIdx.x >= G) return;
+    const int64_t i = blockIdx.x / M;
+    const int w = blockIdx.x % M;
+    const int N = P.N, np1 = N + 1;
+    const size_t S = 2 * (size_t)np1;
+    CoopSolver<DevBK<G>> sol;
+    sol.setup(&P, flags[i], mass[i], x0 + 2 * i, xf ? xf + S * i : nullptr, xb ? xb + S * i : nullptr,
+              xl ? xl + S * i : nullptr);
+    sol.sub_M = M; sol.sub_w = w; sol.shared = keys + i;
+    double* row = rows + ((size_t)i * M + w) * COOP_SPLIT_ROW;
+    int32_t* rmodes = reinterpret_cast<int32_t*>(row + N + S);             // N int32 in the space of N doubles
+    const LocalResult R = sol.solve(row, row + N, rmodes);
+    const int ln = sol.bk.ln;
+    unsigned old = 0;
+    if (ln == 0) {
+        double* tail = row + 2 * N + S;
+        tail[0] = R.obj; tail[1] = (double)R.status; tail[2] = (double)R.nodes; tail[3] = (double)R.qp_iters;
+    }
+    __syncwarp((1u << G) - 1u);
+    __threadfence();
+    if (ln == 0) old = atomicAdd(done + i, 1u);
+    old = __shfl_sync((1u << G) - 1u, old, 0);
+    if (old != (unsigned)(M - 2)) return;                     // not the last worker of this tree
+    __threadfence();
+    // ---- merge: best objective (lowest worker on ties), summed work, worst status ----
+    double bv = HUGE_VAL;
+    int bw = 0, nsum = 0, isum = 0;
+    bool numeric = false, limited = false, timed = false;
+    for (int c = 0; c < M; ++c) {
+        const double* t = rows + ((size_t)i * M + c) * COOP_SPLIT_ROW + 2 * N + S;
+        const double o = *reinterpret_cast<const volatile double*>(t);
+        const int st = (int)*reinterpret_cast<const volatile double*>(t + 1);
+        nsum += (int)*reinterpret_cast<const volatile double*>(t + 2);
+        isum += (int)*reinterpret_cast<const volatile double*>(t + 3);
+        if (o < bv) { bv = o; bw = c; }
+        numeric = numeric || st == HVP_ST_NUMERIC; limited = limited || st == HVP_ST_NODE_LIMIT;
+        timed = timed || st == HVP_ST_TIME_LIMIT;
+    }
+    const double* src = rows + ((size_t)i * M + bw) * COOP_SPLIT_ROW;
+    const int32_t* smodes = reinterpret_cast<const int32_t*>(src + N + S);
+    for (int e = ln; e < N; e += G) { u[(size_t)N * i + e] = src[e]; modes[(size_t)N * i + e] = smodes[e]; }
+    for (int e = ln; e < (int)S; e += G) x[S * i + e] = src[N + e];
+    if (ln == 0) {
+        obj[i] = bv;
+        status[i] = timed ? HVP_ST_TIME_LIMIT : limited ? HVP_ST_NODE_LIMIT
+                          : (numeric ? HVP_ST_NUMERIC : (bv < HUGE_VAL ? HVP_ST_OPTIMAL : HVP_ST_INFEASIBLE));
+        nodes[i] = nsum;
+        if (qp_iters) qp_iters[i] = isum;
+    }
+}
+
 // Persistent flat-state-machine kernel: one warp per CTA, one problem per lane, each warp owns a
 // contiguous share of the batch and a lane that finishes refills from that share at once.
 // STEAL = false compiles the sub-tree adoption of the launch tail OUT (about 900 SASS instructions): the kernel is bound
@@ -284,6 +351,20 @@ cudaError_t launch_local_miqp(const LocalParams& P, unsigned long long* counter,
 #undef HVP_FLAT
     }
     {
+        // a handful of trees (one scenario-timestep = n MIQPs): several workers per tree
+        static const int splitM = env_int("HVP_COOP_SPLIT_M", 8);
+        if (P.N <= 8 && batch <= COOP_SPLIT_MAX && splitM > 1 && splitM <= 32 && steal_scratch && P.max_nodes == 0 &&
+            2 * P.N + 2 * (P.N + 1) + 4 <= COOP_SPLIT_ROW) {
+            const size_t head = (size_t)COOP_SPLIT_MAX * (sizeof(unsigned) + sizeof(unsigned long long));
+            unsigned* done = reinterpret_cast<unsigned*>(steal_scratch);
+            unsigned long long* keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(steal_scratch) + COOP_SPLIT_MAX * sizeof(unsigned));
+            double* rows = reinterpret_cast<double*>(reinterpret_cast<char*>(steal_scratch) + head);
+            cudaError_t e = cudaMemsetAsync(steal_scratch, 0xFF, head, stream);
+            if (e != cudaSuccess) return e;
+            coop_split_kernel<8><<<(unsigned)(batch * splitM), 32, 0, stream>>>(P, batch, splitM, flags, mass, x0, xf, xb, xl, u, x,
+                                                                                modes, obj, status, nodes, qp_iters, done, keys, rows);
+            return cudaGetLastError();
+        }
         if (P.N <= 8) {
             if (batch <= COOP_SPREAD_MAX) {
                 coop_miqp_kernel<8><<<(unsigned)batch, 32, 0, stream>>>(P, batch, flags, mass, x0, xf, xb, xl, u, x, modes,

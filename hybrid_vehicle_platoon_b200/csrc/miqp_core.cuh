@@ -27,6 +27,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define HVP_HD __host__ __device__ __forceinline__
@@ -47,6 +48,18 @@ HVP_HD long long hvp_now_ns() {
 #else
     return 0;
 #endif
+}
+// order-preserving 64-bit key of a double (atomicMin on keys = min of the doubles)
+HVP_HD unsigned long long hvp_d2key(double d) {
+    unsigned long long u;
+    memcpy(&u, &d, 8);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+HVP_HD double hvp_key2d(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
 }
 // an objective must be below this to replace / beat the incumbent
 HVP_HD double hvp_cut(double inc, double gap) {

@@ -51,6 +51,33 @@ extern "C" void hvh_coop_miqp_batch(int batch, int N, const int32_t* flags, doub
     else coop_batch<16>(batch, N, flags, d0, t0, tight, max_nodes, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters);
 }
 
+// Host emulation of the split search of the cooperative solver (CoopSolver::sub_M, local_miqp.cu coop_split_kernel): the
+// M workers of a tree run one after the other WITHOUT exchanging their incumbents (the worst case for pruning); the minimum
+// over the workers must be the optimum of the plain search, and every sub-tree must have exactly one owner.
+extern "C" void hvh_coop_split_batch(int batch, int N, int M, const int32_t* flags, double d0, double t0, double tight,
+                                     const double* mass, const double* x0, const double* xf, const double* xb,
+                                     const double* xl, double* obj, int32_t* nodes_sum, int32_t* nodes_max) {
+    hvp::LocalParams P;
+    hvp::fill_local_params(P, N, d0, t0, tight, 0);
+    size_t S = 2 * (size_t)(N + 1);
+    double u[16], x[40];
+    int32_t modes[16];
+    for (int i = 0; i < batch; ++i) {
+        double best = HUGE_VAL;
+        int ns = 0, nm = 0;
+        for (int w = 0; w < M; ++w) {
+            hvp::CoopSolver<hvp::HostBK<8>> sol;
+            sol.setup(&P, flags[i], mass[i], x0 + 2 * (size_t)i, xf ? xf + S * i : nullptr, xb ? xb + S * i : nullptr,
+                      xl ? xl + S * i : nullptr);
+            sol.sub_M = M; sol.sub_w = w;
+            hvp::LocalResult R = sol.solve(u, x, modes);
+            if (R.obj < best) best = R.obj;
+            ns += R.nodes; if (R.nodes > nm) nm = R.nodes;
+        }
+        obj[i] = best; nodes_sum[i] = ns; nodes_max[i] = nm;
+    }
+}
+
 // Host build of the flat state-machine solver (flat_core.cuh), one problem at a time.
 template <int N>
 static void flat_batch(int batch, const int32_t* flags, double d0, double t0, double tight, int max_nodes,

@@ -51,3 +51,15 @@ def flat_adopt(N, flags, mass, x0, xf, xb, xl, after_nodes=1, d0=50.0, t0=0.0, t
     rc = fn(B, N, c(flags, np.int32), d0, t0, tight, c(mass), c(x0), c(xf), c(xb), c(xl), int(after_nodes), obj, ad, nodes)
     assert rc == 0
     return dict(obj=obj, adopters=ad, nodes=nodes)
+
+
+def coop_split(N, M, flags, mass, x0, xf, xb, xl, d0=50.0, t0=0.0, tight=0.0):
+    """Host emulation of the M-worker split search of the cooperative solver (harness.cpp: hvh_coop_split_batch)."""
+    L = C.CDLL(build())
+    fn = L.hvh_coop_split_batch
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+    B = x0.shape[0]
+    c = lambda a, t=np.float64: np.ascontiguousarray(a, dtype=t)
+    obj = np.zeros(B); ns = np.zeros(B, np.int32); nm = np.zeros(B, np.int32)
+    fn(B, N, int(M), c(flags, np.int32), d0, t0, tight, c(mass), c(x0), c(xf), c(xb), c(xl), obj, ns, nm)
+    return dict(obj=obj, nodes_sum=ns, nodes_max=nm)

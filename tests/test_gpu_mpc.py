@@ -290,7 +290,8 @@ def test_compiled_mip_gap_and_time_limit(hvp):
     ok = exact["status"] == 2
     assert (loose["status"] == exact["status"]).all()
     a = np.abs(exact["obj"][ok])
-    assert (loose["obj"][ok] >= exact["obj"][ok] - 1e-8 * a).all() and (loose["obj"][ok] <= exact["obj"][ok] + 0.05 * a + 1e-8).all()
+    assert (loose["obj"][ok] >= exact["obj"][ok] - 1e-8 * a).all()
+    assert (loose["obj"][ok] - 0.05 * np.abs(loose["obj"][ok]) <= exact["obj"][ok] + 1e-8 * a).all()   # Gurobi's MIPGap definition
     assert loose["nodes"].sum() < exact["nodes"].sum()
     timed = hvp.api.CompiledMpc(G.CENT, N, n_local=n, time_limit_ms=1e-3).solve(x0, 800.0, params)
     assert set(np.unique(timed["status"])) <= {2, 3, 9} and (timed["status"] == 9).any()

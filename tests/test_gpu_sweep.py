@@ -206,8 +206,11 @@ def test_mixed_size_sweep_equals_per_size_sweeps(headway, N):
     for (n, x0, lxs, masses), r in zip(parts, res):
         one = BatchedDecentSweep(n, N, masses=masses, spacing_policy=pol).run(x0, lxs, T)
         assert (r["status"] == 2).all() and (one["status"] == 2).all()
-        assert np.array_equal(r["X"], one["X"]) and np.array_equal(r["U"], one["U"])
-        assert np.array_equal(r["R"], one["R"]) and np.array_equal(r["nodes"], one["nodes"])
+        # to round-off, not bit for bit: the per-size batches here are small enough (<= 64 MIQPs) for the split search of
+        # the latency path (several workers per tree, local_miqp.cu coop_split_kernel), whose workers reach equal-valued
+        # leaves in a different order than the single search of the mixed launch; node counts differ by construction
+        assert np.abs(r["X"] - one["X"]).max() < 1e-8 and np.abs(r["U"] - one["U"]).max() < 1e-8
+        np.testing.assert_allclose(r["R"], one["R"], rtol=1e-10)
 
 
 def test_gadmm_fused_glue_kernel_equals_torch_glue():

@@ -55,3 +55,25 @@ def test_flat_subtree_adoption_partitions_the_tree(N, after, t0):
     assert ok.sum() > 300 and (r["adopters"] > 0).mean() > 0.3          # the split really happened
     assert np.isinf(r["obj"][~ok]).all()
     assert np.allclose(r["obj"][ok], plain["obj"][ok], rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("N,M,stress,t0", [(6, 8, True, 0.0), (6, 3, False, 0.0), (8, 8, True, 3.0), (4, 5, True, 0.0)])
+def test_coop_split_search_partitions_the_tree(N, M, stress, t0):
+    """Latency path (csrc/local_miqp.cu coop_split_kernel): M workers search one tree -- the same root relaxation and
+    first dive on every worker, the sub-trees off the dive path dealt round robin.  Emulated on the host WITHOUT
+    incumbent exchange: the best worker's objective is the plain search's optimum (nothing is lost), and the longest
+    worker is shorter than the plain search wherever the tree has something to share."""
+    rng = np.random.default_rng(300 + N + M)
+    d0 = 10.0 if t0 else 50.0
+    c = platoon_local_problems(rng, 30, 10, N, 0, stress, True)
+    args = (c["flags"], c["mass"], c["x0"], c["xf"], c["xb"], c["xl"])
+    plain = harness.local_miqp(N, *args, d0=d0, t0=t0, coop=True)
+    split = harness.coop_split(N, M, *args, d0=d0, t0=t0)
+    ok = plain["status"] == 2
+    assert np.isinf(split["obj"][~ok]).all()
+    np.testing.assert_allclose(split["obj"][ok], plain["obj"][ok], rtol=1e-9)
+    big = ok & (plain["nodes"] >= 12)
+    assert big.any() and (split["nodes_max"][big] < plain["nodes"][big]).mean() > 0.9
+    print(f"N={N} M={M}: plain nodes mean {plain['nodes'][ok].mean():.1f} p99 {np.percentile(plain['nodes'][ok], 99):.0f}; "
+          f"longest worker mean {split['nodes_max'][ok].mean():.1f} p99 {np.percentile(split['nodes_max'][ok], 99):.0f}; "
+          f"total {split['nodes_sum'][ok].mean():.1f}")
