@@ -187,6 +187,16 @@ def compiled_mpc_legs(hvp, torch, dev, stream, flush, steps=5, with_cpu=True):
         hvp.api.CompiledMpc(G.GADMM, 8, n_front=1, n_behind=1, rho=0.5), x0, params, fm=fm,
         cpu=_Cpu(4096, lambda c: O.mpc_solve(O.GADMM, 1, 8, x0[:c], 800.0, params[:c], n_front=1, n_behind=1, rho=0.5,
                                              fixed_modes=fm[:c])))
+    # 1-norm (MILP) variant, quadratic_cost=False: LP node problems by proximal-point rounds
+    x0, params = G.cent_cases(rng, 512, 3, 5)
+    run("cent_n3_N5_one_norm (configs[0] shape, MILP: quadratic_cost=False)",
+        hvp.api.CompiledMpc(G.CENT, 5, n_local=3, one_norm=True), x0, params)
+    from hybrid_vehicle_platoon_b200.synth_local import platoon_local_problems
+    c = platoon_local_problems(rng, 2048, N_VEH, HORIZON)
+    sel = np.nonzero(c["flags"] == 0)[0]
+    pl = np.concatenate([c[k][sel].reshape(len(sel), -1) for k in ("xf", "xb", "xl")], axis=1)
+    run("local_n10_N6_one_norm (configs[1] shape, interior vehicles, MILP: quadratic_cost=False)",
+        hvp.api.CompiledMpc(G.LOCAL, HORIZON, flags=0, one_norm=True), c["x0"][sel].reshape(-1, 1, 2), pl)
     return legs
 
 
@@ -523,6 +533,23 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(ho["status"], d_status.cpu().numpy())
+    # the same call on PAGEABLE numpy arrays (what a maintainer's script holds): the copies are staged by the driver
+    hpg = {k: np.array(batch[k], copy=True) for k in ("flags", "mass", "x0", "xf", "xb", "xl")}
+    hog = {k: np.empty_like(v) for k, v in ho.items()}
+
+    def step_host_pageable():
+        hvp._lib.check(L.hvp_local_miqp_host(ctx.handle, C.byref(desc), B, hp(hpg["flags"]), hp(hpg["mass"]),
+                                             hp(hpg["x0"]), hp(hpg["xf"]), hp(hpg["xb"]), hp(hpg["xl"]), hp(hog["u"]),
+                                             hp(hog["x"]), hp(hog["modes"]), hp(hog["obj"]), hp(hog["status"]),
+                                             hp(hog["nodes"]), None))
+    step_host_pageable()
+    pg_steps = 3
+    t0 = time.perf_counter()
+    for _ in range(pg_steps):
+        step_host_pageable()
+    torch.cuda.synchronize()
+    pg_s = time.perf_counter() - t0
+    assert np.array_equal(hog["status"], ho["status"])
     # the host path (chunks) and the device path (one launch) agree to round-off: which lane solves a leaf in the tail
     # of a launch depends on the launch shape (sub-tree adoption)
     assert np.allclose(ho["obj"], d_obj.cpu().numpy(), rtol=1e-9, atol=0)
@@ -530,9 +557,10 @@ def main():
 
     # ---- max over ranks ----
     from hybrid_vehicle_platoon_b200.dist import max_over_ranks
-    total_ms, e2e_s = max_over_ranks([total_ms, e2e_s], device=dev)
+    total_ms, e2e_s, pg_s = max_over_ranks([total_ms, e2e_s, pg_s], device=dev)
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * e2e_steps / e2e_s
+    e2e_pageable = world * B * pg_steps / pg_s
 
     # ---- legs that every rank takes part in ----
     shared_legs = {}
@@ -553,6 +581,8 @@ def main():
         f_node = 2 * n * n + n ** 3 / 3 + 2 * n ** 3 + 2 * n * n + 4 * n * n
         f_iter = 14 * n + 2 * n * n + 2 * n * n + n ** 3 / 3 + 2 * n * n + 2 * n * n + 2 * n * n
         flops_per_solve = nodes_mean * f_node + iters_mean * f_iter
+        peak_clk0 = ClockSampler(local_rank)
+        peak_clk0.start()
         fp64_peak = hvp.microbench_fp64(20000, ctx=ctx)
         fp64_ach = B * flops_per_solve / (kern_ms * 1e-3) / 1e12
 
@@ -605,6 +635,10 @@ def main():
             lat.append(time.perf_counter() - t0)
         lat = np.array(lat[200:]) * 1e3
         smem_peak = hvp.api.microbench_smem(20000, ctx)
+        for _ in range(20):                  # long enough for the clock sampler to see the microbenchmarks under load
+            hvp.microbench_fp64(20000, ctx=ctx)
+            hvp.api.microbench_smem(20000, ctx)
+        peak_clocks = peak_clk0.stop()
 
         cpu = None
         if not args.no_cpu:
@@ -623,7 +657,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "call": "hvp_local_miqp_host (pinned numpy in, numpy out)"},
+                    "call": "hvp_local_miqp_host (pinned numpy in, numpy out)",
+                    "pageable_value": e2e_pageable,
+                    "pageable_note": "same call on ordinary (pageable) numpy arrays, 3 steps",
+                    # the other half of BASELINE.json's metric: one scenario-timestep (10 MIQPs) through the same host call
+                    "latency_p50_ms": float(np.percentile(lat, 50)), "latency_p99_ms": float(np.percentile(lat, 99))},
             "gpu_launches": int(launches_timed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
@@ -635,17 +673,18 @@ def main():
                          "note": "on-chip FP64 branch-and-bound: HBM traffic is parameters in + solution "
                                  "out only, so the HBM fraction is small by construction; see fp64_pipe"},
             "fp64_pipe": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,
-                          "peak_source": "hvp_microbench_fp64 (measured DFMA issue peak)",
+                          "peak_source": "hvp_microbench_fp64 (measured DFMA issue peak)", "peak_clocks": peak_clocks,
                           "flops_per_solve_model": flops_per_solve, "nodes_per_solve": nodes_mean,
                           "qp_iters_per_solve": iters_mean},
             "latency": {"what": "one scenario-timestep = 10 local MIQPs through hvp_local_miqp_host (host buffers in, "
-                                "controls out), a different scenario per call",
+                                "controls out), a different scenario per call; 8 workers per tree (coop_split_kernel)",
                         "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                         "max_ms": float(lat.max()), "samples": int(lat.size),
                         "full_batch": {"what": f"{S} scenario-timesteps per launch (device-timed steps above)",
                                        "p50_ms": float(np.percentile(ms, 50)), "max_ms": float(np.max(ms)),
                                        "samples": int(ms.size)}},
             "smem": {"peak_gbs": smem_peak, "peak_source": "hvp_microbench_smem (measured LDS.128 read bandwidth, whole device)",
+                     "peak_clocks": peak_clocks,
                      "note": "achieved shared-memory traffic of the QP kernels is read from ncu "
                              "(l1tex__data_pipe_lsu_wavefronts_mem_shared, profiles/README.md)"},
             "rollout": rollout,

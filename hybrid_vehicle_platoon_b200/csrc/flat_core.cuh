@@ -99,7 +99,9 @@ struct FlatCold {
 // They cut the work per solve by a third (10.4 -> 6.8 nodes, 50.6 -> 25.7 active-set steps at n = 10, N = 6) and the
 // CPU port by the same; on the GPU the kernel is bound by instruction fetch and lane divergence, the extra code costs
 // 10 % and fewer steps per node leave fewer lanes in step, so the CUDA kernels instantiate ALG2 = false.
-template <int N, int ST, bool ALG2 = false>
+// HINTS: compile the incumbent-hint entry (apply_hint) in.  A separate instantiation, because the kernel is bound by
+// instruction fetch: 150 instructions that never run still cost the un-hinted launch 5 % (r02 measurement).
+template <int N, int ST, bool ALG2 = false, bool HINTS = false>
 struct FlatSolver {
     using LY = FlatLayout<N>;
     enum : int { S_NEXT = 0, S_BUILD, S_SELECT, S_STEP, S_DONE };
@@ -500,7 +502,7 @@ struct FlatSolver {
         if (was_warm) { g_warm[3] += it; } else { g_warm[4] += it; g_warm[5] += 1; } was_warm = false;
 #endif
         state = S_NEXT;
-        if (hinted) {
+        if (HINTS && hinted) {
             hinted = false;
             if (st != 0) { --nodes; unhint(hint_c0); return; }   // infeasible hinted leaf: as if there had been no hint
             HVP_ROLL

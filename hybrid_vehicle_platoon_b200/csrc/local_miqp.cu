@@ -123,7 +123,7 @@ coop_split_kernel(const __grid_constant__ LocalParams P, int64_t batch, int M, c
 // contiguous share of the batch and a lane that finishes refills from that share at once.
 // STEAL = false compiles the sub-tree adoption of the launch tail OUT (about 900 SASS instructions): the kernel is bound
 // by instruction fetch, and code that is never executed still spreads the hot loop over more cache lines.
-template <int N, bool STEAL>
+template <int N, bool STEAL, bool HINTS>
 // resident CTAs per SM are set by the shared-memory slab (10 at N = 6); telling the compiler lets it use the registers
 // that occupancy leaves free instead of spilling
 __global__ void __launch_bounds__(32, (N <= 6 ? 10 : (N == 7 ? 7 : (N == 8 ? 6 : 5))))
@@ -135,7 +135,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                  int32_t* __restrict__ nodes, int32_t* __restrict__ qp_iters, unsigned long long* __restrict__ counter,
                  double* __restrict__ scratch) {
     extern __shared__ double smem[];
-    using Solver = FlatSolver<N, 32>;
+    using Solver = FlatSolver<N, 32, false, HINTS>;
     const int lane = threadIdx.x;
     const size_t S = 2 * (size_t)(N + 1);
     // Problems are handed out through one global counter: a warp that needs k new problems takes the next k, so every
@@ -261,7 +261,7 @@ flat_miqp_kernel(const __grid_constant__ LocalParams P, int64_t batch, const int
                           xb ? xb + S * i : nullptr, xl ? xl + S * i : nullptr,
                           adopting ? my_scratch : x + S * i + (N + 2), &cold);
                 if (STEAL && adopting) sol.adopt_prefix(a_modes, a_l, a_c, a_inc);
-                else if (P.hint) sol.apply_hint(P.hint + (size_t)N * i);
+                else if (HINTS && P.hint) sol.apply_hint(P.hint + (size_t)N * i);
                 have = true; thief = adopting; owner = a_owner;
             }
             if (!__any_sync(0xffffffffu, have)) break;
@@ -290,8 +290,10 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
     int& grid_full = (dev >= 0 && dev < HVP_MAX_DEVICES) ? grid_cache[dev] : uncached;
     if (!grid_full) {
         cudaError_t e = cudaSuccess;
-        for (int v = 0; v < 2; ++v) {
-            const void* fn = v ? (const void*)flat_miqp_kernel<N, true> : (const void*)flat_miqp_kernel<N, false>;
+        const void* fns[3] = {(const void*)flat_miqp_kernel<N, true, false>, (const void*)flat_miqp_kernel<N, false, false>,
+                              (const void*)flat_miqp_kernel<N, true, true>};
+        for (int v = 0; v < 3; ++v) {
+            const void* fn = fns[v];
             e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -299,7 +301,7 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
         }
         int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_miqp_kernel<N, true>, 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_miqp_kernel<N, true, false>, 32, smem);
         if (e != cudaSuccess) return e;
         grid_full = sms * (per_sm > 0 ? per_sm : 1);
     }
@@ -315,12 +317,16 @@ static cudaError_t launch_flat(const LocalParams& P, unsigned long long* counter
     if ((size_t)g * 32 * N > HVP_STEAL_SLOT_DOUBLES) steal_scratch = nullptr;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    if (steal_on && steal_scratch)
-        flat_miqp_kernel<N, true><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
-                                                                    status, nodes, qp_iters, counter, steal_scratch);
+    if (Q.hint)              // MIP start given: the instantiation with the hint entry (adoption on when the scratch allows)
+        flat_miqp_kernel<N, true, true><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
+                                                                          status, nodes, qp_iters, counter,
+                                                                          steal_on ? steal_scratch : nullptr);
+    else if (steal_on && steal_scratch)
+        flat_miqp_kernel<N, true, false><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
+                                                                           status, nodes, qp_iters, counter, steal_scratch);
     else
-        flat_miqp_kernel<N, false><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
-                                                                     status, nodes, qp_iters, counter, nullptr);
+        flat_miqp_kernel<N, false, false><<<(unsigned)g, 32, smem, stream>>>(Q, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj,
+                                                                            status, nodes, qp_iters, counter, nullptr);
     return cudaGetLastError();
 }
 

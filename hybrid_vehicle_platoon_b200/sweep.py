@@ -107,10 +107,11 @@ class BatchedDecentSweep:
     with the constant-velocity estimator), pwa_gear model, horizon N."""
 
     def __init__(self, n: int, N: int, masses=None, spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0,
-                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto", use_hint: bool = False):
+                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto", use_hint: bool = False, graph: bool = False):
         import torch
         self.torch = torch
         self.use_hint = use_hint
+        self.graph = graph
         self.n, self.N, self.leader_index = n, N, leader_index
         self.dev = torch.device("cuda", device)
         self.ctx = ctx or default_context(device)
@@ -242,7 +243,9 @@ class BatchedDecentSweep:
             x_cur.copy_(x_next)
             t_idx.add_(1)
 
-        step = _StepGraph(torch, body)
+        # measured (r02): this loop is kernel-bound (one MIQP launch of S*n problems per timestep), eager 54 ms vs graph 59 ms
+        # for 4096 platoons x 20 steps -- the graph is off by default here and on where the glue dominates (g-ADMM)
+        step = _StepGraph(torch, body, enabled=self.graph)
         for t in range(ep_len):
             step()
         torch.cuda.synchronize()
