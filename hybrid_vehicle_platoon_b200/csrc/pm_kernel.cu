@@ -517,25 +517,93 @@ struct Warp {
         built_L = L;
         __syncwarp(gm);
         const double qu = S.qu;
-        LANES(j, nv) {
-            double g = g0[j];
-            if (S.one_norm) g -= S.rho_px * zc[j];          // gradient of rho/2 |z - zc|^2 at 0
-            else if (j < nl * N) {
-                const int i = j / N, kk = j % N;
-                const int d0 = kk * nl + i, d1 = d0 + nl;
-                if (d0 < L) {
-                    const double ib = rcp(bm[d0]);
-                    const double kc = (kk == 0) ? -(am[d0] * v0[i] + cm[d0]) * ib : -cm[d0] * ib;
-                    g += 2.0 * qu * kc * ib;
+        // gradient of the node's smooth part: 2-norm -- g0 + input-cost terms of the fixed stages; 1-norm -- the proximal
+        // term plus the penalty gradients w n of the soft rows that are currently in their saturated orientation
+        auto gradient = [&]() {
+            LANES(j, nv) {
+                double g = g0[j];
+                if (S.one_norm) {
+                    g -= S.rho_px * zc[j];          // gradient of rho/2 |z - zc|^2 at 0
+                    _Pragma("unroll 1")
+                    for (int r = 0; r < S.ng; ++r)
+                        if (orient[r] < 0) g += S.wmax[r] * S.AT[(size_t)j * S.ng + r];
+                    if (j < nl * N) {
+                        const int i = j / N, kk = j % N;
+                        const int d0 = kk * nl + i, d1 = d0 + nl;
+                        if (d0 < L) g += qu * rcp(bm[d0]) * (double)(uor[nv + j] - uor[j]) * 0.5;              // +-1 on own stage
+                        if (kk + 1 < N && d1 < L) g -= qu * rcp(bm[d1]) * am[d1] * (double)(uor[nv + j + 1] - uor[j + 1]) * 0.5;
+                    }
+                } else if (j < nl * N) {
+                    const int i = j / N, kk = j % N;
+                    const int d0 = kk * nl + i, d1 = d0 + nl;
+                    if (d0 < L) {
+                        const double ib = rcp(bm[d0]);
+                        const double kc = (kk == 0) ? -(am[d0] * v0[i] + cm[d0]) * ib : -cm[d0] * ib;
+                        g += 2.0 * qu * kc * ib;
+                    }
+                    if (kk + 1 < N && d1 < L) {
+                        const double ib = rcp(bm[d1]);
+                        g += 2.0 * qu * (-cm[d1] * ib) * (-am[d1] * ib);
+                    }
                 }
-                if (kk + 1 < N && d1 < L) {
-                    const double ib = rcp(bm[d1]);
-                    g += 2.0 * qu * (-cm[d1] * ib) * (-am[d1] * ib);
+                gn[j] = g;
+            }
+            __syncwarp(gm);
+        };
+        // WARM proximal round (1-norm, rounds after the first of a node): the centre has moved to the last solution x,
+        // everything else -- active rows, their normals, (N'H^-1N)^-1, orientations -- is still in place.  New
+        // unconstrained minimiser x_u, residuals of the active rows c = N'(x_u - x) (they were zero at x), multipliers
+        // lambda = Ginv c; if all of them are admissible this is the solution on the same active set and SELECT goes on
+        // from there -- at the fixed point that is the whole round.  Otherwise: the cold start below.
+        if (S.one_norm && ppa > 0 && q > 0) {
+            gradient();
+            LANES(j, nv) wv[j] = -dot2(Hinv + j * ld, 1, gn, nv);          // x_u
+            __syncwarp(gm);
+            LANES(a, q) dv[a] = dot2(Nact + a * ld, 1, wv, nv) - dot2(Nact + a * ld, 1, x, nv);
+            __syncwarp(gm);
+            bool ok = true;
+            LANES(a, q) {
+                const double l = dot2(Ginv + a * ld, 1, dv, q);
+                rv[a] = l;
+                if (!(l >= 0.0) || l > soft_w(act[a])) ok = false;
+            }
+            ok = __all_sync(gm, ok);
+            if (ok) {
+                LANES(a, q) lam[a] = rv[a];
+                __syncwarp(gm);
+                LANES(j, nv) np_[j] = dot2(Nact + j, ld, lam, q);          // N lambda
+                __syncwarp(gm);
+                LANES(j, nv) x[j] = wv[j] - dot2(Hinv + j * ld, 1, np_, nv);
+                it = 0;
+                state = PS_SELECT;
+                __syncwarp(gm);
+                return;
+            }
+            __syncwarp(gm);
+        }
+        // orientation of the soft rows.  2-norm: every L1 row starts in its plain orientation.  1-norm: a cost term whose
+        // row is violated AT THE PROXIMAL CENTRE starts saturated (orientation -1, its penalty gradient w n in the
+        // objective) -- near the solution that is where it ends up, so a round needs about one active-set step per KINK
+        // instead of one per cost term.
+        LANES(r, S.ng) {
+            int o = 1;
+            if (S.one_norm && isfinite(S.wmax[r]) && dot2(S.AT + r, S.ng, zc, nv) - bgen[r] > 0.0) o = -1;
+            orient[r] = o; agen[r] = 0;
+        }
+        LANES(j, nv) {
+            aflag[j] = 0;
+            int op = 1, on = 1;
+            if (S.one_norm && j < nl * N) {
+                const int i = j / N, kk = j % N, d0 = kk * nl + i;
+                if (d0 < L) {
+                    const double du = zc[j] - am[d0] * (kk == 0 ? v0[i] : zc[j - 1]) - cm[d0];
+                    if (du > 0.0) op = -1; else if (du < 0.0) on = -1;
                 }
             }
-            gn[j] = g;
+            uor[j] = op; uor[nv + j] = on;
         }
         __syncwarp(gm);
+        gradient();
         double dpart = 0.0;
         LANES(j, nv) {
             const double s = dot2(Hinv + j * ld, 1, gn, nv);
@@ -549,8 +617,6 @@ struct Warp {
         }
         // value of the node's dual function at the unconstrained minimiser; it only grows from here
         dual = c0 + wsum<GW>(gm, dpart);
-        LANES(r, S.ng) { orient[r] = 1; agen[r] = 0; }
-        LANES(j, nv) { aflag[j] = 0; uor[j] = 1; uor[nv + j] = 1; }
         it = 0; q = 0;
         state = PS_SELECT;
         __syncwarp(gm);
