@@ -46,6 +46,23 @@ class GAdmmRound(C.Structure):     # hvp_gadmm_round
                [(k, C.c_void_p) for k in ("x", "mass", "lwin", "y", "u", "tr", "cost", "ok")]
 
 
+class DecentObserve(C.Structure):  # hvp_decent_observe
+    _fields_ = [("n", C.c_int32), ("N", C.c_int32), ("S", C.c_int32), ("leader_index", C.c_int32),
+                ("leader_len", C.c_int64), ("leader_per_scenario", C.c_int32), ("reserved", C.c_int32), ("ts", C.c_double)] + \
+               [(k, C.c_void_p) for k in ("x", "leader_x", "t", "xf", "xb", "xl")]
+
+
+class AdmmRole(C.Structure):       # hvp_admm_role
+    _fields_ = [("params", C.c_void_p), ("x", C.c_void_p), ("extra", C.c_void_p), ("has_front", C.c_int32),
+                ("has_back", C.c_int32)]
+
+
+class AdmmRound(C.Structure):      # hvp_admm_round
+    _fields_ = [("n", C.c_int32), ("N", C.c_int32), ("S", C.c_int32), ("nroles", C.c_int32), ("pack_only", C.c_int32),
+                ("reserved", C.c_int32), ("rho", C.c_double), ("role", AdmmRole * 4), ("role_of", C.c_int32 * 64)] + \
+               [(k, C.c_void_p) for k in ("lwin", "y_front", "y_back", "zf", "zb", "xs")]
+
+
 MPC_CENT, MPC_LOCAL, MPC_EVENT, MPC_ADMM, MPC_GADMM = 1, 2, 3, 4, 5
 MODEL_PWA_GEAR, MODEL_FRICTION_GEAR = 0, 1
 REAL_VEHICLE_REF, NO_LEADER = 8, -100
@@ -104,6 +121,8 @@ def lib():
     L.hvp_mpc_eval_dev.argtypes = [_vp, C.c_int64] + [_vp] * 6
     L.hvp_mpc_eval_host.argtypes = [_vp, C.c_int64] + [_vp] * 5
     L.hvp_gadmm_round_dev.argtypes = [_vp, C.POINTER(GAdmmRound), _vp]
+    L.hvp_decent_observe_dev.argtypes = [_vp, C.POINTER(DecentObserve), _vp]
+    L.hvp_admm_round_dev.argtypes = [_vp, C.POINTER(AdmmRound), _vp]
     L.hvp_microbench_fp64.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     L.hvp_microbench_smem.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     _lib = L

@@ -215,3 +215,16 @@ def gadmm_round_device(g, *, init: bool, ctx=None, stream=None):
     ctx = ctx or default_context()
     g.init = 1 if init else 0
     check(lib().hvp_gadmm_round_dev(ctx.handle, C.byref(g), _stream_arg(stream)))
+
+
+def decent_observe_device(g, *, ctx=None, stream=None):
+    """Fused observe step of the decentralized controller (hvp_decent_observe_dev); `g` is a _lib.DecentObserve."""
+    ctx = ctx or default_context()
+    check(lib().hvp_decent_observe_dev(ctx.handle, C.byref(g), _stream_arg(stream)))
+
+
+def admm_round_device(g, *, pack_only: bool = False, ctx=None, stream=None):
+    """Fused z / y update of a naive-ADMM round (hvp_admm_round_dev); `g` is a _lib.AdmmRound."""
+    ctx = ctx or default_context()
+    g.pack_only = 1 if pack_only else 0
+    check(lib().hvp_admm_round_dev(ctx.handle, C.byref(g), _stream_arg(stream)))

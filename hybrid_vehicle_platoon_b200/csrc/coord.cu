@@ -187,6 +187,109 @@ gadmm_round_kernel(const __grid_constant__ GArgs A) {
     }
 }
 
+
+// ---- decentralized / sequential controllers: constant-velocity extrapolation of every vehicle's neighbours and the
+// leader-trajectory window of the timestep (fleet_decent_mld.py:329-331, :421-428) in one launch -------------------------
+struct ObsArgs {
+    int n, N, S, leader_index;
+    long long lx_len, lx_sstride;     // leader trajectory: [S or 1][2][lx_len], scenario stride 0 when shared
+    double ts;
+    const double* x;                  // [S][n][2]
+    const double* lx;
+    const long long* t;               // device-side timestep index
+    double *xf, *xb, *xl;             // [S][n][2][N+1] each
+};
+__global__ void __launch_bounds__(128)
+decent_observe_kernel(const __grid_constant__ ObsArgs A) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = A.n, N = A.N, np1 = N + 1, blk = 2 * np1;
+    if (tid >= (int64_t)A.S * n) return;
+    const int s = (int)(tid / n), i = (int)(tid - (int64_t)s * n);
+    // my own prediction is my back neighbour's x_front and my front neighbour's x_back
+    double p = A.x[2 * tid];
+    const double v = A.x[2 * tid + 1];
+    double* f = i + 1 < n ? A.xf + (size_t)(tid + 1) * blk : nullptr;
+    double* b = i > 0 ? A.xb + (size_t)(tid - 1) * blk : nullptr;
+    for (int k = 0; k <= N; ++k) {
+        if (f) { f[k] = p; f[np1 + k] = v; }
+        if (b) { b[k] = p; b[np1 + k] = v; }
+        p = __dadd_rn(p, __dmul_rn(A.ts, v));            // sequential sums, as the reference (p_{k+1} = p_k + ts v_k)
+    }
+    if (i == A.leader_index) {
+        const long long t = *A.t;
+        const double* l = A.lx + (size_t)s * A.lx_sstride;
+        double* o = A.xl + (size_t)tid * blk;
+        for (int k = 0; k <= N; ++k) { o[k] = l[t + k]; o[np1 + k] = l[A.lx_len + t + k]; }
+    }
+}
+
+// ---- naive ADMM: z- and y-update of a consensus round and the next round's parameter vectors
+// (fleet_naive_admm.py:421-468) in one launch, read straight from the role solves' outputs -------------------------------
+struct ARole {
+    double* params;                   // [count*S][5 * 2(N+1)]: leader window | y_front | z_front | y_back | z_back
+    const double* xo;                 // [count*S][2][N+1]   own prediction of the round just solved
+    const double* eo;                 // [count*S][ne]       copies: x_front (if not front) then x_back (if not trailer)
+    int count, ne, has_front, has_back;
+};
+struct AdmmArgs {
+    int n, N, S, nroles, pack_only;
+    double rho;
+    ARole role[4];
+    int role_of[64], local_of[64];    // vehicle -> role, index among the role's vehicles
+    const double* lwin;               // [S][2][N+1]
+    double *y_front, *y_back, *zf, *zb, *xs;   // [S][n][2][N+1] each
+};
+struct AOut { const double *own, *cf, *cb; };
+__device__ __forceinline__ AOut aout(const AdmmArgs& A, int s, int j) {
+    const ARole& R = A.role[A.role_of[j]];
+    const int64_t b = (int64_t)s * R.count + A.local_of[j];
+    const int blk = 2 * (A.N + 1);
+    AOut o;
+    o.own = R.xo + b * blk;
+    const double* e = R.eo + b * R.ne;
+    o.cf = R.has_front ? e : nullptr;
+    o.cb = R.has_back ? e + (R.has_front ? blk : 0) : nullptr;
+    return o;
+}
+// z of vehicle j: (own + x_front copy held by j+1) / 2 at the front, (own + x_back copy held by j-1) / 2 at the rear,
+// (own + both) / 3 inside -- in exactly this order of additions (fleet_naive_admm.py:421-447)
+__device__ __forceinline__ double azval(const AdmmArgs& A, int s, int j, int e) {
+    const double own = aout(A, s, j).own[e];
+    if (j == 0) return __dadd_rn(own, aout(A, s, 1).cf[e]) / 2.0;
+    if (j == A.n - 1) return __dadd_rn(own, aout(A, s, j - 1).cb[e]) / 2.0;
+    return __dadd_rn(__dadd_rn(own, aout(A, s, j + 1).cf[e]), aout(A, s, j - 1).cb[e]) / 3.0;
+}
+__global__ void __launch_bounds__(128)
+admm_round_kernel(const __grid_constant__ AdmmArgs A) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = A.n, blk = 2 * (A.N + 1);
+    if (tid >= (int64_t)A.S * n) return;
+    const int s = (int)(tid / n), j = (int)(tid - (int64_t)s * n);
+    const AOut me = aout(A, s, j);
+    const ARole& R = A.role[A.role_of[j]];
+    double* P = R.params + ((size_t)s * R.count + A.local_of[j]) * (5 * blk);
+    const size_t o = (size_t)tid * blk;
+    const double* lw = A.lwin + (size_t)s * blk;
+    for (int e = 0; e < blk; ++e) {
+        double yf = A.y_front[o + e], yb = A.y_back[o + e], zfv = A.zf[o + e], zbv = A.zb[o + e];
+        if (A.pack_only) {
+            P[e] = lw[e]; P[blk + e] = yf; P[2 * blk + e] = zfv; P[3 * blk + e] = yb; P[4 * blk + e] = zbv;
+            continue;
+        }
+        A.xs[o + e] = me.own[e];
+        if (j > 0) {                  // y_front += rho (x_front copy - z of the vehicle in front); next target z_{j-1}
+            zfv = azval(A, s, j - 1, e);
+            yf = __dadd_rn(yf, __dmul_rn(A.rho, __dadd_rn(me.cf[e], -zfv)));
+        }
+        if (j < n - 1) {
+            zbv = azval(A, s, j + 1, e);
+            yb = __dadd_rn(yb, __dmul_rn(A.rho, __dadd_rn(me.cb[e], -zbv)));
+        }
+        A.y_front[o + e] = yf; A.y_back[o + e] = yb; A.zf[o + e] = zfv; A.zb[o + e] = zbv;
+        P[e] = lw[e]; P[blk + e] = yf; P[2 * blk + e] = zfv; P[3 * blk + e] = yb; P[4 * blk + e] = zbv;
+    }
+}
+
 }  // namespace hvp
 
 using namespace hvp;
@@ -225,6 +328,69 @@ extern "C" int hvp_gadmm_round_dev(hvp_ctx* c, const hvp_gadmm_round* g, void* s
     gadmm_round_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A);
     e = cudaGetLastError();
     if (e != cudaSuccess) return hvp_fail(-100 - (int)e, "gadmm_round: launch failed: %s", cudaGetErrorString(e));
+    c->launches += 1;
+    return 0;
+}
+
+// hvp.h: hvp_decent_observe_dev
+extern "C" int hvp_decent_observe_dev(hvp_ctx* c, const hvp_decent_observe* g, void* stream) {
+    if (!c || !g) return hvp_fail(-1, "decent_observe: NULL argument");
+    if (g->n < 1 || g->N < 1 || g->S < 0 || g->leader_index < 0 || g->leader_index >= g->n)
+        return hvp_fail(-4, "decent_observe: bad sizes (n=%d N=%d S=%d leader=%d)", g->n, g->N, g->S, g->leader_index);
+    if (g->S == 0) return 0;
+    if (!g->x || !g->leader_x || !g->t || !g->xf || !g->xb || !g->xl) return hvp_fail(-1, "decent_observe: NULL array argument");
+    ObsArgs A;
+    A.n = g->n; A.N = g->N; A.S = g->S; A.leader_index = g->leader_index; A.ts = g->ts;
+    A.lx_len = g->leader_len; A.lx_sstride = g->leader_per_scenario ? 2 * g->leader_len : 0;
+    A.x = g->x; A.lx = g->leader_x; A.t = (const long long*)g->t; A.xf = g->xf; A.xb = g->xb; A.xl = g->xl;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return hvp_fail(-100 - (int)e, "decent_observe: cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int64_t threads = (int64_t)g->S * g->n;
+    decent_observe_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return hvp_fail(-100 - (int)e, "decent_observe: launch failed: %s", cudaGetErrorString(e));
+    c->launches += 1;
+    return 0;
+}
+
+// hvp.h: hvp_admm_round_dev
+extern "C" int hvp_admm_round_dev(hvp_ctx* c, const hvp_admm_round* g, void* stream) {
+    if (!c || !g) return hvp_fail(-1, "admm_round: NULL argument");
+    if (g->n < 2 || g->n > 64 || g->N < 1 || g->S < 0 || g->nroles < 1 || g->nroles > 4)
+        return hvp_fail(-4, "admm_round: bad sizes (n=%d N=%d S=%d roles=%d)", g->n, g->N, g->S, g->nroles);
+    if (g->S == 0) return 0;
+    if (!g->lwin || !g->y_front || !g->y_back || !g->zf || !g->zb || !g->xs) return hvp_fail(-1, "admm_round: NULL array argument");
+    AdmmArgs A;
+    A.n = g->n; A.N = g->N; A.S = g->S; A.nroles = g->nroles; A.rho = g->rho; A.pack_only = g->pack_only;
+    const int blk = 2 * (g->N + 1);
+    int counts[4] = {0, 0, 0, 0};
+    for (int i = 0; i < g->n; ++i) {
+        const int r = g->role_of[i];
+        if (r < 0 || r >= g->nroles) return hvp_fail(-4, "admm_round: role_of[%d] = %d out of range", i, r);
+        A.role_of[i] = r; A.local_of[i] = counts[r]++;
+    }
+    for (int r = 0; r < g->nroles; ++r) {
+        const hvp_admm_role& s = g->role[r];
+        ARole& R = A.role[r];
+        R.params = s.params; R.xo = s.x; R.eo = s.extra; R.count = counts[r];
+        R.has_front = s.has_front; R.has_back = s.has_back; R.ne = (s.has_front + s.has_back) * blk;
+        if (counts[r] > 0 && (!R.params || !R.xo || (R.ne > 0 && !R.eo))) return hvp_fail(-1, "admm_round: NULL role buffer (role %d)", r);
+    }
+    // a vehicle reads the copies its neighbours hold of it: vehicle i > 0 must hold x_front, i < n-1 must hold x_back
+    for (int i = 0; i < g->n; ++i) {
+        const ARole& R = A.role[A.role_of[i]];
+        if ((i > 0) != (R.has_front != 0) || (i < g->n - 1) != (R.has_back != 0))
+            return hvp_fail(-4, "admm_round: role of vehicle %d does not match its position (front / trailer copies)", i);
+    }
+    A.lwin = g->lwin; A.y_front = g->y_front; A.y_back = g->y_back; A.zf = g->zf; A.zb = g->zb; A.xs = g->xs;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return hvp_fail(-100 - (int)e, "admm_round: cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int64_t threads = (int64_t)g->S * g->n;
+    admm_round_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return hvp_fail(-100 - (int)e, "admm_round: launch failed: %s", cudaGetErrorString(e));
     c->launches += 1;
     return 0;
 }

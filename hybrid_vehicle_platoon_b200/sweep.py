@@ -107,11 +107,14 @@ class BatchedDecentSweep:
     with the constant-velocity estimator), pwa_gear model, horizon N."""
 
     def __init__(self, n: int, N: int, masses=None, spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0,
-                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto", use_hint: bool = False, graph: bool = False):
+                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto", use_hint: bool = False, graph: bool = False, fused=None):
+        import os
         import torch
         self.torch = torch
         self.use_hint = use_hint
         self.graph = graph
+        # fused: the observe step as one CUDA kernel (csrc/coord.cu hvp_decent_observe_dev) instead of ~N + 6 torch launches
+        self.fused = (os.environ.get("HVP_SWEEP_FUSED", "1") != "0") if fused is None else bool(fused)
         self.n, self.N, self.leader_index = n, N, leader_index
         self.dev = torch.device("cuda", device)
         self.ctx = ctx or default_context(device)
@@ -196,17 +199,29 @@ class BatchedDecentSweep:
         # a good start (a Gurobi MIP start is the same kind of advice).
         hint = torch.full((B, N), -1, dtype=torch.int32, device=dev) if self.use_hint else None
 
+        obs = None
+        if self.fused:
+            from . import _lib
+            obs = _lib.DecentObserve()
+            obs.n, obs.N, obs.S, obs.leader_index, obs.ts = n, N, S, self.leader_index, ts
+            obs.leader_len, obs.leader_per_scenario = lxc.shape[2], 1
+            obs.x, obs.leader_x, obs.t = x_cur.data_ptr(), lxc.data_ptr(), t_idx.data_ptr()
+            obs.xf, obs.xb, obs.xl = xf.data_ptr(), xb.data_ptr(), xl.data_ptr()
+
         def body():
             stream = torch.cuda.current_stream().cuda_stream
-            # ---- observe: p_{k+1} = p_k + ts v_k (sequential sums, as the reference), v constant ----
             xv = x_cur.view(S, n, 2)
-            pred[:, :, 0, 0] = xv[:, :, 0]
-            pred[:, :, 1, :] = xv[:, :, 1:2]
-            for k in range(N):
-                pred[:, :, 0, k + 1] = pred[:, :, 0, k] + ts * pred[:, :, 1, k]
-            xf[:, 1:] = pred[:, :-1]
-            xb[:, :-1] = pred[:, 1:]
-            xl[:, self.leader_index] = lxc.index_select(2, t_idx + win)           # leader_x[:, t:t+N+1] (:329-331)
+            if obs is not None:
+                api.decent_observe_device(obs, ctx=self.ctx, stream=stream)
+            else:
+                # ---- observe: p_{k+1} = p_k + ts v_k (sequential sums, as the reference), v constant ----
+                pred[:, :, 0, 0] = xv[:, :, 0]
+                pred[:, :, 1, :] = xv[:, :, 1:2]
+                for k in range(N):
+                    pred[:, :, 0, k + 1] = pred[:, :, 0, k] + ts * pred[:, :, 1, k]
+                xf[:, 1:] = pred[:, :-1]
+                xb[:, :-1] = pred[:, 1:]
+                xl[:, self.leader_index] = lxc.index_select(2, t_idx + win)           # leader_x[:, t:t+N+1] (:329-331)
             # ---- solve all S*n local MIQPs ----
             if self.use_compiled:      # one launch per role (front / interior / trailer, leader where applicable)
                 for cm, ii, k in self.role_groups:
@@ -452,10 +467,14 @@ class BatchedAdmmSweep:
 
     def __init__(self, n: int, N: int, admm_iters: int = 20, rho: float = 0.5, masses=None,
                  spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0, d_safe: float = Params.d_safe,
-                 device: int = 0, ctx=None, graph: bool = False, fork: bool = True):
+                 device: int = 0, ctx=None, graph: bool = False, fork: bool = True, fused=None):
+        import os
         import torch
         from ._lib import MPC_ADMM
         self.graph, self.fork = graph, fork
+        # fused: z / y update and parameter packing of a round as one CUDA kernel (csrc/coord.cu hvp_admm_round_dev);
+        # False keeps them as torch ops (the reference the kernel is tested against)
+        self.fused = (os.environ.get("HVP_SWEEP_FUSED", "1") != "0") if fused is None else bool(fused)
         if n < 2:
             raise ValueError("the ADMM scheme needs at least two vehicles")
         self.torch, self.n, self.N, self.iters, self.rho, self.leader_index = torch, n, N, admm_iters, rho, leader_index
@@ -513,6 +532,7 @@ class BatchedAdmmSweep:
         stat = torch.empty((S, n), dtype=torch.int32, device=dev)
         x_cur = x.clone()                                         # state the rounds of this timestep start from (static)
         lwin = torch.empty((S, 1, 2 * np1), dtype=f64, device=dev)
+        three = torch.full((), 3.0, dtype=f64, device=dev)
 
         def role_piece(fl, g):
             def piece():
@@ -535,7 +555,31 @@ class BatchedAdmmSweep:
                     cb[:, idx] = e[:, :, o:o + 2 * np1].reshape(S, k, 2, np1)
             return piece
 
-        pieces = [role_piece(fl, g) for fl, g in groups.items()]
+        ar = None
+        if self.fused:
+            from . import _lib
+            ar = _lib.AdmmRound()
+            ar.n, ar.N, ar.S, ar.nroles, ar.rho = n, N, S, len(groups), rho
+            order = list(groups)
+            for i in range(n):
+                ar.role_of[i] = order.index(self.role_of[i])
+            for r, fl in enumerate(order):
+                g = groups[fl]
+                g["params"] = torch.zeros((g["B"], g["cm"].n_param), dtype=f64, device=dev)
+                g["x0"] = torch.zeros((g["B"], 1, 2), dtype=f64, device=dev)
+                g["m"] = d_mass[:, g["idx"]].reshape(g["B"], 1).contiguous()
+                R_ = ar.role[r]
+                R_.params, R_.x, R_.extra = g["params"].data_ptr(), g["x"].data_ptr(), g["e"].data_ptr()
+                R_.has_front, R_.has_back = int(not fl & FRONT), int(not fl & TRAILER)
+            ar.lwin = lwin.data_ptr()
+            ar.y_front, ar.y_back, ar.zf, ar.zb, ar.xs = (t_.data_ptr() for t_ in (y_front, y_back, zf, zb, xs))
+
+            def fused_piece(g):
+                def piece():
+                    g["cm"].solve_device(g["B"], g["x0"], g["m"], g["params"], None, g["u"], g["x"], g["e"], g["mo"], g["ob"],
+                                         g["st"], g["no"], None, stream=torch.cuda.current_stream().cuda_stream)
+                return piece
+        pieces = [fused_piece(g) for g in groups.values()] if ar is not None else [role_piece(fl, g) for fl, g in groups.items()]
         # Measured (r02, 1024 scenarios, n = 15, N = 8, 20 rounds x 3 timesteps): eager 1584 ms, round as a graph 1187 ms,
         # roles on forked streams 976 ms, both 1425 ms -- the MIQP rounds are kernel-bound (2.8 ms per interior launch), what
         # pays is running the two one-vehicle roles beside the interior one; inside a graph the branches did not overlap.
@@ -544,11 +588,14 @@ class BatchedAdmmSweep:
         def one_round():
             # ---- x-update: all vehicles of a role in one launch, the roles side by side on forked streams ----
             fork.run(pieces)
+            if ar is not None:       # z / y update + next round's parameters: one kernel
+                api.admm_round_device(ar, ctx=self.ctx, stream=torch.cuda.current_stream().cuda_stream)
+                return
             # ---- z-update: average of a vehicle's own prediction and its neighbours' copies of it (:421-447) ----
             z[:, 0] = (xs[:, 0] + cf[:, 1]) / 2.0
             z[:, n - 1] = (xs[:, n - 1] + cb[:, n - 2]) / 2.0
-            if n > 2:
-                z[:, 1:n - 1] = (xs[:, 1:n - 1] + cf[:, 2:] + cb[:, :n - 2]) / 3.0
+            if n > 2:     # a TRUE division, as numpy's in the reference (torch turns `/ 3.0` into a product with 1/3: one ulp off)
+                z[:, 1:n - 1] = torch.div(xs[:, 1:n - 1] + cf[:, 2:] + cb[:, :n - 2], three)
             # ---- y-update and the z each copy is pulled towards in the next round (:426-468) ----
             y_front[:, 1:] += rho * (cf[:, 1:] - z[:, :-1])
             y_back[:, :-1] += rho * (cb[:, :-1] - z[:, 1:])
@@ -567,8 +614,16 @@ class BatchedAdmmSweep:
                 zb[:, :-1] = sh[:, 1:]
             lwin.copy_(lx[:, :, t:t + np1].reshape(S, 1, 2 * np1))
             x_cur.copy_(x)
+            if ar is not None:       # this timestep's states and first parameter vectors of every role
+                for g in groups.values():
+                    g["x0"].copy_(x_cur.view(S, n, 2)[:, g["idx"]].reshape(g["B"], 1, 2))
+                api.admm_round_device(ar, pack_only=True, ctx=self.ctx, stream=stream)
             for _ in range(self.iters):
                 rnd()
+            if ar is not None:       # inputs and statuses of the last round
+                for g in groups.values():
+                    u0[:, g["idx"]] = g["u"].view(S, g["k"], N)[:, :, 0]
+                    stat[:, g["idx"]] = g["st"].view(S, g["k"])
             have_pred = True
             U[t] = u0
             ST[t] = stat

@@ -269,6 +269,45 @@ typedef struct {
 } hvp_gadmm_round;
 int hvp_gadmm_round_dev(hvp_ctx* ctx, const hvp_gadmm_round* g, void* stream);
 
+/* ---- fused observe step of the decentralized / sequential controllers -----------------------------------
+ * fleet_decent_mld.py:329-331, :421-428 for all scenarios at once: every vehicle's constant-velocity extrapolation
+ * (p_{k+1} = p_k + ts v_k, summed sequentially as the reference does) is written as x_front of the vehicle behind it
+ * and x_back of the vehicle in front, and the leader gets leader_x[:, t : t + N + 1].  t is read from DEVICE memory
+ * so that a timestep can be replayed as a CUDA graph. */
+typedef struct {
+    int32_t n, N, S, leader_index;
+    int64_t leader_len;           /* columns of the leader trajectory */
+    int32_t leader_per_scenario;  /* leader_x is [S][2][leader_len] (1) or [2][leader_len] shared (0) */
+    int32_t reserved;
+    double ts;
+    const double* x;              /* [S][n][2] */
+    const double* leader_x;
+    const int64_t* t;             /* device pointer: timestep index */
+    double* xf; double* xb; double* xl; /* [S][n][2][N+1] each; rows without a neighbour / not the leader are left alone */
+} hvp_decent_observe;
+int hvp_decent_observe_dev(hvp_ctx* ctx, const hvp_decent_observe* g, void* stream);
+
+/* ---- fused z- / y-update of a naive-ADMM consensus round ------------------------------------------------
+ * fleet_naive_admm.py:421-468 for all scenarios at once, read straight from the outputs of the role solves
+ * (hvp_mpc_solve_dev of the ADMM formulations: x = own prediction, extra = the copies x_front / x_back), writing the
+ * consensus variables and the next round's parameter vectors [leader window | y_front | z_front | y_back | z_back].
+ * role_of[i] = index into role[] of vehicle i; problems of a role are ordered [scenario][vehicle of the role]. */
+typedef struct {
+    double* params; const double* x; const double* extra;
+    int32_t has_front, has_back;  /* the role's formulation holds an x_front / x_back copy (not FRONT / not TRAILER) */
+} hvp_admm_role;
+typedef struct {
+    int32_t n, N, S, nroles;
+    int32_t pack_only;            /* 1: only (re)write the parameter vectors from the consensus variables (start of a timestep) */
+    int32_t reserved;
+    double rho;
+    hvp_admm_role role[4];
+    int32_t role_of[64];
+    const double* lwin;           /* [S][2][N+1] leader window (a parameter block of every role) */
+    double* y_front; double* y_back; double* zf; double* zb; double* xs; /* [S][n][2][N+1] each */
+} hvp_admm_round;
+int hvp_admm_round_dev(hvp_ctx* ctx, const hvp_admm_round* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -263,3 +263,23 @@ def test_long_horizon_sweeps_match_oracle_closed_loops(n, N, headway):
     for j, ref in enumerate(refs):
         dX, dU = np.abs(out["X"][:, j] - ref["X"]).max(), np.abs(out["U"][:, j] - ref["U"]).max()
         assert dX < 1e-6 and dU < 1e-6, (n, N, headway, j, dX, dU)
+
+
+def test_fused_observe_and_admm_round_kernels_equal_torch_glue():
+    """csrc/coord.cu: hvp_decent_observe_dev (extrapolators + leader window) and hvp_admm_round_dev (z / y update +
+    parameter packing of a naive-ADMM round) against the same steps as torch ops -- identical arithmetic order, so the
+    closed loops must be bit-equal (leader in the middle: four ADMM roles)."""
+    from hybrid_vehicle_platoon_b200.sweep import BatchedDecentSweep, BatchedAdmmSweep
+    from hybrid_vehicle_platoon_b200.misc import StopAndGoLeaderTrajectory, ConstantTimePolicy
+    rng = np.random.default_rng(31)
+    for n, N, S, T, li in ((6, 5, 40, 4, 0), (5, 4, 24, 3, 2)):
+        v = np.floor(rng.uniform(10, 30, (S, n))); gaps = rng.uniform(60, 140, (S, n))
+        p = np.floor(3000.0 - np.cumsum(gaps, 1) + gaps[:, :1])
+        x0 = np.empty((S, 2 * n)); x0[:, 0::2] = p; x0[:, 1::2] = v
+        lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=12, vf=26, v_change_steps=[1, 3], trajectory_len=T + N + 6,
+                                       ts=1).get_leader_trajectory()
+        for make in (lambda f: BatchedDecentSweep(n, N, leader_index=li, spacing_policy=ConstantTimePolicy(10, 3), fused=f),
+                     lambda f: BatchedAdmmSweep(n, N, admm_iters=4, leader_index=li, fused=f)):
+            a, b = make(False).run(x0, lx, T), make(True).run(x0, lx, T)
+            for k in ("X", "U", "R", "status"):
+                assert np.array_equal(a[k], b[k], equal_nan=(a[k].dtype.kind == "f")), (n, N, li, k)
