@@ -428,6 +428,7 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
             for (int j = 0; j < nv; ++j) H0[(size_t)i * nv + j] += 2.0 * w * e.z[i] * e.z[j];
         }
     }
+    S.sibling = getenv("HVP_MPC_SIBLING") ? atoi(getenv("HVP_MPC_SIBLING")) : 1;
     S.one_norm = B.one_norm ? 1 : 0;
     // rho: small enough that a round reaches the solution set in one or two steps (step ~ cost slope / rho), large
     // enough that saturating a w = 1e4 slack row does not send the iterate through 1e8 (round-off 1e-8: measured, 2.5 %

@@ -120,6 +120,13 @@ struct Warp {
     double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best, *zc;
     double *cres, *bgen, *pvec;
     double *inv_m, *pc, *v0, *xstar, *rlo, *rhi, *am, *bm, *cm, *amax, *amin;
+    // Sibling bounds (levels 0..D): what the SOLVED parent of a level says about forcing its branching velocity out of the
+    // relaxed value -- pf the parent's optimum (-inf: the level was opened without solving its parent), pnz the curvature
+    // of its dual function along the bound row +-e_j, ptp / ptm how far that dual step may go before an active multiplier
+    // leaves [0, w].  A child that fixes the velocity into a region at distance bd costs at least
+    // pf + t bd - t^2 pnz / 2, t = min(bd / pnz, tmax): cheaper than building the child to find out (flat_core.cuh ALG2;
+    // there it loses to SIMT divergence, here control flow is warp-uniform and fewer nodes are simply less time).
+    double *pf, *pnz, *ptp, *ptm;
     int *act, *cand, *modes, *bmodes, *built, *orient, *aflag, *agen, *uor;
     double f_prev;
     int ppa, retry;                    // proximal-point rounds / restarts done on the current node (1-norm cost)
@@ -148,6 +155,7 @@ struct Warp {
         inv_m = m; pc = m + nl; v0 = m + 2 * nl; xstar = m + 3 * nl; rlo = xstar + D + 1;
         rhi = rlo + nl * (N + 1); am = rhi + nl * (N + 1); bm = am + D; cm = bm + D;
         amax = cm + D; amin = amax + D;
+        pf = amin + D; pnz = pf + (D + 1); ptp = pnz + (D + 1); ptm = ptp + (D + 1);
         int* ib = reinterpret_cast<int*>(base + S.smem_doubles);
         act = ib; cand = ib + nv; modes = cand + D + 1; bmodes = modes + D; built = bmodes + D;
         orient = built + D; aflag = orient + S.ng; agen = aflag + nv; uor = agen + S.ng;
@@ -285,6 +293,38 @@ struct Warp {
             if (S.M.lo[r] <= hi && S.M.hi[r] >= lo && S.M.lo[r] <= S.M.hi[r]) cn |= (1 << r);
         cand[lv] = cn;
         xstar[lv] = (k == 0) ? v0[i] : x[i * N + k - 1];
+        pf[lv] = -HUGE_VAL;
+    }
+
+    // dual information of the node that has just been solved for the level that branches next (all lanes)
+    __device__ void parent_info(double fnode) {
+        const int nl = S.nl, N = S.N, nv = S.nv, ld = S.ld;
+        const int i = lev % nl, k = lev / nl;
+        if (k == 0 || S.one_norm) return;                 // v0 is data; LP nodes: no curvature, bounds come from the LP
+        const int j = i * N + k - 1;
+        LANES(a, q) dv[a] = dot2(Nact + a * ld, 1, Hinv + j * ld, nv);          // d = N' H^-1 e_j
+        __syncwarp(gm);
+        double part = 0.0, tp = HUGE_VAL, tm = HUGE_VAL;
+        LANES(a, q) {
+            const double s = dot2(Ginv + a * ld, 1, dv, q);
+            part += s * dv[a];
+            const double la = lam[a], wm = soft_w(act[a]);
+            if (s > 1e-14) {
+                tp = fmin(tp, la * rcp(s));
+                if (isfinite(wm)) tm = fmin(tm, (wm - la) * rcp(s));
+            } else if (s < -1e-14) {
+                tm = fmin(tm, la * rcp(-s));
+                if (isfinite(wm)) tp = fmin(tp, (wm - la) * rcp(-s));
+            }
+        }
+        const double nHn0 = Hinv[j * ld + j];
+        double nz = nHn0 - wsum<GW>(gm, part);
+        int dummy = 0;
+        wargmin<GW>(gm, tp, dummy);
+        wargmin<GW>(gm, tm, dummy);
+        if (q == nv || !(nz > 1e-11 * nHn0)) nz = 0.0;      // dependent row: the dual is linear along the step
+        if (lane == 0) { pf[lev] = fmin(fnode, dual); pnz[lev] = nz; ptp[lev] = fmax(tp, 0.0); ptm[lev] = fmax(tm, 0.0); }
+        __syncwarp(gm);
     }
 
     // ---- NEXT: next node of the depth-first search (scalar; lane 0, result broadcast) ----------
@@ -316,6 +356,14 @@ struct Warp {
                     }
                 }
                 cand[nlev] = cset & ~(1 << rg);
+                if (bd > 0.0 && inc < HUGE_VAL && pf[nlev] > -HUGE_VAL) {
+                    // sibling bound from the solved parent (parent_info)
+                    const double nz = pnz[nlev];
+                    const double tmax = (xs > S.M.hi[rg]) ? ptp[nlev] : ptm[nlev];
+                    const double t = (nz > 0.0) ? fmin(bd * rcp(nz), tmax) : tmax;
+                    const double bound = (t < HUGE_VAL) ? pf[nlev] + t * bd - 0.5 * t * t * nz : HUGE_VAL;
+                    if (bound > inc) continue;
+                }
                 modes[nlev] = rg;
                 const double jlo = fmax(rlo[i * (N + 1) + k], S.M.lo[rg]), jhi = fmin(rhi[i * (N + 1) + k], S.M.hi[rg]);
                 if (jlo > jhi + eps) continue;
@@ -445,6 +493,8 @@ struct Warp {
         ++lev;
         if (lane == 0) open_level(lev);
         __syncwarp(gm);
+        static_assert(true, "");
+        if (S.sibling) parent_info(obj);
     }
 
     // L1 weight of a row id (+inf: hard row).  Soft rows: generic rows with a finite wmax, and the |u| pair of a fixed stage.
@@ -1260,11 +1310,27 @@ void pm_layout(PmDev& S) {
     S.o_cres = o; o += S.nres + S.nlin;
     S.o_bgen = o; o += S.ng;
     S.o_pvec = o; o += S.npv;
-    S.o_misc = o; o += 3 * S.nl + (D + 1) + 2 * S.nl * (S.N + 1) + 5 * D;
+    S.o_misc = o; o += 3 * S.nl + (D + 1) + 2 * S.nl * (S.N + 1) + 5 * D + 4 * (D + 1);
     S.smem_doubles = o;
     const int ints = nv + (D + 1) + 3 * D + S.ng + nv + S.ng + 2 * nv;
     S.o_int = o;
     S.smem_bytes = (o * 8 + ints * 4 + 15) / 16 * 16;
+}
+
+// MaxDynamicSharedMemorySize of pm_miqp_kernel<GW>: grow-only, cached per device, shared by EVERY launch path of the kernel
+// (the sharded path used to set its own, smaller value on every call and left the cache of the plain path stale:
+// a later launch with more shared memory failed with "invalid argument")
+template <int GW>
+static cudaError_t pm_miqp_smem_attr(size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static size_t attr_set[HVP_MAX_DEVICES] = {0};
+    if (dev < 0 || dev >= HVP_MAX_DEVICES || smem > attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < HVP_MAX_DEVICES) attr_set[dev] = smem;
+    }
+    return cudaSuccess;
 }
 
 template <int GW>
@@ -1281,11 +1347,9 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     // function attributes are per DEVICE (one process may drive several: Context(device)): cached per device
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
-    static size_t attr_set[HVP_MAX_DEVICES] = {0};
-    if (dev < 0 || dev >= HVP_MAX_DEVICES || smem > attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = pm_miqp_smem_attr<GW>(smem);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < HVP_MAX_DEVICES) attr_set[dev] = smem;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int threads = gpb * GW;
@@ -1353,7 +1417,7 @@ static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double
     while (gpb > 1 && (size_t)gpb * S.smem_bytes > 200 * 1024) gpb >>= 1;
     const size_t smem = (size_t)gpb * S.smem_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pm_miqp_smem_attr<GW>(smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
