@@ -657,7 +657,7 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
             const PmDev& S = m->S;
             const size_t items = cap * (size_t)envM, nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
             const size_t ne = S.ne > 0 ? (size_t)S.ne : 1;
-            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + cap * (4 + 8 + 4) + 64 + 13 * 256;
+            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + cap * (4 + 8) + 64 + 12 * 256;
             void* p = nullptr;
             CUDA_TRY(cudaMalloc(&p, bytes));
             m->scratch_mem = p;
@@ -669,8 +669,6 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
             sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
             sc.sp.inc_shared = (unsigned long long*)take(cap * 8); sc.sp.flagged = (int*)take(cap * 4);
             sc.sp.nflag = (int*)take(4);
-            static const int dyn = getenv("HVP_MPC_DEAL") ? atoi(getenv("HVP_MPC_DEAL")) : 1;
-            sc.sp.claim = dyn ? (int*)take(cap * 4) : nullptr;
             sc.sp.M = envM; sc.sp.D = m->split_D;
             m->scratch_cap = cap;
         }
@@ -722,7 +720,7 @@ extern "C" int hvp_mpc_solve_shard_dev(hvp_mpc* m, int64_t batch, const double* 
     if (items > m->shard_items || (size_t)batch > (size_t)m->shard.sp.cap) {
         if (m->shard_mem) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->shard_mem)); m->shard_mem = nullptr; }
         const size_t nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1), ne = S.ne > 0 ? (size_t)S.ne : 1;
-        const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + (size_t)batch * (4 + 8 + 4) + 64 + 13 * 256;
+        const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + (size_t)batch * (4 + 8) + 64 + 12 * 256;
         void* p = nullptr;
         CUDA_TRY(cudaMalloc(&p, bytes));
         m->shard_mem = p;
@@ -734,8 +732,6 @@ extern "C" int hvp_mpc_solve_shard_dev(hvp_mpc* m, int64_t batch, const double* 
         sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
         sc.sp.inc_shared = (unsigned long long*)take((size_t)batch * 8); sc.sp.flagged = (int*)take((size_t)batch * 4);
         sc.sp.nflag = (int*)take(4);
-        static const int dyn = getenv("HVP_MPC_DEAL") ? atoi(getenv("HVP_MPC_DEAL")) : 1;
-        sc.sp.claim = dyn ? (int*)take((size_t)batch * 4) : nullptr;
         sc.sp.cap = (int)batch;
         m->shard_items = items;
     }

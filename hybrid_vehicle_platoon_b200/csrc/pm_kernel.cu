@@ -137,8 +137,6 @@ struct Warp {
     long long t_start;
     // tree splitting (PmSplit)
     int sub_M, sub_D, sub_code, sub_ord, budget, stop_nodes;
-    int my_ord, ord_stride, ord_off;   // dynamic dealing (lane 0): the prefix ordinal this warp has claimed; ordinal = off + stride k
-    int* claim;
     double own;                        // objective of this warp's own best leaf
     const double* yel;                 // gE, hE of the eliminated copies of this problem (PmDev::nel)
     unsigned long long* shared;        // incumbent shared by the warps working on one problem
@@ -164,7 +162,6 @@ struct Warp {
         ppa = 0; retry = 0;
         (void)ld;
         sub_M = sub_D = sub_code = sub_ord = budget = stop_nodes = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
-        my_ord = 0; ord_stride = 1; ord_off = 0; claim = nullptr;
     }
 
     __device__ __forceinline__ double ma(int i, int r) const { return 1.0 - S.M.cf[r] * inv_m[i]; }
@@ -383,13 +380,7 @@ struct Warp {
                         open_level(nlev);
                         continue;
                     }
-                    if (nL == sub_D) {
-                        const int o = sub_ord++;
-                        if (claim) {                                  // dynamic: is this the prefix I claimed?
-                            if (o != my_ord) continue;
-                            my_ord = ord_off + ord_stride * atomicAdd(claim, 1);      // ... and take the next one
-                        } else if ((o % sub_M) != sub_code) continue;   // static residue classes
-                    }
+                    if (nL == sub_D && (sub_ord++ % sub_M) != sub_code) continue;   // another warp's sub-tree
                 }
                 if (dive && nodes >= 1 && nL < S.depth) {
                     // first descent: without an incumbent the relaxations along the path cannot prune, they
@@ -1149,7 +1140,6 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
             W.sub_M = sp.M * sp.world; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M) * sp.world + sp.rank;   // ordinal o -> rank o % world
             W.shared = sp.inc_shared + i;
             W.stop_nodes = sp.budget;
-            W.claim = sp.claim ? sp.claim + i : nullptr; W.ord_stride = sp.world; W.ord_off = sp.rank;
         } else if (sp.mode == 2) {
             int nf = *reinterpret_cast<volatile int*>(sp.nflag);
             if (nf > sp.cap) nf = sp.cap;
@@ -1157,10 +1147,7 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
             const int f = (int)(w / sp.M);
             i = sp.flagged[f];
             W.sub_M = sp.M; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M); W.shared = sp.inc_shared + f;
-            W.claim = sp.claim ? sp.claim + f : nullptr; W.ord_stride = 1; W.ord_off = 0;
         } else if (w >= batch) break;
-        if (sp.mode < 2) W.claim = nullptr;
-        if (W.claim && lane == 0) W.my_ord = W.ord_off + W.ord_stride * atomicAdd(W.claim, 1);
         W.prob = i;
         W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar,
                 fixed_modes ? fixed_modes + su * i : nullptr, Y ? Y + (size_t)S.mw * i : nullptr);
@@ -1393,10 +1380,6 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     sp.mode = 2;
-    if (sp.claim) {
-        e = cudaMemsetAsync(sp.claim, 0, (size_t)sp.cap * sizeof(int), stream);
-        if (e != cudaSuccess) return e;
-    }
     int64_t b2 = ((int64_t)sp.cap * sp.M + gpb - 1) / gpb;
     if (b2 > full) b2 = full;
     pm_miqp_kernel<GW><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
@@ -1450,10 +1433,6 @@ static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double
     if (blocks > full) blocks = full;
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    if (sp.claim) {
-        e = cudaMemsetAsync(sp.claim, 0, (size_t)batch * sizeof(int), stream);
-        if (e != cudaSuccess) return e;
-    }
     pm_shard_init_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(batch, incumbent, sp, obj, nodes, qp_iters);
     pm_miqp_kernel<GW><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
                                                                     sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,

@@ -89,8 +89,6 @@ struct PmSplit {
     int* nflag;                        // [1] flagged problems so far
     int* flagged;                      // [cap] their batch indices
     unsigned long long* inc_shared;    // [cap] best objective known for each (order-preserving key)
-    int* claim;                        // [cap] next unclaimed sub-tree (prefix index) of each split problem: the warps of a
-                                       // problem TAKE prefixes as they finish instead of owning a fixed residue class
 };
 
 // device scratch of the sub-tree pass: outputs of cap * M work items, same layout as the real outputs
