@@ -110,7 +110,10 @@ __device__ __forceinline__ double dval(unsigned long long k) {
     return __longlong_as_double((long long)u);
 }
 
-template <int GW>
+// ONE: the 1-norm (MILP) variant.  A template parameter, not a run-time flag: this kernel is bound by instruction fetch, and the
+// proximal-point code of the LP nodes, never executed by a 2-norm launch, still cost it 7 % (r02 measurement).
+// FX: the fixed-sequence QP of g-ADMM (fixed_modes given): no search at all, so the branch-and-bound code is compiled out.
+template <int GW, bool ONE, bool FX = false>
 struct Warp {
     const PmDev& S;
     int lane;
@@ -254,7 +257,7 @@ struct Warp {
                 g0[j] = s;
             }
         }
-        if (S.one_norm) {                  // proximal centre: constant velocity
+        if (ONE) {                  // proximal centre: constant velocity
             LANES(j, nv) zc[j] = (j < nl * N) ? x0[2 * (j / N) + 1] : 0.0;
         }
         ppa = 0; retry = 0;
@@ -262,9 +265,9 @@ struct Warp {
         iters = nodes = it = q = 0;
         inc = HUGE_VAL; own = HUGE_VAL; trouble = limit = timeout = false; dive = true; sub_ord = 0;
         t_start = S.time_limit_ns > 0 ? hvp_now_ns() : 0;
-        lev = 0; L = 0; fixed = (fm != nullptr);
+        lev = 0; L = 0; fixed = FX;
         if (infeas) { state = PS_DONE; __syncwarp(gm); return; }
-        if (fixed) {
+        if (FX) {
             bool bad = false;
             LANES(d, S.depth) {
                 const int i = d % nl, k = d / nl, r = fm[i * N + k];
@@ -300,7 +303,7 @@ struct Warp {
     __device__ void parent_info(double fnode) {
         const int nl = S.nl, N = S.N, nv = S.nv, ld = S.ld;
         const int i = lev % nl, k = lev / nl;
-        if (k == 0 || S.one_norm) return;                 // v0 is data; LP nodes: no curvature, bounds come from the LP
+        if (k == 0 || ONE) return;                 // v0 is data; LP nodes: no curvature, bounds come from the LP
         const int j = i * N + k - 1;
         LANES(a, q) dv[a] = dot2(Nact + a * ld, 1, Hinv + j * ld, nv);          // d = N' H^-1 e_j
         __syncwarp(gm);
@@ -439,7 +442,7 @@ struct Warp {
     // st: 0 solved, 1 infeasible, 2 numerical trouble
     __device__ void node_done(int st, double obj) {
         iters += it;
-        if (S.one_norm) {
+        if (ONE) {
             // An LP node is degenerate far more often than a QP node (a full active set is the rule, ties between a
             // partial and a full step are common): a round that ends in numerical trouble is repeated from a slightly
             // different proximal centre, which changes the path of the active-set method but not the LP it converges to.
@@ -457,7 +460,7 @@ struct Warp {
             retry = 0;
         }
         ++nodes;
-        state = fixed ? PS_DONE : PS_NEXT;
+        state = FX ? PS_DONE : PS_NEXT;
         if (st != 0 || L == S.depth) dive = false;
         if (st == 2) { trouble = true; return; }
         if (st == 1) return;
@@ -553,7 +556,7 @@ struct Warp {
             c = 0; built_L = 0;
             __syncwarp(gm);
         }
-        if (!S.one_norm) {                 // 1-norm: no quadratic input cost, H^-1 = I / rho_px for every node
+        if (!ONE) {                 // 1-norm: no quadratic input cost, H^-1 = I / rho_px for every node
             _Pragma("unroll 1")
             for (int d = built_L - 1; d >= c; --d) rank1(d, built[d], -1.0);
             _Pragma("unroll 1")
@@ -572,7 +575,7 @@ struct Warp {
         auto gradient = [&]() {
             LANES(j, nv) {
                 double g = g0[j];
-                if (S.one_norm) {
+                if (ONE) {
                     g -= S.rho_px * zc[j];          // gradient of rho/2 |z - zc|^2 at 0
                     _Pragma("unroll 1")
                     for (int r = 0; r < S.ng; ++r)
@@ -605,7 +608,7 @@ struct Warp {
         // unconstrained minimiser x_u, residuals of the active rows c = N'(x_u - x) (they were zero at x), multipliers
         // lambda = Ginv c; if all of them are admissible this is the solution on the same active set and SELECT goes on
         // from there -- at the fixed point that is the whole round.  Otherwise: the cold start below.
-        if (S.one_norm && ppa > 0 && q > 0) {
+        if (ONE && ppa > 0 && q > 0) {
             gradient();
             LANES(j, nv) wv[j] = -dot2(Hinv + j * ld, 1, gn, nv);          // x_u
             __syncwarp(gm);
@@ -637,13 +640,13 @@ struct Warp {
         // instead of one per cost term.
         LANES(r, S.ng) {
             int o = 1;
-            if (S.one_norm && isfinite(S.wmax[r]) && dot2(S.AT + r, S.ng, zc, nv) - bgen[r] > 0.0) o = -1;
+            if (ONE && isfinite(S.wmax[r]) && dot2(S.AT + r, S.ng, zc, nv) - bgen[r] > 0.0) o = -1;
             orient[r] = o; agen[r] = 0;
         }
         LANES(j, nv) {
             aflag[j] = 0;
             int op = 1, on = 1;
-            if (S.one_norm && j < nl * N) {
+            if (ONE && j < nl * N) {
                 const int i = j / N, kk = j % N, d0 = kk * nl + i;
                 if (d0 < L) {
                     const double du = zc[j] - am[d0] * (kk == 0 ? v0[i] : zc[j - 1]) - cm[d0];
@@ -697,7 +700,7 @@ struct Warp {
             if (d0 >= L) {       // stage kk not fixed: reachable interval of v_{kk+1}
                 lo = fmax(lo, rlo[i * (N + 1) + kk + 1]); hi = fmin(hi, rhi[i * (N + 1) + kk + 1]);
             }
-            if (S.one_norm && soft && d0 < L) {      // qu |u| of a fixed stage: the pair of soft rows on b u
+            if (ONE && soft && d0 < L) {      // qu |u| of a fixed stage: the pair of soft rows on b u
                 const double du = xv - am[d0] * (kk == 0 ? v0[i] : x[j - 1]) - cm[d0];
                 PM_CAND(PT_USP, j, uor[j] > 0 ? du : -du);
                 PM_CAND(PT_USN, j, uor[nv + j] > 0 ? -du : du);
@@ -749,7 +752,7 @@ struct Warp {
     __device__ double objective() {
         const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
         double f = 0.0;
-        if (!S.one_norm) {
+        if (!ONE) {
             LANES(j, nv) {
                 const double s = dot2(S.H0 + (size_t)j * nv, 1, x, nv);
                 f += x[j] * (g0[j] + 0.5 * s);
@@ -759,7 +762,7 @@ struct Warp {
             const int i = d % nl, k = d / nl, jk = i * N + k;
             const double xp = (k >= 1) ? x[jk - 1] : v0[i];
             const double uu = (x[jk] - am[d] * xp - cm[d]) * rcp(bm[d]);
-            f += S.one_norm ? S.qu * fabs(uu) : S.qu * uu * uu;     // the proximal term is not part of the LP objective
+            f += ONE ? S.qu * fabs(uu) : S.qu * uu * uu;     // the proximal term is not part of the LP objective
         }
         LANES(r, ng) {
             const double wm = S.wmax[r];
@@ -777,7 +780,7 @@ struct Warp {
         double best_v; int bid;
         scan(best_v, bid, 1e-9, true);
         if (bid == 0x7fffffff) {
-            if (S.one_norm) {
+            if (ONE) {
                 // Proximal-point round done.  The node LP is solved once the centre stops moving -- or, when the
                 // optimum is a face and round-off keeps the point wandering on it, once the LP objective stops
                 // decreasing: f(zc) - f(x) >= rho/2 |x - zc|^2, so a stalled objective means a stalled point, and a
@@ -851,7 +854,7 @@ struct Warp {
     __device__ void do_step() {
         const int nv = S.nv, ld = S.ld;
         const double tol = 1e-9, INF = HUGE_VAL;
-        if (++it > (S.one_norm ? 200 * nv + 2000 : 40 * nv + 200)) { node_done(2, 0.0); return; }
+        if (++it > (ONE ? 200 * nv + 2000 : 40 * nv + 200)) { node_done(2, 0.0); return; }
         // p can reach its boundary exactly at the end of a PARTIAL step (t1 = t2 tie): it then joins the
         // active set with the multiplier it has accumulated (a full step of length zero) -- returning to
         // SELECT here would drop lam_p * n_p from the stationarity condition
@@ -893,7 +896,7 @@ struct Warp {
         // d(dual)/dt = violation of p along the step: the dual value is a lower bound on the node optimum
         dual += t * cp - (dependent ? 0.0 : 0.5 * t * t * nz);
         // (not under the 1-norm cost: the dual of a proximal sub-problem does not bound the node LP)
-        if (!S.one_norm && dual > inc) { node_done(1, 0.0); return; }          // the node cannot beat the incumbent
+        if (!ONE && dual > inc) { node_done(1, 0.0); return; }          // the node cannot beat the incumbent
         __syncwarp(gm);
         if (!dependent) {
             // w = n_p - N r ;  x -= t H^-1 w ;  the violation of p shrinks by t nz
@@ -979,7 +982,7 @@ struct Warp {
 
     __device__ void solve() {
         while (state != PS_DONE) {
-            if (state == PS_NEXT) do_next();
+            if (!FX && state == PS_NEXT) do_next();
             if (state == PS_BUILD) do_build();
             if (state == PS_SELECT) do_select();
             if (state == PS_STEP) do_step();
@@ -1109,7 +1112,7 @@ struct Warp {
 
 }  // namespace
 
-template <int GW>
+template <int GW, bool ONE, bool FX>
 __global__ void __launch_bounds__(128)
 pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __restrict__ x0,
                const double* __restrict__ mass, const double* __restrict__ params,
@@ -1121,7 +1124,7 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
     const int lane = threadIdx.x % GW, wib = threadIdx.x / GW;       // lane within the group, group within the CTA
     const unsigned gm = GW == 32 ? FULL : (0xffffu << (16 * ((threadIdx.x >> 4) & 1)));
     double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
-    Warp<GW> W(S, base, lane, gm);
+    Warp<GW, ONE, FX> W(S, base, lane, gm);
     const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
     // problems are handed out one at a time (tree sizes vary by orders of magnitude)
     W.sp = &sp;
@@ -1211,7 +1214,7 @@ pm_eval_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
     constexpr int GW = 32;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
-    Warp<GW> W(S, base, lane, FULL);
+    Warp<GW, false> W(S, base, lane, FULL);
     const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
     for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < batch; i += (int64_t)gridDim.x * wpb) {
         W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar, nullptr);
@@ -1320,20 +1323,20 @@ void pm_layout(PmDev& S) {
 // MaxDynamicSharedMemorySize of pm_miqp_kernel<GW>: grow-only, cached per device, shared by EVERY launch path of the kernel
 // (the sharded path used to set its own, smaller value on every call and left the cache of the plain path stale:
 // a later launch with more shared memory failed with "invalid argument")
-template <int GW>
+template <int GW, bool ONE, bool FX>
 static cudaError_t pm_miqp_smem_attr(size_t smem) {
     int dev = 0;
     cudaGetDevice(&dev);
     static size_t attr_set[HVP_MAX_DEVICES] = {0};
     if (dev < 0 || dev >= HVP_MAX_DEVICES || smem > attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW, ONE, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < HVP_MAX_DEVICES) attr_set[dev] = smem;
     }
     return cudaSuccess;
 }
 
-template <int GW>
+template <int GW, bool ONE>
 static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double* x0, const double* mass,
                                     const double* params, const int32_t* fixed_modes, const double* Y, double* u,
                                     double* x, double* extra, int32_t* modes, double* obj, int32_t* status,
@@ -1348,7 +1351,7 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     {
-        cudaError_t e = pm_miqp_smem_attr<GW>(smem);
+        cudaError_t e = pm_miqp_smem_attr<GW, ONE, false>(smem);
         if (e != cudaSuccess) return e;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1365,7 +1368,16 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     PmSplit sp;
     memset(&sp, 0, sizeof sp);
     if (!split) {
-        pm_miqp_kernel<GW><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,
+        if (fixed_modes) {                   // fixed-sequence QPs: the instantiation without the search
+            if (ONE) return cudaErrorInvalidValue;
+            e = pm_miqp_smem_attr<GW, false, true>(smem);
+            if (e != cudaSuccess) return e;
+            pm_miqp_kernel<GW, false, true><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u,
+                                                                                         x, extra, modes, obj, status, nodes, qp_iters,
+                                                                                         counter, sp);
+            return cudaGetLastError();
+        }
+        pm_miqp_kernel<GW, ONE, false><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,
                                                                         extra, modes, obj, status, nodes, qp_iters, counter, sp);
         return cudaGetLastError();
     }
@@ -1374,7 +1386,7 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     sp.mode = 1;
     e = cudaMemsetAsync(sp.nflag, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
-    pm_miqp_kernel<GW><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, u, x, extra,
+    pm_miqp_kernel<GW, ONE, false><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, u, x, extra,
                                                                     modes, obj, status, nodes, qp_iters, counter, sp);
     // pass 2: M groups per flagged problem, sub-trees by prefix ordinal, incumbent shared through global memory
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
@@ -1382,7 +1394,7 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     sp.mode = 2;
     int64_t b2 = ((int64_t)sp.cap * sp.M + gpb - 1) / gpb;
     if (b2 > full) b2 = full;
-    pm_miqp_kernel<GW><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
+    pm_miqp_kernel<GW, ONE, false><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
                                                                 sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
                                                                 sc->iters, counter, sp);
     // pass 3: keep the best sub-result of every flagged problem
@@ -1407,7 +1419,7 @@ pm_shard_init_kernel(int64_t batch, const double* __restrict__ incumbent, PmSpli
     if (qp_iters) qp_iters[i] = 0;
 }
 
-template <int GW>
+template <int GW, bool ONE>
 static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double* x0, const double* mass,
                                      const double* params, const double* Y, const double* incumbent, double* u,
                                      double* x, double* extra, int32_t* modes, double* obj, int32_t* status,
@@ -1417,7 +1429,7 @@ static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double
     while (gpb > 1 && (size_t)gpb * S.smem_bytes > 200 * 1024) gpb >>= 1;
     const size_t smem = (size_t)gpb * S.smem_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = pm_miqp_smem_attr<GW>(smem);
+    cudaError_t e = pm_miqp_smem_attr<GW, ONE, false>(smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1434,7 +1446,7 @@ static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     pm_shard_init_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(batch, incumbent, sp, obj, nodes, qp_iters);
-    pm_miqp_kernel<GW><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
+    pm_miqp_kernel<GW, ONE, false><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
                                                                     sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
                                                                     sc->iters, counter, sp);
     pm_merge_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, stream>>>(S, sp, sc->u, sc->x, sc->extra, sc->modes, sc->obj,
@@ -1448,11 +1460,10 @@ cudaError_t launch_pm_shard(const PmDev& S, int64_t batch, const double* x0, con
                             int32_t* modes, double* obj, int32_t* status, int32_t* nodes, int32_t* qp_iters,
                             unsigned long long* counter, const PmScratch* sc, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
-    if (S.nv <= 16)
-        return launch_pm_shard_t<16>(S, batch, x0, mass, params, Y, incumbent, u, x, extra, modes, obj, status, nodes,
-                                     qp_iters, counter, sc, stream);
-    return launch_pm_shard_t<32>(S, batch, x0, mass, params, Y, incumbent, u, x, extra, modes, obj, status, nodes,
-                                 qp_iters, counter, sc, stream);
+#define HVP_SHARD(GW_, ONE_) launch_pm_shard_t<GW_, ONE_>(S, batch, x0, mass, params, Y, incumbent, u, x, extra, modes, obj, status, nodes, qp_iters, counter, sc, stream)
+    if (S.nv <= 16) return S.one_norm ? HVP_SHARD(16, true) : HVP_SHARD(16, false);
+    return S.one_norm ? HVP_SHARD(32, true) : HVP_SHARD(32, false);
+#undef HVP_SHARD
 }
 
 cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, const double* mass,
@@ -1463,11 +1474,10 @@ cudaError_t launch_pm_miqp(const PmDev& S, int64_t batch, const double* x0, cons
     // problems with at most 16 variables (e.g. the centralized n = 3, N = 5 MIQP) get a 16-lane group: two per warp
     static const int force = getenv("HVP_MPC_GROUP") ? atoi(getenv("HVP_MPC_GROUP")) : 0;
     const bool half = force ? force == 16 : (S.nv <= 16);
-    if (half)
-        return launch_pm_miqp_t<16>(S, batch, x0, mass, params, fixed_modes, Y, u, x, extra, modes, obj, status, nodes,
-                                    qp_iters, counter, sc, stream);
-    return launch_pm_miqp_t<32>(S, batch, x0, mass, params, fixed_modes, Y, u, x, extra, modes, obj, status, nodes,
-                                qp_iters, counter, sc, stream);
+#define HVP_MIQP(GW_, ONE_) launch_pm_miqp_t<GW_, ONE_>(S, batch, x0, mass, params, fixed_modes, Y, u, x, extra, modes, obj, status, nodes, qp_iters, counter, sc, stream)
+    if (half) return S.one_norm ? HVP_MIQP(16, true) : HVP_MIQP(16, false);
+    return S.one_norm ? HVP_MIQP(32, true) : HVP_MIQP(32, false);
+#undef HVP_MIQP
 }
 
 cudaError_t launch_pm_eval(const PmDev& S, int64_t batch, const double* x0, const double* mass,
