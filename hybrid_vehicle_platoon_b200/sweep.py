@@ -429,7 +429,12 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
         groups.setdefault((sc["N"], spacing_params(pol)), {}).setdefault(sc["n"], []).append(i)
     import torch
     out, work = {}, []
-    for (N, _), by_n in sorted(groups.items()):
+    # longest horizons first and on high-priority streams: the N = 10 / time-headway group alone is more than half of the
+    # sweep's critical path (scripts/diag_mixed_groups.py), the short-horizon groups fit into its tails
+    def weight(item):
+        (N_, (d0_, t0_)), _ = item
+        return -(N_ + (0.5 if t0_ != 0.0 else 0.0))
+    for (N, _), by_n in sorted(groups.items(), key=weight):
         first = next(iter(by_n.values()))[0]
         pol = scenarios[first].get("spacing_policy") or ConstantSpacingPolicy(50)
         parts, index = [], []
@@ -439,7 +444,7 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
             parts.append((n, np.stack([scenarios[i]["x0"] for i in idx]), np.stack([scenarios[i]["leader_x"] for i in idx]), masses))
             index.append(idx)
         sw = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx)
-        stream = torch.cuda.Stream(device=sw.dev)
+        stream = torch.cuda.Stream(device=sw.dev, priority=-1 if N >= 9 else 0)
         with torch.cuda.stream(stream):
             sw.prepare(parts, ep_len)
         work.append((sw, stream, index))
