@@ -93,6 +93,12 @@ class PlatoonEnv:
             u, gears = action[:n, :], action[n:, :].astype(np.int32).reshape(1, n)
         else:
             u = action
+            # gears derived from the velocities exist for PWA-gear vehicles only (Platoon.get_gear_from_vehicle_velocity,
+            # models.py:259-264 raises for any other vehicle type)
+            from .models import PwaGearVehicle
+            for i, veh in enumerate(getattr(self.platoon, "vehicles", [])):
+                if not isinstance(veh, PwaGearVehicle):
+                    raise RuntimeError(f"Gear from velocity asked but the given vehicle {i} is not a PWA vehicle.")
         xo, cost, viol, err = api.rollout_step(
             np.asarray(self.x, dtype=np.float64).reshape(1, 2 * n), u.reshape(1, n), gears, self.masses,
             self.leader_x[:, self.step_counter].reshape(1, 2), d0=self.d0, t0=self.t0,
@@ -108,12 +114,16 @@ class PlatoonEnv:
         return self.x, r, False, False, {}
 
     def get_stage_cost(self, state, action) -> float:
-        """env.py:126-180 on the GPU (state/action need not be the env's own)."""
-        _, cost, _, _ = api.rollout_step(
+        """env.py:126-180 on the GPU (state/action need not be the env's own), with the reference's side effects: the
+        violation counter of the current step and previous_action / previous_state (env.py:165-179)."""
+        _, cost, viol, _ = api.rollout_step(
             np.asarray(state, dtype=np.float64).reshape(1, -1), np.asarray(action, dtype=np.float64).reshape(1, -1),
             None, self.masses, self.leader_x[:, self.step_counter].reshape(1, 2), d0=self.d0, t0=self.t0,
             leader_index=self.leader_index, d_safe=self.d_safe, quadratic=self.quadratic_cost,
             real_ref=self.real_vehicle_as_reference, ctx=self._ctx)
+        if viol[0] and self.step_counter < len(self.viol_counter[-1]):
+            self.viol_counter[-1][self.step_counter] = 100
+        self.previous_action, self.previous_state = action, state
         return np.array([[cost[0]]])
 
     def get_state(self):

@@ -32,7 +32,7 @@ class TrackingCentralizedAgent(MldAgent):
         return super().on_episode_start(env, episode, state)
 
 
-def simulate(sim: Sim, save: bool = False, plot: bool = False, seed: int = 2, thread_limit=None,
+def simulate(sim: Sim, save: bool = False, plot: bool = False, seed: int = 1, thread_limit=None,
              leader_index: int = 0, ep_len=None, env_class=None):
     """fleet_cent_mld.simulate (:104-213); returns the 7 result objects as a dict."""
     n, N = sim.n, sim.N
