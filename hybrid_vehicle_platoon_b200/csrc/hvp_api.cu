@@ -57,10 +57,20 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
     hvp_ctx* c = new hvp_ctx();
     c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0; c->hbuf = nullptr; c->hcap = 0;
     c->counters = nullptr; c->counter_next = 0; c->side_ok = false; c->n_slots = 0;
-    CUDA_TRY(cudaMalloc(&c->counters, (HVP_STREAM_SLOTS + HVP_COUNTER_RING) * sizeof(unsigned long long)));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&c->ev0));
-    CUDA_TRY(cudaEventCreate(&c->ev1));
+    c->stream = nullptr; c->ev0 = nullptr; c->ev1 = nullptr;
+    // a failure half-way must not leak what was created before it
+    cudaError_t e = cudaMalloc(&c->counters, (HVP_STREAM_SLOTS + HVP_COUNTER_RING) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->counters) cudaFree(c->counters);
+        delete c;
+        return fail(-100 - (int)e, "hvp_ctx_create: %s", cudaGetErrorString(e));
+    }
     *out = c;
     return 0;
 }
@@ -168,6 +178,11 @@ extern "C" int hvp_rollout_step_host(hvp_ctx* c, const hvp_env_desc* desc, int64
     if (batch < 0) return fail(-4, "rollout: negative batch");
     if (batch == 0) return 0;
     if (!x || !u || !leader || !x_out || !cost || !viol || !err) return fail(-1, "rollout: NULL array argument");
+    {   // validate the descriptor BEFORE buffer sizes are derived from it (n <= 0 would wrap the size_t arithmetic)
+        RolloutParams chk;
+        const int rc0 = fill_rollout_params(chk, desc);
+        if (rc0) return rc0;
+    }
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t n = (size_t)desc->n, B = (size_t)batch;
     const bool mass_per = desc->flags & HVP_ENV_MASS_PER_SCENARIO;
