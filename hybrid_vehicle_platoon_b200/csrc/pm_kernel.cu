@@ -1320,6 +1320,30 @@ void pm_layout(PmDev& S) {
     S.smem_bytes = (o * 8 + ints * 4 + 15) / 16 * 16;
 }
 
+// Groups (= problems in flight) per CTA and CTAs per SM of pm_miqp_kernel: the kernel is latency bound (r02o ncu: issue slots
+// 21 % busy), so what counts is how many groups an SM holds, and that is set by shared memory -- 227 KB minus 1 KB
+// per CTA -- and by the register file (~128 registers per thread: 16 warps).  Round 1 always packed 128 threads per
+// CTA: 76 KB per CTA at 15 variables = 2 CTAs = 16 groups per SM where 22 fit as eleven one-warp CTAs.
+template <int GW>
+static void pm_launch_shape(const PmDev& S, int& gpb, int& per_sm) {
+    static const int force = getenv("HVP_MPC_GPB") ? atoi(getenv("HVP_MPC_GPB")) : 0;
+    const size_t sm_smem = 233472, cta_overhead = 1024;
+    int best_g = 0, best_c = 0;
+    for (int g = 128 / GW; g >= (GW == 16 ? 2 : 1); g >>= 1) {
+        if (force && g != force) continue;
+        const size_t smem = (size_t)g * S.smem_bytes;
+        if (smem > 227 * 1024) continue;
+        int c = (int)(sm_smem / (smem + cta_overhead));
+        const int threads = g * GW;
+        if (c * threads > 512) c = 512 / threads;          // register file: 16 warps of ~128 registers per thread
+        if (c > 32) c = 32;
+        if (c < 1) c = 1;
+        if (c * g > best_c * best_g) { best_g = g; best_c = c; }
+    }
+    if (best_g == 0) { best_g = GW == 16 ? 2 : 1; best_c = 1; }
+    gpb = best_g; per_sm = best_c;
+}
+
 // MaxDynamicSharedMemorySize of pm_miqp_kernel<GW>: grow-only, cached per device, shared by EVERY launch path of the kernel
 // (the sharded path used to set its own, smaller value on every call and left the cache of the plain path stale:
 // a later launch with more shared memory failed with "invalid argument")
@@ -1343,8 +1367,8 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
                                     int32_t* nodes, int32_t* qp_iters, unsigned long long* counter,
                                     const PmScratch* sc, cudaStream_t stream) {
     // gpb groups (= problems in flight) per CTA of gpb * GW threads
-    int gpb = 128 / GW;
-    while (gpb > 1 && (size_t)gpb * S.smem_bytes > 200 * 1024) gpb >>= 1;
+    int gpb = 0, per_sm = 0;
+    pm_launch_shape<GW>(S, gpb, per_sm);
     const size_t smem = (size_t)gpb * S.smem_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     // function attributes are per DEVICE (one process may drive several: Context(device)): cached per device
@@ -1356,9 +1380,6 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int threads = gpb * GW;
-    int per_sm = (int)((220 * 1024) / smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm * threads > 2048) per_sm = 2048 / threads;
     const int64_t full = (int64_t)sms * per_sm;
     int64_t blocks = (batch + gpb - 1) / gpb;
     if (blocks > full) blocks = full;
@@ -1425,8 +1446,8 @@ static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double
                                      double* x, double* extra, int32_t* modes, double* obj, int32_t* status,
                                      int32_t* nodes, int32_t* qp_iters, unsigned long long* counter,
                                      const PmScratch* sc, cudaStream_t stream) {
-    int gpb = 128 / GW;
-    while (gpb > 1 && (size_t)gpb * S.smem_bytes > 200 * 1024) gpb >>= 1;
+    int gpb = 0, per_sm = 0;
+    pm_launch_shape<GW>(S, gpb, per_sm);
     const size_t smem = (size_t)gpb * S.smem_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = pm_miqp_smem_attr<GW, ONE, false>(smem);
@@ -1435,9 +1456,6 @@ static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int threads = gpb * GW;
-    int per_sm = (int)((220 * 1024) / smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm * threads > 2048) per_sm = 2048 / threads;
     const int64_t full = (int64_t)sms * per_sm;
     PmSplit sp = sc->sp;
     sp.mode = 3;
