@@ -434,6 +434,7 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     // enough that saturating a w = 1e4 slack row does not send the iterate through 1e8 (round-off 1e-8: measured, 2.5 %
     // of the C1-shaped problems did not settle at rho = 1e-4, 0.1 % at 1e-3 .. 1e-2 before the objective criterion)
     S.rho_px = getenv("HVP_RHO_PX") ? atof(getenv("HVP_RHO_PX")) : 1e-3;
+    S.ppa_stall = getenv("HVP_PPA_STALL") ? atof(getenv("HVP_PPA_STALL")) : 1e-12;
     if (B.one_norm)                    // no quadratic cost term: the proximal term of the node LPs (pm_types.h)
         for (int j = 0; j < nv; ++j) H0[(size_t)j * nv + j] = S.rho_px;
     if (!spd_inverse(nv, H0, H0inv)) {

@@ -120,7 +120,8 @@ struct Warp {
     unsigned gm;                       // lane mask of this group
     // shared-memory views
     double *Hinv, *Ginv, *Nact;
-    double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best, *zc;
+    double *x, *g0, *gn, *yp, *wv, *zd, *dv, *rv, *lam, *np_, *best, *zc;     // zd: right-hand sides of the active rows (1-norm)
+    double bp;
     double *cres, *bgen, *pvec;
     double *inv_m, *pc, *v0, *xstar, *rlo, *rhi, *am, *bm, *cm, *amax, *amin;
     // Sibling bounds (levels 0..D): what the SOLVED parent of a level says about forcing its branching velocity out of the
@@ -774,6 +775,22 @@ struct Warp {
         return c0 + wsum<GW>(gm, f);
     }
 
+    // 1-norm: one step of iterative refinement on the active rows.  With H = rho I (rho = 1e-3) and multipliers up to
+    // w = 1e4 the point x = -H^-1 (g + N lambda) carries a round-off of ~1e-8, which a kink of weight w turns into 1e-4
+    // of objective.  The minimum-norm correction dx = -H^-1 N (N'H^-1 N)^-1 (N'x - b) puts x back on its active rows.
+    __device__ void refine() {
+        const int nv = S.nv, ld = S.ld;
+        if (q == 0) return;
+        LANES(a, q) dv[a] = dot2(Nact + a * ld, 1, x, nv) - zd[a];
+        __syncwarp(gm);
+        LANES(a, q) rv[a] = dot2(Ginv + a * ld, 1, dv, q);
+        __syncwarp(gm);
+        LANES(j, nv) np_[j] = dot2(Nact + j, ld, rv, q);
+        __syncwarp(gm);
+        LANES(j, nv) x[j] -= dot2(Hinv + j * ld, 1, np_, nv);
+        __syncwarp(gm);
+    }
+
     // ---- SELECT: most violated row, or the node is solved --------------------------------------
     __device__ void do_select() {
         const int nl = S.nl, N = S.N, nv = S.nv, ng = S.ng;
@@ -789,7 +806,7 @@ struct Warp {
                 LANES(j, nv) { const double a = fabs(x[j] - zc[j]); if (a > dl) dl = a; }
                 wargmax<GW>(gm, dl, dj);
                 const double f = objective();
-                const bool stalled = ppa >= 1 && f_prev - f <= 1e-12 * fmax(1.0, fabs(f));
+                const bool stalled = ppa >= 1 && f_prev - f <= S.ppa_stall * fmax(1.0, fabs(f));
                 if (dl > 1e-6 && !stalled && ppa < 200) {
                     LANES(j, nv) zc[j] = x[j];
                     ++ppa;
@@ -801,7 +818,8 @@ struct Warp {
                 }
                 if (dl > 1e-6 && !stalled) { node_done(2, 0.0); return; }
                 ppa = 0;
-                node_done(0, f);
+                refine();
+                node_done(0, objective());
                 return;
             }
             ppa = 0;
@@ -844,6 +862,11 @@ struct Warp {
             acc += s * np_[j];
         }
         nHn = wsum<GW>(gm, acc);
+        if (ONE) {          // right-hand side of p in its current orientation (best_v = n_p'x - b_p), kept for refine()
+            double nx = 0.0;
+            LANES(j, nv) nx += np_[j] * x[j];
+            bp = wsum<GW>(gm, nx) - best_v;
+        }
         cp = best_v;
         lam_p = 0.0;
         state = PS_STEP;
@@ -926,6 +949,7 @@ struct Warp {
                 Ginv[q * ld + q] = is;
                 act[q] = pid;
                 lam[q] = lam_p;
+                if (ONE) zd[q] = bp;
                 const int pt_ = pid / 4096, ix_ = pid % 4096;
                 if (pt_ == PT_GEN) agen[ix_] = 1; else aflag[ix_] |= (1 << pt_);
             }
@@ -971,6 +995,7 @@ struct Warp {
                     Ginv[drop * ld + drop] = Ginv[last * ld + last];
                     act[drop] = act[last];
                     lam[drop] = lam[last];
+                    if (ONE) zd[drop] = zd[last];
                 }
                 LANES(j, nv) Nact[drop * ld + j] = Nact[last * ld + j];
             }
@@ -1389,13 +1414,12 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     PmSplit sp;
     memset(&sp, 0, sizeof sp);
     if (!split) {
-        if (fixed_modes) {                   // fixed-sequence QPs: the instantiation without the search
-            if (ONE) return cudaErrorInvalidValue;
-            e = pm_miqp_smem_attr<GW, false, true>(smem);
+        if (fixed_modes) {                   // fixed-sequence QPs (LPs under the 1-norm cost): the instantiation without the search
+            e = pm_miqp_smem_attr<GW, ONE, true>(smem);
             if (e != cudaSuccess) return e;
-            pm_miqp_kernel<GW, false, true><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u,
-                                                                                         x, extra, modes, obj, status, nodes, qp_iters,
-                                                                                         counter, sp);
+            pm_miqp_kernel<GW, ONE, true><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u,
+                                                                                       x, extra, modes, obj, status, nodes, qp_iters,
+                                                                                       counter, sp);
             return cudaGetLastError();
         }
         pm_miqp_kernel<GW, ONE, false><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, fixed_modes, Y, u, x,

@@ -38,6 +38,7 @@ struct PmDev {                   // kernel argument
     // centre z_k that moves to the solution until it stops moving (finite for an LP; one or two rounds in practice).
     int one_norm;
     double rho_px;
+    double ppa_stall;            // a proximal round whose LP objective decreases by less than this (relative) ends the node
     int sibling;                 // prune siblings by the dual of their solved parent (pm_kernel.cu parent_info)
     double mip_gap;              // relative pruning gap (0: proven optimal)
     long long time_limit_ns;     // per-problem budget on the device clock (0: none)

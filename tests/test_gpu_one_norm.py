@@ -55,6 +55,41 @@ def test_local_one_norm_vs_milp(hvp_ctx, N, stress, t0):
             assert ok2 and abs(obj2 - obj) <= 1e-5 * max(1.0, abs(obj)), (b, fl, obj2, obj)
 
 
+def test_one_norm_fixed_sequence_lp_vs_highs(hvp_ctx):
+    """fixed_modes under the 1-norm cost is one LP per problem (a one-leaf tree): re-solving with the optimal sequence
+    returns the optimum; any other sequence is an upper bound, equal to HiGHS on the model with its binaries fixed.  The
+    LP value is held to 1e-7: the refinement step on the active rows (pm_kernel.cu refine()) is what makes that hold."""
+    import hybrid_vehicle_platoon_b200 as hvp
+    N, d0, t0 = 4, 10.0, 3.0
+    rng = np.random.default_rng(91)
+    c = platoon_local_problems(rng, 6, 4, N, 0, True, True)
+    for fl in sorted(set(int(f) for f in c["flags"])):
+        sel = np.nonzero(c["flags"] == fl)[0]
+        mpc = hvp.api.CompiledMpc(G.LOCAL, N, flags=fl, d0=d0, t0=t0, one_norm=True, ctx=hvp_ctx)
+        params = np.concatenate([c[k][sel].reshape(len(sel), -1) for k in ("xf", "xb", "xl")], axis=1)
+        x0, mass = c["x0"][sel].reshape(-1, 1, 2), c["mass"][sel].reshape(-1, 1)
+        r = mpc.solve(x0, mass, params)
+        keep = np.nonzero(r["status"] == 2)[0]
+        assert len(keep)
+        rf = mpc.solve(x0[keep], mass[keep], params[keep], fixed_modes=r["modes"][keep])
+        assert (rf["status"] == 2).all()
+        np.testing.assert_allclose(rf["obj"], r["obj"][keep], rtol=1e-9, atol=1e-9)
+        shifted = np.clip(r["modes"][keep] + 1, 0, 6).astype(np.int32)
+        rs = mpc.solve(x0[keep], mass[keep], params[keep], fixed_modes=shifted)
+        for j, b in enumerate(sel[keep]):
+            M, x, u, dl = MB.build_local(_sysd(float(c["mass"][b])), N, c["x0"][b], c["xf"][b], c["xb"][b], c["xl"][b],
+                                         is_front=bool(fl & 1), is_leader=bool(fl & 2), is_trailer=bool(fl & 4),
+                                         d0=d0, t0=t0, quadratic=False)
+            for res, md in ((rf, r["modes"][keep][j].reshape(-1)), (rs, shifted[j].reshape(-1))):
+                fixed = {int(dl[rg, k]): (1.0 if md[k] == rg else 0.0) for rg in range(dl.shape[0]) for k in range(N)}
+                ok, _, obj = MB.solve_qp_fixed(M, fixed)
+                if not ok:
+                    assert res["status"][j] == 3, (b, fl, res["status"][j])
+                    continue
+                assert res["status"][j] == 2 and abs(res["obj"][j] - obj) <= 1e-7 * max(1.0, abs(obj)), (b, fl, res["obj"][j], obj)
+                assert res["obj"][j] >= r["obj"][keep][j] - 1e-7 * max(1.0, abs(obj))
+
+
 @pytest.mark.parametrize("n,N,stress", [(2, 3, True), (3, 3, False), (3, 5, False)])
 def test_centralized_one_norm_vs_milp(hvp_ctx, n, N, stress):
     """BASELINE configs[0] shape (n = 3, N = 5) with quadratic_cost=False."""
