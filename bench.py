@@ -200,6 +200,23 @@ def compiled_mpc_legs(hvp, torch, dev, stream, flush, steps=5, with_cpu=True):
     return legs
 
 
+def _episodes(run, reps=3, sync=None, reduce=None):
+    """Wall-clock time of a whole-episode leg: one untimed run at FULL size first (the CPU-side work of the previous leg
+    leaves the GPU at idle clocks and the caching allocator without blocks of this size: measured 55 ms for the first
+    runs of the decentralized loop against 40-43 ms from the third on, scripts/diag_decent_loop.py), then the MEDIAN of
+    `reps` timed runs; every run includes the upload of the initial states and the read-back of all result arrays."""
+    run()
+    times, out = [], None
+    for _ in range(reps):
+        if sync:
+            sync()
+        t0 = time.perf_counter()
+        out = run()
+        dt = time.perf_counter() - t0
+        times.append(reduce(dt) if reduce else dt)
+    return out, sorted(times)[len(times) // 2], times
+
+
 def closed_loop_leg(ctx, S=4096, T=20):
     """Whole closed-loop episodes of the decentralized controller for S scenarios, state resident on the device
     (sweep.BatchedDecentSweep): observe -> S*n MIQPs -> rollout per timestep, wall-clock incl. result read-back."""
@@ -212,12 +229,9 @@ def closed_loop_leg(ctx, S=4096, T=20):
     lx = StopAndGoLeaderTrajectory(p=3000, vh=20, vl=10, vf=30, v_change_steps=[5, 12], trajectory_len=T + HORIZON + 10,
                                    ts=1).get_leader_trajectory()
     sw = BatchedDecentSweep(N_VEH, HORIZON, ctx=ctx)
-    sw.run(x0[:256], lx, 3)
-    t0 = time.perf_counter()
-    out = sw.run(x0, lx, T)
-    dt = time.perf_counter() - t0
+    out, dt, runs = _episodes(lambda: sw.run(x0, lx, T))
     return {"value": S * T / dt, "unit": "scenario-timesteps/s", "solves_per_s": S * T * N_VEH / dt, "scenarios": S,
-            "timesteps": T, "seconds": dt, "optimal_frac": float((out["status"] == 2).mean()),
+            "timesteps": T, "seconds": dt, "seconds_runs": runs, "optimal_frac": float((out["status"] == 2).mean()),
             "rollout_exceptions": int((out["errors"] != 0).any(0).sum()),
             "mean_nodes": float(out["nodes"].mean())}
 
@@ -233,12 +247,9 @@ def admm_loop_leg(ctx, S=1024, T=2, n=15, N=8, iters=20):
     x0 = np.empty((S, 2 * n)); x0[:, 0::2] = p; x0[:, 1::2] = v
     lx = ConstantVelocityLeaderTrajectory(p=3000, v=20, trajectory_len=T + N + 10, ts=1).get_leader_trajectory()
     sw = BatchedAdmmSweep(n, N, admm_iters=iters, rho=0.5, ctx=ctx)
-    sw.run(x0[:64], lx, 1)
-    t0 = time.perf_counter()
-    out = sw.run(x0, lx, T)
-    dt = time.perf_counter() - t0
+    out, dt, runs = _episodes(lambda: sw.run(x0, lx, T))
     return {"value": S * T * iters / dt, "unit": "scenario-ADMM-rounds/s", "solves_per_s": S * T * iters * n / dt,
-            "scenarios": S, "timesteps": T, "admm_iters": iters, "seconds": dt,
+            "scenarios": S, "timesteps": T, "admm_iters": iters, "seconds": dt, "seconds_runs": runs,
             "optimal_frac": float((out["status"] == 2).mean()), "rollout_exceptions": int((out["errors"] != 0).any(0).sum())}
 
 
@@ -256,12 +267,10 @@ def gadmm_loop_leg(ctx, S=1024, T=2, n=15, N=8, iters=100):
     lx = ConstantVelocityLeaderTrajectory(p=3000, v=20, trajectory_len=T + N + 10, ts=1).get_leader_trajectory()
     sw = BatchedGAdmmSweep(n, N, admm_iters=iters, rho=0.5, ctx=ctx)
     sw.run(x0[:16], lx, 1)
-    t0 = time.perf_counter()
-    out = sw.run(x0, lx, T)
-    dt = time.perf_counter() - t0
+    out, dt, runs = _episodes(lambda: sw.run(x0, lx, T))
     rounds = S * iters * (1 + 2 * (T - 1))            # one warm start at t = 0, two afterwards
     return {"value": rounds / dt, "unit": "scenario-ADMM-rounds/s", "qp_solves_per_s": rounds * n / dt, "scenarios": S,
-            "timesteps": T, "admm_iters": iters, "seconds": dt, "solved_frac": float(out["solved"].mean()),
+            "timesteps": T, "admm_iters": iters, "seconds": dt, "seconds_runs": runs, "solved_frac": float(out["solved"].mean()),
             "rollout_exceptions": int((out["errors"] != 0).any(0).sum())}
 
 
@@ -286,20 +295,23 @@ def mixed_sweep_leg(ctx, rank, world, dev, S=4096, T=10):
                                        trajectory_len=T + 10 + 12, ts=1).get_leader_trajectory()
         pol = ConstantSpacingPolicy(50) if rng.random() < 0.5 else ConstantTimePolicy(10, 3)
         scen.append(dict(n=n, N=N, x0=x0, leader_x=lx, masses=None, spacing_policy=pol))
-    run_mixed_sweep(scen[:64], 2, rank=0, world=1, device=dev.index, ctx=ctx)          # warm-up (builds nothing new)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = run_mixed_sweep(scen, T, rank=rank, world=world, device=dev.index, ctx=ctx)
-    torch.cuda.synchronize()
-    dt = max_over_ranks([time.perf_counter() - t0], device=dev)[0]
+    def sync():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run():
+        r = run_mixed_sweep(scen, T, rank=rank, world=world, device=dev.index, ctx=ctx)
+        torch.cuda.synchronize()
+        return r
+
+    out, dt, runs = _episodes(run, sync=sync, reduce=lambda d: max_over_ranks([d], device=dev)[0])
     solves = sum(scen[i]["n"] for i in out) * T
     opt = sum(int((r["status"] == 2).sum()) for r in out.values())
     tot_s, tot_o, tot_n = sum_over_ranks([solves, opt, len(out)], device=dev)
     return {"value": S * T / dt, "unit": "scenario-timesteps/s", "solves_per_s": tot_s / dt, "scenarios": int(tot_n),
-            "timesteps": T, "seconds": dt, "optimal_frac": tot_o / max(tot_s, 1), "n_range": [5, 15], "N_range": [4, 10],
+            "timesteps": T, "seconds": dt, "seconds_runs": runs, "optimal_frac": tot_o / max(tot_s, 1), "n_range": [5, 15], "N_range": [4, 10],
             "sharding": "dist.balanced_shards by 7 n N, no data-path collective", "n_gpus": world}
 
 

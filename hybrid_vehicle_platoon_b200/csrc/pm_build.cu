@@ -648,17 +648,33 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
     }
     if (m->split_D >= 1 && !fixed_modes && m->S.max_nodes == 0) {
         // cap heavy problems x M warps each; sized from the batch (grow-only)
-        static const int envM = getenv("HVP_MPC_SPLIT_M") ? atoi(getenv("HVP_MPC_SPLIT_M")) : 128;
-        static const int envB = getenv("HVP_MPC_BUDGET") ? atoi(getenv("HVP_MPC_BUDGET")) : 128;
-        size_t cap = (size_t)batch / 8;
+        static const int envM = getenv("HVP_MPC_SPLIT_M") ? atoi(getenv("HVP_MPC_SPLIT_M")) : 64;
+        static const int envB = getenv("HVP_MPC_BUDGET") ? atoi(getenv("HVP_MPC_BUDGET")) : 64;
+        // Room for EVERY problem of the batch on the flagged list, as far as 512 MB of result slots go: a heavy tree
+        // that finds the list full is finished by the single worker of the budgeted pass -- r02q launch list of the
+        // N = 10 time-headway group: after the leader's speed change more than batch / 8 trees are heavy, and the
+        // budgeted pass went from 8 ms to 60-106 ms (one 6 880-node tree on one 16-lane group).
+        size_t cap = (size_t)batch;
+        {
+            const PmDev& S0 = m->S;
+            const size_t nu0 = (size_t)S0.nl * S0.N, nx0 = (size_t)S0.nl * 2 * (S0.N + 1), ne0 = S0.ne > 0 ? (size_t)S0.ne : 1;
+            const size_t slot = (nu0 + nx0 + ne0 + 1) * 8 + (nu0 + 3) * 4;
+            size_t cap_max = ((size_t)512 << 20) / (slot * (size_t)envM);
+            if (cap_max > 32768) cap_max = 32768;
+            if (cap > cap_max) cap = cap_max;
+        }
         if (cap < 256) cap = 256;
-        if (cap > 4096) cap = 4096;
         if (cap > m->scratch_cap || m->scratch.sp.M != envM) {
             if (m->scratch_mem) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->scratch_mem)); m->scratch_mem = nullptr; }
             const PmDev& S = m->S;
-            const size_t items = cap * (size_t)envM, nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
+            // result slots: cap * M work items + the pool of the adopted sub-trees (PmSplit::ad)
+            static const int envAD = getenv("HVP_MPC_ADOPT") ? atoi(getenv("HVP_MPC_ADOPT")) : 1;
+            static const int envFree = getenv("HVP_MPC_ADOPT_FREE") ? atoi(getenv("HVP_MPC_ADOPT_FREE")) : 2;
+            const size_t pool = 32768, mail_cap = 20480, mail_stride = (size_t)S.depth + 3;
+            const size_t items = cap * (size_t)envM + pool, nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
             const size_t ne = S.ne > 0 ? (size_t)S.ne : 1;
-            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + cap * (4 + 8) + 64 + 12 * 256;
+            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + cap * (4 + 8) + 64 + 16 * 256 +
+                                 (16 + mail_cap * 4) + pool * 4 + mail_cap * mail_stride * 4;
             void* p = nullptr;
             CUDA_TRY(cudaMalloc(&p, bytes));
             m->scratch_mem = p;
@@ -670,6 +686,14 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
             sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
             sc.sp.inc_shared = (unsigned long long*)take(cap * 8); sc.sp.flagged = (int*)take(cap * 4);
             sc.sp.nflag = (int*)take(4);
+            {   // counters and mailbox states in ONE region (a single memset arms a launch): [ad_count 8][pool_used 4][pad 4][mail_state]
+                char* z = take(16 + mail_cap * 4);
+                sc.sp.ad_count = (unsigned long long*)z; sc.sp.pool_used = (int*)(z + 8); sc.sp.mail_state = (int*)(z + 16);
+            }
+            sc.sp.pool_owner = (int*)take(pool * 4);
+            sc.sp.mail_job = (int*)take(mail_cap * mail_stride * 4);
+            sc.sp.pool_cap = (int)pool; sc.sp.mail_cap = (int)mail_cap; sc.sp.mail_stride = (int)mail_stride;
+            sc.sp.ad = envAD; sc.sp.ad_free = envFree;
             sc.sp.M = envM; sc.sp.D = m->split_D;
             m->scratch_cap = cap;
         }

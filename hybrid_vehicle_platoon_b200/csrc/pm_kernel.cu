@@ -113,7 +113,10 @@ __device__ __forceinline__ double dval(unsigned long long k) {
 // ONE: the 1-norm (MILP) variant.  A template parameter, not a run-time flag: this kernel is bound by instruction fetch, and the
 // proximal-point code of the LP nodes, never executed by a 2-norm launch, still cost it 7 % (r02 measurement).
 // FX: the fixed-sequence QP of g-ADMM (fixed_modes given): no search at all, so the branch-and-bound code is compiled out.
-template <int GW, bool ONE, bool FX = false>
+// AD: adoption of sub-trees between the workers of the sub-tree pass (PmSplit::ad) -- its own instantiation, launched for
+// that pass only, because even never-executed code costs this kernel time (dealing prefixes from a counter: -23 % on
+// every launch when it was a run-time path).
+template <int GW, bool ONE, bool FX = false, bool AD = false>
 struct Warp {
     const PmDev& S;
     int lane;
@@ -141,6 +144,7 @@ struct Warp {
     long long t_start;
     // tree splitting (PmSplit)
     int sub_M, sub_D, sub_code, sub_ord, budget, stop_nodes;
+    int job_P, fidx, ad_nwork, ad_probe;      // adoption: forced prefix length of an adopted sub-tree, flagged index, workers, probe cursor
     double own;                        // objective of this warp's own best leaf
     const double* yel;                 // gE, hE of the eliminated copies of this problem (PmDev::nel)
     unsigned long long* shared;        // incumbent shared by the warps working on one problem
@@ -165,7 +169,7 @@ struct Warp {
         orient = built + D; aflag = orient + S.ng; agen = aflag + nv; uor = agen + S.ng;
         ppa = 0; retry = 0;
         (void)ld;
-        sub_M = sub_D = sub_code = sub_ord = budget = stop_nodes = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
+        sub_M = sub_D = sub_code = sub_ord = budget = stop_nodes = 0; job_P = fidx = ad_nwork = ad_probe = 0; shared = nullptr; sp = nullptr; prob = 0; own = HUGE_VAL;
     }
 
     __device__ __forceinline__ double ma(int i, int r) const { return 1.0 - S.M.cf[r] * inv_m[i]; }
@@ -295,6 +299,7 @@ struct Warp {
         _Pragma("unroll 1")
         for (int r = 0; r < S.M.R; ++r)
             if (S.M.lo[r] <= hi && S.M.hi[r] >= lo && S.M.lo[r] <= S.M.hi[r]) cn |= (1 << r);
+        if (AD && lv < job_P) cn &= (1 << modes[lv]);        // adopted sub-tree: the donor's path, nothing beside it
         cand[lv] = cn;
         xstar[lv] = (k == 0) ? v0[i] : x[i * N + k - 1];
         pf[lv] = -HUGE_VAL;
@@ -332,7 +337,54 @@ struct Warp {
     }
 
     // ---- NEXT: next node of the depth-first search (scalar; lane 0, result broadcast) ----------
+    // Adoption, donor side (all lanes).  If workers are waiting, give away the shallowest untried sibling of the own
+    // part of the depth-first stack (the largest piece of remaining work) to one of them: the candidate leaves cand[],
+    // the waiting worker gets the path to it as a mode prefix and a result slot of its own.
+    __device__ void try_donate() {
+        const PmSplit& P = *sp;
+        unsigned long long c = 0;
+        if (lane == 0) c = *reinterpret_cast<volatile unsigned long long*>(P.ad_count);
+        c = __shfl_sync(gm, c, 0, GW);
+        if ((unsigned)c == 0u) return;
+        int dl = -1;
+        if (lane == 0) {
+            const int top = min(lev, S.depth - 1 - P.ad_free);
+            _Pragma("unroll 1")
+            for (int l = (sub_M > 0 ? sub_D : 0); l <= top; ++l)
+                if (cand[l]) { dl = l; break; }
+            if (dl >= 0 && *reinterpret_cast<volatile int*>(P.pool_used) >= P.pool_cap) dl = -1;
+        }
+        dl = __shfl_sync(gm, dl, 0, GW);
+        if (dl < 0) return;
+        const int k = (ad_probe + lane) % ad_nwork;
+        ad_probe = (ad_probe + GW + 1) % ad_nwork;
+        const int s = *reinterpret_cast<volatile int*>(P.mail_state + k);
+        const unsigned hit = __ballot_sync(gm, s == 1) & gm;
+        if (!hit) return;
+        const int kk = __shfl_sync(gm, k, (__ffs(hit) - 1) & (GW - 1), GW);
+        if (lane == 0 && atomicCAS(P.mail_state + kk, 1, 3) == 1) {
+            const int slot = atomicAdd(P.pool_used, 1);
+            if (slot >= P.pool_cap) {
+                atomicExch(P.mail_state + kk, 1);
+            } else {
+                atomicAdd(P.ad_count, ~0ull);                  // one waiting worker less
+                const int rg = __ffs(cand[dl]) - 1;
+                cand[dl] &= ~(1 << rg);
+                int* job = P.mail_job + (size_t)kk * P.mail_stride;
+                job[0] = fidx; job[1] = dl + 1; job[2] = slot;
+                _Pragma("unroll 1")
+                for (int l = 0; l < dl; ++l) job[3 + l] = modes[l];
+                job[3 + dl] = rg;
+                P.pool_owner[slot] = fidx;
+                __threadfence();
+                atomicExch(P.mail_state + kk, 2);
+            }
+        }
+        __syncwarp(gm);
+    }
+
     __device__ void do_next() {
+        if (AD && ad_nwork > 0 && !dive) try_donate();
         int st = PS_DONE, nlev = lev, nL = L;
         if (lane == 0) {
             const double eps = 1e-9;
@@ -1137,7 +1189,27 @@ struct Warp {
 
 }  // namespace
 
-template <int GW, bool ONE, bool FX>
+// Adoption, receiving side (lane 0 polls): registers as waiting and returns true once a donor has posted a job in this
+// worker's mailbox, false when every started worker is waiting (nothing left anywhere: a busy worker is never waiting).
+__device__ __forceinline__ bool pm_wait_job(const PmSplit& sp, int wid, int lane, unsigned gm, int GW) {
+    int s = 0;
+    if (lane == 0) {
+        atomicAdd(sp.ad_count, 1ull);
+        __threadfence();
+        atomicExch(sp.mail_state + wid, 1);
+        for (;;) {
+            s = *reinterpret_cast<volatile int*>(sp.mail_state + wid);
+            if (s == 2) break;
+            const unsigned long long c = *reinterpret_cast<volatile unsigned long long*>(sp.ad_count);
+            if (s == 1 && (unsigned)(c >> 32) == (unsigned)c && atomicCAS(sp.mail_state + wid, 1, 0) == 1) { s = 0; break; }
+            __nanosleep(400);
+        }
+        __threadfence();
+    }
+    return __shfl_sync(gm, s, 0, GW) == 2;
+}
+
+template <int GW, bool ONE, bool FX, bool AD = false>
 __global__ void __launch_bounds__(128)
 pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __restrict__ x0,
                const double* __restrict__ mass, const double* __restrict__ params,
@@ -1149,16 +1221,25 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
     const int lane = threadIdx.x % GW, wib = threadIdx.x / GW;       // lane within the group, group within the CTA
     const unsigned gm = GW == 32 ? FULL : (0xffffu << (16 * ((threadIdx.x >> 4) & 1)));
     double* base = pm_smem + (size_t)wib * (S.smem_bytes / 8);
-    Warp<GW, ONE, FX> W(S, base, lane, gm);
+    Warp<GW, ONE, FX, AD> W(S, base, lane, gm);
     const size_t sx = (size_t)S.nl * 2 * (S.N + 1), su = (size_t)S.nl * S.N;
     // problems are handed out one at a time (tree sizes vary by orders of magnitude)
     W.sp = &sp;
+    const int wid = (int)blockIdx.x * (int)(blockDim.x / GW) + wib;
+    bool ad_on = false;
+    W.ad_probe = wid;
+    if (AD) {
+        ad_on = sp.ad && sp.mode == 2 && wid < sp.mail_cap;
+        if (ad_on && lane == 0) atomicAdd(sp.ad_count, 1ull << 32);
+    }
     for (;;) {
         unsigned long long nxt = 0;
         if (lane == 0) nxt = atomicAdd(counter, 1ull);
         const int64_t w = (int64_t)__shfl_sync(gm, nxt, 0, GW);
         int64_t i = w, o = w;                    // problem (input) index, output index
+        const int* job = nullptr;                // adopted sub-tree: {flagged index, prefix length, slot, prefix modes}
         W.sub_M = 0; W.sub_D = 0; W.sub_code = 0; W.shared = nullptr; W.stop_nodes = 0;
+        if (AD) { W.job_P = 0; W.ad_nwork = 0; }
         W.budget = (sp.mode == 1 && !fixed_modes) ? sp.budget : 0;
         if (sp.mode == 3) {
             // sharded pass: M groups of THIS device per problem; the sub-trees of a problem are dealt to
@@ -1171,14 +1252,33 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
         } else if (sp.mode == 2) {
             int nf = *reinterpret_cast<volatile int*>(sp.nflag);
             if (nf > sp.cap) nf = sp.cap;
-            if (w >= (int64_t)nf * sp.M) break;
-            const int f = (int)(w / sp.M);
+            int f;
+            if (w >= (int64_t)nf * sp.M) {
+                if (!AD || !ad_on || !pm_wait_job(sp, wid, lane, gm, GW)) break;
+                job = sp.mail_job + (size_t)wid * sp.mail_stride;
+                f = *reinterpret_cast<const volatile int*>(job);
+                W.sub_M = 1; W.sub_D = *reinterpret_cast<const volatile int*>(job + 1); W.sub_code = 0;
+                o = (int64_t)sp.cap * sp.M + *reinterpret_cast<const volatile int*>(job + 2);
+            } else {
+                f = (int)(w / sp.M);
+                W.sub_M = sp.M; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M);
+            }
             i = sp.flagged[f];
-            W.sub_M = sp.M; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M); W.shared = sp.inc_shared + f;
+            W.shared = sp.inc_shared + f;
+            if (AD && ad_on) { W.fidx = f; W.ad_nwork = min((int)gridDim.x * (int)(blockDim.x / GW), sp.mail_cap); }
         } else if (w >= batch) break;
         W.prob = i;
         W.setup(x0 + (size_t)i * 2 * S.nl, mass + (size_t)i * S.nl, params + (size_t)i * S.npar,
                 fixed_modes ? fixed_modes + su * i : nullptr, Y ? Y + (size_t)S.mw * i : nullptr);
+        if (AD && job) {
+            // the donor's path becomes the forced prefix; there is an incumbent already, so no first dive
+            W.job_P = W.sub_D;
+            for (int l = lane; l < W.job_P; l += GW) W.modes[l] = *reinterpret_cast<const volatile int*>(job + 3 + l);
+            W.dive = false;
+            __syncwarp(gm);
+            if (lane == 0) { W.open_level(0); atomicExch(sp.mail_state + wid, 0); }
+            __syncwarp(gm);
+        }
         W.solve();
         W.finish(u + su * o, x + sx * o, extra ? extra + (size_t)S.ne * o : nullptr, modes + su * o, obj + o,
                  status + o, nodes + o, qp_iters ? qp_iters + o : nullptr);
@@ -1212,6 +1312,35 @@ pm_merge_kernel(const __grid_constant__ PmDev S, const __grid_constant__ PmSplit
         if (sst[w] == HVP_ST_NUMERIC) numeric = true;
         if (sst[w] == HVP_ST_NODE_LIMIT) limited = true;
         if (sst[w] == HVP_ST_TIME_LIMIT) timed = true;
+    }
+    if (sp.mode == 2 && sp.ad) {
+        // results of the adopted sub-trees: pool slots p (at cap * M + p) whose owner is this problem
+        int pu = *sp.pool_used;
+        if (pu > sp.pool_cap) pu = sp.pool_cap;
+        double pv = HUGE_VAL; int pw = -1, pn = 0, pi = 0, pflags = 0;
+        for (int p = lane; p < pu; p += 32) {
+            if (sp.pool_owner[p] != f) continue;
+            const size_t w = (size_t)sp.cap * sp.M + p;
+            if (sobj[w] < pv) { pv = sobj[w]; pw = (int)w; }
+            pn += sno[w];
+            if (sit) pi += sit[w];
+            if (sst[w] == HVP_ST_NUMERIC) pflags |= 1;
+            if (sst[w] == HVP_ST_NODE_LIMIT) pflags |= 2;
+            if (sst[w] == HVP_ST_TIME_LIMIT) pflags |= 4;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, pv, o);
+            const int ow = __shfl_xor_sync(0xffffffffu, pw, o);
+            if (ov < pv || (ov == pv && ow >= 0 && (pw < 0 || ow < pw))) { pv = ov; pw = ow; }
+            pn += __shfl_xor_sync(0xffffffffu, pn, o);
+            pi += __shfl_xor_sync(0xffffffffu, pi, o);
+            pflags |= __shfl_xor_sync(0xffffffffu, pflags, o);
+        }
+        if (pw >= 0 && pv < bestv) { bestv = pv; bw = pw; }
+        nsum += pn; isum += pi;
+        if (pflags & 1) numeric = true;
+        if (pflags & 2) limited = true;
+        if (pflags & 4) timed = true;
     }
     if (bw >= 0) {
         for (size_t e = lane; e < nu; e += 32) { u[nu * i + e] = su_[nu * bw + e]; modes[nu * i + e] = sm_[nu * bw + e]; }
@@ -1372,13 +1501,13 @@ static void pm_launch_shape(const PmDev& S, int& gpb, int& per_sm) {
 // MaxDynamicSharedMemorySize of pm_miqp_kernel<GW>: grow-only, cached per device, shared by EVERY launch path of the kernel
 // (the sharded path used to set its own, smaller value on every call and left the cache of the plain path stale:
 // a later launch with more shared memory failed with "invalid argument")
-template <int GW, bool ONE, bool FX>
+template <int GW, bool ONE, bool FX, bool AD = false>
 static cudaError_t pm_miqp_smem_attr(size_t smem) {
     int dev = 0;
     cudaGetDevice(&dev);
     static size_t attr_set[HVP_MAX_DEVICES] = {0};
     if (dev < 0 || dev >= HVP_MAX_DEVICES || smem > attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW, ONE, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(pm_miqp_kernel<GW, ONE, FX, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < HVP_MAX_DEVICES) attr_set[dev] = smem;
     }
@@ -1439,9 +1568,21 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     sp.mode = 2;
     int64_t b2 = ((int64_t)sp.cap * sp.M + gpb - 1) / gpb;
     if (b2 > full) b2 = full;
-    pm_miqp_kernel<GW, ONE, false><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
-                                                                sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
-                                                                sc->iters, counter, sp);
+    if (!ONE && sp.ad) {
+        // with adoption: the waiting workers' mailboxes and the counters start from zero (one contiguous region)
+        e = cudaMemsetAsync(sp.ad_count, 0, 16 + (size_t)sp.mail_cap * sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        e = pm_miqp_smem_attr<GW, ONE, false, !ONE>(smem);
+        if (e != cudaSuccess) return e;
+        pm_miqp_kernel<GW, ONE, false, !ONE><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u,
+                                                                             sc->x, sc->extra, sc->modes, sc->obj, sc->status,
+                                                                             sc->nodes, sc->iters, counter, sp);
+    } else {
+        sp.ad = 0;
+        pm_miqp_kernel<GW, ONE, false><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
+                                                                    sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
+                                                                    sc->iters, counter, sp);
+    }
     // pass 3: keep the best sub-result of every flagged problem
     pm_merge_kernel<<<(unsigned)((sp.cap + 3) / 4), 128, 0, stream>>>(S, sp, sc->u, sc->x, sc->extra, sc->modes, sc->obj,
                                                                      sc->status, sc->nodes, sc->iters, u, x, extra,

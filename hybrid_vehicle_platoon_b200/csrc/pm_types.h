@@ -90,6 +90,16 @@ struct PmSplit {
     int* nflag;                        // [1] flagged problems so far
     int* flagged;                      // [cap] their batch indices
     unsigned long long* inc_shared;    // [cap] best objective known for each (order-preserving key)
+    // Adoption in the sub-tree pass (mode 2): a worker that finds the work counter exhausted WAITS; a busy worker that
+    // sees waiting ones gives away the shallowest untried sibling of its depth-first stack as a mode prefix.
+    int ad;                            // 1: on in this launch
+    int ad_free;                       // a donated sub-tree keeps at least this many free levels
+    int pool_cap, mail_cap, mail_stride;
+    unsigned long long* ad_count;      // started workers << 32 | waiting workers
+    int* pool_used;                    // result slots handed to adopted sub-trees so far (slot p lives at cap * M + p)
+    int* pool_owner;                   // [pool_cap] flagged index of the problem a slot belongs to
+    int* mail_state;                   // [mail_cap] 0 busy, 1 waiting, 3 claimed by a donor, 2 job posted
+    int* mail_job;                     // [mail_cap][mail_stride] flagged index, prefix length, slot, prefix modes
 };
 
 // device scratch of the sub-tree pass: outputs of cap * M work items, same layout as the real outputs

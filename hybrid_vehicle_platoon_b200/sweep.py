@@ -70,6 +70,14 @@ class _StepGraph:
         self.calls += 1
         self.graph.replay()
 
+    def close(self):
+        """Drops the captured graph and the closure NOW.  body <-> graph <-> the run's tensors form reference cycles, so
+        without this a finished run's graph (and the private memory pool of its capture) lives until the cycle collector
+        gets to it, and the next run's capture allocates beside it: measured 0.92-1.19 s instead of 0.245 s for the
+        g-ADMM leg run back to back (scripts/diag_gadmm_repeat.py)."""
+        self.graph = None
+        self.body = None
+
 
 class _Fork:
     """Runs independent pieces of a timestep on side streams (fork from / join to torch's current stream; both are
@@ -78,13 +86,14 @@ class _Fork:
     and the small ones (1 vehicle per scenario) are pure latency next to the interior one."""
     _pool = {}
 
-    def __init__(self, torch, k, enabled: bool = True):
+    def __init__(self, torch, k, enabled: bool = True, private: bool = False, priority: int = 0):
         import os
         self.enabled = enabled and os.environ.get("HVP_SWEEP_FORK", "1") != "0"
         d = torch.cuda.current_device()
-        pool = _Fork._pool.setdefault(d, [])
+        # private: streams of its own (sweeps that run side by side on different streams must not meet on shared ones)
+        pool = [] if private else _Fork._pool.setdefault(d, [])
         while self.enabled and len(pool) < k:
-            pool.append(torch.cuda.Stream(device=d))
+            pool.append(torch.cuda.Stream(device=d, priority=priority))
         self.torch, self.streams = torch, pool[:k]
 
     def run(self, pieces):
@@ -264,6 +273,7 @@ class BatchedDecentSweep:
         for t in range(ep_len):
             step()
         torch.cuda.synchronize()
+        step.close()
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
                     errors=E.cpu().numpy(), nodes=ND.cpu().numpy(), status=ST.cpu().numpy())
 
@@ -285,6 +295,7 @@ class MixedSizeDecentSweep:
         probe = BatchedDecentSweep(2, N, spacing_policy=spacing_policy, device=device, ctx=self.ctx, solver=solver)
         self.use_compiled = probe.use_compiled                      # same measured crossover
         self.cms = {}
+        self._fork = None
 
     def _cm(self, fl):
         from ._lib import MPC_LOCAL
@@ -379,15 +390,24 @@ class MixedSizeDecentSweep:
         xl[w["lead_idx"]] = LX[t:t + np1].permute(1, 2, 0)                     # leader window leader_x[:, t:t+N+1]
         # ---- ONE solve for the vehicles of every platoon ----
         if self.use_compiled:
-            for fl, ii in w["roles"]:
-                Bk = ii.numel()
-                params = torch.cat((xf[ii].reshape(Bk, -1), xb[ii].reshape(Bk, -1), xl[ii].reshape(Bk, -1)), dim=1).contiguous()
-                uo = torch.empty((Bk, 1, N), dtype=f64, device=dev); xo = torch.empty((Bk, 1, 2, np1), dtype=f64, device=dev)
-                mo = torch.empty((Bk, 1, N), dtype=i32, device=dev); ob = torch.empty(Bk, dtype=f64, device=dev)
-                st = torch.empty(Bk, dtype=i32, device=dev); no = torch.empty(Bk, dtype=i32, device=dev)
-                self._cm(fl).solve_device(Bk, x[ii].reshape(Bk, 1, 2).contiguous(), d_mass[ii].reshape(Bk, 1).contiguous(),
-                                          params, None, uo, xo, None, mo, ob, st, no, None, stream=stream)
-                u[ii] = uo.view(Bk, N); status[ii] = st; nodes[ii] = no
+            # one launch sequence per role (front / interior / trailer, leader), each formulation with its own handle and
+            # scratch: independent, so they run on forked streams -- the budgeted pass of a small role (a few hundred
+            # trees, 2-4 ms of pure latency) hides behind the interior one instead of following it
+            def role(fl, ii):
+                def piece():
+                    Bk = ii.numel()
+                    params = torch.cat((xf[ii].reshape(Bk, -1), xb[ii].reshape(Bk, -1), xl[ii].reshape(Bk, -1)), dim=1).contiguous()
+                    uo = torch.empty((Bk, 1, N), dtype=f64, device=dev); xo = torch.empty((Bk, 1, 2, np1), dtype=f64, device=dev)
+                    mo = torch.empty((Bk, 1, N), dtype=i32, device=dev); ob = torch.empty(Bk, dtype=f64, device=dev)
+                    st = torch.empty(Bk, dtype=i32, device=dev); no = torch.empty(Bk, dtype=i32, device=dev)
+                    self._cm(fl).solve_device(Bk, x[ii].reshape(Bk, 1, 2).contiguous(), d_mass[ii].reshape(Bk, 1).contiguous(),
+                                              params, None, uo, xo, None, mo, ob, st, no, None,
+                                              stream=torch.cuda.current_stream().cuda_stream)
+                    u[ii] = uo.view(Bk, N); status[ii] = st; nodes[ii] = no
+                return piece
+            if self._fork is None or len(self._fork.streams) < len(w["roles"]):
+                self._fork = _Fork(torch, len(w["roles"]), private=True, priority=-1 if N >= 9 else 0)
+            self._fork.run([role(fl, ii) for fl, ii in w["roles"]])
         elif B:
             api.local_miqp_device(self.ldesc, B, w["d_flags"], d_mass, x, xf, xb, xl, u, w["xs"], w["modes"], w["obj"], status,
                                   nodes, None, ctx=self.ctx, stream=stream)
@@ -412,6 +432,9 @@ class MixedSizeDecentSweep:
                             violations=p["V"].cpu().numpy(), errors=p["E"].cpu().numpy(), nodes=Nh[:, sl].reshape(T, S, n),
                             status=Sh[:, sl].reshape(T, S, n)))
         return out
+
+
+_MIXED_CACHE: dict = {}          # (ctx, device, N, policy) -> (MixedSizeDecentSweep, its stream, ctx kept alive)
 
 
 def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, device: int = 0, ctx=None):
@@ -443,8 +466,16 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
                                else np.asarray(scenarios[i]["masses"], dtype=np.float64) for i in idx])
             parts.append((n, np.stack([scenarios[i]["x0"] for i in idx]), np.stack([scenarios[i]["leader_x"] for i in idx]), masses))
             index.append(idx)
-        sw = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx)
-        stream = torch.cuda.Stream(device=sw.dev, priority=-1 if N >= 9 else 0)
+        # The sweep object of a (horizon, policy) group -- its compiled formulations with their device scratch -- and the
+        # stream it runs on are kept for the next call: building them is host work and device allocations inside every
+        # run, and the library keys its per-stream launch state (work counter, adoption scratch) on the stream handle, of
+        # which it keeps 64: fresh streams per run exhausted them after five runs and the later runs lost the adoption
+        # scratch of the per-vehicle kernel.
+        key = (id(ctx), device, N, spacing_params(pol))
+        if key not in _MIXED_CACHE:
+            sw = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx)
+            _MIXED_CACHE[key] = (sw, torch.cuda.Stream(device=sw.dev, priority=-1 if N >= 9 else 0), ctx)
+        sw, stream, _ = _MIXED_CACHE[key]
         with torch.cuda.stream(stream):
             sw.prepare(parts, ep_len)
         work.append((sw, stream, index))
@@ -636,6 +667,7 @@ class BatchedAdmmSweep:
                                     E[t], ctx=self.ctx, stream=stream)
             x = X[t + 1]
         torch.cuda.synchronize()
+        rnd.close()
         return dict(X=X.cpu().numpy(), U=U.cpu().numpy(), R=R.cpu().numpy(), violations=V.cpu().numpy(),
                     errors=E.cpu().numpy(), status=ST.cpu().numpy())
 
@@ -845,6 +877,7 @@ class BatchedGAdmmSweep:
             infeas = ((tr[:, :, 1, 1:] > 45.84 + 1e-6) | (tr[:, :, 1, 1:] < 3.94 - 1e-6)).any(dim=2).any(dim=1)
             return u.clone(), cost.clone(), ok.bool() & ~infeas
 
+        admm.close = rnd.close
         return admm
 
     def _make_admm(self, S, x, mass, lwin):
@@ -944,7 +977,16 @@ class BatchedGAdmmSweep:
             infeas = ((tr[:, :, 1, 1:] > 45.84 + 1e-6) | (tr[:, :, 1, 1:] < 3.94 - 1e-6)).any(dim=2).any(dim=1)
             return u.clone(), cost.clone(), ok & ~infeas
 
+        admm.close = rnd.close
+
         return admm
+
+    def close(self):
+        """Releases the cached consensus round (static buffers + captured graph) of the last batch size."""
+        cached = getattr(self, "_round", None)
+        if cached is not None:
+            cached[4].close()
+            self._round = None
 
     def run(self, x0, leader_x, ep_len: int, strict: bool = False):
         torch, dev, n, N = self.torch, self.dev, self.n, self.N
@@ -967,9 +1009,19 @@ class BatchedGAdmmSweep:
         X[0] = x
         stream = torch.cuda.current_stream().cuda_stream
         prev = None
-        x_cur = x.clone()
-        lwin = torch.empty((S, 2, np1), dtype=f64, device=dev)
-        admm = self._make_admm(S, x_cur, mass, lwin)
+        # The consensus round (its static buffers and, with graph=True, the captured CUDA graph) is kept for the next run
+        # of the same batch size: a capture costs a device synchronisation, a collection and torch.cuda.empty_cache()
+        # (torch.cuda.graph does all three on entry), which made one run in six take 0.56-0.65 s instead of 0.245 s.
+        cached = getattr(self, "_round", None)
+        if cached is not None and cached[0] == S:
+            _, x_cur, mass_c, lwin, admm = cached
+            x_cur.copy_(x); mass_c.copy_(mass); mass = mass_c
+        else:
+            self.close()
+            x_cur = x.clone()
+            lwin = torch.empty((S, 2, np1), dtype=f64, device=dev)
+            admm = self._make_admm(S, x_cur, mass, lwin)
+            self._round = (S, x_cur, mass, lwin, admm)
         for t in range(ep_len):
             lwin.copy_(lx[:, :, t:t + np1])
             x_cur.copy_(x)

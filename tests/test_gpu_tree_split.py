@@ -110,3 +110,20 @@ def test_tree_split_bench_problem_matches_oracle():
         uniq = ro["second"] - ro["obj"] > 1e-6 * np.maximum(1.0, np.abs(ro["obj"]))
         assert (r["modes"][uniq] == ro["modes"][uniq]).all()
         assert np.abs(r["u"][uniq] - ro["u"][uniq]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_adoption_stress_campaign_vs_oracle():
+    """The sub-tree pass with adoption (pm_kernel.cu try_donate / pm_wait_job) under the conditions that exercise it
+    hardest: a node budget of 3 sends nearly every tree to the sub-tree pass, 3 static workers per tree leave most of
+    the grid waiting, and no minimum size for a donated sub-tree -- every formulation of scripts/stress_parity.py
+    (centralized, event-based, ADMM, gear models; random roles, horizons and spacing policies) against the oracle's
+    branch and bound: statuses equal, objectives 5e-7, modes and inputs where the optimum is unique.  The knobs are read
+    once per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HVP_MPC_BUDGET="3", HVP_MPC_SPLIT_M="3", HVP_MPC_ADOPT_FREE="0", HVP_MPC_ADOPT="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "stress_parity.py"), "11", "64"], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "failures: 0" in r.stdout
