@@ -315,7 +315,7 @@ def mixed_sweep_leg(ctx, rank, world, dev, S=4096, T=10):
             "sharding": "dist.balanced_shards by 7 n N, no data-path collective", "n_gpus": world}
 
 
-def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=20, groups=256):
+def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=0, groups=256, stress=False, seed=5):
     """ONE large centralized MIQP tree (n = 8, N = 6: 48 variables) searched by all ranks together: every rank takes
     the sub-trees whose mode-prefix ordinal is congruent to its rank, the incumbent bound is exchanged with an NCCL
     allreduce(min) (dist.solve_tree_split).  EVERY rank calls this; time = CUDA events, max over ranks."""
@@ -323,8 +323,8 @@ def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=20, groups=256):
     import hybrid_vehicle_platoon_b200 as hvp
     from hybrid_vehicle_platoon_b200 import dist as D
     from hybrid_vehicle_platoon_b200 import synth_mpc as G
-    rng = np.random.default_rng(5)
-    x0, params = G.cent_cases(rng, problems, n, N, stress=False)
+    rng = np.random.default_rng(seed)
+    x0, params = G.cent_cases(rng, problems, n, N, stress=stress)
     mpc = hvp.api.CompiledMpc(G.CENT, N, n_local=n, ctx=ctx)
     tx0 = torch.as_tensor(x0, device=dev); tp = torch.as_tensor(params, device=dev)
     tm = torch.full((problems, n), 800.0, dtype=torch.float64, device=dev)
@@ -340,7 +340,7 @@ def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=20, groups=256):
         if rep > 0:
             ms.append(D.max_over_ranks([a.elapsed_time(b)], device=dev)[0])
     return {"value": problems / (float(np.mean(ms)) * 1e-3), "unit": "solves/s", "ms": float(np.mean(ms)), "problems": problems,
-            "variables": n * N, "prefix_depth": depth, "warps_per_problem_per_gpu": groups,
+            "variables": n * N, "prefix_depth": depth if depth else "library default (n + 2)", "warps_per_problem_per_gpu": groups,
             "optimal_frac": float((out["status"] == 2).double().mean()), "nodes_per_solve": float(out["nodes"].double().mean()),
             "collective": "allreduce(min) of the incumbent objective, 8 B per problem, twice per solve"}
 
@@ -581,6 +581,8 @@ def main():
             mixed_sweep_leg(ctx, rank, world, dev)
         shared_legs["tree_split_cent_n8_N6 (one large MIQP tree searched by all GPUs, allreduce-min of the incumbent)"] = \
             tree_split_leg(ctx, dev)
+        shared_legs["tree_split_cent_n10_N6 (the centralized size BASELINE.json's metric names: 60 variables)"] = \
+            tree_split_leg(ctx, dev, n=10, N=6)
 
     out = None
     if rank == 0:

@@ -77,6 +77,7 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
 
 extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
     if (!c) return 0;
+    HvpRelaxedCapture relaxed__;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->dbuf) cudaFree(c->dbuf);

@@ -48,6 +48,16 @@ inline cudaError_t hvp_mark(hvp_ctx* c, cudaEvent_t ev, cudaStream_t st, bool la
     return e;
 }
 
+// Destroying a handle frees device memory, and a handle is destroyed whenever its owner's garbage collector gets to it --
+// possibly while ANOTHER object of the same thread is capturing a CUDA graph (sweep._StepGraph; torch captures in the
+// global mode, where a cudaFree anywhere invalidates the capture: seen as a 1-in-3 failure of the GPU suite).  The
+// destroy paths therefore run in the relaxed capture mode, as torch's own allocator does for its cudaMalloc calls.
+struct HvpRelaxedCapture {
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    HvpRelaxedCapture() { cudaThreadExchangeStreamCaptureMode(&mode); }
+    ~HvpRelaxedCapture() { cudaThreadExchangeStreamCaptureMode(&mode); }
+};
+
 constexpr int HVP_COUNTER_RING = 256;
 constexpr int HVP_STREAM_SLOTS = 64;
 constexpr int HVP_MAX_DEVICES = 64;   // per-device caches of function attributes / occupancy

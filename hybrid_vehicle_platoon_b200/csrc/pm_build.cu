@@ -29,6 +29,26 @@ using namespace hvp;
                         __FILE__, __LINE__);                                                   \
     } while (0)
 
+// Adoption scratch of a sub-tree pass (PmSplit::ad, pm_kernel.cu): result slots of the adopted sub-trees (the POOL,
+// appended to the work items' slots), one mailbox per worker, and the counters -- in ONE region with the mailbox states,
+// so that a single memset arms a launch.
+static const size_t PM_POOL = 32768, PM_MAIL_CAP = 20480;
+static int pm_env_adopt() { static const int v = getenv("HVP_MPC_ADOPT") ? atoi(getenv("HVP_MPC_ADOPT")) : 1; return v; }
+static int pm_env_adopt_free() { static const int v = getenv("HVP_MPC_ADOPT_FREE") ? atoi(getenv("HVP_MPC_ADOPT_FREE")) : 2; return v; }
+static size_t pm_adopt_bytes(int depth) {
+    return (16 + PM_MAIL_CAP * 4 + 256) + (PM_POOL * 4 + 256) + (PM_MAIL_CAP * ((size_t)depth + 3) * 4 + 256);
+}
+template <class Take>
+static void pm_adopt_take(hvp::PmSplit& sp, Take&& take, int depth) {
+    char* z = take(16 + PM_MAIL_CAP * 4);            // [ad_count 8][pool_used 4][pad 4][mail_state]
+    sp.ad_count = (unsigned long long*)z; sp.pool_used = (int*)(z + 8); sp.mail_state = (int*)(z + 16);
+    sp.pool_owner = (int*)take(PM_POOL * 4);
+    sp.mail_stride = depth + 3;
+    sp.mail_job = (int*)take(PM_MAIL_CAP * (size_t)sp.mail_stride * 4);
+    sp.pool_cap = (int)PM_POOL; sp.mail_cap = (int)PM_MAIL_CAP;
+    sp.ad = pm_env_adopt(); sp.ad_free = pm_env_adopt_free();
+}
+
 struct hvp_mpc {
     // Calls on one handle are serialised: the scratch buffers (ybuf, split / shard scratch, work counter) belong to the
     // handle, and a call both (re)allocates them and enqueues a launch SEQUENCE that must not interleave with another
@@ -373,6 +393,7 @@ static int upload(hvp_mpc* m, const std::vector<double>& h, const double** out) 
 
 extern "C" int hvp_mpc_destroy(hvp_mpc* m) {
     if (!m) return 0;
+    HvpRelaxedCapture relaxed__;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     for (void* p : m->dev) cudaFree(p);
@@ -596,7 +617,10 @@ extern "C" int hvp_mpc_create(hvp_ctx* c, const hvp_mpc_desc* d, hvp_mpc** out) 
     memset(&m->shard, 0, sizeof m->shard);
     {
         const char* env = getenv("HVP_MPC_SPLIT");
-        int D = 3 * S.nl > 5 ? 3 * S.nl : 5;
+        // prefix levels are enumerated, never solved, so nothing prunes inside them: deep prefixes multiply the node count
+        // (centralized n = 10, N = 6: 280 000 nodes per MIQP at depth 30, 2 000 at depth 16; 1-norm n = 3, N = 5: 370 at depth
+        // 9, 223 at depth 5) and, with waiting workers adopting sub-trees, are no longer needed for balance
+        int D = S.nl + 2 > 5 ? S.nl + 2 : 5;
         if (D > S.depth - 1) D = S.depth - 1;
         if (env && atoi(env) == 0) D = 0;
         else if (env && atoi(env) > 1) D = atoi(env) < S.depth - 1 ? atoi(env) : S.depth - 1;   // explicit prefix depth
@@ -668,13 +692,10 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
             if (m->scratch_mem) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->scratch_mem)); m->scratch_mem = nullptr; }
             const PmDev& S = m->S;
             // result slots: cap * M work items + the pool of the adopted sub-trees (PmSplit::ad)
-            static const int envAD = getenv("HVP_MPC_ADOPT") ? atoi(getenv("HVP_MPC_ADOPT")) : 1;
-            static const int envFree = getenv("HVP_MPC_ADOPT_FREE") ? atoi(getenv("HVP_MPC_ADOPT_FREE")) : 2;
-            const size_t pool = 32768, mail_cap = 20480, mail_stride = (size_t)S.depth + 3;
-            const size_t items = cap * (size_t)envM + pool, nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
+            const size_t items = cap * (size_t)envM + PM_POOL, nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1);
             const size_t ne = S.ne > 0 ? (size_t)S.ne : 1;
-            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + cap * (4 + 8) + 64 + 16 * 256 +
-                                 (16 + mail_cap * 4) + pool * 4 + mail_cap * mail_stride * 4;
+            const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + cap * (4 + 8) + 64 + 12 * 256 +
+                                 pm_adopt_bytes(S.depth);
             void* p = nullptr;
             CUDA_TRY(cudaMalloc(&p, bytes));
             m->scratch_mem = p;
@@ -686,14 +707,7 @@ extern "C" int hvp_mpc_solve_dev(hvp_mpc* m, int64_t batch, const double* x0, co
             sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
             sc.sp.inc_shared = (unsigned long long*)take(cap * 8); sc.sp.flagged = (int*)take(cap * 4);
             sc.sp.nflag = (int*)take(4);
-            {   // counters and mailbox states in ONE region (a single memset arms a launch): [ad_count 8][pool_used 4][pad 4][mail_state]
-                char* z = take(16 + mail_cap * 4);
-                sc.sp.ad_count = (unsigned long long*)z; sc.sp.pool_used = (int*)(z + 8); sc.sp.mail_state = (int*)(z + 16);
-            }
-            sc.sp.pool_owner = (int*)take(pool * 4);
-            sc.sp.mail_job = (int*)take(mail_cap * mail_stride * 4);
-            sc.sp.pool_cap = (int)pool; sc.sp.mail_cap = (int)mail_cap; sc.sp.mail_stride = (int)mail_stride;
-            sc.sp.ad = envAD; sc.sp.ad_free = envFree;
+            pm_adopt_take(sc.sp, take, S.depth);
             sc.sp.M = envM; sc.sp.D = m->split_D;
             m->scratch_cap = cap;
         }
@@ -741,11 +755,12 @@ extern "C" int hvp_mpc_solve_shard_dev(hvp_mpc* m, int64_t batch, const double* 
         CUDA_TRY(cudaMalloc(&m->ybuf, need + need / 4));
         m->ycap = need + need / 4;
     }
-    const size_t items = (size_t)batch * (size_t)groups;
+    const size_t items = (size_t)batch * (size_t)groups + PM_POOL;      // work items + the pool of the adopted sub-trees
     if (items > m->shard_items || (size_t)batch > (size_t)m->shard.sp.cap) {
         if (m->shard_mem) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(m->shard_mem)); m->shard_mem = nullptr; }
         const size_t nu = (size_t)S.nl * S.N, nx = (size_t)S.nl * 2 * (S.N + 1), ne = S.ne > 0 ? (size_t)S.ne : 1;
-        const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + (size_t)batch * (4 + 8) + 64 + 12 * 256;
+        const size_t bytes = items * ((nu + nx + ne + 1) * 8 + (nu + 3) * 4) + (size_t)batch * (4 + 8) + 64 + 12 * 256 +
+                             pm_adopt_bytes(S.depth);
         void* p = nullptr;
         CUDA_TRY(cudaMalloc(&p, bytes));
         m->shard_mem = p;
@@ -757,6 +772,7 @@ extern "C" int hvp_mpc_solve_shard_dev(hvp_mpc* m, int64_t batch, const double* 
         sc.nodes = (int32_t*)take(items * 4); sc.iters = (int32_t*)take(items * 4);
         sc.sp.inc_shared = (unsigned long long*)take((size_t)batch * 8); sc.sp.flagged = (int*)take((size_t)batch * 4);
         sc.sp.nflag = (int*)take(4);
+        pm_adopt_take(sc.sp, take, S.depth);
         sc.sp.cap = (int)batch;
         m->shard_items = items;
     }

@@ -1229,7 +1229,7 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
     bool ad_on = false;
     W.ad_probe = wid;
     if (AD) {
-        ad_on = sp.ad && sp.mode == 2 && wid < sp.mail_cap;
+        ad_on = sp.ad && (sp.mode == 2 || sp.mode == 3) && wid < sp.mail_cap;
         if (ad_on && lane == 0) atomicAdd(sp.ad_count, 1ull << 32);
     }
     for (;;) {
@@ -1244,11 +1244,19 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
         if (sp.mode == 3) {
             // sharded pass: M groups of THIS device per problem; the sub-trees of a problem are dealt to
             // world * M groups over all devices by prefix ordinal; the incumbent slot was seeded by the caller
-            if (w >= batch * sp.M) break;
-            i = w / sp.M;
-            W.sub_M = sp.M * sp.world; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M) * sp.world + sp.rank;   // ordinal o -> rank o % world
+            if (w >= batch * sp.M) {
+                if (!AD || !ad_on || !pm_wait_job(sp, wid, lane, gm, GW)) break;
+                job = sp.mail_job + (size_t)wid * sp.mail_stride;
+                i = *reinterpret_cast<const volatile int*>(job);
+                W.sub_M = 1; W.sub_D = *reinterpret_cast<const volatile int*>(job + 1); W.sub_code = 0;
+                o = (int64_t)sp.pool_base + *reinterpret_cast<const volatile int*>(job + 2);
+            } else {
+                i = w / sp.M;
+                W.sub_M = sp.M * sp.world; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M) * sp.world + sp.rank;   // ordinal o -> rank o % world
+            }
             W.shared = sp.inc_shared + i;
             W.stop_nodes = sp.budget;
+            if (AD && ad_on) { W.fidx = (int)i; W.ad_nwork = min((int)gridDim.x * (int)(blockDim.x / GW), sp.mail_cap); }
         } else if (sp.mode == 2) {
             int nf = *reinterpret_cast<volatile int*>(sp.nflag);
             if (nf > sp.cap) nf = sp.cap;
@@ -1258,7 +1266,7 @@ pm_miqp_kernel(const __grid_constant__ PmDev S, int64_t batch, const double* __r
                 job = sp.mail_job + (size_t)wid * sp.mail_stride;
                 f = *reinterpret_cast<const volatile int*>(job);
                 W.sub_M = 1; W.sub_D = *reinterpret_cast<const volatile int*>(job + 1); W.sub_code = 0;
-                o = (int64_t)sp.cap * sp.M + *reinterpret_cast<const volatile int*>(job + 2);
+                o = (int64_t)sp.pool_base + *reinterpret_cast<const volatile int*>(job + 2);
             } else {
                 f = (int)(w / sp.M);
                 W.sub_M = sp.M; W.sub_D = sp.D; W.sub_code = (int)(w % sp.M);
@@ -1313,14 +1321,14 @@ pm_merge_kernel(const __grid_constant__ PmDev S, const __grid_constant__ PmSplit
         if (sst[w] == HVP_ST_NODE_LIMIT) limited = true;
         if (sst[w] == HVP_ST_TIME_LIMIT) timed = true;
     }
-    if (sp.mode == 2 && sp.ad) {
-        // results of the adopted sub-trees: pool slots p (at cap * M + p) whose owner is this problem
+    if (sp.ad) {
+        // results of the adopted sub-trees: pool slots p (at pool_base + p) whose owner is this problem
         int pu = *sp.pool_used;
         if (pu > sp.pool_cap) pu = sp.pool_cap;
         double pv = HUGE_VAL; int pw = -1, pn = 0, pi = 0, pflags = 0;
         for (int p = lane; p < pu; p += 32) {
             if (sp.pool_owner[p] != f) continue;
-            const size_t w = (size_t)sp.cap * sp.M + p;
+            const size_t w = (size_t)sp.pool_base + p;
             if (sobj[w] < pv) { pv = sobj[w]; pw = (int)w; }
             pn += sno[w];
             if (sit) pi += sit[w];
@@ -1568,13 +1576,14 @@ static cudaError_t launch_pm_miqp_t(const PmDev& S, int64_t batch, const double*
     sp.mode = 2;
     int64_t b2 = ((int64_t)sp.cap * sp.M + gpb - 1) / gpb;
     if (b2 > full) b2 = full;
-    if (!ONE && sp.ad) {
+    sp.pool_base = sp.cap * sp.M;
+    if (sp.ad) {
         // with adoption: the waiting workers' mailboxes and the counters start from zero (one contiguous region)
         e = cudaMemsetAsync(sp.ad_count, 0, 16 + (size_t)sp.mail_cap * sizeof(int), stream);
         if (e != cudaSuccess) return e;
-        e = pm_miqp_smem_attr<GW, ONE, false, !ONE>(smem);
+        e = pm_miqp_smem_attr<GW, ONE, false, true>(smem);
         if (e != cudaSuccess) return e;
-        pm_miqp_kernel<GW, ONE, false, !ONE><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u,
+        pm_miqp_kernel<GW, ONE, false, true><<<(unsigned)b2, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u,
                                                                              sc->x, sc->extra, sc->modes, sc->obj, sc->status,
                                                                              sc->nodes, sc->iters, counter, sp);
     } else {
@@ -1629,9 +1638,22 @@ static cudaError_t launch_pm_shard_t(const PmDev& S, int64_t batch, const double
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     pm_shard_init_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(batch, incumbent, sp, obj, nodes, qp_iters);
-    pm_miqp_kernel<GW, ONE, false><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
-                                                                    sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
-                                                                    sc->iters, counter, sp);
+    sp.pool_base = (int)(batch * sp.M);
+    if (sp.budget > 0) sp.ad = 0;           // a budgeted (probing) wave: an adopted sub-tree would start a budget of its own
+    if (sp.ad) {
+        e = cudaMemsetAsync(sp.ad_count, 0, 16 + (size_t)sp.mail_cap * sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        e = pm_miqp_smem_attr<GW, ONE, false, true>(smem);
+        if (e != cudaSuccess) return e;
+        pm_miqp_kernel<GW, ONE, false, true><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u,
+                                                                                 sc->x, sc->extra, sc->modes, sc->obj, sc->status,
+                                                                                 sc->nodes, sc->iters, counter, sp);
+    } else {
+        sp.ad = 0;
+        pm_miqp_kernel<GW, ONE, false><<<(unsigned)blocks, threads, smem, stream>>>(S, batch, x0, mass, params, nullptr, Y, sc->u, sc->x,
+                                                                        sc->extra, sc->modes, sc->obj, sc->status, sc->nodes,
+                                                                        sc->iters, counter, sp);
+    }
     pm_merge_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, stream>>>(S, sp, sc->u, sc->x, sc->extra, sc->modes, sc->obj,
                                                                     sc->status, sc->nodes, sc->iters, u, x, extra, modes,
                                                                     obj, status, nodes, qp_iters);

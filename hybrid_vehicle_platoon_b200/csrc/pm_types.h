@@ -95,6 +95,7 @@ struct PmSplit {
     int ad;                            // 1: on in this launch
     int ad_free;                       // a donated sub-tree keeps at least this many free levels
     int pool_cap, mail_cap, mail_stride;
+    int pool_base;                     // first result slot of the pool (mode 2: cap * M, mode 3: batch * M)
     unsigned long long* ad_count;      // started workers << 32 | waiting workers
     int* pool_used;                    // result slots handed to adopted sub-trees so far (slot p lives at cap * M + p)
     int* pool_owner;                   // [pool_cap] flagged index of the problem a slot belongs to

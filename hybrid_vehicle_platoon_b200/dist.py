@@ -119,7 +119,22 @@ def solve_tree_split(cm, x0, mass, params, *, groups=64, prefix_depth=0, wave_bu
     if rank is None:
         on = dist.is_available() and dist.is_initialized()
         rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    if prefix_depth == 0 and world > 1:
+        # The ranks own residue classes of the prefix ORDINAL, so there must be several prefixes per rank -- and the first
+        # nl decisions (stage 0 of every vehicle) are all but fixed by the initial velocities.  Within a device waiting
+        # workers adopt sub-trees, so one device takes the library default (nl + 2: a handful of prefixes); every doubling
+        # of the world adds two levels.  Deeper is not free: prefix levels are enumerated, never solved, nothing prunes there.
+        import math
+        prefix_depth = int(cm.n_local + 2 + 2 * math.ceil(math.log2(world)))
     kw = dict(groups=groups, prefix_depth=prefix_depth)
+    if world == 1:
+        # one device: its workers share the incumbent through global memory and waiting workers adopt sub-trees of busy
+        # ones (pm_kernel.cu), so the probing wave buys nothing -- r02r launch list: wave A 31 ms, wave B 24 ms
+        b = shard_wave(cm, x0, mass, params, rank, world, node_budget=0, incumbent=None, **kw)
+        b["numeric"] = (b["status"] == ST_NUMERIC).to(b["status"].dtype)
+        out = reduce_winner(b, rank, world, allreduce)
+        out["bound_after_wave_a"] = out["obj"].clone()
+        return out
     a = shard_wave(cm, x0, mass, params, rank, world, node_budget=wave_budget, incumbent=None, **kw)
     bound = a["obj"].clone()
     allreduce(bound, "min")

@@ -62,10 +62,20 @@ class _StepGraph:
             cur.wait_stream(self.stream)
             return
         if self.graph is None:
+            # No cyclic collection while capturing: a collected handle of an earlier sweep frees device memory in its
+            # finaliser, and any cudaFree invalidates a capture in torch's (global) capture mode.  torch.cuda.graph
+            # collects once on entry; this keeps it from happening again inside the body.
+            import gc
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.stream):
-                self.body()
+            was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, stream=self.stream):
+                    self.body()
+            finally:
+                if was_on:
+                    gc.enable()
             self.graph = g
         self.calls += 1
         self.graph.replay()
