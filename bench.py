@@ -334,7 +334,7 @@ def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=0, groups=256, stress=F
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        out = D.solve_tree_split(mpc, tx0, tm, tp, groups=groups, prefix_depth=depth, wave_budget=16)
+        out = D.solve_tree_split(mpc, tx0, tm, tp, groups=groups, prefix_depth=depth)
         b.record()
         torch.cuda.synchronize()
         if rep > 0:
@@ -342,7 +342,7 @@ def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=0, groups=256, stress=F
     return {"value": problems / (float(np.mean(ms)) * 1e-3), "unit": "solves/s", "ms": float(np.mean(ms)), "problems": problems,
             "variables": n * N, "prefix_depth": depth if depth else "library default (n + 2)", "warps_per_problem_per_gpu": groups,
             "optimal_frac": float((out["status"] == 2).double().mean()), "nodes_per_solve": float(out["nodes"].double().mean()),
-            "collective": "allreduce(min) of the incumbent objective, 8 B per problem, twice per solve"}
+            "collective": "allreduce(min) of the incumbent objective, 8 B per problem, twice per solve (one device: none)"}
 
 
 def workload_config(S):

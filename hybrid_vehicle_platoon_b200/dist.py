@@ -111,8 +111,8 @@ def dist_allreduce(t, op):
         dist.all_reduce(t, op={"min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX}[op])
 
 
-def solve_tree_split(cm, x0, mass, params, *, groups=64, prefix_depth=0, wave_budget=32, rank=None, world=None,
-                     allreduce=dist_allreduce):
+def solve_tree_split(cm, x0, mass, params, *, groups=64, prefix_depth=0, wave_budget=8, probe_groups=16, rank=None,
+                     world=None, allreduce=dist_allreduce):
     """Every rank calls this with the same problems (torch CUDA tensors on its own GPU): the tree of every MIQP is
     searched by all ranks together; the proven optimum comes back on every rank."""
     import torch.distributed as dist
@@ -135,7 +135,10 @@ def solve_tree_split(cm, x0, mass, params, *, groups=64, prefix_depth=0, wave_bu
         out = reduce_winner(b, rank, world, allreduce)
         out["bound_after_wave_a"] = out["obj"].clone()
         return out
-    a = shard_wave(cm, x0, mass, params, rank, world, node_budget=wave_budget, incumbent=None, **kw)
+    # wave A is a probe (first dives under a node budget, no adoption): a few workers per problem are enough for a first
+    # incumbent, and its length is pure latency in front of wave B (r02t: 256 workers x 16 nodes cost 20-50 ms at n = 8 / 10)
+    a = shard_wave(cm, x0, mass, params, rank, world, node_budget=wave_budget, incumbent=None,
+                   groups=min(groups, probe_groups), prefix_depth=prefix_depth)
     bound = a["obj"].clone()
     allreduce(bound, "min")
     b = shard_wave(cm, x0, mass, params, rank, world, node_budget=0, incumbent=bound, **kw)

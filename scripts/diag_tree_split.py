@@ -16,7 +16,7 @@ ctx = hvp.Context(local)
 CASES = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("CASES", "8:6:20,10:6:30").split(",")]
 for n, N, depth in CASES:
     for groups in (int(g) for g in os.environ.get("NGROUPS", "256").split(",")):
-        r = bench.tree_split_leg(ctx, dev, n=n, N=N, depth=depth, groups=groups, stress=bool(int(os.environ.get('STRESS', '0'))), seed=int(os.environ.get('SEED', '5')))
+        r = bench.tree_split_leg(ctx, dev, n=n, N=N, depth=depth, groups=groups, problems=int(os.environ.get('PROBLEMS', '4')), stress=bool(int(os.environ.get('STRESS', '0'))), seed=int(os.environ.get('SEED', '5')))
         if rank == 0:
             print(f"n={n} N={N} depth={depth} groups={groups} world={world}: {r['ms']:.1f} ms  nodes/solve {r['nodes_per_solve']:.0f}  opt {r['optimal_frac']}", flush=True)
 if world > 1:
