@@ -126,7 +126,8 @@ class BatchedDecentSweep:
     with the constant-velocity estimator), pwa_gear model, horizon N."""
 
     def __init__(self, n: int, N: int, masses=None, spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0,
-                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto", use_hint: bool = False, graph: bool = False, fused=None):
+                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto", use_hint: bool = False, graph: bool = False, fused=None,
+                 batch_hint=None):
         import os
         import torch
         self.torch = torch
@@ -148,10 +149,17 @@ class BatchedDecentSweep:
         # (N = 10, headway: worst tree 13 000 -> 6 000 nodes and searched by 64-128 warps; 464 -> 52 ms per 20 480 MIQPs).
         if solver not in ("auto", "local", "compiled"):
             raise ValueError("solver must be 'auto', 'local' or 'compiled'")
-        # "auto" follows the measured crossover (scripts/diag_mixed.py, n = 10, 5 timesteps, 53 / 4096 scenarios):
-        #   constant spacing: local wins up to N = 9 (N = 9: 22 / 123 ms vs 39 / 168 ms), compiled from N = 10 at large
-        #   batches (440 vs 207 ms); time headway: local up to N = 6, compiled from N = 8 (132 / 486 vs 40 / 179 ms).
-        self.use_compiled = solver == "compiled" or (solver == "auto" and (N >= 10 or (self.t0 != 0.0 and N >= 8)))
+        # "auto" follows the measured crossover (scripts/diag_mixed.py, n = 10, 5 timesteps, 300 / 4096 scenarios, end of
+        # round 2 -- with waiting workers adopting sub-trees the compiled route's tail is short, its throughput is still the
+        # lower one, so the crossover depends on the batch):
+        #   constant spacing, ms local | compiled:  N = 8: 10 | 23 and 29 | 78;  N = 9: 38 | 33 and 54 | 101;  N = 10: 66 | 46 and 369 | 137
+        #   time headway:  N = 6: 18 | 18 and 23 | 62;  N = 7: 48 | 26 and 57 | 97;  N = 8: 123 | 35 and 151 | 158;  N = 9: 605 | 48 and 411 | 270
+        # batch_hint = problems per launch the caller expects (None: large).
+        if solver == "auto" and os.environ.get("HVP_SWEEP_SOLVER") in ("local", "compiled"):      # A/B runs of the crossover
+            solver = os.environ["HVP_SWEEP_SOLVER"]
+        small = batch_hint is not None and batch_hint <= 8192
+        n_const, n_headway = (9, 7) if small else (10, 8)
+        self.use_compiled = solver == "compiled" or (solver == "auto" and (N >= n_const or (self.t0 != 0.0 and N >= n_headway)))
         self.role_groups = []
         if self.use_compiled:
             from ._lib import MPC_LOCAL
@@ -295,14 +303,15 @@ class MixedSizeDecentSweep:
     GPU filled in the Monte-Carlo sweep of BASELINE.json configs[3], where a (n, N, policy) cell holds ~25 scenarios."""
 
     def __init__(self, N: int, spacing_policy=ConstantSpacingPolicy(50), leader_index: int = 0,
-                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto"):
+                 d_safe: float = Params.d_safe, device: int = 0, ctx=None, solver: str = "auto", batch_hint=None):
         import torch
         self.torch, self.N, self.leader_index, self.d_safe = torch, N, leader_index, d_safe
         self.dev = torch.device("cuda", device)
         self.ctx = ctx or default_context(device)
         self.d0, self.t0 = spacing_params(spacing_policy)
         self.ldesc = api.local_desc(N, self.d0, self.t0)
-        probe = BatchedDecentSweep(2, N, spacing_policy=spacing_policy, device=device, ctx=self.ctx, solver=solver)
+        probe = BatchedDecentSweep(2, N, spacing_policy=spacing_policy, device=device, ctx=self.ctx, solver=solver,
+                                   batch_hint=batch_hint)
         self.use_compiled = probe.use_compiled                      # same measured crossover
         self.cms = {}
         self._fork = None
@@ -481,9 +490,10 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
         # run, and the library keys its per-stream launch state (work counter, adoption scratch) on the stream handle, of
         # which it keeps 64: fresh streams per run exhausted them after five runs and the later runs lost the adoption
         # scratch of the per-vehicle kernel.
-        key = (id(ctx), device, N, spacing_params(pol))
+        vehicles = sum(n * len(idx) for n, idx in by_n.items())          # problems per launch of this group
+        key = (id(ctx), device, N, spacing_params(pol), vehicles <= 8192)
         if key not in _MIXED_CACHE:
-            sw = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx)
+            sw = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx, batch_hint=vehicles)
             _MIXED_CACHE[key] = (sw, torch.cuda.Stream(device=sw.dev, priority=-1 if N >= 9 else 0), ctx)
         sw, stream, _ = _MIXED_CACHE[key]
         with torch.cuda.stream(stream):

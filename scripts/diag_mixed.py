@@ -1,5 +1,5 @@
 """Dev helper: closed-loop decentralized sweep, specialised local kernel vs compiled-MPC LOCAL formulation, by horizon and
-spacing policy (n = 10, 5 timesteps, 53 and 4096 scenarios) -- the measurements behind BatchedDecentSweep's "auto" rule."""
+spacing policy (n = 10, 5 timesteps, 300 and 4096 scenarios) -- the measurements behind BatchedDecentSweep's "auto" rule."""
 import sys, time, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
@@ -9,8 +9,8 @@ from hybrid_vehicle_platoon_b200.sweep import BatchedDecentSweep
 from hybrid_vehicle_platoon_b200.misc import ConstantSpacingPolicy, ConstantTimePolicy, StopAndGoLeaderTrajectory
 T = 5
 for pol in (ConstantSpacingPolicy(50), ConstantTimePolicy(10, 3)):
-    for N in (6, 8, 9, 10):
-        for S in (53, 4096):
+    for N in (5, 6, 7, 8, 9, 10):
+        for S in (300, 4096):
             rng = np.random.default_rng(3)
             n = 10
             v = np.floor(rng.uniform(8, 30, (S, n))); gaps = rng.uniform(60, 160, (S, n))
@@ -21,6 +21,7 @@ for pol in (ConstantSpacingPolicy(50), ConstantTimePolicy(10, 3)):
             for solver in ("local", "compiled"):
                 sw = BatchedDecentSweep(n, N, spacing_policy=pol, solver=solver)
                 sw.run(x0[:8], lx, 1)
+                sw.run(x0, lx, T)                       # full-size warm-up (allocator, clocks)
                 torch.cuda.synchronize(); t0 = time.perf_counter()
                 out = sw.run(x0, lx, T)
                 res.append(((time.perf_counter() - t0) * 1e3, out["nodes"].mean(), out["nodes"].max(), (out["status"] == 2).mean()))
