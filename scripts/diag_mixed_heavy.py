@@ -23,7 +23,7 @@ for sc in scen:
     groups.setdefault((sc["N"], spacing_params(sc["spacing_policy"])), []).append(sc)
 import os
 KEYS = {"a": (10, (10.0, 3.0)), "b": (9, (10.0, 3.0)), "c": (10, (50.0, 0.0))}
-for key in [KEYS[k] for k in os.environ.get("GROUPS", "abc")]:
+for key in [KEYS[k] for k in os.environ.get("HEAVY_GROUPS", "abc")]:
     g = groups[key]
     run_mixed_sweep(g[:16], 1, device=0, ctx=ctx)
     for rep in range(int(os.environ.get("REPS", 5))):
