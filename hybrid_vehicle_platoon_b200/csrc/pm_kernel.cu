@@ -135,7 +135,7 @@ struct Warp {
     // there it loses to SIMT divergence, here control flow is warp-uniform and fewer nodes are simply less time).
     double *pf, *pnz, *ptp, *ptm;
     int *act, *cand, *modes, *bmodes, *built, *orient, *aflag, *agen, *uor;
-    double f_prev;
+    double f_prev, xu_scale;           // xu_scale: size of the unconstrained minimiser of the current proximal round
     int ppa, retry;                    // proximal-point rounds / restarts done on the current node (1-norm cost)
     // warp-uniform scalars (replicated in registers)
     int state, lev, L, built_L, q, it, iters, nodes, pid, fixed;
@@ -663,7 +663,10 @@ struct Warp {
         // from there -- at the fixed point that is the whole round.  Otherwise: the cold start below.
         if (ONE && ppa > 0 && q > 0) {
             gradient();
-            LANES(j, nv) wv[j] = -dot2(Hinv + j * ld, 1, gn, nv);          // x_u
+            double xs_ = 0.0; int xi_ = 0;
+            LANES(j, nv) { const double v_ = -dot2(Hinv + j * ld, 1, gn, nv); wv[j] = v_; xs_ = fmax(xs_, fabs(v_)); }          // x_u
+            wargmax<GW>(gm, xs_, xi_);
+            xu_scale = xs_;
             __syncwarp(gm);
             LANES(a, q) dv[a] = dot2(Nact + a * ld, 1, wv, nv) - dot2(Nact + a * ld, 1, x, nv);
             __syncwarp(gm);
@@ -710,12 +713,14 @@ struct Warp {
         }
         __syncwarp(gm);
         gradient();
-        double dpart = 0.0;
+        double dpart = 0.0, xs_ = 0.0;
         LANES(j, nv) {
             const double s = dot2(Hinv + j * ld, 1, gn, nv);
             x[j] = -s;
             dpart -= 0.5 * gn[j] * s;
+            if (ONE) xs_ = fmax(xs_, fabs(s));
         }
+        if (ONE) { int xi_ = 0; wargmax<GW>(gm, xs_, xi_); xu_scale = xs_; }
         LANES(d, L) {
             const int i = d % nl, k = d / nl;
             const double kc = ((k == 0) ? -(am[d] * v0[i] + cm[d]) : -cm[d]) * rcp(bm[d]);
@@ -858,8 +863,13 @@ struct Warp {
                 LANES(j, nv) { const double a = fabs(x[j] - zc[j]); if (a > dl) dl = a; }
                 wargmax<GW>(gm, dl, dj);
                 const double f = objective();
+                // x = x_u - H^-1 N lambda is a difference of vectors of size |x_u|: with penalty gradients of 1e5 (a platoon
+                // deep inside its safety distance) and rho = 1e-3 that is 1e8, and the iterates jitter by ~1e-6 for ever --
+                // 5 of 49 152 per-vehicle MILPs ended as "numerical trouble" at the correct optimum.  The movement test
+                // therefore scales with the round-off level of the round; refine() then puts x on its active rows.
+                const double dtol = fmax(1e-6, 1e-13 * xu_scale);
                 const bool stalled = ppa >= 1 && f_prev - f <= S.ppa_stall * fmax(1.0, fabs(f));
-                if (dl > 1e-6 && !stalled && ppa < 200) {
+                if (dl > dtol && !stalled && ppa < 200) {
                     LANES(j, nv) zc[j] = x[j];
                     ++ppa;
                     f_prev = f;
@@ -868,7 +878,7 @@ struct Warp {
                     __syncwarp(gm);
                     return;
                 }
-                if (dl > 1e-6 && !stalled) { node_done(2, 0.0); return; }
+                if (dl > dtol && !stalled) { node_done(2, 0.0); return; }
                 ppa = 0;
                 refine();
                 node_done(0, objective());
