@@ -102,3 +102,55 @@ def test_tree_split_exchange_world2():
     assert [u[0][0] for u in o["u"]] == [2.0, 1.0, 0.0, 1.0]
     assert [m[0][0] for m in o["modes"]] == [4, 3, -1, 3]
     assert o["nodes"] == [15] * 4
+
+
+class _StubMpc:
+    """Stands in for api.CompiledMpc in the protocol test: records every shard call and answers with made-up results
+    (rank r finds objective 10 - r in the probing wave and, given a bound, bound - 1 - r in the full wave)."""
+    n_local, N, n_extra = 3, 4, 0
+
+    def __init__(self):
+        self.calls = []
+
+    def solve_shard_device(self, B, x0, mass, params, rank, world, groups, prefix_depth, node_budget, incumbent, u, x, extra,
+                           modes, obj, status, nodes, qp_iters, stream=None):
+        self.calls.append(dict(rank=rank, world=world, groups=groups, prefix_depth=prefix_depth, node_budget=node_budget,
+                               incumbent=None if incumbent is None else incumbent.clone()))
+        val = (10.0 - rank) if incumbent is None else float(incumbent[0]) - 1.0 - rank
+        obj.fill_(val); u.fill_(val); x.fill_(val); extra.zero_(); modes.fill_(rank); status.fill_(2)
+        nodes.fill_(5); qp_iters.fill_(50)
+
+
+def test_tree_split_protocol_waves_and_defaults(monkeypatch):
+    """dist.solve_tree_split with a stub formulation (no GPU): one device = ONE full wave (its workers share the incumbent
+    and adopt sub-trees, so there is nothing to probe); several devices = a probing wave with few workers and a node budget,
+    allreduce(min) of the bound, the full wave from that bound -- and, when the caller leaves the prefix depth to the
+    library, two more levels per doubling of the world on top of n + 2."""
+    import types
+    import torch
+    from hybrid_vehicle_platoon_b200 import dist as D
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+    B = 2
+    x0 = torch.zeros((B, 3, 2), dtype=torch.float64); mass = torch.ones((B, 3), dtype=torch.float64)
+    params = torch.zeros((B, 10), dtype=torch.float64)
+    # one device
+    cm = _StubMpc()
+    out = D.solve_tree_split(cm, x0, mass, params, groups=256, rank=0, world=1, allreduce=lambda t, op: None)
+    assert len(cm.calls) == 1
+    assert cm.calls[0]["node_budget"] == 0 and cm.calls[0]["incumbent"] is None and cm.calls[0]["groups"] == 256
+    assert cm.calls[0]["prefix_depth"] == 0                                   # library default (n + 2), chosen in pm_build.cu
+    assert out["obj"].tolist() == [10.0, 10.0] and out["status"].tolist() == [2, 2] and out["nodes"].tolist() == [5, 5]
+    # four devices, played by threads
+    cms = [_StubMpc() for _ in range(4)]
+    ranks = D.ThreadRanks(4)
+    outs = ranks.run(lambda r, w, ar: D.solve_tree_split(cms[r], x0, mass, params, groups=256, wave_budget=8, rank=r, world=w,
+                                                         allreduce=ar))
+    for r, c in enumerate(cms):
+        a, b = c.calls
+        assert a["node_budget"] == 8 and a["groups"] == 16 and a["incumbent"] is None          # the probe
+        assert b["node_budget"] == 0 and b["groups"] == 256
+        assert b["incumbent"].tolist() == [7.0, 7.0]                                          # min over ranks of 10 - r
+        assert a["prefix_depth"] == b["prefix_depth"] == 3 + 2 + 2 * 2
+    for o in outs:                                                          # rank 3 wins the full wave: 7 - 1 - 3
+        assert o["obj"].tolist() == [3.0, 3.0] and o["winner"].tolist() == [3, 3]
+        assert o["nodes"].tolist() == [40, 40] and o["bound_after_wave_a"].tolist() == [7.0, 7.0]
