@@ -340,7 +340,7 @@ def tree_split_leg(ctx, dev, n=8, N=6, problems=4, depth=0, groups=256, stress=F
         if rep > 0:
             ms.append(D.max_over_ranks([a.elapsed_time(b)], device=dev)[0])
     return {"value": problems / (float(np.mean(ms)) * 1e-3), "unit": "solves/s", "ms": float(np.mean(ms)), "problems": problems,
-            "variables": n * N, "prefix_depth": depth if depth else "library default (n + 2)", "warps_per_problem_per_gpu": groups,
+            "variables": n * N, "prefix_depth": depth if depth else "library default (n + 2 on one device, two more levels per doubling of the world)", "warps_per_problem_per_gpu": groups,
             "optimal_frac": float((out["status"] == 2).double().mean()), "nodes_per_solve": float(out["nodes"].double().mean()),
             "collective": "allreduce(min) of the incumbent objective, 8 B per problem, twice per solve (one device: none)"}
 
