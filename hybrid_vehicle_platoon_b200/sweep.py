@@ -146,7 +146,8 @@ class BatchedDecentSweep:
         # fastest on the short-horizon, constant-spacing problems of the headline benchmark.  "compiled": the LOCAL
         # formulation of the compiled-MPC kernel (csrc/pm_kernel.cu), whose interval-hull tightening and splitting of
         # heavy trees over many warps tame the long tail of hard instances -- long horizons and the time-headway policy
-        # (N = 10, headway: worst tree 13 000 -> 6 000 nodes and searched by 64-128 warps; 464 -> 52 ms per 20 480 MIQPs).
+        # (N = 10, headway: worst tree 13 000 -> 6 000 nodes, searched by 64 static workers plus every waiting worker that
+        # adopts a piece of it; 464 -> 13 ms per timestep of ~3 000 MIQPs).
         if solver not in ("auto", "local", "compiled"):
             raise ValueError("solver must be 'auto', 'local' or 'compiled'")
         # "auto" follows the measured crossover (scripts/diag_mixed.py, n = 10, 5 timesteps, 300 / 4096 scenarios, end of
