@@ -494,6 +494,8 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
         vehicles = sum(n * len(idx) for n, idx in by_n.items())          # problems per launch of this group
         key = (id(ctx), device, N, spacing_params(pol), vehicles <= 8192)
         if key not in _MIXED_CACHE:
+            while len(_MIXED_CACHE) >= 48:                     # bounded: the oldest group object (and its device scratch) goes
+                _MIXED_CACHE.pop(next(iter(_MIXED_CACHE)))
             sw = MixedSizeDecentSweep(N, spacing_policy=pol, device=device, ctx=ctx, batch_hint=vehicles)
             _MIXED_CACHE[key] = (sw, torch.cuda.Stream(device=sw.dev, priority=-1 if N >= 9 else 0), ctx)
         sw, stream, _ = _MIXED_CACHE[key]
