@@ -56,7 +56,7 @@ extern "C" int hvp_ctx_create(int device, hvp_ctx** out) {
     CUDA_TRY(cudaSetDevice(device));
     hvp_ctx* c = new hvp_ctx();
     c->device = device; c->timed = false; c->launches = 0; c->dbuf = nullptr; c->dcap = 0; c->hbuf = nullptr; c->hcap = 0;
-    c->counters = nullptr; c->counter_next = 0; c->side_ok = false; c->n_slots = 0;
+    c->counters = nullptr; c->counter_next = 0; c->side_ok = false; c->n_slots = 0; c->use_clock = 0;
     c->stream = nullptr; c->ev0 = nullptr; c->ev1 = nullptr;
     // a failure half-way must not leak what was created before it
     cudaError_t e = cudaMalloc(&c->counters, (HVP_STREAM_SLOTS + HVP_COUNTER_RING) * sizeof(unsigned long long));
@@ -83,7 +83,7 @@ extern "C" int hvp_ctx_destroy(hvp_ctx* c) {
     if (c->dbuf) cudaFree(c->dbuf);
     if (c->hbuf) cudaFreeHost(c->hbuf);
     if (c->counters) cudaFree(c->counters);
-    for (int i = 0; i < c->n_slots; ++i) if (c->slot_scratch[i]) cudaFree(c->slot_scratch[i]);
+    for (int i = 0; i < c->n_slots; ++i) { if (c->slot_scratch[i]) cudaFree(c->slot_scratch[i]); cudaEventDestroy(c->slot_done[i]); }
     if (c->side_ok) { for (int i = 0; i < 3; ++i) cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->side_ev); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -222,22 +222,49 @@ extern "C" int hvp_rollout_step_host(hvp_ctx* c, const hvp_env_desc* desc, int64
 // local MIQP
 // ------------------------------------------------------------------------------------------
 // counter and adoption scratch of a launch on `st` (see hvp_ctx): per stream, allocated on first use
-static int launch_slot(hvp_ctx* c, cudaStream_t st, unsigned long long** counter, double** scratch) {
-    for (int i = 0; i < c->n_slots; ++i)
-        if (c->slot_stream[i] == st) { *counter = c->counters + i; *scratch = c->slot_scratch[i]; return 0; }
+static int launch_slot(hvp_ctx* c, cudaStream_t st, unsigned long long** counter, double** scratch, int* slot) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
-    if (c->n_slots < HVP_STREAM_SLOTS && !capturing) {      // no allocation while the stream is being captured
-        double* p = nullptr;
-        CUDA_TRY(cudaMalloc(&p, HVP_STEAL_SLOT_DOUBLES * sizeof(double)));
-        const int i = c->n_slots++;
-        c->slot_stream[i] = st; c->slot_scratch[i] = p;
-        *counter = c->counters + i; *scratch = p;
-        return 0;
+    for (int i = 0; i < c->n_slots; ++i)
+        if (c->slot_stream[i] == st) {
+            c->slot_use[i] = ++c->use_clock;
+            if (capturing) c->slot_pinned[i] = true;
+            *counter = c->counters + i; *scratch = c->slot_scratch[i]; *slot = i;
+            return 0;
+        }
+    if (!capturing) {                                       // no allocation, no event query while the stream is being captured
+        int i = -1;
+        if (c->n_slots < HVP_STREAM_SLOTS) {
+            double* p = nullptr;
+            CUDA_TRY(cudaMalloc(&p, HVP_STEAL_SLOT_DOUBLES * sizeof(double)));
+            i = c->n_slots;
+            if (cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming) != cudaSuccess) { cudaFree(p); return fail(-3, "launch_slot: cudaEventCreate failed"); }
+            c->slot_scratch[i] = p; c->slot_pinned[i] = false;
+            ++c->n_slots;
+        } else {
+            for (int k = 0; k < c->n_slots; ++k) {          // least recently used slot whose last launch has finished
+                if (c->slot_pinned[k] || (i >= 0 && c->slot_use[k] >= c->slot_use[i])) continue;
+                if (cudaEventQuery(c->slot_done[k]) == cudaSuccess) i = k;
+            }
+            cudaGetLastError();                             // cudaErrorNotReady of a busy slot is not an error
+        }
+        if (i >= 0) {
+            c->slot_stream[i] = st; c->slot_use[i] = ++c->use_clock;
+            *counter = c->counters + i; *scratch = c->slot_scratch[i]; *slot = i;
+            return 0;
+        }
     }
     *counter = c->counters + HVP_STREAM_SLOTS + (c->counter_next++ % HVP_COUNTER_RING);
-    *scratch = nullptr;
+    *scratch = nullptr; *slot = -1;
     return 0;
+}
+
+// after the launch that used `slot`: remember when it is done (not while capturing: the event would belong to the graph)
+static void slot_mark(hvp_ctx* c, int slot, cudaStream_t st) {
+    if (slot < 0) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return;
+    cudaEventRecord(c->slot_done[slot], st);
 }
 
 static int check_local_desc(const hvp_local_desc* d) {
@@ -268,9 +295,11 @@ extern "C" int hvp_local_miqp_dev(hvp_ctx* c, const hvp_local_desc* desc, int64_
     CUDA_TRY(hvp_mark(c, c->ev0, st, false));
     unsigned long long* counter = nullptr;
     double* steal = nullptr;
-    rc = launch_slot(c, st, &counter, &steal);
+    int slot = -1;
+    rc = launch_slot(c, st, &counter, &steal, &slot);
     if (rc) return rc;
     CUDA_TRY(launch_local_miqp(P, counter, steal, batch, flags, mass, x0, xf, xb, xl, u, x, modes, obj, status, nodes, qp_iters, st));
+    slot_mark(c, slot, st);
     CUDA_TRY(hvp_mark(c, c->ev1, st, true));
     c->launches += 1;
     return 0;
@@ -362,11 +391,13 @@ extern "C" int hvp_local_miqp_host(hvp_ctx* c, const hvp_local_desc* desc, int64
             fill_local_params(P, desc->N, desc->d0, desc->t0, desc->tight, desc->max_nodes, desc->mip_gap, desc->time_limit_ms);
             unsigned long long* counter = nullptr;
             double* steal = nullptr;
-            rc = launch_slot(c, ss, &counter, &steal);
+            int slot = -1;
+            rc = launch_slot(c, ss, &counter, &steal, &slot);
             if (rc) return rc;
             CUDA_TRY(launch_local_miqp(P, counter, steal, (int64_t)nb, dfl + o, dma + o, dx0 + 2 * o, dxf ? dxf + S * o : nullptr,
                                        dxb ? dxb + S * o : nullptr, dxl ? dxl + S * o : nullptr, du + N * o, dx + S * o,
                                        dmo + N * o, dob + o, dst + o, dno + o, dit ? dit + o : nullptr, ss));
+            slot_mark(c, slot, ss);
             c->launches += 1;
             CUDA_TRY(cudaMemcpyAsync(u + N * o, du + N * o, nb * N * 8, cudaMemcpyDeviceToHost, ss));
             CUDA_TRY(cudaMemcpyAsync(x + S * o, dx + S * o, nb * S * 8, cudaMemcpyDeviceToHost, ss));

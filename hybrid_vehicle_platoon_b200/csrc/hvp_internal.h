@@ -21,13 +21,22 @@ struct hvp_ctx {
     size_t hcap;
     // Per-STREAM launch state of the persistent local-MIQP kernel: its work-distribution counter and the scratch rows of
     // the sub-tree adoption (one row per lane of the persistent grid).  Launches on one stream are serialised, so one
-    // slot per stream can never be shared by two launches in flight; a stream beyond the table runs without adoption
-    // and with a counter of its own from a ring that is only reused after HVP_COUNTER_RING further launches.
+    // slot per stream can never be shared by two launches in flight; a stream that finds neither a free nor a reusable
+    // slot runs without adoption and with a counter of its own from a ring that is only reused after HVP_COUNTER_RING
+    // further launches.
     unsigned long long* counters;                 // [HVP_STREAM_SLOTS + HVP_COUNTER_RING]
     int counter_next;
     cudaStream_t slot_stream[64];
     double* slot_scratch[64];
     int n_slots;
+    // When the table is full a NEW stream takes over the least recently used slot whose last launch has FINISHED
+    // (slot_done, recorded after every launch outside a capture) -- a caller that creates fresh streams for every call
+    // keeps its adoption scratch that way.  A slot that was used while its stream was being captured is pinned: the
+    // graph replays its launches later, on streams this table never sees.
+    cudaEvent_t slot_done[64];
+    unsigned long long slot_use[64];
+    bool slot_pinned[64];
+    unsigned long long use_clock;
     // side streams of the chunked *_host path (copies of one chunk overlap the kernel of another)
     cudaStream_t side[3];
     cudaEvent_t side_ev;

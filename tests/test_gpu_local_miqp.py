@@ -190,3 +190,50 @@ def test_modes_hint_never_changes_the_optimum(hvp_ctx):
         assert rel.max() < 1e-9, (name, rel.max(), int(rel.argmax()))
         if name == "optimal":
             assert r["nodes"][ok].mean() < base["nodes"][ok].mean(), (r["nodes"][ok].mean(), base["nodes"][ok].mean())
+
+
+@pytest.mark.gpu
+def test_more_streams_than_launch_slots(hvp_ctx):
+    """The library keeps the launch state of the per-vehicle kernel (work counter, adoption scratch) per STREAM, for 64
+    streams; a caller that keeps creating streams takes over the least recently used slot whose last launch has finished.
+    90 fresh streams one after the other, then 8 of them in flight at once: every launch returns the first one's answers
+    (objective to round-off -- adoption makes the order of incumbents timing-dependent -- statuses exactly)."""
+    import torch
+    from hybrid_vehicle_platoon_b200 import api
+    rng = np.random.default_rng(33)
+    N, n, S = 6, 10, 1024                                   # 10 240 problems: the flat kernel
+    c = platoon_local_problems(rng, S, n, N, stress=True)
+    B = S * n
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in c.items()}
+    f64, i32 = torch.float64, torch.int32
+
+    def launch(stream):
+        out = dict(u=torch.empty((B, N), dtype=f64, device=dev), x=torch.empty((B, 2, N + 1), dtype=f64, device=dev),
+                   mo=torch.empty((B, N), dtype=i32, device=dev), ob=torch.empty(B, dtype=f64, device=dev),
+                   st=torch.empty(B, dtype=i32, device=dev), no=torch.empty(B, dtype=i32, device=dev))
+        with torch.cuda.stream(stream):
+            api.local_miqp_device(api.local_desc(N), B, d["flags"], d["mass"], d["x0"], d["xf"], d["xb"], d["xl"], out["u"],
+                                  out["x"], out["mo"], out["ob"], out["st"], out["no"], None, ctx=hvp_ctx, stream=stream.cuda_stream)
+        return out
+
+    torch.cuda.synchronize()
+    base = launch(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    ok = base["st"] == 2
+
+    def same(o):
+        assert torch.equal(o["st"], base["st"])
+        assert torch.allclose(o["ob"][ok], base["ob"][ok], rtol=1e-9, atol=0)
+
+    keep = []
+    for _ in range(90):
+        s = torch.cuda.Stream(device=dev)
+        keep.append(s)
+        o = launch(s)
+        s.synchronize()
+        same(o)
+    outs = [launch(s) for s in keep[-8:]]                   # eight launches in flight, each on a stream of its own
+    torch.cuda.synchronize()
+    for o in outs:
+        same(o)
