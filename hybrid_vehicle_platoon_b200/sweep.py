@@ -851,7 +851,6 @@ class BatchedGAdmmSweep:
     def _make_admm_fused(self, S, x, mass, lwin):
         """_make_admm with the glue of a round in ONE kernel (csrc/coord.cu, hvp_gadmm_round_dev): a round is the three
         role solves (precompute + QP kernel each) and that kernel -- 7 launches instead of ~290 -- replayed as a graph."""
-        import ctypes as C
         from . import _lib
         torch, n, N, dev = self.torch, self.n, self.N, self.dev
         f64, i32, np1 = torch.float64, torch.int32, N + 1

@@ -22,6 +22,3 @@ for kw in (dict(fused=False), dict(), dict(graph=True), dict(fused=False), dict(
         torch.cuda.synchronize()
         t0 = time.perf_counter(); out = sw.run(x0, lx, T); dt = time.perf_counter() - t0
         print(kw, "T", T, "%.1f ms" % (dt * 1e3), "nodes %.2f" % out["nodes"].mean(), flush=True)
-# the MIQP launch alone on the states of the episode
-X = out["X"]
-from hybrid_vehicle_platoon_b200 import api
