@@ -213,8 +213,9 @@ int hvp_mpc_solve_host(hvp_mpc* mpc, int64_t batch, const double* x0, const doub
  * every problem, the sub-trees whose depth-`prefix_depth` mode-prefix ordinal o has o % world == rank (dealt to the
  * `groups` warps this device gives each problem by (o / world) % groups; the warps of a device share their
  * incumbent through global memory).  incumbent [batch] (device, or NULL = +inf) seeds the bound: only leaves
- * strictly better are accepted.  node_budget > 0 stops every warp after that many nodes (status 8) -- the cheap
- * first wave that produces a bound to exchange; 0 searches the share to completion.  obj [batch] = best leaf of
+ * strictly better are accepted.  node_budget > 0 stops every warp after that many nodes (every node counts: solved,
+ * pruned, infeasible, leaf; status 8) -- the cheap first wave that produces a bound to exchange; 0 searches the share to
+ * completion, and then warps of this device that run out of work adopt sub-trees of busy ones (any problem of the batch).  obj [batch] = best leaf of
  * THIS device's share (+inf: none better than the incumbent; status 3).  The caller combines the devices with
  * allreduce(min) over obj (NCCL) and takes u/x/modes from the device that attains it
  * (hybrid_vehicle_platoon_b200/dist.py: solve_tree_split).  prefix_depth 0 = the handle's default. */
