@@ -151,6 +151,13 @@ class Context:
         check(L.hvp_ctx_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        # compiled formulations built on this context: destroyed WITH it (hvp_mpc_destroy reads its context, so a handle
+        # must never outlive it -- and sweeps keep handles in caches that do)
+        import weakref
+        self._children = weakref.WeakSet()
+
+    def _register(self, child):
+        self._children.add(child)
 
     @property
     def handle(self):
@@ -172,6 +179,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):
+                child.close()
             lib().hvp_ctx_destroy(self._h)
             self._h = None
 

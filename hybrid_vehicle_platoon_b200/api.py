@@ -119,6 +119,8 @@ class CompiledMpc:
         h = C.c_void_p()
         check(lib().hvp_mpc_create(self.ctx.handle, C.byref(self.desc), C.byref(h)))
         self._h = h
+        if hasattr(self.ctx, "_register"):
+            self.ctx._register(self)
         info = (C.c_int32 * 8)()
         check(lib().hvp_mpc_info(h, info))
         (self.n_var, self.n_extra, self.n_param, self.n_modes, self.n_local, self.N, self.n_rows,

@@ -472,6 +472,9 @@ def run_mixed_sweep(scenarios, ep_len: int, rank: int = 0, world: int = 1, devic
         groups.setdefault((sc["N"], spacing_params(pol)), {}).setdefault(sc["n"], []).append(i)
     import torch
     out, work = {}, []
+    for k_, (_, _, cx_) in list(_MIXED_CACHE.items()):          # group objects of a context that has been closed since
+        if cx_ is not None and getattr(cx_, "handle", None) is None:
+            del _MIXED_CACHE[k_]
     # longest horizons first and on high-priority streams: the N = 10 / time-headway group alone is more than half of the
     # sweep's critical path (scripts/diag_mixed_groups.py), the short-horizon groups fit into its tails
     def weight(item):
