@@ -33,3 +33,23 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_episode_legs_warm_up_at_full_size_and_report_the_median():
+    """bench._episodes: one untimed run first (idle clocks, cold allocator), then the median of the timed runs, each
+    bracketed by the caller's sync and reduced over the ranks by the caller's reduction."""
+    import importlib
+    import time as _time
+    bench = importlib.import_module("bench")
+    calls, syncs = [], []
+    durations = iter([0.0, 0.03, 0.01, 0.02])               # warm-up, then three timed runs
+
+    def run():
+        calls.append(len(calls))
+        _time.sleep(next(durations))
+        return len(calls)
+
+    out, med, runs = bench._episodes(run, reps=3, sync=lambda: syncs.append(1), reduce=lambda d: round(d, 2))
+    assert calls == [0, 1, 2, 3] and out == 4               # warm-up + 3 timed; the last result is returned
+    assert len(syncs) == 3 and len(runs) == 3
+    assert med == sorted(runs)[1] and min(runs) <= med <= max(runs)
